@@ -1,0 +1,302 @@
+"""Pins the NumPy oracle against the known-answer tests held by the reference's own test-suite
+(SURVEY.md section 8c.1).  Each test names the reference test file:line it ports; literal inputs and
+expected values are the reference's."""
+import numpy as np
+import pytest
+
+from oracle import stencil, grids, halo, particles as opart, diagnostics, yee, fixtures as fx, evolve
+from oracle.params import TiledParticles, SpeciesConfig
+
+BC_P, BC_C = stencil.BC_PERIODIC, stencil.BC_CONDUCTING
+
+
+# ---- tests/code_tests/grid_and_stencil_test.py:27-110 ---------------------------------------------
+def test_wrap_periodic_position():
+    w = stencil.wrap_periodic_position(np.array([-2.5, -2.0, 1.75, 2.0, 2.25, 6.5]), 4.0)
+    assert np.allclose(w, [1.5, -2.0, 1.75, 2.0, -1.75, -1.5])
+
+
+def test_axis_activity_and_inactive_index():
+    assert stencil.axis_has_active_cells(6, ghost_cells=True)
+    assert not stencil.axis_has_active_cells(3, ghost_cells=True)
+    assert stencil.inactive_axis_index(3, ghost_cells=True) == 1
+    assert stencil.inactive_axis_index(1, ghost_cells=False) == 0
+
+
+def test_axis_spacing_and_anchor_helpers():
+    axis = grids.build_collocated_axis(-1.0, 0.5, 4)
+    pos = np.array([0.1, 0.6])
+    a = stencil.compute_particle_anchor(pos, axis, 1)
+    assert float(stencil.uniform_axis_spacing(axis)) == pytest.approx(0.5)
+    assert np.array_equal(a, [3, 4])
+    assert np.allclose(stencil.particle_axis_offset(pos, a, axis), [0.1, 0.1])
+
+
+def test_build_axis_stencil_points_periodic_and_conducting():
+    anchor, off = np.array([0, 5]), np.array([-1, 0, 1])
+    p = stencil.build_axis_stencil_points(anchor, 6, BC_P, off)
+    c = stencil.build_axis_stencil_points(anchor, 6, BC_C, off)
+    assert np.array_equal(p[:, 0], [5, 0, 1]) and np.array_equal(p[:, 1], [4, 5, 0])
+    assert np.array_equal(c[:, 0], [-1, 0, 1]) and np.array_equal(c[:, 1], [4, 5, 6])
+
+
+def test_prepare_particle_axis_stencil_wraps_periodic_indices():
+    axis = grids.build_collocated_axis(-1.0, 0.5, 4)
+    _, a, off, pts = stencil.prepare_particle_axis_stencil(np.array([1.1]), axis, 6, 1, BC_P, ghost_cells=True)
+    assert np.array_equal(a, [5]) and np.allclose(off, [0.1]) and np.array_equal(pts[:, 0], [4, 5, 0])
+
+
+def test_collapse_axis_stencil_for_inactive_axis():
+    pts = np.array([[0, 1], [1, 1], [2, 1]])
+    w = np.array([[0.2, 0.1], [0.5, 0.6], [0.3, 0.3]])
+    cp, cw = stencil.collapse_axis_stencil(pts, w, 3, ghost_cells=True)
+    assert np.array_equal(cp, [[1, 1]]) and np.allclose(cw, [[1.0, 1.0]])
+
+
+def test_build_axis_helpers_include_ghost_cells():
+    assert np.allclose(grids.build_collocated_axis(-1.0, 0.5, 4), [-1.5, -1.0, -0.5, 0.0, 0.5, 1.0])
+    assert np.allclose(grids.build_staggered_axis(-1.0, 0.5, 4), [-1.25, -0.75, -0.25, 0.25, 0.75, 1.25])
+
+
+# ---- tests/code_tests/distributed_ghost_cells_test.py:238-500 (g=1 KATs with hand-set ghosts) -----
+class _SP:
+    def __init__(self, bcs, tile_shape, pbcs=(0, 0, 0)):
+        self.boundary_conditions, self.tile_shape, self.particle_boundary_conditions = bcs, tile_shape, pbcs
+
+
+def _coordinate_tiles(mesh, tile, g=1):
+    t = np.zeros(tuple(mesh) + tuple(w + 2 * g for w in tile))
+    ii, jj, kk = np.meshgrid(*(np.arange(w, dtype=float) for w in tile), indexing="ij")
+    for tx in range(mesh[0]):
+        for ty in range(mesh[1]):
+            for tz in range(mesh[2]):
+                t[tx, ty, tz, g:-g, g:-g, g:-g] = 100.0 * tx + 10.0 * ty + tz + 0.01 * ii + 0.001 * jj + 0.0001 * kk
+    return t
+
+
+def test_one_device_periodic_refresh_self_exchange():
+    tiles = _coordinate_tiles((1, 1, 1), (3, 2, 2))
+    out = halo.update_tiled_ghost_cells(tiles, _SP((0, 0, 0), (3, 2, 2)), 1)
+    assert np.allclose(out[0, 0, 0, 0, 1:-1, 1:-1], tiles[0, 0, 0, -2, 1:-1, 1:-1])
+    assert np.allclose(out[0, 0, 0, -1, 1:-1, 1:-1], tiles[0, 0, 0, 1, 1:-1, 1:-1])
+
+
+def _ghost_deposits(shape=(5, 4, 4)):
+    t = np.zeros((1, 1, 1) + shape)
+    t[0, 0, 0, 0, 1:-1, 1:-1] = 3.0
+    t[0, 0, 0, -1, 1:-1, 1:-1] = 5.0
+    return t
+
+
+def test_one_device_periodic_fold():
+    out = halo.fold_tiled_ghost_cells(_ghost_deposits(), _SP((0, 0, 0), (3, 2, 2)), 1)
+    assert np.allclose(out[0, 0, 0, -2, 1:-1, 1:-1], 3.0) and np.allclose(out[0, 0, 0, 1, 1:-1, 1:-1], 5.0)
+    assert np.allclose(out[0, 0, 0, 0], 0.0) and np.allclose(out[0, 0, 0, -1], 0.0)
+
+
+def test_one_device_conducting_fold_sign():
+    out = halo.fold_tiled_ghost_cells(_ghost_deposits(), _SP((1, 0, 0), (3, 2, 2)), 1)
+    assert np.allclose(out[0, 0, 0, 1, 1:-1, 1:-1], -3.0) and np.allclose(out[0, 0, 0, -2, 1:-1, 1:-1], -5.0)
+    assert np.allclose(out[0, 0, 0, 0], 0.0) and np.allclose(out[0, 0, 0, -1], 0.0)
+
+
+def test_reduced_axis_refresh_uses_single_interior_cell():
+    tiles = _coordinate_tiles((1, 1, 1), (1, 3, 2))
+    tiles[0, 0, 0, 0] = -100.0
+    tiles[0, 0, 0, -1] = 100.0
+    out = halo.update_tiled_ghost_cells(tiles, _SP((0, 0, 0), (1, 3, 2)), 1)
+    assert np.allclose(out[0, 0, 0, 0], out[0, 0, 0, 1]) and np.allclose(out[0, 0, 0, -1], out[0, 0, 0, 1])
+    tiles = _coordinate_tiles((2, 2, 1), (2, 2, 1))
+    out = halo.update_tiled_ghost_cells(tiles, _SP((0, 0, 0), (2, 2, 1)), 1)
+    assert np.allclose(out[..., 0], out[..., 1]) and np.allclose(out[..., -1], out[..., 1])
+
+
+def test_bc_type_selects_field_or_particle_boundaries():
+    tiles = _coordinate_tiles((1, 1, 1), (3, 2, 2))
+    sp = _SP((0, 0, 0), (3, 2, 2), pbcs=(2, 0, 0))
+    f = halo.update_tiled_ghost_cells(tiles, sp, 1, bc_type=0)
+    p = halo.update_tiled_ghost_cells(tiles, sp, 1, bc_type=1)
+    assert np.allclose(f[0, 0, 0, 0, 1:-1, 1:-1], tiles[0, 0, 0, -2, 1:-1, 1:-1])
+    assert np.allclose(p[0, 0, 0, 0], 0.0) and np.allclose(p[0, 0, 0, -1], 0.0)
+    ff = halo.fold_tiled_ghost_cells(_ghost_deposits(), sp, 1, bc_type=0)
+    pf = halo.fold_tiled_ghost_cells(_ghost_deposits(), sp, 1, bc_type=1)
+    assert np.allclose(ff[0, 0, 0, -2, 1:-1, 1:-1], 3.0) and np.allclose(ff[0, 0, 0, 1, 1:-1, 1:-1], 5.0)
+    assert np.allclose(pf[0, 0, 0, 1:-1, 1:-1, 1:-1], 0.0) and np.allclose(pf[0, 0, 0, 0], 0.0)
+
+
+def test_reduced_absorbing_particle_axis_discards_ghosts():
+    sp = _SP((0, 0, 0), (1, 2, 2), pbcs=(2, 0, 0))
+    r = halo.update_tiled_ghost_cells(_coordinate_tiles((1, 1, 1), (1, 2, 2)), sp, 1, bc_type=1)
+    assert np.allclose(r[0, 0, 0, 0], 0.0) and np.allclose(r[0, 0, 0, -1], 0.0)
+    f = halo.fold_tiled_ghost_cells(_ghost_deposits((3, 4, 4)), sp, 1, bc_type=1)
+    assert np.allclose(f[0, 0, 0], 0.0)
+
+
+# ---- tests/code_tests/particle_refresh_test.py:80-183 ---------------------------------------------
+def _refresh_params(pbc=(0, 0, 0)):
+    return fx.kernel_parameters(Nx=4, Ny=1, Nz=1, x_wind=4.0, y_wind=1.0, z_wind=1.0, dt=1.0, tile_shape=(2, 1, 1),
+                                particle_boundary_conditions=pbc)
+
+
+def _moving_species(x1, v1, active=None, update_x=True):
+    return fx.particle_species("moving", 2.0, 3.0, weight=4.0, x1=x1, u1=v1, active_mask=active, update_x=update_x)
+
+
+def _active_rows(tp):
+    a = tp.active.reshape(-1)
+    x, u = tp.x.reshape(-1, 3)[a], tp.u.reshape(-1, 3)[a]
+    o = np.argsort(x[:, 0], kind="stable")
+    return x[o], u[o]
+
+
+def test_update_positions_respects_active_and_update_flags():
+    sp, dp = _refresh_params()
+    tp, sc = fx.build_tiled_particles([_moving_species([-1.5, -0.5, 0.5], [0.25, 0.5, 0.75], active=[True, False, True])], sp, dp)
+    moved = opart.update_tiled_particle_positions(tp, sc, 1.0)
+    x, _ = _active_rows(moved)
+    assert np.allclose(x[:, 0], [-1.25, 1.25])
+    assert np.allclose(moved.x[~tp.active], tp.x[~tp.active])
+    tp, sc = fx.build_tiled_particles([_moving_species([-1.5], [0.25], update_x=False)], sp, dp)
+    assert np.allclose(opart.update_tiled_particle_positions(tp, sc, 1.0).x, tp.x)
+
+
+def test_adjacent_tile_offset_periodic_edges():
+    assert np.array_equal(opart.adjacent_tile_offset(np.array([0, 1, 0, 1]), np.array([0, 0, 1, 1]), 2), [0, 1, -1, 0])
+
+
+def test_refresh_moves_to_neighbor_static_shape():
+    sp, dp = _refresh_params()
+    tp, sc = fx.build_tiled_particles([_moving_species([-1.5, -0.25, 0.25], [0.0] * 3)], sp, dp)
+    x = tp.x.copy(); x[0, 0, 0, 0, 1, 0] = 0.25
+    r, ovf = opart.refresh_tiled_particle_tiles(tp._replace(x=x), sp, dp)
+    assert r.x.shape == tp.x.shape and not ovf
+    assert r.active[0, 0, 0, 0].sum() == 1 and r.active[1, 0, 0, 0].sum() == 2
+    xs, us = _active_rows(r)
+    assert np.allclose(xs[:, 0], [-1.5, 0.25, 0.25]) and np.allclose(us[:, 0], 0.0)
+
+
+def test_refresh_wraps_periodic():
+    sp, dp = _refresh_params()
+    tp, sc = fx.build_tiled_particles([_moving_species([1.75], [0.0])], sp, dp)
+    x = tp.x.copy(); x[1, 0, 0, 0, 0, 0] = 2.25
+    r, ovf = opart.refresh_tiled_particle_tiles(tp._replace(x=x), sp, dp)
+    assert not ovf and r.active[0, 0, 0, 0, 0] and np.isclose(r.x[0, 0, 0, 0, 0, 0], -1.75)
+
+
+def test_refresh_reflects():
+    sp, dp = _refresh_params((1, 0, 0))
+    tp, sc = fx.build_tiled_particles([_moving_species([1.75, -1.75], [0.5, -0.25])], sp, dp)
+    x = tp.x.copy(); x[1, 0, 0, 0, 0, 0] = 2.25; x[0, 0, 0, 0, 0, 0] = -2.10
+    r, ovf = opart.refresh_tiled_particle_tiles(tp._replace(x=x), sp, dp)
+    xs, us = _active_rows(r)
+    assert not ovf and np.allclose(xs[:, 0], [-1.90, 1.75]) and np.allclose(us[:, 0], [0.25, -0.5])
+
+
+def test_refresh_absorbs():
+    sp, dp = _refresh_params((2, 0, 0))
+    tp, sc = fx.build_tiled_particles([_moving_species([1.75, -0.25], [0.5, 0.0])], sp, dp)
+    x = tp.x.copy(); x[1, 0, 0, 0, 0, 0] = 2.25
+    r, ovf = opart.refresh_tiled_particle_tiles(tp._replace(x=x), sp, dp)
+    xs, us = _active_rows(r)
+    assert not ovf and r.active.sum() == 1 and np.allclose(xs[:, 0], [-0.25]) and np.allclose(us[:, 0], [0.0])
+
+
+def test_refresh_reports_overflow():
+    sp, dp = _refresh_params()
+    tp, sc = fx.build_tiled_particles([_moving_species([-1.5, 0.5, 1.5], [0.0] * 3)], sp, dp)
+    x = tp.x.copy(); x[0, 0, 0, 0, 0, 0] = 0.25
+    r, ovf = opart.refresh_tiled_particle_tiles(tp._replace(x=x), sp, dp)
+    assert r.x.shape == tp.x.shape and ovf and r.active.sum() == 2
+
+
+# ---- tests/code_tests/distributed_particle_refresh_test.py:105-169 --------------------------------
+def _dist_params(mesh, tile):
+    n = [mesh[a] * tile[a] for a in range(3)]
+    return fx.kernel_parameters(Nx=n[0], Ny=n[1], Nz=n[2], x_wind=float(n[0]), y_wind=float(n[1]), z_wind=float(n[2]),
+                                tile_shape=tile)
+
+
+def _empty_particles(mesh, slots=2):
+    return TiledParticles(np.zeros(mesh + (1, slots, 3)), np.zeros(mesh + (1, slots, 3)), np.zeros(mesh + (1, slots), dtype=bool))
+
+
+def _put(p, tile, slot, x):
+    p.x[tile + (0, slot)] = x
+    p.active[tile + (0, slot)] = True
+    return p
+
+
+def test_dist_refresh_x_neighbor():
+    sp, dp = _dist_params((2, 1, 1), (2, 1, 1))
+    r, ovf = opart.refresh_tiled_particle_tiles(_put(_empty_particles((2, 1, 1)), (0, 0, 0), 0, (0.25, 0, 0)), sp, dp)
+    assert not ovf and r.active[0, 0, 0, 0].sum() == 0 and r.active[1, 0, 0, 0].sum() == 1
+    assert np.isclose(r.x[1, 0, 0, 0, 0, 0], 0.25)
+
+
+def test_dist_refresh_periodic_edge():
+    sp, dp = _dist_params((2, 1, 1), (2, 1, 1))
+    r, ovf = opart.refresh_tiled_particle_tiles(_put(_empty_particles((2, 1, 1)), (1, 0, 0), 0, (2.25, 0, 0)), sp, dp)
+    assert not ovf and r.active[1, 0, 0, 0].sum() == 0 and r.active[0, 0, 0, 0].sum() == 1
+    assert np.isclose(r.x[0, 0, 0, 0, 0, 0], -1.75)
+
+
+def test_dist_refresh_diagonal():
+    sp, dp = _dist_params((2, 2, 1), (2, 2, 1))
+    r, ovf = opart.refresh_tiled_particle_tiles(_put(_empty_particles((2, 2, 1)), (0, 0, 0), 0, (0.25, 0.25, 0)), sp, dp)
+    assert not ovf and r.active[0, 0, 0, 0].sum() == 0 and r.active[1, 1, 0, 0].sum() == 1
+    assert np.allclose(r.x[1, 1, 0, 0, 0, :2], [0.25, 0.25])
+
+
+def test_dist_refresh_capacity_overflow():
+    sp, dp = _dist_params((2, 1, 1), (2, 1, 1))
+    p = _put(_put(_empty_particles((2, 1, 1), 1), (0, 0, 0), 0, (0.25, 0, 0)), (1, 0, 0), 0, (1.25, 0, 0))
+    r, ovf = opart.refresh_tiled_particle_tiles(p, sp, dp)
+    assert ovf and r.x.shape == p.x.shape and r.active.sum() == 1
+
+
+# ---- tests/code_tests/utils_test.py:286-346 (energy KATs) -----------------------------------------
+def _one_species():
+    return SpeciesConfig(np.array([1.0]), np.array([1.0]), np.array([1.0]), np.ones((1, 3), bool), np.ones((1, 3), bool))
+
+
+def test_energy_kat():
+    sp, dp = fx.kernel_parameters(Nx=1, Ny=1, Nz=1, x_wind=1.0, y_wind=1.0, z_wind=1.0, eps=2.0, mu=4.0, C=10.0)
+    E, B = fx.empty_tiled_vector(sp, dp), fx.empty_tiled_vector(sp, dp)
+    g = 2
+    I = (0, 0, 0, slice(g, g + 1), slice(g, g + 1), slice(g, g + 1))
+    E[0][I] = 2.0
+    B[1][I] = 3.0
+    tp = TiledParticles(np.zeros((1, 1, 1, 1, 0, 3)), np.zeros((1, 1, 1, 1, 0, 3)), np.zeros((1, 1, 1, 1, 0), bool))
+    e, b, k = diagnostics.compute_energy(tp, E, B, sp, dp, _one_species())
+    assert np.isclose(e, 4.0) and np.isclose(b, 1.125) and k == 0.0
+
+
+def test_energy_ignores_inactive():
+    sp, dp = fx.kernel_parameters(Nx=1, Ny=1, Nz=1, x_wind=1.0, y_wind=1.0, z_wind=1.0, C=10.0)
+    E, B = fx.empty_tiled_vector(sp, dp), fx.empty_tiled_vector(sp, dp)
+    tp = TiledParticles(np.array([[[[[[0.6, 0, 0]]]]]]), np.array([[[[[[1.0, 0, 0]]]]]]), np.array([[[[[False]]]]]))
+    assert np.isclose(diagnostics.compute_energy(tp, E, B, sp, dp, _one_species())[2], 0.0)
+
+
+# ---- tests/code_tests/esirkepov_test.py:510-529 (update_E KAT) ------------------------------------
+def test_update_E_reads_two_guard_current_interior():
+    sp, dp = fx.kernel_parameters(Nx=4, Ny=1, Nz=1, x_wind=4.0, y_wind=1.0, z_wind=1.0, dt=0.25, tile_shape=(2, 1, 1), C=1.0, eps=2.0)
+    E, B, J = fx.empty_tiled_vector(sp, dp), fx.empty_tiled_vector(sp, dp), fx.empty_tiled_vector(sp, dp)
+    J[0][:, :, :, 2:-2, 2:-2, 2:-2] = 4.0
+    Ea = yee.update_E(E, B, J, sp, dp)
+    assert np.allclose(Ea[0][:, :, :, 2:-2, 2:-2, 2:-2], -0.5)
+
+
+# ---- code-is-authority pin for the half-step B update (SURVEY.md section 4 "stale pins") -----------
+def test_update_B_is_a_half_step():
+    # first_order_yee.py:116 sets dt = dt/2; yee_convergence_test.py:69-75 (expects dt*cos x) is stale.
+    n = 16
+    sp, dp = fx.kernel_parameters(Nx=n, Ny=1, Nz=1, x_wind=2 * np.pi, y_wind=1.0, z_wind=1.0, dt=0.1)
+    xc = -np.pi + np.arange(n) * dp.dx
+    Ez = np.zeros((n + 2, 3, 3)); Ez[1:-1, 1, 1] = np.sin(xc)
+    z = np.zeros_like(Ez)
+    E = fx.vector_tiles_from_global((z, z, Ez), sp, dp)
+    B = update = yee.update_B(E, fx.empty_tiled_vector(sp, dp), sp, dp)
+    By = diagnostics.assemble_tiled_scalar_field(B[1], sp.tile_shape, 2)[1:-1, 1, 1]
+    dEz = (np.roll(np.sin(xc), -1) - np.sin(xc)) / dp.dx
+    assert np.allclose(By, +0.5 * dp.dt * dEz, atol=1e-14)   # By -= (dt/2) * (dEx/dz - dEz/dx)
