@@ -1,0 +1,186 @@
+/*
+ * pic_b200.h -- C ABI of libpic_b200.so: hand-written sm_100a CUDA kernels for the PyPIC3D
+ * electrodynamic PIC step (push + deposit + Yee + guard cells).
+ *
+ * The reference (uwplasma/PyPIC3D v0.1.3) is pure Python/JAX and has NO FFI; its boundary is the Python
+ * calling convention of PyPIC3D/evolve.py:16-22 and of the sub-entry points listed next to each function
+ * below.  Every entry point here is what a binding for that call site would bind: plain device pointers,
+ * sizes and one POD parameter block -- no torch / JAX types.  All functions
+ *   - run asynchronously on the CUDA stream passed as `stream` (a cudaStream_t cast to void*),
+ *   - return 0 on success, a negative PIC_E* code on a bad argument, or a positive cudaError_t,
+ *   - never throw, never allocate device memory, never synchronise (except where stated).
+ * Threading: one host thread per GPU; calls on one stream are ordered.
+ *
+ * Layouts (identical to the reference so import/export are plain copies):
+ *   tiled scalar field : (ntx,nty,ntz, Lx,Ly,Lz), L = W + 2g, C order, z fastest   (ghost_cells.py:13)
+ *   tiled vector field : three such arrays (x,y,z components)                       (evolve.py:27)
+ *   TiledParticles     : x,u (ntx,nty,ntz,S,cap,3) reals, active (ntx,nty,ntz,S,cap) bytes
+ *                        (particles/particle_class.py:17-31); u is the velocity v, not gamma*v.
+ *   SpeciesConfig      : charge, mass, weight (S,) doubles; update_x, update_u (S,3) bytes
+ *                        (particles/particle_class.py:5-14)
+ * `dtype` in PicParams selects float (0) or double (1) for every `void*` real array.
+ */
+#ifndef PIC_B200_H
+#define PIC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PIC_F32 0
+#define PIC_F64 1
+
+#define PIC_PUSHER_BORIS 0        /* pusher/boris.py:15  boris_single_particle              */
+#define PIC_PUSHER_BORIS_REL 1    /* pusher/boris.py:61  relativistic_boris_single_particle */
+#define PIC_PUSHER_HC 2           /* pusher/higuera_cary.py:58                              */
+
+#define PIC_BC_PERIODIC 0         /* grid_and_stencil.py:10 ; particles: periodic wrap      */
+#define PIC_BC_CONDUCTING 1       /* grid_and_stencil.py:11 ; particles: reflecting         */
+#define PIC_BC_ABSORBING 2        /* particles only (particle_tile_communication.py:45)     */
+
+#define PIC_FILTER_DIGITAL 0      /* utilities/filters.py:98  */
+#define PIC_FILTER_BILINEAR 1     /* utilities/filters.py:73  */
+
+#define PIC_HALO_SET 0
+#define PIC_HALO_ADD 1
+#define PIC_HALO_SUB 2
+
+#define PIC_EINVAL (-1)
+#define PIC_EUNSUPPORTED (-2)
+
+#define PIC_MAX_SPECIES 16
+
+/* POD mirror of StaticParameters + the scalar leaves of DynamicParameters (parameters.py:14-53).
+ * `mesh` is the tile-array shape resident on THIS GPU, `gmesh`/`moff` place it in the global tile mesh
+ * (one process per GPU: mesh = (1,1,1), gmesh = process grid, moff = this rank's coordinates). */
+typedef struct PicParams {
+    int32_t dtype;            /* PIC_F32 / PIC_F64                                         */
+    int32_t shape_factor;     /* 1 = CIC, 2 = TSC (deposition/shapes.py)                    */
+    int32_t pusher;           /* PIC_PUSHER_*                                               */
+    int32_t g;                /* guard cells                                                */
+    int32_t mesh[3];          /* local tile-array shape                                     */
+    int32_t gmesh[3];         /* global tile mesh shape                                     */
+    int32_t moff[3];          /* offset of the local tile array inside the global mesh      */
+    int32_t tile[3];          /* tile widths W (cells)                                      */
+    int32_t field_bc[3];      /* StaticParameters.boundary_conditions                       */
+    int32_t particle_bc[3];   /* StaticParameters.particle_boundary_conditions              */
+    int32_t n_species;
+    int32_t pad0;
+    double dt, dx, dy, dz;
+    double wind[3];           /* x_wind, y_wind, z_wind                                     */
+    double C, eps, mu, alpha;
+    double center0[3];        /* grids.center[a][0]  (= -wind/2 - d)                        */
+    double vertex0[3];        /* grids.vertex[a][0]  (= -wind/2 - d/2)                      */
+    double charge[PIC_MAX_SPECIES], mass[PIC_MAX_SPECIES], weight[PIC_MAX_SPECIES];
+    uint8_t update_x[PIC_MAX_SPECIES][3], update_u[PIC_MAX_SPECIES][3];
+} PicParams;
+
+const char* pic_version(void);
+int pic_params_size(void);       /* sizeof(PicParams) -- lets a binding verify its struct layout */
+
+/* ---------------- reference-layout operators (drop-in for the reference's sub-entry points) ------------ */
+
+/* pusher/particle_push.py:13 particle_push: gather E,B (6x up-to-27-point) + Boris/HC; writes u_out.
+ * E/B: 3 tiled component arrays each (already E+E_ext, B+B_ext: utils.py:205). */
+int pic_push(const PicParams* p, const void* x, const void* u_in, void* u_out, const uint8_t* active,
+             int64_t cap, const void* const E[3], const void* const B[3], void* stream);
+
+/* deposition/Esirkepov.py:105-331 deposit_one_tile for every local tile: J must be zeroed by the caller;
+ * ghost deposits are left in the ghosts (fold with pic_halo_fold_axis). */
+int pic_deposit_esirkepov(const PicParams* p, const void* x, const void* u, const uint8_t* active, int64_t cap,
+                          void* const J[3], void* stream);
+/* deposition/J_from_rhov.py:83-200 deposit_one_tile (node/face rho*v weights). */
+int pic_deposit_direct(const PicParams* p, const void* x, const void* u, const uint8_t* active, int64_t cap,
+                       void* const J[3], void* stream);
+/* deposition/rho.py:66-150 deposit_one_tile. */
+int pic_deposit_rho(const PicParams* p, const void* x, const uint8_t* active, int64_t cap, void* rho, void* stream);
+
+/* particles/particle_tile_communication.py:82 update_tiled_particle_positions: x_out = x + active*upd*u*dt. */
+int pic_move(const PicParams* p, const void* x_in, void* x_out, const void* u, const uint8_t* active, int64_t cap,
+             double dt, void* stream);
+
+/* particles/particle_tile_communication.py:440 refresh_tiled_particle_tiles over the LOCAL tile mesh:
+ * global particle BCs, re-own by tile, move to the <=26 neighbour tiles (k-th incoming -> k-th free slot),
+ * overflow flag (int32 on device, OR-ed in).  Out arrays must not alias the inputs.
+ * scratch: int32[ntiles*S*cap * 2].  Requires mesh == gmesh (single process). */
+int pic_retile(const PicParams* p, const void* x_in, const void* u_in, const uint8_t* active_in, void* x_out,
+               void* u_out, uint8_t* active_out, int64_t cap, int32_t* scratch, int32_t* overflow, void* stream);
+
+/* solvers/first_order_yee.py:42-72 : E[A] += dt*(C^2 curl B - J/eps) on every tile interior (no refresh). */
+int pic_update_E(const PicParams* p, void* const E[3], const void* const B[3], const void* const J[3], void* stream);
+/* solvers/first_order_yee.py:116-142 : B[A] -= (dt/2) curl E on every tile interior (half step). */
+int pic_update_B(const PicParams* p, void* const B[3], const void* const E[3], void* stream);
+
+/* utilities/filters.py:73/98 : out[A] = sum_27 k*in[A+off]; ghosts copied.  in != out. */
+int pic_filter(const PicParams* p, int kind, double alpha, const void* in, void* out, void* stream);
+
+/* boundary_conditions/ghost_cells.py:142-196 (_local_refresh_reduced_axis/_refresh_axis) for one axis over the
+ * local tile mesh, in place, for `ncomp` arrays.  bc = the selected tuple's entry for this axis. */
+int pic_halo_refresh_axis(const PicParams* p, int axis, int bc, int ncomp, void* const* fields, void* stream);
+/* boundary_conditions/ghost_cells.py:218-289 (_local_fold_reduced_axis/_fold_axis incl. conducting wall). */
+int pic_halo_fold_axis(const PicParams* p, int axis, int bc, int ncomp, void* const* fields, void* stream);
+/* boundary_conditions/ghost_cells.py:344-362 _apply_local_zero_boundary_axis (planes g and -g-1 on wall tiles). */
+int pic_zero_wall(const PicParams* p, int axis, void* field, void* stream);
+
+/* Multi-GPU halo plumbing for one distributed axis (mesh[axis]==1 < gmesh[axis]): copy `nplanes` planes
+ * starting at local index `start` of `ncomp` arrays to/from a packed buffer [comp][plane][transverse].
+ * The packed faces travel by ncclSend/ncclRecv (ghost_cells.py:187,191,271,272 ppermute). */
+int pic_pack_planes(const PicParams* p, int axis, int start, int nplanes, int ncomp, const void* const* fields,
+                    void* buf, void* stream);
+int pic_unpack_planes(const PicParams* p, int axis, int start, int nplanes, int ncomp, void* const* fields,
+                      const void* buf, int mode, void* stream);
+
+/* utils.py:160-187 compute_energy pieces: out[0] += sum over interiors of f^2 (double accumulate). */
+int pic_sum_squares_interior(const PicParams* p, const void* field, double* out, void* stream);
+/* out[0] += sum active*(sqrt(p^2C^2+m^2C^4)-mC^2), out[1] += sum active*|v|*m  (utils.py:170-202). */
+int pic_particle_energy(const PicParams* p, const void* u, const uint8_t* active, int64_t cap, double* out, void* stream);
+
+/* ---------------- resident fast path: cell-sorted SoA particles, one tile per GPU ---------------------- */
+
+/* One species in the resident layout: SoA rows x,y,z,vx,vy,vz of capacity `cap` (dead slots have x = NaN). */
+typedef struct PicSoA {
+    void* comp[6];
+    int32_t* id;        /* original reference slot (tile-major s*cap+slot) or -1; may be NULL */
+    int64_t cap;
+    int64_t n;          /* slots in use (live + dead holes) */
+} PicSoA;
+
+/* TiledParticles (reference layout, single local tile) -> compact SoA of species s.  d_count: int32 device counter
+ * (zeroed by the caller) receiving the number of particles written. */
+int pic_soa_import(const PicParams* p, int species, const void* x, const void* u, const uint8_t* active, int64_t cap_ref,
+                   const PicSoA* soa, int32_t* d_count, void* stream);
+/* SoA -> reference layout (slots by id when id != NULL, else compacted); outputs must be pre-zeroed. */
+int pic_soa_export(const PicParams* p, int species, const PicSoA* soa, void* x, void* u, uint8_t* active, int64_t cap_ref,
+                   int32_t* d_count, void* stream);
+
+/* Counting sort by local cell (K2).  Three calls: histogram -> exclusive scan -> scatter.
+ * cell_count/cell_offset: int32[ncells+1] (ncells = tile[0]*tile[1]*tile[2], last bin = dead particles). */
+int pic_sort_histogram(const PicParams* p, const PicSoA* src, int32_t* cell_count, void* stream);
+int pic_sort_scan(int64_t n, const int32_t* in, int32_t* out, int32_t* block_scratch, void* stream);
+int pic_sort_scatter(const PicParams* p, const PicSoA* src, const PicSoA* dst, const int32_t* cell_offset,
+                     int32_t* cell_cursor, void* stream);
+
+/* K1: the fused step for one species over the resident layout --
+ *   gather E,B (+ext) -> Boris/HC -> deposit (Esirkepov: x -> x+v*dt ; direct: at x+v*dt/2) -> move -> particle BC
+ * == evolve.py:33-79 for one local tile.  J is accumulated with atomics into the ghosted tile (fold afterwards).
+ * deposition: 0 = esirkepov, 1 = direct.  ext_E/ext_B may be NULL (external fields absent).
+ * Leavers (multi-GPU, distributed axes) are appended to `leave` (6+1 rows: x,y,z,vx,vy,vz,dir code) with
+ * counter d_leave_count; pass NULL when mesh == gmesh.  flags[0] |= 1 on overflow / invalid jump. */
+int pic_fused_push_deposit(const PicParams* p, int species, int deposition, const PicSoA* soa,
+                           const void* const E[3], const void* const B[3], const void* const extE[3],
+                           const void* const extB[3], void* const J[3], void* leave, int64_t leave_cap,
+                           int32_t* d_leave_count, int32_t* flags, void* stream);
+
+/* Append `n_in` migrated particles (7-row packet as written by the fused kernel) to the SoA tail. */
+int pic_soa_append(const PicParams* p, const PicSoA* soa, const void* packet, int64_t packet_cap, int64_t n_in,
+                   int32_t* flags, void* stream);
+
+/* Microbenchmarks used for design evidence (profiles/): returns elapsed device ms for `iters` launches. */
+int pic_microbench(int which, int iters, float* ms_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PIC_B200_H */

@@ -1,0 +1,201 @@
+"""ctypes binding of libpic_b200.so (the C ABI declared in include/pic_b200.h).
+
+There is NO CPU fallback: if the shared library cannot be built/loaded, or a tensor is not on a CUDA device, the
+operators raise.  PyTorch is used only for device memory and streams; every computation on the hot path is a
+hand-written sm_100a kernel behind the C ABI.
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(_HERE)
+LIB_PATH = os.path.join(_HERE, "libpic_b200.so")
+SOURCES = ["kernels_particles_ref.cu", "kernels_fields.cu", "kernels_fast.cu", "microbench.cu"]
+HEADERS = ["pic_common.cuh", "pic_math.cuh", "pic_slots.cuh"]
+MAX_SPECIES = 16
+
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "-Xcompiler", "-fPIC", "-shared"]
+
+
+class PicParams(ctypes.Structure):
+    """Mirror of `struct PicParams` (include/pic_b200.h)."""
+    _fields_ = [
+        ("dtype", ctypes.c_int32), ("shape_factor", ctypes.c_int32), ("pusher", ctypes.c_int32), ("g", ctypes.c_int32),
+        ("mesh", ctypes.c_int32 * 3), ("gmesh", ctypes.c_int32 * 3), ("moff", ctypes.c_int32 * 3),
+        ("tile", ctypes.c_int32 * 3), ("field_bc", ctypes.c_int32 * 3), ("particle_bc", ctypes.c_int32 * 3),
+        ("n_species", ctypes.c_int32), ("pad0", ctypes.c_int32),
+        ("dt", ctypes.c_double), ("dx", ctypes.c_double), ("dy", ctypes.c_double), ("dz", ctypes.c_double),
+        ("wind", ctypes.c_double * 3),
+        ("C", ctypes.c_double), ("eps", ctypes.c_double), ("mu", ctypes.c_double), ("alpha", ctypes.c_double),
+        ("center0", ctypes.c_double * 3), ("vertex0", ctypes.c_double * 3),
+        ("charge", ctypes.c_double * MAX_SPECIES), ("mass", ctypes.c_double * MAX_SPECIES),
+        ("weight", ctypes.c_double * MAX_SPECIES),
+        ("update_x", (ctypes.c_uint8 * 3) * MAX_SPECIES), ("update_u", (ctypes.c_uint8 * 3) * MAX_SPECIES),
+    ]
+
+
+class PicSoA(ctypes.Structure):
+    """Mirror of `struct PicSoA`."""
+    _fields_ = [("comp", ctypes.c_void_p * 6), ("id", ctypes.c_void_p), ("cap", ctypes.c_int64), ("n", ctypes.c_int64)]
+
+
+def needs_build():
+    if not os.path.exists(LIB_PATH):
+        return True
+    t = os.path.getmtime(LIB_PATH)
+    deps = [os.path.join(_HERE, "csrc", f) for f in SOURCES + HEADERS] + [os.path.join(_ROOT, "include", "pic_b200.h")]
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force=False, verbose=False):
+    """Compile every CUDA translation unit for sm_100a into pypic3d_b200/libpic_b200.so (in-tree)."""
+    if not force and not needs_build():
+        return LIB_PATH
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    if not os.path.exists(nvcc):
+        nvcc = "nvcc"
+    cmd = [nvcc] + NVCC_FLAGS + ["-o", LIB_PATH] + [os.path.join(_HERE, "csrc", f) for f in SOURCES]
+    if verbose:
+        print(" ".join(cmd))
+    subprocess.run(cmd, check=True)
+    return LIB_PATH
+
+
+_LIB = None
+
+_VP = ctypes.c_void_p
+_PP = ctypes.POINTER(PicParams)
+_I64 = ctypes.c_int64
+_INT = ctypes.c_int
+_DBL = ctypes.c_double
+_V3 = ctypes.POINTER(ctypes.c_void_p)
+_SOA = ctypes.POINTER(PicSoA)
+
+# name -> argtypes; every symbol declared in include/pic_b200.h
+SIGNATURES = {
+    "pic_push": [_PP, _VP, _VP, _VP, _VP, _I64, _V3, _V3, _VP],
+    "pic_deposit_esirkepov": [_PP, _VP, _VP, _VP, _I64, _V3, _VP],
+    "pic_deposit_direct": [_PP, _VP, _VP, _VP, _I64, _V3, _VP],
+    "pic_deposit_rho": [_PP, _VP, _VP, _I64, _VP, _VP],
+    "pic_move": [_PP, _VP, _VP, _VP, _VP, _I64, _DBL, _VP],
+    "pic_retile": [_PP, _VP, _VP, _VP, _VP, _VP, _VP, _I64, _VP, _VP, _VP],
+    "pic_update_E": [_PP, _V3, _V3, _V3, _VP],
+    "pic_update_B": [_PP, _V3, _V3, _VP],
+    "pic_filter": [_PP, _INT, _DBL, _VP, _VP, _VP],
+    "pic_halo_refresh_axis": [_PP, _INT, _INT, _INT, _V3, _VP],
+    "pic_halo_fold_axis": [_PP, _INT, _INT, _INT, _V3, _VP],
+    "pic_zero_wall": [_PP, _INT, _VP, _VP],
+    "pic_pack_planes": [_PP, _INT, _INT, _INT, _INT, _V3, _VP, _VP],
+    "pic_unpack_planes": [_PP, _INT, _INT, _INT, _INT, _V3, _VP, _INT, _VP],
+    "pic_sum_squares_interior": [_PP, _VP, _VP, _VP],
+    "pic_particle_energy": [_PP, _VP, _VP, _I64, _VP, _VP],
+    "pic_soa_import": [_PP, _INT, _VP, _VP, _VP, _I64, _SOA, _VP, _VP],
+    "pic_soa_export": [_PP, _INT, _SOA, _VP, _VP, _VP, _I64, _VP, _VP],
+    "pic_sort_histogram": [_PP, _SOA, _VP, _VP],
+    "pic_sort_scan": [_I64, _VP, _VP, _VP, _VP],
+    "pic_sort_scatter": [_PP, _SOA, _SOA, _VP, _VP, _VP],
+    "pic_fused_push_deposit": [_PP, _INT, _INT, _SOA, _V3, _V3, _V3, _V3, _V3, _VP, _I64, _VP, _VP, _VP],
+    "pic_soa_append": [_PP, _SOA, _VP, _I64, _I64, _VP, _VP],
+    "pic_microbench": [_INT, _INT, ctypes.POINTER(ctypes.c_float)],
+    "pic_params_size": [],
+    "pic_version": [],
+}
+
+
+def lib():
+    """Load (building first if sources are newer) the CUDA library.  Raises if unavailable: no CPU fallback."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    if needs_build():
+        build()
+    try:
+        L = ctypes.CDLL(LIB_PATH)
+    except OSError as exc:  # pragma: no cover
+        raise RuntimeError(f"pypic3d_b200: cannot load {LIB_PATH}: {exc}; the CUDA extension is mandatory") from exc
+    for name, argtypes in SIGNATURES.items():
+        fn = getattr(L, name)
+        fn.argtypes = argtypes
+        fn.restype = ctypes.c_char_p if name == "pic_version" else ctypes.c_int
+    if L.pic_params_size() != ctypes.sizeof(PicParams):
+        raise RuntimeError("pypic3d_b200: PicParams layout mismatch between Python and libpic_b200.so")
+    _LIB = L
+    return L
+
+
+class PicError(RuntimeError):
+    pass
+
+
+def check(code, what):
+    if code != 0:
+        kind = {-1: "invalid argument", -2: "unsupported configuration"}.get(code, f"CUDA error {code}")
+        raise PicError(f"{what}: {kind}")
+
+
+PUSHERS = {("boris", False): 0, ("boris", True): 1, ("higuera_cary", True): 2, ("higuera_cary", False): 2}
+
+
+def _scalar(v):
+    if hasattr(v, "item"):
+        return v.item()
+    return v
+
+
+def make_params(static_parameters, dynamic_parameters, species_config=None, dtype=np.float64, mesh=None, gmesh=None,
+                moff=(0, 0, 0)):
+    """POD parameter block from the reference-shaped pytrees (parameters.py:14-53, particle_class.py:5-14)."""
+    sp, dp = static_parameters, dynamic_parameters
+    p = PicParams()
+    p.dtype = 0 if np.dtype(dtype) == np.float32 else 1
+    p.shape_factor = int(sp.shape_factor)
+    key = (sp.particle_pusher, bool(sp.relativistic))
+    if key not in PUSHERS:
+        raise ValueError(f"Unknown particle_pusher: {sp.particle_pusher}")
+    p.pusher = PUSHERS[key]
+    p.g = int(sp.guard_cells)
+    tile = [int(w) for w in sp.tile_shape]
+    N = [int(_scalar(dp.Nx)), int(_scalar(dp.Ny)), int(_scalar(dp.Nz))]
+    full_mesh = [N[a] // tile[a] for a in range(3)]
+    gmesh = full_mesh if gmesh is None else [int(v) for v in gmesh]
+    mesh = gmesh if mesh is None else [int(v) for v in mesh]
+    d = [float(_scalar(dp.dx)), float(_scalar(dp.dy)), float(_scalar(dp.dz))]
+    wind = [float(_scalar(dp.x_wind)), float(_scalar(dp.y_wind)), float(_scalar(dp.z_wind))]
+    for a in range(3):
+        p.mesh[a], p.gmesh[a], p.moff[a], p.tile[a] = mesh[a], gmesh[a], int(moff[a]), tile[a]
+        p.field_bc[a] = int(sp.boundary_conditions[a])
+        p.particle_bc[a] = int(sp.particle_boundary_conditions[a])
+        p.wind[a] = wind[a]
+        grids = getattr(dp, "grids", None)
+        center = getattr(grids, "center", ()) if grids is not None else ()
+        vertex = getattr(grids, "vertex", ()) if grids is not None else ()
+        p.center0[a] = float(center[a][0]) if len(center) == 3 else -wind[a] / 2 - d[a]
+        p.vertex0[a] = float(vertex[a][0]) if len(vertex) == 3 else -wind[a] / 2 - 0.5 * d[a]
+    p.dt, p.dx, p.dy, p.dz = float(_scalar(dp.dt)), d[0], d[1], d[2]
+    p.C, p.eps, p.mu, p.alpha = (float(_scalar(dp.C)), float(_scalar(dp.eps)), float(_scalar(dp.mu)), float(_scalar(dp.alpha)))
+    if species_config is not None:
+        charge = np.asarray(_to_numpy(species_config.charge), dtype=np.float64).reshape(-1)
+        S = charge.shape[0]
+        if S > MAX_SPECIES:
+            raise ValueError(f"at most {MAX_SPECIES} species are supported")
+        mass = np.asarray(_to_numpy(species_config.mass), dtype=np.float64).reshape(-1)
+        weight = np.asarray(_to_numpy(species_config.weight), dtype=np.float64).reshape(-1)
+        ux = np.asarray(_to_numpy(species_config.update_x)).astype(bool).reshape(S, 3)
+        uu = np.asarray(_to_numpy(species_config.update_u)).astype(bool).reshape(S, 3)
+        p.n_species = S
+        for s in range(S):
+            p.charge[s], p.mass[s], p.weight[s] = charge[s], mass[s], weight[s]
+            for c in range(3):
+                p.update_x[s][c] = int(ux[s, c])
+                p.update_u[s][c] = int(uu[s, c])
+    return p
+
+
+def _to_numpy(a):
+    if hasattr(a, "detach"):
+        return a.detach().cpu().numpy()
+    return np.asarray(a)

@@ -1,0 +1,285 @@
+// kernels_fast.cu -- the resident throughput path: one tile per GPU, compact cell-sorted SoA particles.
+//   K1  k_fused        gather E,B -> push -> deposit -> move -> particle BC (+ leaver extraction), one pass over
+//                      particle memory: reads x,y,z,vx,vy,vz once, writes them once (48 B f32 / 96 B f64 per particle)
+//   K2  k_sort_*       counting sort by local cell (histogram, exclusive scan, scatter), run every few steps
+//   import / export    TiledParticles (reference AoS + active mask) <-> compact SoA
+#include "pic_common.cuh"
+
+namespace pic {
+
+// ---------------------------------------------------------------- import / export
+template <typename T>
+__global__ void __launch_bounds__(256) k_import(int species, int n_species, const T* __restrict__ x, const T* __restrict__ u,
+                                                const uint8_t* __restrict__ active, int64_t cap_ref, SoAView<T> s, int32_t* count) {
+    for (int64_t slot = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; slot < cap_ref; slot += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = (int64_t)species * cap_ref + slot;
+        if (!active[i]) continue;
+        const int64_t j = atomicAdd(count, 1);
+        if (j >= s.cap) continue;  // caller checks count <= cap
+        for (int c = 0; c < 3; ++c) { s.c[c][j] = x[3 * i + c]; s.c[3 + c][j] = u[3 * i + c]; }
+        if (s.id) s.id[j] = (int32_t)slot;
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_export(int species, SoAView<T> s, T* __restrict__ x, T* __restrict__ u,
+                                                uint8_t* __restrict__ active, int64_t cap_ref, int32_t* count) {
+    for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < s.n; j += (int64_t)gridDim.x * blockDim.x) {
+        const T px = s.c[0][j];
+        if (pic_isnan(px)) continue;
+        int64_t slot;
+        if (s.id && s.id[j] >= 0) { slot = s.id[j]; atomicAdd(count, 1); }
+        else slot = atomicAdd(count, 1);
+        if (slot >= cap_ref) continue;
+        const int64_t i = (int64_t)species * cap_ref + slot;
+        for (int c = 0; c < 3; ++c) { x[3 * i + c] = s.c[c][j]; u[3 * i + c] = s.c[3 + c][j]; }
+        active[i] = 1;
+    }
+}
+
+// ---------------------------------------------------------------- counting sort by local cell
+template <typename T>
+__global__ void __launch_bounds__(256) k_sort_hist(const __grid_constant__ PicParams p, SoAView<T> s, int32_t* __restrict__ count) {
+    for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < s.n; j += (int64_t)gridDim.x * blockDim.x)
+        atomicAdd(&count[local_cell<T>(p, s.c[0][j], s.c[1][j], s.c[2][j])], 1);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_sort_scatter(const __grid_constant__ PicParams p, SoAView<T> s, SoAView<T> d,
+                                                      const int32_t* __restrict__ offset, int32_t* __restrict__ cursor) {
+    for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < s.n; j += (int64_t)gridDim.x * blockDim.x) {
+        const T px = s.c[0][j], py = s.c[1][j], pz = s.c[2][j];
+        const int cell = local_cell<T>(p, px, py, pz);
+        const int64_t dst = (int64_t)offset[cell] + atomicAdd(&cursor[cell], 1);
+        if (dst >= d.cap) continue;
+        d.c[0][dst] = px; d.c[1][dst] = py; d.c[2][dst] = pz;
+        d.c[3][dst] = s.c[3][j]; d.c[4][dst] = s.c[4][j]; d.c[5][dst] = s.c[5][j];
+        if (s.id && d.id) d.id[dst] = s.id[j];
+    }
+}
+
+// exclusive scan of int32: 2048 elements per CTA (256 threads x 8), block sums scanned by one CTA, then added back.
+constexpr int SCAN_ITEMS = 8;
+constexpr int SCAN_TILE = 256 * SCAN_ITEMS;
+
+__device__ __forceinline__ int block_scan_excl_256(int v, int* total, int* sm) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int n = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += n;
+    }
+    __syncthreads();
+    if (lane == 31) sm[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        const int w = lane < 8 ? sm[lane] : 0;
+        int winc = w;
+#pragma unroll
+        for (int o = 1; o < 8; o <<= 1) {
+            const int n = __shfl_up_sync(0xffffffffu, winc, o);
+            if (lane >= o) winc += n;
+        }
+        if (lane < 8) sm[lane] = winc - w;
+        if (lane == 7) sm[8] = winc;
+    }
+    __syncthreads();
+    *total = sm[8];
+    return sm[warp] + inc - v;
+}
+
+__global__ void __launch_bounds__(256) k_scan_local(int64_t n, const int32_t* __restrict__ in, int32_t* __restrict__ out,
+                                                    int32_t* __restrict__ block_sums) {
+    __shared__ int sm[9];
+    const int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
+    int v[SCAN_ITEMS];
+    int sum = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) {
+        v[k] = (base + k < n) ? in[base + k] : 0;
+        sum += v[k];
+    }
+    int total;
+    int pre = block_scan_excl_256(sum, &total, sm);
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) {
+        if (base + k < n) out[base + k] = pre;
+        pre += v[k];
+    }
+    if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(256) k_scan_sums(int64_t nblocks, int32_t* __restrict__ block_sums) {
+    __shared__ int sm[9];
+    int carry = 0;
+    for (int64_t c0 = 0; c0 < nblocks; c0 += 256) {
+        const int64_t i = c0 + threadIdx.x;
+        const int v = i < nblocks ? block_sums[i] : 0;
+        int total;
+        const int pre = block_scan_excl_256(v, &total, sm);
+        if (i < nblocks) block_sums[i] = carry + pre;
+        carry += total;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_scan_add(int64_t n, int32_t* __restrict__ out, const int32_t* __restrict__ block_sums) {
+    const int add = block_sums[blockIdx.x];
+    const int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k)
+        if (base + k < n) out[base + k] += add;
+}
+
+// ---------------------------------------------------------------- K1: fused gather + push + deposit + move + BC
+template <typename T, int SF, int DEP, bool ALL3D>
+__global__ void __launch_bounds__(256) k_fused(const __grid_constant__ PicParams p, int species, SoAView<T> s, Field6<T> F,
+                                               Field6<T> X, int has_ext, Field3W<T> J, LeaveBuf leave, int32_t* flags) {
+    Geom<T> gm;
+    make_geom<T>(p, 0, 0, 0, gm);
+    TileSink<T> sink;
+    for (int c = 0; c < 3; ++c) { sink.J[c] = J.f[c]; sink.L[c] = gm.L[c]; }
+    sink.off = 0;
+    bool distributed = false;
+    for (int c = 0; c < 3; ++c) distributed |= (p.gmesh[c] != p.mesh[c]);
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < s.n; i += (int64_t)gridDim.x * blockDim.x)
+        fused_particle<T, SF, DEP, ALL3D>(p, species, gm, i, s, F, X, has_ext, sink, leave, distributed, flags);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_append(SoAView<T> s, const T* __restrict__ packet, int64_t n_in, int32_t* flags) {
+    for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < n_in; j += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t dst = s.n + j;
+        if (dst >= s.cap) { atomicOr(flags, 2); continue; }
+        for (int c = 0; c < 6; ++c) s.c[c][dst] = packet[j * 7 + c];
+        if (s.id) s.id[dst] = -1;
+    }
+}
+
+// ---------------------------------------------------------------- launchers
+template <typename T>
+static int launch_import(const PicParams* p, int species, const void* x, const void* u, const uint8_t* active, int64_t cap_ref,
+                         const PicSoA* soa, int32_t* count, cudaStream_t st) {
+    if (cap_ref == 0) return 0;
+    k_import<T><<<grid_for(cap_ref, 256), 256, 0, st>>>(species, p->n_species, (const T*)x, (const T*)u, active, cap_ref, view_of<T>(soa), count);
+    PIC_LAUNCH_RET();
+}
+template <typename T>
+static int launch_export(const PicParams* p, int species, const PicSoA* soa, void* x, void* u, uint8_t* active, int64_t cap_ref,
+                         int32_t* count, cudaStream_t st) {
+    if (soa->n == 0) return 0;
+    k_export<T><<<grid_for(soa->n, 256), 256, 0, st>>>(species, view_of<T>(soa), (T*)x, (T*)u, active, cap_ref, count);
+    PIC_LAUNCH_RET();
+}
+template <typename T>
+static int launch_hist(const PicParams* p, const PicSoA* src, int32_t* count, cudaStream_t st) {
+    if (src->n == 0) return 0;
+    k_sort_hist<T><<<grid_for(src->n, 256), 256, 0, st>>>(*p, view_of<T>(src), count);
+    PIC_LAUNCH_RET();
+}
+template <typename T>
+static int launch_scatter(const PicParams* p, const PicSoA* src, const PicSoA* dst, const int32_t* offset, int32_t* cursor, cudaStream_t st) {
+    if (src->n == 0) return 0;
+    k_sort_scatter<T><<<grid_for(src->n, 256), 256, 0, st>>>(*p, view_of<T>(src), view_of<T>(dst), offset, cursor);
+    PIC_LAUNCH_RET();
+}
+
+template <typename T, int SF>
+static int launch_fused(const PicParams* p, int species, int deposition, const PicSoA* soa, const void* const E[3],
+                        const void* const B[3], const void* const extE[3], const void* const extB[3], void* const J[3],
+                        void* leave, int64_t leave_cap, int32_t* d_leave_count, int32_t* flags, cudaStream_t st) {
+    if (soa->n == 0) return 0;
+    Field6<T> F, X;
+    Field3W<T> Jw;
+    const int has_ext = (extE && extB) ? 1 : 0;
+    for (int c = 0; c < 3; ++c) {
+        F.f[c] = (const T*)E[c]; F.f[3 + c] = (const T*)B[c];
+        X.f[c] = has_ext ? (const T*)extE[c] : nullptr; X.f[3 + c] = has_ext ? (const T*)extB[c] : nullptr;
+        Jw.f[c] = (T*)J[c];
+    }
+    LeaveBuf lb{leave, leave_cap, d_leave_count};
+    const bool all3d = (p->gmesh[0] * p->tile[0] > 1) && (p->gmesh[1] * p->tile[1] > 1) && (p->gmesh[2] * p->tile[2] > 1) && p->g >= 2;
+    const int grid = grid_for(soa->n, 256, 8);
+    const SoAView<T> sv = view_of<T>(soa);
+    if (deposition == 0) {
+        if (all3d) k_fused<T, SF, 0, true><<<grid, 256, 0, st>>>(*p, species, sv, F, X, has_ext, Jw, lb, flags);
+        else k_fused<T, SF, 0, false><<<grid, 256, 0, st>>>(*p, species, sv, F, X, has_ext, Jw, lb, flags);
+    } else {
+        if (all3d) k_fused<T, SF, 1, true><<<grid, 256, 0, st>>>(*p, species, sv, F, X, has_ext, Jw, lb, flags);
+        else k_fused<T, SF, 1, false><<<grid, 256, 0, st>>>(*p, species, sv, F, X, has_ext, Jw, lb, flags);
+    }
+    PIC_LAUNCH_RET();
+}
+
+template <typename T>
+static int launch_append(const PicParams* p, const PicSoA* soa, const void* packet, int64_t n_in, int32_t* flags, cudaStream_t st) {
+    if (n_in == 0) return 0;
+    k_append<T><<<grid_for(n_in, 256), 256, 0, st>>>(view_of<T>(soa), (const T*)packet, n_in, flags);
+    PIC_LAUNCH_RET();
+}
+
+}  // namespace pic
+
+using namespace pic;
+
+extern "C" {
+
+int pic_soa_import(const PicParams* p, int species, const void* x, const void* u, const uint8_t* active, int64_t cap_ref,
+                   const PicSoA* soa, int32_t* d_count, void* stream) {
+    PIC_CHECK_ARG(p && x && u && active && soa && d_count && species >= 0 && species < p->n_species);
+    PIC_CHECK_ARG(p->mesh[0] == 1 && p->mesh[1] == 1 && p->mesh[2] == 1);
+    PIC_DISPATCH_T(p, launch_import, p, species, x, u, active, cap_ref, soa, d_count, (cudaStream_t)stream);
+}
+
+int pic_soa_export(const PicParams* p, int species, const PicSoA* soa, void* x, void* u, uint8_t* active, int64_t cap_ref,
+                   int32_t* d_count, void* stream) {
+    PIC_CHECK_ARG(p && x && u && active && soa && d_count && species >= 0 && species < p->n_species);
+    PIC_DISPATCH_T(p, launch_export, p, species, soa, x, u, active, cap_ref, d_count, (cudaStream_t)stream);
+}
+
+int pic_sort_histogram(const PicParams* p, const PicSoA* src, int32_t* cell_count, void* stream) {
+    PIC_CHECK_ARG(p && src && cell_count);
+    PIC_DISPATCH_T(p, launch_hist, p, src, cell_count, (cudaStream_t)stream);
+}
+
+int pic_sort_scan(int64_t n, const int32_t* in, int32_t* out, int32_t* block_scratch, void* stream) {
+    PIC_CHECK_ARG(in && out && block_scratch && n >= 0);
+    if (n == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t nblocks = (n + SCAN_TILE - 1) / SCAN_TILE;
+    k_scan_local<<<(unsigned)nblocks, 256, 0, st>>>(n, in, out, block_scratch);
+    if (nblocks > 1) {
+        k_scan_sums<<<1, 256, 0, st>>>(nblocks, block_scratch);
+        k_scan_add<<<(unsigned)nblocks, 256, 0, st>>>(n, out, block_scratch);
+    }
+    PIC_LAUNCH_RET();
+}
+
+int pic_sort_scatter(const PicParams* p, const PicSoA* src, const PicSoA* dst, const int32_t* cell_offset, int32_t* cell_cursor,
+                     void* stream) {
+    PIC_CHECK_ARG(p && src && dst && cell_offset && cell_cursor);
+    PIC_DISPATCH_T(p, launch_scatter, p, src, dst, cell_offset, cell_cursor, (cudaStream_t)stream);
+}
+
+int pic_fused_push_deposit(const PicParams* p, int species, int deposition, const PicSoA* soa, const void* const E[3],
+                           const void* const B[3], const void* const extE[3], const void* const extB[3], void* const J[3],
+                           void* leave, int64_t leave_cap, int32_t* d_leave_count, int32_t* flags, void* stream) {
+    PIC_CHECK_ARG(p && soa && E && B && J && flags && species >= 0 && species < p->n_species && (deposition == 0 || deposition == 1));
+    PIC_CHECK_ARG(p->mesh[0] == 1 && p->mesh[1] == 1 && p->mesh[2] == 1);
+    bool distributed = false;
+    for (int c = 0; c < 3; ++c) distributed |= (p->gmesh[c] != p->mesh[c]);
+    if (distributed) {
+        PIC_CHECK_ARG(leave && d_leave_count && leave_cap > 0);
+        if (deposition == 1) return PIC_EUNSUPPORTED;  // centred deposit across ranks needs a mid-step migration
+    }
+    PIC_DISPATCH_T_SF(p, launch_fused, p, species, deposition, soa, E, B, extE, extB, J, leave, leave_cap, d_leave_count, flags,
+                      (cudaStream_t)stream);
+}
+
+int pic_soa_append(const PicParams* p, const PicSoA* soa, const void* packet, int64_t packet_cap, int64_t n_in, int32_t* flags,
+                   void* stream) {
+    PIC_CHECK_ARG(p && soa && packet && flags && n_in >= 0 && n_in <= packet_cap);
+    PIC_DISPATCH_T(p, launch_append, p, soa, packet, n_in, flags, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,499 @@
+// kernels_fields.cu -- grid kernels: Yee E / B(half) updates, 27-point filters, guard-cell refresh / fold,
+// wall planes, face pack / unpack for NCCL halo exchange, energy reductions.
+// All are HBM-bandwidth-bound streaming/stencil kernels: z (fastest axis) maps to threadIdx.x for coalescing.
+#include "pic_common.cuh"
+
+namespace pic {
+
+struct Dims {
+    int L[3];
+    int W[3];
+    int g;
+    int64_t ntiles;
+    size_t tile_elems;
+};
+
+static inline Dims dims_of(const PicParams* p) {
+    Dims d;
+    for (int a = 0; a < 3; ++a) { d.W[a] = p->tile[a]; d.L[a] = p->tile[a] + 2 * p->g; }
+    d.g = p->g;
+    d.ntiles = (int64_t)p->mesh[0] * p->mesh[1] * p->mesh[2];
+    d.tile_elems = (size_t)d.L[0] * d.L[1] * d.L[2];
+    return d;
+}
+
+// Interior-cell launch geometry: block (x=z cells, y=y cells), grid.x over (tile, x cell, y/z blocks).
+struct CellGrid {
+    dim3 grid, block;
+    int nbz, nby;
+};
+static inline CellGrid cell_grid(const Dims& d) {
+    CellGrid c;
+    int bx = d.W[2] >= 128 ? 128 : (d.W[2] >= 64 ? 64 : 32);
+    int by = 256 / bx;
+    if (by > d.W[1]) by = d.W[1] < 1 ? 1 : d.W[1];
+    c.block = dim3(bx, by, 1);
+    c.nbz = (d.W[2] + bx - 1) / bx;
+    c.nby = (d.W[1] + by - 1) / by;
+    const int64_t blocks = d.ntiles * d.W[0] * c.nby * c.nbz;
+    c.grid = dim3((unsigned)blocks, 1, 1);
+    return c;
+}
+__device__ __forceinline__ bool cell_of_block(const Dims& d, int nby, int nbz, int64_t& tile, int& ix, int& iy, int& iz) {
+    int64_t b = blockIdx.x;
+    const int bz = (int)(b % nbz); b /= nbz;
+    const int by = (int)(b % nby); b /= nby;
+    ix = (int)(b % d.W[0]) + d.g; b /= d.W[0];
+    tile = b;
+    iy = by * blockDim.y + threadIdx.y;
+    iz = bz * blockDim.x + threadIdx.x;
+    if (iy >= d.W[1] || iz >= d.W[2]) return false;
+    iy += d.g; iz += d.g;
+    return true;
+}
+
+// ---------------------------------------------------------------- Yee (first_order_yee.py:42-72, :121-142)
+template <typename T>
+__global__ void __launch_bounds__(256) k_update_B(Dims d, int nby, int nbz, T* __restrict__ Bx, T* __restrict__ By,
+                                                  T* __restrict__ Bz, const T* __restrict__ Ex, const T* __restrict__ Ey,
+                                                  const T* __restrict__ Ez, T hdt, T dx, T dy, T dz) {
+    int64_t tile; int ix, iy, iz;
+    if (!cell_of_block(d, nby, nbz, tile, ix, iy, iz)) return;
+    const size_t sx = (size_t)d.L[1] * d.L[2], sy = d.L[2];
+    const size_t i = tile * d.tile_elems + ix * sx + iy * sy + iz;
+    const T ex = Ex[i], ey = Ey[i], ez = Ez[i];
+    const T dEz_dy = (Ez[i + sy] - ez) / dy;   // forward differences
+    const T dEy_dz = (Ey[i + 1] - ey) / dz;
+    const T dEx_dz = (Ex[i + 1] - ex) / dz;
+    const T dEx_dy = (Ex[i + sy] - ex) / dy;
+    const T dEz_dx = (Ez[i + sx] - ez) / dx;
+    const T dEy_dx = (Ey[i + sx] - ey) / dx;
+    Bx[i] = Bx[i] - hdt * (dEz_dy - dEy_dz);
+    By[i] = By[i] - hdt * (dEx_dz - dEz_dx);
+    Bz[i] = Bz[i] - hdt * (dEy_dx - dEx_dy);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_update_E(Dims d, int nby, int nbz, T* __restrict__ Ex, T* __restrict__ Ey,
+                                                  T* __restrict__ Ez, const T* __restrict__ Bx, const T* __restrict__ By,
+                                                  const T* __restrict__ Bz, const T* __restrict__ Jx, const T* __restrict__ Jy,
+                                                  const T* __restrict__ Jz, T dt, T dx, T dy, T dz, T C2, T eps) {
+    int64_t tile; int ix, iy, iz;
+    if (!cell_of_block(d, nby, nbz, tile, ix, iy, iz)) return;
+    const size_t sx = (size_t)d.L[1] * d.L[2], sy = d.L[2];
+    const size_t i = tile * d.tile_elems + ix * sx + iy * sy + iz;
+    const T bx = Bx[i], by = By[i], bz = Bz[i];
+    const T dBz_dy = (bz - Bz[i - sy]) / dy;   // backward differences
+    const T dBy_dz = (by - By[i - 1]) / dz;
+    const T dBx_dz = (bx - Bx[i - 1]) / dz;
+    const T dBx_dy = (bx - Bx[i - sy]) / dy;
+    const T dBz_dx = (bz - Bz[i - sx]) / dx;
+    const T dBy_dx = (by - By[i - sx]) / dx;
+    Ex[i] = Ex[i] + (C2 * (dBz_dy - dBy_dz) - Jx[i] / eps) * dt;
+    Ey[i] = Ey[i] + (C2 * (dBx_dz - dBz_dx) - Jy[i] / eps) * dt;
+    Ez[i] = Ez[i] + (C2 * (dBy_dx - dBx_dy) - Jz[i] / eps) * dt;
+}
+
+template <typename T>
+static int launch_update_B(const PicParams* p, void* const B[3], const void* const E[3], cudaStream_t st) {
+    const Dims d = dims_of(p);
+    const CellGrid cg = cell_grid(d);
+    k_update_B<T><<<cg.grid, cg.block, 0, st>>>(d, cg.nby, cg.nbz, (T*)B[0], (T*)B[1], (T*)B[2], (const T*)E[0], (const T*)E[1],
+                                                (const T*)E[2], (T)(p->dt / 2), (T)p->dx, (T)p->dy, (T)p->dz);
+    PIC_LAUNCH_RET();
+}
+template <typename T>
+static int launch_update_E(const PicParams* p, void* const E[3], const void* const B[3], const void* const J[3], cudaStream_t st) {
+    const Dims d = dims_of(p);
+    const CellGrid cg = cell_grid(d);
+    k_update_E<T><<<cg.grid, cg.block, 0, st>>>(d, cg.nby, cg.nbz, (T*)E[0], (T*)E[1], (T*)E[2], (const T*)B[0], (const T*)B[1],
+                                                (const T*)B[2], (const T*)J[0], (const T*)J[1], (const T*)J[2], (T)p->dt, (T)p->dx,
+                                                (T)p->dy, (T)p->dz, (T)(p->C * p->C), (T)p->eps);
+    PIC_LAUNCH_RET();
+}
+
+// ---------------------------------------------------------------- 27-point filter (filters.py:73-129)
+template <typename T>
+__global__ void __launch_bounds__(256) k_filter(Dims d, int nby, int nbz, const T* __restrict__ in, T* __restrict__ out,
+                                                int kind, T alpha) {
+    int64_t tile; int ix, iy, iz;
+    if (!cell_of_block(d, nby, nbz, tile, ix, iy, iz)) return;
+    const ptrdiff_t sx = (ptrdiff_t)d.L[1] * d.L[2], sy = d.L[2];
+    const size_t i = tile * d.tile_elems + ix * sx + iy * sy + iz;
+    T acc = (T)0;
+    if (kind == PIC_FILTER_DIGITAL) {
+        const T nw = ((T)1 - alpha) / (T)6;
+        // same accumulation order as a row-major 3x3x3 kernel walk
+        acc += nw * in[i - sx];
+        acc += nw * in[i - sy];
+        acc += nw * in[i - 1];
+        acc += alpha * in[i];
+        acc += nw * in[i + 1];
+        acc += nw * in[i + sy];
+        acc += nw * in[i + sx];
+    } else {
+        const T k1[3] = {(T)1, (T)2, (T)1};
+        for (int a = 0; a < 3; ++a)
+            for (int b = 0; b < 3; ++b)
+                for (int c = 0; c < 3; ++c)
+                    acc += ((k1[a] * k1[b] * k1[c]) / (T)64) * in[i + (a - 1) * sx + (b - 1) * sy + (c - 1)];
+    }
+    out[i] = acc;
+}
+
+template <typename T>
+static int launch_filter(const PicParams* p, int kind, double alpha, const void* in, void* out, cudaStream_t st) {
+    const Dims d = dims_of(p);
+    cudaError_t e = cudaMemcpyAsync(out, in, d.ntiles * d.tile_elems * sizeof(T), cudaMemcpyDeviceToDevice, st);  // ghosts unchanged
+    if (e != cudaSuccess) return (int)e;
+    const CellGrid cg = cell_grid(d);
+    k_filter<T><<<cg.grid, cg.block, 0, st>>>(d, cg.nby, cg.nbz, (const T*)in, (T*)out, kind, (T)alpha);
+    PIC_LAUNCH_RET();
+}
+
+// ---------------------------------------------------------------- per-axis halo passes over the local tile mesh
+struct Ptrs8 {
+    void* f[8];
+};
+
+// Decompose a flat index over (comp, tile, plane, u, v) where (u, v) span the FULL transverse extent (ghosts included,
+// ghost_cells.py:162-178) and v is the fastest-varying memory axis available.
+struct AxisView {
+    int axis, ua, va;      // axis and the two transverse axes (ua slower, va faster in memory)
+    int64_t stride[3];
+};
+__host__ __device__ inline AxisView axis_view(const Dims& d, int axis) {
+    AxisView v;
+    v.axis = axis;
+    v.ua = axis == 0 ? 1 : 0;
+    v.va = axis == 2 ? 1 : 2;
+    v.stride[0] = (int64_t)d.L[1] * d.L[2];
+    v.stride[1] = d.L[2];
+    v.stride[2] = 1;
+    return v;
+}
+
+// refresh (ghost_cells.py:142-196): ghost_lo[0:g] <- neighbour(-1).[-2g:-g]; ghost_hi[-g:] <- neighbour(+1).[g:2g];
+// zeros at a non-periodic chain end; reduced axis: both ghosts <- the single interior plane (periodic) or 0.
+template <typename T>
+__global__ void __launch_bounds__(256) k_refresh_axis(Dims d, int axis, int bc, int reduced, int mesh0, int mesh1, int mesh2,
+                                                      int ncomp, Ptrs8 F) {
+    const AxisView av = axis_view(d, axis);
+    const int g = d.g, La = d.L[axis], Lu = d.L[av.ua], Lv = d.L[av.va];
+    const int mesh[3] = {mesh0, mesh1, mesh2};
+    const int64_t per_tile = (int64_t)2 * g * Lu * Lv;
+    const int64_t total = (int64_t)ncomp * d.ntiles * per_tile;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int64_t r = i;
+        const int v = (int)(r % Lv); r /= Lv;
+        const int u = (int)(r % Lu); r /= Lu;
+        const int pl = (int)(r % (2 * g)); r /= (2 * g);
+        const int64_t tile = r % d.ntiles;
+        const int comp = (int)(r / d.ntiles);
+        T* f = (T*)F.f[comp];
+        const bool lower = pl < g;
+        const int dst_l = lower ? pl : La - 2 * g + pl;           // [0,g) or [La-g, La)
+        const int64_t tv = (int64_t)u * av.stride[av.ua] + (int64_t)v * av.stride[av.va];
+        T val = (T)0;
+        if (reduced) {
+            if (bc == PIC_BC_PERIODIC) val = f[tile * d.tile_elems + (int64_t)g * av.stride[axis] + tv];
+        } else {
+            TileCoord tc = tile_coord(tile, mesh);
+            int t[3] = {tc.tx, tc.ty, tc.tz};
+            int nt = t[axis] + (lower ? -1 : 1);
+            bool have = true;
+            if (nt < 0 || nt >= mesh[axis]) {
+                if (bc == PIC_BC_PERIODIC) nt = (nt + mesh[axis]) % mesh[axis];
+                else have = false;
+            }
+            if (have) {
+                t[axis] = nt;
+                const int64_t ntile = ((int64_t)t[0] * mesh[1] + t[1]) * mesh[2] + t[2];
+                const int src_l = lower ? (La - 2 * g + pl) : (g + (pl - g));   // [-2g:-g] or [g:2g]
+                val = f[ntile * d.tile_elems + (int64_t)src_l * av.stride[axis] + tv];
+            }
+        }
+        f[tile * d.tile_elems + (int64_t)dst_l * av.stride[axis] + tv] = val;
+    }
+}
+
+// fold, phase 1 (ghost_cells.py:218-289): every interior plane gathers the ghost deposits it owns.
+// plane l in [g, g+W): if l < 2g it receives neighbour(-1).ghost_hi[l-g] (+) and, on a conducting lower wall, -own
+// ghost_lo[l-g]; if l >= W it receives neighbour(+1).ghost_lo[l-W] (+) and, on a conducting upper wall, -own ghost_hi.
+template <typename T>
+__global__ void __launch_bounds__(256) k_fold_axis(Dims d, int axis, int bc, int reduced, int mesh0, int mesh1, int mesh2,
+                                                   int ncomp, Ptrs8 F) {
+    const AxisView av = axis_view(d, axis);
+    const int g = d.g, La = d.L[axis], W = d.W[axis], Lu = d.L[av.ua], Lv = d.L[av.va];
+    const int mesh[3] = {mesh0, mesh1, mesh2};
+    const int npl = reduced ? 1 : (W < 2 * g ? W : 2 * g);        // interior planes that can receive anything
+    const int64_t per_tile = (int64_t)npl * Lu * Lv;
+    const int64_t total = (int64_t)ncomp * d.ntiles * per_tile;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int64_t r = i;
+        const int v = (int)(r % Lv); r /= Lv;
+        const int u = (int)(r % Lu); r /= Lu;
+        const int pl = (int)(r % npl); r /= npl;
+        const int64_t tile = r % d.ntiles;
+        const int comp = (int)(r / d.ntiles);
+        T* f = (T*)F.f[comp];
+        const int64_t tv = (int64_t)u * av.stride[av.ua] + (int64_t)v * av.stride[av.va];
+        const int64_t base = tile * d.tile_elems + tv;
+        if (reduced) {
+            T gs = (T)0;
+            for (int k = 0; k < g; ++k) gs += f[base + (int64_t)k * av.stride[axis]];
+            T gs2 = (T)0;
+            for (int k = 0; k < g; ++k) gs2 += f[base + (int64_t)(La - g + k) * av.stride[axis]];
+            gs = gs + gs2;
+            T* tgt = f + base + (int64_t)g * av.stride[axis];
+            if (bc == PIC_BC_PERIODIC) *tgt += gs;
+            else if (bc == PIC_BC_CONDUCTING) *tgt -= gs;
+            continue;
+        }
+        // map pl to an interior plane: first min(g, .) planes from the bottom, the rest from the top
+        int l;
+        if (W >= 2 * g) l = pl < g ? g + pl : (La - 2 * g) + (pl - g);
+        else l = g + pl;
+        TileCoord tc = tile_coord(tile, mesh);
+        const int t0[3] = {tc.tx, tc.ty, tc.tz};
+        T* tgt = f + base + (int64_t)l * av.stride[axis];
+        T acc = *tgt;
+        if (l >= La - 2 * g) {      // upper interior <- lower ghost of neighbour(+1)   (ghost_cells.py:271,274)
+            const int k = l - (La - 2 * g);
+            int nt = t0[axis] + 1;
+            bool have = true;
+            if (nt >= mesh[axis]) { if (bc == PIC_BC_PERIODIC) nt = 0; else have = false; }
+            if (have) {
+                int t[3] = {t0[0], t0[1], t0[2]};
+                t[axis] = nt;
+                const int64_t ntile = ((int64_t)t[0] * mesh[1] + t[1]) * mesh[2] + t[2];
+                acc += f[ntile * d.tile_elems + tv + (int64_t)k * av.stride[axis]];
+            }
+        }
+        if (l < 2 * g) {            // lower interior <- upper ghost of neighbour(-1)   (ghost_cells.py:272,275)
+            const int k = l - g;
+            int nt = t0[axis] - 1;
+            bool have = true;
+            if (nt < 0) { if (bc == PIC_BC_PERIODIC) nt = mesh[axis] - 1; else have = false; }
+            if (have) {
+                int t[3] = {t0[0], t0[1], t0[2]};
+                t[axis] = nt;
+                const int64_t ntile = ((int64_t)t[0] * mesh[1] + t[1]) * mesh[2] + t[2];
+                acc += f[ntile * d.tile_elems + tv + (int64_t)(La - g + k) * av.stride[axis]];
+            }
+        }
+        if (bc == PIC_BC_CONDUCTING) {  // _add_exterior_conducting_fold (ghost_cells.py:238-260): wall tiles only
+            if (t0[axis] == 0 && l < 2 * g) acc -= f[base + (int64_t)(l - g) * av.stride[axis]];
+            if (t0[axis] == mesh[axis] - 1 && l >= La - 2 * g) acc -= f[base + (int64_t)(La - g + (l - (La - 2 * g))) * av.stride[axis]];
+        }
+        *tgt = acc;
+    }
+}
+
+// fold, phase 2: ghosts of this axis <- 0 (ghost_cells.py:232-233, 286-287).  Also used stand-alone.
+template <typename T>
+__global__ void __launch_bounds__(256) k_zero_ghost_axis(Dims d, int axis, int ncomp, Ptrs8 F) {
+    const AxisView av = axis_view(d, axis);
+    const int g = d.g, La = d.L[axis], Lu = d.L[av.ua], Lv = d.L[av.va];
+    const int64_t per_tile = (int64_t)2 * g * Lu * Lv;
+    const int64_t total = (int64_t)ncomp * d.ntiles * per_tile;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int64_t r = i;
+        const int v = (int)(r % Lv); r /= Lv;
+        const int u = (int)(r % Lu); r /= Lu;
+        const int pl = (int)(r % (2 * g)); r /= (2 * g);
+        const int64_t tile = r % d.ntiles;
+        const int comp = (int)(r / d.ntiles);
+        const int l = pl < g ? pl : La - 2 * g + pl;
+        ((T*)F.f[comp])[tile * d.tile_elems + (int64_t)l * av.stride[axis] + (int64_t)u * av.stride[av.ua] + (int64_t)v * av.stride[av.va]] = (T)0;
+    }
+}
+
+static inline int axis_reduced(const PicParams* p, int axis) { return (p->tile[axis] == 1 && p->gmesh[axis] == 1) ? 1 : 0; }
+
+template <typename T>
+static int launch_refresh(const PicParams* p, int axis, int bc, int ncomp, void* const* fields, cudaStream_t st) {
+    const Dims d = dims_of(p);
+    Ptrs8 F;
+    for (int c = 0; c < ncomp; ++c) F.f[c] = fields[c];
+    const AxisView av = axis_view(d, axis);
+    const int64_t total = (int64_t)ncomp * d.ntiles * 2 * d.g * d.L[av.ua] * d.L[av.va];
+    k_refresh_axis<T><<<grid_for(total, 256), 256, 0, st>>>(d, axis, bc, axis_reduced(p, axis), p->mesh[0], p->mesh[1], p->mesh[2], ncomp, F);
+    PIC_LAUNCH_RET();
+}
+
+template <typename T>
+static int launch_fold(const PicParams* p, int axis, int bc, int ncomp, void* const* fields, cudaStream_t st) {
+    const Dims d = dims_of(p);
+    Ptrs8 F;
+    for (int c = 0; c < ncomp; ++c) F.f[c] = fields[c];
+    const AxisView av = axis_view(d, axis);
+    const int red = axis_reduced(p, axis);
+    const int npl = red ? 1 : (d.W[axis] < 2 * d.g ? d.W[axis] : 2 * d.g);
+    const int64_t total = (int64_t)ncomp * d.ntiles * npl * d.L[av.ua] * d.L[av.va];
+    k_fold_axis<T><<<grid_for(total, 256), 256, 0, st>>>(d, axis, bc, red, p->mesh[0], p->mesh[1], p->mesh[2], ncomp, F);
+    const int64_t tz = (int64_t)ncomp * d.ntiles * 2 * d.g * d.L[av.ua] * d.L[av.va];
+    k_zero_ghost_axis<T><<<grid_for(tz, 256), 256, 0, st>>>(d, axis, ncomp, F);
+    PIC_LAUNCH_RET();
+}
+
+// wall planes (ghost_cells.py:344-362): plane g on the first tile and plane -g-1 on the last tile of `axis`.
+template <typename T>
+__global__ void __launch_bounds__(256) k_zero_wall(Dims d, int axis, int mesh0, int mesh1, int mesh2, int lo_wall, int hi_wall, T* f) {
+    const AxisView av = axis_view(d, axis);
+    const int Lu = d.L[av.ua], Lv = d.L[av.va];
+    const int mesh[3] = {mesh0, mesh1, mesh2};
+    const int64_t total = d.ntiles * 2 * Lu * Lv;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int64_t r = i;
+        const int v = (int)(r % Lv); r /= Lv;
+        const int u = (int)(r % Lu); r /= Lu;
+        const int side = (int)(r % 2); r /= 2;
+        const int64_t tile = r;
+        const TileCoord tc = tile_coord(tile, mesh);
+        const int t[3] = {tc.tx, tc.ty, tc.tz};
+        if (side == 0 && !(lo_wall && t[axis] == 0)) continue;
+        if (side == 1 && !(hi_wall && t[axis] == mesh[axis] - 1)) continue;
+        const int l = side == 0 ? d.g : d.L[axis] - d.g - 1;
+        f[tile * d.tile_elems + (int64_t)l * av.stride[axis] + (int64_t)u * av.stride[av.ua] + (int64_t)v * av.stride[av.va]] = (T)0;
+    }
+}
+
+template <typename T>
+static int launch_zero_wall(const PicParams* p, int axis, void* field, cudaStream_t st) {
+    const Dims d = dims_of(p);
+    const AxisView av = axis_view(d, axis);
+    const int64_t total = d.ntiles * 2 * d.L[av.ua] * d.L[av.va];
+    const int lo_wall = (p->moff[axis] == 0), hi_wall = (p->moff[axis] + p->mesh[axis] == p->gmesh[axis]);
+    k_zero_wall<T><<<grid_for(total, 256), 256, 0, st>>>(d, axis, p->mesh[0], p->mesh[1], p->mesh[2], lo_wall, hi_wall, (T*)field);
+    PIC_LAUNCH_RET();
+}
+
+// ---------------------------------------------------------------- face pack / unpack (multi-GPU halo exchange)
+// buffer layout [comp][tile][plane][u][v]; planes start..start+nplanes-1 along `axis`, full transverse extent.
+template <typename T, int DIR /*0 pack, 1 unpack*/>
+__global__ void __launch_bounds__(256) k_planes(Dims d, int axis, int start, int nplanes, int ncomp, Ptrs8 F, T* buf, int mode) {
+    const AxisView av = axis_view(d, axis);
+    const int Lu = d.L[av.ua], Lv = d.L[av.va];
+    const int64_t total = (int64_t)ncomp * d.ntiles * nplanes * Lu * Lv;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int64_t r = i;
+        const int v = (int)(r % Lv); r /= Lv;
+        const int u = (int)(r % Lu); r /= Lu;
+        const int pl = (int)(r % nplanes); r /= nplanes;
+        const int64_t tile = r % d.ntiles;
+        const int comp = (int)(r / d.ntiles);
+        T* f = (T*)F.f[comp] + tile * d.tile_elems + (int64_t)(start + pl) * av.stride[axis] + (int64_t)u * av.stride[av.ua] + (int64_t)v * av.stride[av.va];
+        if (DIR == 0) buf[i] = *f;
+        else if (mode == PIC_HALO_SET) *f = buf[i];
+        else if (mode == PIC_HALO_ADD) *f += buf[i];
+        else *f -= buf[i];
+    }
+}
+
+template <typename T>
+static int launch_planes(const PicParams* p, int dir, int axis, int start, int nplanes, int ncomp, void* const* fields, void* buf,
+                         int mode, cudaStream_t st) {
+    const Dims d = dims_of(p);
+    Ptrs8 F;
+    for (int c = 0; c < ncomp; ++c) F.f[c] = fields[c];
+    const AxisView av = axis_view(d, axis);
+    const int64_t total = (int64_t)ncomp * d.ntiles * nplanes * d.L[av.ua] * d.L[av.va];
+    if (total == 0) return 0;
+    if (dir == 0) k_planes<T, 0><<<grid_for(total, 256), 256, 0, st>>>(d, axis, start, nplanes, ncomp, F, (T*)buf, mode);
+    else k_planes<T, 1><<<grid_for(total, 256), 256, 0, st>>>(d, axis, start, nplanes, ncomp, F, (T*)buf, mode);
+    PIC_LAUNCH_RET();
+}
+
+// ---------------------------------------------------------------- sum of squares over tile interiors (utils.py:160-166)
+template <typename T>
+__global__ void __launch_bounds__(256) k_sumsq(Dims d, const T* __restrict__ f, double* out) {
+    const int64_t per_tile = (int64_t)d.W[0] * d.W[1] * d.W[2];
+    const int64_t total = d.ntiles * per_tile;
+    double acc = 0.0;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int64_t r = i;
+        const int z = (int)(r % d.W[2]); r /= d.W[2];
+        const int y = (int)(r % d.W[1]); r /= d.W[1];
+        const int x = (int)(r % d.W[0]); r /= d.W[0];
+        const double v = (double)f[r * d.tile_elems + ((size_t)(x + d.g) * d.L[1] + (y + d.g)) * d.L[2] + (z + d.g)];
+        acc += v * v;
+    }
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) atomicAdd(out, acc);
+}
+
+template <typename T>
+static int launch_sumsq(const PicParams* p, const void* f, double* out, cudaStream_t st) {
+    const Dims d = dims_of(p);
+    const int64_t total = d.ntiles * d.W[0] * d.W[1] * d.W[2];
+    k_sumsq<T><<<grid_for(total, 256, 4), 256, 0, st>>>(d, (const T*)f, out);
+    PIC_LAUNCH_RET();
+}
+
+}  // namespace pic
+
+using namespace pic;
+
+static bool halo_args_ok(const PicParams* p, int axis, int ncomp, void* const* fields) {
+    if (!p || !fields || axis < 0 || axis > 2 || ncomp < 1 || ncomp > 8) return false;
+    for (int c = 0; c < ncomp; ++c)
+        if (!fields[c]) return false;
+    return true;
+}
+
+extern "C" {
+
+const char* pic_version(void) { return "pic_b200 0.1 (sm_100a)"; }
+int pic_params_size(void) { return (int)sizeof(PicParams); }
+
+int pic_update_E(const PicParams* p, void* const E[3], const void* const B[3], const void* const J[3], void* stream) {
+    PIC_CHECK_ARG(p && E && B && J);
+    PIC_DISPATCH_T(p, launch_update_E, p, E, B, J, (cudaStream_t)stream);
+}
+
+int pic_update_B(const PicParams* p, void* const B[3], const void* const E[3], void* stream) {
+    PIC_CHECK_ARG(p && E && B);
+    PIC_DISPATCH_T(p, launch_update_B, p, B, E, (cudaStream_t)stream);
+}
+
+int pic_filter(const PicParams* p, int kind, double alpha, const void* in, void* out, void* stream) {
+    PIC_CHECK_ARG(p && in && out && in != out && (kind == PIC_FILTER_DIGITAL || kind == PIC_FILTER_BILINEAR) && p->g >= 1);
+    PIC_DISPATCH_T(p, launch_filter, p, kind, alpha, in, out, (cudaStream_t)stream);
+}
+
+int pic_halo_refresh_axis(const PicParams* p, int axis, int bc, int ncomp, void* const* fields, void* stream) {
+    PIC_CHECK_ARG(halo_args_ok(p, axis, ncomp, fields));
+    PIC_DISPATCH_T(p, launch_refresh, p, axis, bc, ncomp, fields, (cudaStream_t)stream);
+}
+
+int pic_halo_fold_axis(const PicParams* p, int axis, int bc, int ncomp, void* const* fields, void* stream) {
+    PIC_CHECK_ARG(halo_args_ok(p, axis, ncomp, fields));
+    PIC_DISPATCH_T(p, launch_fold, p, axis, bc, ncomp, fields, (cudaStream_t)stream);
+}
+
+int pic_zero_wall(const PicParams* p, int axis, void* field, void* stream) {
+    PIC_CHECK_ARG(p && field && axis >= 0 && axis <= 2);
+    PIC_DISPATCH_T(p, launch_zero_wall, p, axis, field, (cudaStream_t)stream);
+}
+
+int pic_pack_planes(const PicParams* p, int axis, int start, int nplanes, int ncomp, const void* const* fields, void* buf,
+                    void* stream) {
+    PIC_CHECK_ARG(halo_args_ok(p, axis, ncomp, (void* const*)fields) && buf && start >= 0 && nplanes >= 0 &&
+                  start + nplanes <= p->tile[axis] + 2 * p->g);
+    PIC_DISPATCH_T(p, launch_planes, p, 0, axis, start, nplanes, ncomp, (void* const*)fields, buf, 0, (cudaStream_t)stream);
+}
+
+int pic_unpack_planes(const PicParams* p, int axis, int start, int nplanes, int ncomp, void* const* fields, const void* buf,
+                      int mode, void* stream) {
+    PIC_CHECK_ARG(halo_args_ok(p, axis, ncomp, fields) && buf && start >= 0 && nplanes >= 0 &&
+                  start + nplanes <= p->tile[axis] + 2 * p->g && mode >= 0 && mode <= 2);
+    PIC_DISPATCH_T(p, launch_planes, p, 1, axis, start, nplanes, ncomp, fields, (void*)buf, mode, (cudaStream_t)stream);
+}
+
+int pic_sum_squares_interior(const PicParams* p, const void* field, double* out, void* stream) {
+    PIC_CHECK_ARG(p && field && out);
+    PIC_DISPATCH_T(p, launch_sumsq, p, field, out, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,146 @@
+"""CPU check of the CUDA kernels' per-particle arithmetic (no GPU needed).
+
+The __host__ __device__ bodies in pypic3d_b200/csrc/pic_slots.cuh (the exact code the __global__ kernels execute)
+are compiled for the host by g++ into a TEST-ONLY library and compared with the oracle.  This is not a product
+path: the package never loads this library."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import fixtures as fx, pusher, deposition as dep, particles as opart
+from pypic3d_b200 import _lib
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SRC = os.path.join(HERE, "hostcheck", "hostcheck.cpp")
+OUT = os.path.join(HERE, "hostcheck", "_build", "libhostcheck.so")
+
+
+@pytest.fixture(scope="module")
+def hc():
+    os.makedirs(os.path.dirname(OUT), exist_ok=True)
+    subprocess.run(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-x", "c++", SRC, "-o", OUT], check=True)
+    L = ctypes.CDLL(OUT)
+    assert L.hc_params_size() == ctypes.sizeof(_lib.PicParams)
+    return L
+
+
+def _ptr(a):
+    return ctypes.c_void_p(a.ctypes.data)
+
+
+def _v3(arrs):
+    return (ctypes.c_void_p * 3)(*[a.ctypes.data for a in arrs])
+
+
+CASES = [((8, 6, 4), (2, 3, 2)), ((8, 6, 4), (8, 6, 4)), ((8, 1, 1), (2, 1, 1)), ((6, 6, 1), (3, 2, 1)), ((1, 6, 4), (1, 3, 2))]
+
+
+def _setup(N, tile, sf, pusher_name="boris", rel=True, dtype=np.float64, **kw):
+    sp, dp = fx.kernel_parameters(Nx=N[0], Ny=N[1], Nz=N[2], x_wind=4.0 if N[0] > 1 else 1.0, y_wind=3.0 if N[1] > 1 else 1.0,
+                                  z_wind=2.0 if N[2] > 1 else 1.0, shape_factor=sf, dt=0.05, tile_shape=tile,
+                                  particle_tile_capacity_factor=2.0, particle_pusher=pusher_name, relativistic=rel, **kw)
+    rng = np.random.default_rng(11)
+    n = 60
+    species = []
+    for s, (q, m) in enumerate(((-1.0, 1.0), (2.0, 5.0))):
+        pos = [rng.uniform(-w / 2, w / 2, n) if NN > 1 else np.zeros(n) for w, NN in ((dp.x_wind, dp.Nx), (dp.y_wind, dp.Ny), (dp.z_wind, dp.Nz))]
+        vel = [rng.uniform(-0.4, 0.4, n) for _ in range(3)]
+        species.append(fx.particle_species(f"s{s}", q, m, weight=0.5 + s, x1=pos[0], x2=pos[1], x3=pos[2], u1=vel[0], u2=vel[1], u3=vel[2],
+                                           update_u=(True, s == 0, True)))
+    tp, sc = fx.build_tiled_particles(species, sp, dp)
+    Eg = tuple(rng.normal(size=(N[0] + 2, N[1] + 2, N[2] + 2)) for _ in range(3))
+    Bg = tuple(rng.normal(size=(N[0] + 2, N[1] + 2, N[2] + 2)) for _ in range(3))
+    E, B = fx.vector_tiles_from_global(Eg, sp, dp), fx.vector_tiles_from_global(Bg, sp, dp)
+    return sp, dp, tp, sc, E, B
+
+
+@pytest.mark.parametrize("N,tile", CASES)
+@pytest.mark.parametrize("sf", (1, 2))
+@pytest.mark.parametrize("pn,rel", [("boris", True), ("boris", False), ("higuera_cary", True)])
+def test_push_body_matches_oracle(hc, N, tile, sf, pn, rel):
+    sp, dp, tp, sc, E, B = _setup(N, tile, sf, pn, rel)
+    ref = pusher.particle_push(tp, sc, E, B, sp, dp)
+    p = _lib.make_params(sp, dp, sc, np.float64)
+    x = np.ascontiguousarray(tp.x); u = np.ascontiguousarray(tp.u); a = np.ascontiguousarray(tp.active.astype(np.uint8))
+    out = np.zeros_like(u)
+    Ec = [np.ascontiguousarray(c) for c in E]; Bc = [np.ascontiguousarray(c) for c in B]
+    hc.hc_push(ctypes.byref(p), _ptr(x), _ptr(u), _ptr(out), _ptr(a), ctypes.c_int64(tp.x.shape[4]), _v3(Ec), _v3(Bc))
+    assert np.allclose(out, ref.u, rtol=1e-12, atol=1e-12)
+
+
+@pytest.mark.parametrize("N,tile", CASES)
+@pytest.mark.parametrize("sf", (1, 2))
+@pytest.mark.parametrize("mode", (0, 1, 2))
+def test_deposit_body_matches_oracle(hc, N, tile, sf, mode):
+    sp, dp, tp, sc, E, B = _setup(N, tile, sf)
+    z = fx.empty_tiled_vector(sp, dp)
+    if mode == 0:
+        ref = dep.Esirkepov_current(tp, sc, z, sp, dp, fold=False)
+    elif mode == 1:
+        ref = dep.J_from_rhov(tp, sc, z, sp, dp, fold=False)
+    else:
+        r = dep.compute_rho(tp, sc, z[0], sp, dp, fold=False)
+        ref = (r, np.zeros_like(r), np.zeros_like(r))
+    p = _lib.make_params(sp, dp, sc, np.float64)
+    x = np.ascontiguousarray(tp.x); u = np.ascontiguousarray(tp.u); a = np.ascontiguousarray(tp.active.astype(np.uint8))
+    J = [np.zeros_like(z[0]) for _ in range(3)]
+    hc.hc_deposit(ctypes.byref(p), mode, _ptr(x), _ptr(u), _ptr(a), ctypes.c_int64(tp.x.shape[4]), _v3(J))
+    scale = max(1.0, max(np.abs(r).max() for r in ref))
+    for c in range(3 if mode < 2 else 1):
+        assert np.allclose(J[c], ref[c], rtol=1e-12, atol=1e-12 * scale), (mode, c)
+
+
+@pytest.mark.parametrize("pbc", [(0, 0, 0), (1, 0, 2), (2, 1, 0)])
+def test_retile_classify_body_matches_oracle(hc, pbc):
+    sp, dp, tp, sc, E, B = _setup((8, 6, 4), (2, 3, 2), 1, particle_boundary_conditions=pbc)
+    moved = opart.update_tiled_particle_positions(tp, sc, 1.0)   # dt=1: up to 0.4 -> crosses tiles and walls
+    ref, ovf = opart.refresh_tiled_particle_tiles(moved, sp, dp)
+    p = _lib.make_params(sp, dp, sc, np.float64)
+    x = np.ascontiguousarray(moved.x); u = np.ascontiguousarray(moved.u); a = np.ascontiguousarray(moved.active.astype(np.uint8))
+    xo, uo, ao = np.zeros_like(x), np.zeros_like(u), np.zeros_like(a)
+    code = np.zeros(a.size, dtype=np.int32); flag = np.zeros(1, dtype=np.int32)
+    hc.hc_retile_classify(ctypes.byref(p), _ptr(x), _ptr(u), _ptr(a), _ptr(xo), _ptr(uo), _ptr(ao), ctypes.c_int64(x.shape[4]), _ptr(code), _ptr(flag))
+    # staying particles are identical; movers+stayers == oracle's active count (unless overflow)
+    stay = ao.astype(bool)
+    assert np.allclose(xo[stay], ref.x[stay], rtol=1e-13, atol=1e-13) and np.all(ref.active[stay])
+    if not ovf:
+        assert (code >= 1).sum() == ref.active.sum()
+
+
+@pytest.mark.parametrize("sf", (1, 2))
+@pytest.mark.parametrize("depmode", (0, 1))
+@pytest.mark.parametrize("dtype,tol", [(np.float64, 1e-12), (np.float32, 2e-5)])
+@pytest.mark.parametrize("N", [(8, 6, 4), (8, 1, 1), (6, 6, 1)])
+def test_fused_body_matches_oracle_step(hc, sf, depmode, dtype, tol, N):
+    """K1 body on a single tile == oracle push -> deposit -> move -> retile (evolve.py:33-79)."""
+    sp, dp, tp, sc, E, B = _setup(N, N, sf, current_deposition="esirkepov" if depmode == 0 else "direct")
+    pushed = pusher.particle_push(tp, sc, E, B, sp, dp)
+    z = fx.empty_tiled_vector(sp, dp)
+    if depmode == 0:
+        Jref = dep.Esirkepov_current(pushed, sc, z, sp, dp, fold=False)
+        moved, _ = opart.refresh_tiled_particle_tiles(opart.update_tiled_particle_positions(pushed, sc, dp.dt), sp, dp)
+    else:
+        half, _ = opart.refresh_tiled_particle_tiles(opart.update_tiled_particle_positions(pushed, sc, dp.dt / 2), sp, dp)
+        Jref = dep.J_from_rhov(half, sc, z, sp, dp, fold=False)
+        moved, _ = opart.refresh_tiled_particle_tiles(opart.update_tiled_particle_positions(half, sc, dp.dt / 2), sp, dp)
+    p = _lib.make_params(sp, dp, sc, dtype)
+    Ec = [np.ascontiguousarray(c[0, 0, 0], dtype=dtype) for c in E]; Bc = [np.ascontiguousarray(c[0, 0, 0], dtype=dtype) for c in B]
+    J = [np.zeros_like(Ec[0]) for _ in range(3)]
+    flags = np.zeros(1, dtype=np.int32)
+    for s in range(2):
+        act = tp.active[0, 0, 0, s]
+        comp = [np.ascontiguousarray(tp.x[0, 0, 0, s][act][:, c], dtype=dtype) for c in range(3)] + \
+               [np.ascontiguousarray(tp.u[0, 0, 0, s][act][:, c], dtype=dtype) for c in range(3)]
+        cp = (ctypes.c_void_p * 6)(*[a.ctypes.data for a in comp])
+        hc.hc_fused(ctypes.byref(p), s, depmode, cp, ctypes.c_int64(int(act.sum())), _v3(Ec), _v3(Bc), _v3(J), None, ctypes.c_int64(0), None, _ptr(flags))
+        xr = moved.x[0, 0, 0, s][act]; ur = moved.u[0, 0, 0, s][act]
+        for c in range(3):
+            assert np.allclose(comp[c], xr[:, c], rtol=tol, atol=tol * 4), ("x", s, c)
+            assert np.allclose(comp[3 + c], ur[:, c], rtol=tol, atol=tol), ("u", s, c)
+    scale = max(np.abs(r).max() for r in Jref)
+    for c in range(3):
+        assert np.allclose(J[c], Jref[c][0, 0, 0], rtol=tol, atol=tol * scale), ("J", c)
+    assert flags[0] == 0
