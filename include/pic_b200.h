@@ -166,16 +166,18 @@ int pic_sort_scatter(const PicParams* p, const PicSoA* src, const PicSoA* dst, c
  *   gather E,B (+ext) -> Boris/HC -> deposit (Esirkepov: x -> x+v*dt ; direct: at x+v*dt/2) -> move -> particle BC
  * == evolve.py:33-79 for one local tile.  J is accumulated with atomics into the ghosted tile (fold afterwards).
  * deposition: 0 = esirkepov, 1 = direct.  ext_E/ext_B may be NULL (external fields absent).
- * Leavers (multi-GPU, distributed axes) are appended to `leave` (6+1 rows: x,y,z,vx,vy,vz,dir code) with
- * counter d_leave_count; pass NULL when mesh == gmesh.  flags[0] |= 1 on overflow / invalid jump. */
+ * Leavers (multi-GPU, distributed axes) go to `leave`: [27 directions][leave_cap][7] packets (x,y,z,vx,vy,vz,species),
+ * direction = ((1-ox)*3 + (1-oy))*3 + (1-oz), with per-direction counters d_leave_count[27]; pass NULL when
+ * mesh == gmesh.  flags[0] |= 1 on an invalid (>1 tile) jump, |= 2 when a packet / SoA capacity overflowed. */
 int pic_fused_push_deposit(const PicParams* p, int species, int deposition, const PicSoA* soa,
                            const void* const E[3], const void* const B[3], const void* const extE[3],
                            const void* const extB[3], void* const J[3], void* leave, int64_t leave_cap,
                            int32_t* d_leave_count, int32_t* flags, void* stream);
 
-/* Append `n_in` migrated particles (7-row packet as written by the fused kernel) to the SoA tail. */
-int pic_soa_append(const PicParams* p, const PicSoA* soa, const void* packet, int64_t packet_cap, int64_t n_in,
-                   int32_t* flags, void* stream);
+/* Append the particles of `species` among `n_in` migrated packets ([n_in][7] = x,y,z,vx,vy,vz,species as written by
+ * the fused kernel) at the SoA tail; d_count (device int32) accumulates how many were appended. */
+int pic_soa_append(const PicParams* p, const PicSoA* soa, const void* packet, int64_t n_in, int species,
+                   int32_t* d_count, int32_t* flags, void* stream);
 
 /* Microbenchmarks used for design evidence (profiles/): returns elapsed device ms for `iters` launches. */
 int pic_microbench(int which, int iters, float* ms_out);

@@ -99,7 +99,7 @@ SIGNATURES = {
     "pic_sort_scan": [_I64, _VP, _VP, _VP, _VP],
     "pic_sort_scatter": [_PP, _SOA, _SOA, _VP, _VP, _VP],
     "pic_fused_push_deposit": [_PP, _INT, _INT, _SOA, _V3, _V3, _V3, _V3, _V3, _VP, _I64, _VP, _VP, _VP],
-    "pic_soa_append": [_PP, _SOA, _VP, _I64, _I64, _VP, _VP],
+    "pic_soa_append": [_PP, _SOA, _VP, _I64, _INT, _VP, _VP, _VP],
     "pic_microbench": [_INT, _INT, ctypes.POINTER(ctypes.c_float)],
     "pic_params_size": [],
     "pic_version": [],
@@ -152,10 +152,10 @@ def make_params(static_parameters, dynamic_parameters, species_config=None, dtyp
     sp, dp = static_parameters, dynamic_parameters
     p = PicParams()
     p.dtype = 0 if np.dtype(dtype) == np.float32 else 1
-    p.shape_factor = int(sp.shape_factor)
-    key = (sp.particle_pusher, bool(sp.relativistic))
+    p.shape_factor = int(getattr(sp, "shape_factor", 1))
+    key = (getattr(sp, "particle_pusher", "boris"), bool(getattr(sp, "relativistic", True)))
     if key not in PUSHERS:
-        raise ValueError(f"Unknown particle_pusher: {sp.particle_pusher}")
+        raise ValueError(f"Unknown particle_pusher: {key[0]}")
     p.pusher = PUSHERS[key]
     p.g = int(sp.guard_cells)
     tile = [int(w) for w in sp.tile_shape]
@@ -167,16 +167,16 @@ def make_params(static_parameters, dynamic_parameters, species_config=None, dtyp
     wind = [float(_scalar(dp.x_wind)), float(_scalar(dp.y_wind)), float(_scalar(dp.z_wind))]
     for a in range(3):
         p.mesh[a], p.gmesh[a], p.moff[a], p.tile[a] = mesh[a], gmesh[a], int(moff[a]), tile[a]
-        p.field_bc[a] = int(sp.boundary_conditions[a])
-        p.particle_bc[a] = int(sp.particle_boundary_conditions[a])
+        p.field_bc[a] = int(getattr(sp, "boundary_conditions", (0, 0, 0))[a])
+        p.particle_bc[a] = int(getattr(sp, "particle_boundary_conditions", (0, 0, 0))[a])
         p.wind[a] = wind[a]
         grids = getattr(dp, "grids", None)
         center = getattr(grids, "center", ()) if grids is not None else ()
         vertex = getattr(grids, "vertex", ()) if grids is not None else ()
         p.center0[a] = float(center[a][0]) if len(center) == 3 else -wind[a] / 2 - d[a]
         p.vertex0[a] = float(vertex[a][0]) if len(vertex) == 3 else -wind[a] / 2 - 0.5 * d[a]
-    p.dt, p.dx, p.dy, p.dz = float(_scalar(dp.dt)), d[0], d[1], d[2]
-    p.C, p.eps, p.mu, p.alpha = (float(_scalar(dp.C)), float(_scalar(dp.eps)), float(_scalar(dp.mu)), float(_scalar(dp.alpha)))
+    p.dt, p.dx, p.dy, p.dz = float(_scalar(getattr(dp, "dt", 0.0))), d[0], d[1], d[2]
+    p.C, p.eps, p.mu, p.alpha = (float(_scalar(getattr(dp, k, 1.0))) for k in ("C", "eps", "mu", "alpha"))
     if species_config is not None:
         charge = np.asarray(_to_numpy(species_config.charge), dtype=np.float64).reshape(-1)
         S = charge.shape[0]

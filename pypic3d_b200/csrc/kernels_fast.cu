@@ -146,10 +146,14 @@ __global__ void __launch_bounds__(256) k_fused(const __grid_constant__ PicParams
         fused_particle<T, SF, DEP, ALL3D>(p, species, gm, i, s, F, X, has_ext, sink, leave, distributed, flags);
 }
 
+// Append the migrated particles of `species` (packet rows [x,y,z,vx,vy,vz,species]) at the SoA tail; the number appended is
+// accumulated in d_count so the host can advance soa.n.
 template <typename T>
-__global__ void __launch_bounds__(256) k_append(SoAView<T> s, const T* __restrict__ packet, int64_t n_in, int32_t* flags) {
+__global__ void __launch_bounds__(256) k_append(SoAView<T> s, const T* __restrict__ packet, int64_t n_in, int species,
+                                                int32_t* d_count, int32_t* flags) {
     for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < n_in; j += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t dst = s.n + j;
+        if ((int)packet[j * 7 + 6] != species) continue;
+        const int64_t dst = s.n + atomicAdd(d_count, 1);
         if (dst >= s.cap) { atomicOr(flags, 2); continue; }
         for (int c = 0; c < 6; ++c) s.c[c][dst] = packet[j * 7 + c];
         if (s.id) s.id[dst] = -1;
@@ -212,9 +216,10 @@ static int launch_fused(const PicParams* p, int species, int deposition, const P
 }
 
 template <typename T>
-static int launch_append(const PicParams* p, const PicSoA* soa, const void* packet, int64_t n_in, int32_t* flags, cudaStream_t st) {
+static int launch_append(const PicParams* p, const PicSoA* soa, const void* packet, int64_t n_in, int species, int32_t* d_count,
+                         int32_t* flags, cudaStream_t st) {
     if (n_in == 0) return 0;
-    k_append<T><<<grid_for(n_in, 256), 256, 0, st>>>(view_of<T>(soa), (const T*)packet, n_in, flags);
+    k_append<T><<<grid_for(n_in, 256), 256, 0, st>>>(view_of<T>(soa), (const T*)packet, n_in, species, d_count, flags);
     PIC_LAUNCH_RET();
 }
 
@@ -276,10 +281,10 @@ int pic_fused_push_deposit(const PicParams* p, int species, int deposition, cons
                       (cudaStream_t)stream);
 }
 
-int pic_soa_append(const PicParams* p, const PicSoA* soa, const void* packet, int64_t packet_cap, int64_t n_in, int32_t* flags,
-                   void* stream) {
-    PIC_CHECK_ARG(p && soa && packet && flags && n_in >= 0 && n_in <= packet_cap);
-    PIC_DISPATCH_T(p, launch_append, p, soa, packet, n_in, flags, (cudaStream_t)stream);
+int pic_soa_append(const PicParams* p, const PicSoA* soa, const void* packet, int64_t n_in, int species, int32_t* d_count,
+                   int32_t* flags, void* stream) {
+    PIC_CHECK_ARG(p && soa && packet && flags && d_count && n_in >= 0 && species >= 0 && species < p->n_species);
+    PIC_DISPATCH_T(p, launch_append, p, soa, packet, n_in, species, d_count, flags, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -1,0 +1,251 @@
+"""Resident throughput path: the electrodynamic step of PyPIC3D/evolve.py:16-103 on compact, cell-sorted SoA particles.
+
+`Simulation` takes the reference's pytrees (`TiledParticles`, `SpeciesConfig`, the `fields` 8-tuple, Static/Dynamic
+parameters) for ONE tile per GPU, keeps the state resident in HBM in the kernels' native layout and advances it with
+
+    K1  pic_fused_push_deposit   gather -> push -> deposit -> move -> particle BC     (one pass over particle memory)
+        halo fold + refresh of J  (particle BCs)                                      ghost_cells.py:703-736
+    K6  pic_update_B (half)  K5 pic_update_E  K6 pic_update_B (half) + refreshes      first_order_yee.py:12-162
+    K2  counting sort by cell every `sort_interval` steps
+
+`export_state()` hands the reference pytrees back (same shapes / slot identity on a single GPU).
+Host orchestration is Python; every array operation on the step is a hand-written kernel behind the C ABI.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib, ops
+from ._lib import PicSoA, PicError, check
+from .particles.particle_class import TiledParticles
+from .boundary_conditions.grid_and_stencil import BC_CONDUCTING
+
+
+class _Species:
+    __slots__ = ("buf", "ids", "cur", "n", "cap")
+
+
+class LocalHalo:
+    """Guard-cell exchange when every axis is local to this GPU (periodic self-exchange / walls / reduced axes)."""
+
+    def __init__(self, params):
+        self.p = params
+
+    def refresh_(self, fields, bcs):
+        ops.halo_refresh_(self.p, fields, bcs)
+
+    def fold_(self, fields, bcs):
+        ops.halo_fold_(self.p, fields, bcs)
+
+    def migrate(self, sim):
+        return None
+
+
+class Simulation:
+    def __init__(self, particles, species_config, fields, static_parameters, dynamic_parameters, *, sort_interval=10,
+                 capacity_factor=1.25, track_ids=True, halo=None, gmesh=None, moff=(0, 0, 0), leave_capacity=None):
+        sp, dp = static_parameters, dynamic_parameters
+        if getattr(sp, "pml_active", False):
+            raise NotImplementedError("PML is outside the hot path of pypic3d_b200")
+        x = ops._chk(particles.x, "particles.x")
+        if tuple(x.shape[:3]) != (1, 1, 1):
+            raise ValueError("Simulation holds one tile per GPU; use pypic3d_b200.distributed for a multi-tile mesh "
+                             f"(got particle tile topology {tuple(x.shape[:3])})")
+        self.sp, self.dp, self.species_config = sp, dp, species_config
+        self.dtype = x.dtype
+        self.device = x.device
+        gm = (1, 1, 1) if gmesh is None else tuple(int(v) for v in gmesh)
+        self.p = ops.params_for(sp, dp, species_config, x, mesh=(1, 1, 1), gmesh=gm, moff=moff)
+        self.S = int(self.p.n_species)
+        self.deposition = 0 if sp.current_deposition == "esirkepov" else 1
+        self.current_filter = sp.current_filter if self.deposition == 1 else "none"
+        self.alpha = float(self.p.alpha)
+        self.g = int(self.p.g)
+        if self.g < 1:
+            raise ValueError("guard_cells must be >= 1")
+        self.sort_interval = int(sort_interval)
+        self.step_count = 0
+        self.halo = halo if halo is not None else LocalHalo(self.p)
+        self.distributed = any(self.p.gmesh[a] != self.p.mesh[a] for a in range(3))
+        E, B, J, rho, phi, ext, pml_state, overflow = fields
+        if pml_state is not None:
+            raise NotImplementedError("PML is outside the hot path of pypic3d_b200")
+        self._passthrough = (rho, phi, ext)
+        clone = lambda t: ops._chk(t, "field", self.dtype).clone()
+        self.E = [clone(c) for c in E]
+        self.B = [clone(c) for c in B]
+        self.J = [clone(c) for c in J]
+        ext_E, ext_B = ext
+        has_ext = any(bool(torch.any(c != 0)) for c in tuple(ext_E) + tuple(ext_B))
+        self.ext_E = [clone(c) for c in ext_E] if has_ext else None
+        self.ext_B = [clone(c) for c in ext_B] if has_ext else None
+        self.overflow_previous = bool(overflow) if not isinstance(overflow, torch.Tensor) else bool(overflow.item())
+        self.flags = torch.zeros(4, dtype=torch.int32, device=self.device)
+        self.ncells = int(self.p.tile[0]) * int(self.p.tile[1]) * int(self.p.tile[2])
+        self._cell_count = torch.zeros(self.ncells + 1, dtype=torch.int32, device=self.device)
+        self._cell_offset = torch.zeros(self.ncells + 1, dtype=torch.int32, device=self.device)
+        self._scan_scratch = torch.zeros((self.ncells + 1 + 2047) // 2048 + 1, dtype=torch.int32, device=self.device)
+        self._counter = torch.zeros(max(self.S, 1) + 27, dtype=torch.int32, device=self.device)
+        self.cap_ref = int(x.shape[4])
+        self.track_ids = bool(track_ids)
+        self._import(particles, capacity_factor)
+        self.leave_cap = 0
+        self.leave = None
+        self.leave_count = None
+        if self.distributed:
+            ntot = max(1, sum(s.n for s in self.species))
+            self.leave_cap = int(leave_capacity) if leave_capacity else max(1024, ntot // 8)
+            self.leave = torch.empty(27 * self.leave_cap * 7, dtype=self.dtype, device=self.device)
+            self.leave_count = torch.zeros(27, dtype=torch.int32, device=self.device)
+        self.sort()
+
+    # ------------------------------------------------------------------------------------------ layout
+    def _soa(self, sp_, which=None):
+        k = sp_.cur if which is None else which
+        s = PicSoA()
+        for c in range(6):
+            s.comp[c] = sp_.buf[k][c].data_ptr()
+        s.id = sp_.ids[k].data_ptr() if sp_.ids is not None else None
+        s.cap = sp_.cap
+        s.n = sp_.n
+        return s
+
+    def _import(self, particles, capacity_factor):
+        L = _lib.lib()
+        x, u, a = particles.x, ops._chk(particles.u, "particles.u", self.dtype), ops._chk(particles.active, "particles.active")
+        counts = a.reshape(self.S, -1).sum(dim=1).tolist() if a.numel() else [0] * self.S
+        self.species = []
+        st = ops._stream()
+        self._counter.zero_()
+        for s in range(self.S):
+            sp_ = _Species()
+            sp_.cap = max(16, int(np.ceil(counts[s] * float(capacity_factor))) + 16)
+            sp_.buf = [torch.empty((6, sp_.cap), dtype=self.dtype, device=self.device) for _ in range(2)]
+            sp_.ids = [torch.empty(sp_.cap, dtype=torch.int32, device=self.device) for _ in range(2)] if self.track_ids else None
+            sp_.cur = 0
+            sp_.n = 0
+            soa = self._soa(sp_)
+            check(L.pic_soa_import(ctypes.byref(self.p), s, ops._p(x), ops._p(u), ops._p(a), self.cap_ref, ctypes.byref(soa),
+                                   ops._p(self._counter[s:s + 1]), st), "pic_soa_import")
+            sp_.n = int(counts[s])
+            self.species.append(sp_)
+
+    def sort(self):
+        """K2: counting sort of every species by local cell; also compacts dead (absorbed / migrated) slots away."""
+        L = _lib.lib()
+        st = ops._stream()
+        n = self.ncells + 1
+        for sp_ in self.species:
+            if sp_.n == 0:
+                continue
+            src, dst = self._soa(sp_), self._soa(sp_, 1 - sp_.cur)
+            self._cell_count.zero_()
+            check(L.pic_sort_histogram(ctypes.byref(self.p), ctypes.byref(src), ops._p(self._cell_count), st), "pic_sort_histogram")
+            check(L.pic_sort_scan(n, ops._p(self._cell_count), ops._p(self._cell_offset), ops._p(self._scan_scratch), st), "pic_sort_scan")
+            self._cell_count.zero_()
+            check(L.pic_sort_scatter(ctypes.byref(self.p), ctypes.byref(src), ctypes.byref(dst), ops._p(self._cell_offset),
+                                     ops._p(self._cell_count), st), "pic_sort_scatter")
+            sp_.cur = 1 - sp_.cur
+            if self._may_have_dead:
+                sp_.n = int(self._cell_offset[self.ncells].item())   # live particles precede the trash bin
+
+    @property
+    def _may_have_dead(self):
+        return self.distributed or any(int(b) == 2 for b in self.p.particle_bc)
+
+    # ------------------------------------------------------------------------------------------ the step
+    def step(self, n_steps=1):
+        for _ in range(int(n_steps)):
+            self._step_once()
+
+    def _step_once(self):
+        L = _lib.lib()
+        p, st = self.p, ops._stream()
+        fbc = tuple(p.field_bc)
+        pbc = tuple(p.particle_bc)
+        for c in self.J:
+            c.zero_()
+        if self.distributed:
+            self.leave_count.zero_()
+        extE = ops._v(self.ext_E) if self.ext_E is not None else None
+        extB = ops._v(self.ext_B) if self.ext_B is not None else None
+        for s, sp_ in enumerate(self.species):
+            if sp_.n == 0:
+                continue
+            soa = self._soa(sp_)
+            check(L.pic_fused_push_deposit(ctypes.byref(p), s, self.deposition, ctypes.byref(soa), ops._v(self.E), ops._v(self.B),
+                                           extE, extB, ops._v(self.J), ops._p(self.leave) if self.leave is not None else None,
+                                           self.leave_cap, ops._p(self.leave_count) if self.leave_count is not None else None,
+                                           ops._p(self.flags), st), "pic_fused_push_deposit")
+        self.halo.migrate(self)
+        # J: fold ghost deposits to their owners, then refresh (Esirkepov.py:357-359 / J_from_rhov.py:226-228)
+        self.halo.fold_(self.J, pbc)
+        self.halo.refresh_(self.J, pbc)
+        if self.current_filter in ("bilinear", "digital"):                       # J_from_rhov.py:234-255
+            self.J = [ops.filter27(p, self.current_filter, self.alpha, c) for c in self.J]
+            self.halo.refresh_(self.J, pbc)
+        # B half step from E_old (evolve.py:88); E halos are valid from the previous step
+        ops.update_B_(p, self.B, self.E)
+        self.halo.refresh_(self.B, fbc)
+        # E full step (evolve.py:92)
+        ops.update_E_(p, self.E, self.B, self.J)
+        self.halo.refresh_(self.E, fbc)
+        if self.alpha != 1.0:
+            self.E = [ops.filter27(p, "digital", self.alpha, c) for c in self.E]
+        walls = False
+        for axis in range(3):
+            if fbc[axis] == BC_CONDUCTING:                                        # first_order_yee.py:80-89
+                for c in range(3):
+                    if c != axis:
+                        ops.zero_wall_(p, self.E[c], axis)
+                walls = True
+        if walls or self.alpha != 1.0:
+            self.halo.refresh_(self.E, fbc)
+        # B half step from E_new (+ filter) (evolve.py:96)
+        ops.update_B_(p, self.B, self.E)
+        if self.alpha != 1.0:
+            self.halo.refresh_(self.B, fbc)
+            self.B = [ops.filter27(p, "digital", self.alpha, c) for c in self.B]
+        self.halo.refresh_(self.B, fbc)
+        self.step_count += 1
+        if self.sort_interval > 0 and self.step_count % self.sort_interval == 0:
+            self.sort()
+
+    # ------------------------------------------------------------------------------------------ results
+    def overflow(self):
+        """Host sync: the reference's overflow flag (invalid > 1 tile jump or a capacity overflow), OR-ed over steps."""
+        return self.overflow_previous or bool((self.flags[0] != 0).item())
+
+    def n_particles(self):
+        return sum(s.n for s in self.species)
+
+    def export_state(self, cap_ref=None):
+        """Reference pytrees: (TiledParticles, fields 8-tuple).  Slots are restored by id on a single GPU."""
+        L = _lib.lib()
+        st = ops._stream()
+        cap = self.cap_ref if cap_ref is None else int(cap_ref)
+        if not (self.track_ids and not self.distributed):
+            cap = max(cap, max((s.n for s in self.species), default=0))
+        x = torch.zeros((1, 1, 1, self.S, cap, 3), dtype=self.dtype, device=self.device)
+        u = torch.zeros_like(x)
+        a = torch.zeros((1, 1, 1, self.S, cap), dtype=torch.bool, device=self.device)
+        self._counter.zero_()
+        for s, sp_ in enumerate(self.species):
+            soa = self._soa(sp_)
+            if self.distributed:
+                soa.id = None
+            check(L.pic_soa_export(ctypes.byref(self.p), s, ctypes.byref(soa), ops._p(x), ops._p(u), ops._p(a), cap,
+                                   ops._p(self._counter[s:s + 1]), st), "pic_soa_export")
+        rho, phi, ext = self._passthrough
+        overflow = torch.tensor(self.overflow(), device=self.device)
+        fields = (tuple(c.clone() for c in self.E), tuple(c.clone() for c in self.B), tuple(c.clone() for c in self.J), rho, phi, ext,
+                  None, overflow)
+        return TiledParticles(x=x, u=u, active=a), fields
+
+
+def time_loop_electrodynamic_resident(particles, species_config, fields, static_parameters, dynamic_parameters, n_steps=1, **kw):
+    """Convenience: import -> n_steps fused steps -> export, with the reference's (particles, fields) signature."""
+    sim = Simulation(particles, species_config, fields, static_parameters, dynamic_parameters, **kw)
+    sim.step(n_steps)
+    return sim.export_state()

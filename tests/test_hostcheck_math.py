@@ -35,7 +35,7 @@ def _v3(arrs):
     return (ctypes.c_void_p * 3)(*[a.ctypes.data for a in arrs])
 
 
-CASES = [((8, 6, 4), (2, 3, 2)), ((8, 6, 4), (8, 6, 4)), ((8, 1, 1), (2, 1, 1)), ((6, 6, 1), (3, 2, 1)), ((1, 6, 4), (1, 3, 2))]
+from tests.cases import CASES
 
 
 def _setup(N, tile, sf, pusher_name="boris", rel=True, dtype=np.float64, **kw):
