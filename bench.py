@@ -1,0 +1,385 @@
+#!/usr/bin/env python
+"""bench.py -- particle-steps/s of the PIC hot path (push + deposit + Yee + guard cells) on N B200s.
+
+A "step" is one electrodynamic PIC step (PyPIC3D/evolve.py:16-103) over the whole synthetic thermal plasma:
+BASELINE.json configs[3] at N=1 (256^3 cells x 16 ppc, Esirkepov + Yee, periodic) and configs[4] for N>1 (the same box
+per GPU, weak scaling, NCCL halo exchange + particle migration).
+
+    python bench.py --gpus 1 --steps 20 --warmup 5            # ours (CUDA, C ABI)
+    python bench.py --impl reference --steps 3 --warmup 1      # CPU arm: NumPy restatement of the reference (oracle)
+    torchrun ... bench.py --gpus N ...                         # N>1: one rank per GPU
+
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for every key.
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np
+
+C_LIGHT = 299792458.0
+EPS0 = 8.8541878128e-12
+MU0 = 1.25663706212e-6
+QE = 1.602176634e-19
+ME = 9.1093837015e-31
+MP = 1.67262192369e-27
+
+
+def physical_setup(n_local, mesh, ppc, shape_factor, dtype_name):
+    """SURVEY.md section 8d input 4: thermal e-/p+ plasma, n0 = 1e18 m^-3, dx = lambda_D, vth_e = 0.05 c, dt = 0.99 dx/(3c)."""
+    vth_e = 0.05 * C_LIGHT
+    n0 = 1e18
+    kT = ME * vth_e ** 2
+    lam = math.sqrt(EPS0 * kT / (n0 * QE ** 2))
+    dx = lam
+    N = [n_local * mesh[a] for a in range(3)]
+    dt = 0.99 / (C_LIGHT * 3.0 / dx)                        # utils.py:761-801 courant_condition, 3 active axes
+    weight = n0 * dx ** 3 / (ppc // 2)
+    return dict(N=N, dx=dx, dt=dt, weight=weight, vth=(vth_e, vth_e * math.sqrt(ME / MP)), charge=(-QE, QE), mass=(ME, MP),
+                wind=[N[a] * dx for a in range(3)])
+
+
+def make_params(cfg, n_local, mesh, shape_factor, deposition="esirkepov"):
+    from pypic3d_b200.parameters import StaticParameters, DynamicParameters, GridParameters
+    from pypic3d_b200.utilities.grids import build_yee_grid
+    N, dx = cfg["N"], cfg["dx"]
+    sp = StaticParameters(name="bench", output_dir=".", Nt=0, verbose=False, GPUs=True, benchmark=True, solver="electrodynamic_yee",
+                          electrostatic=False, relativistic=True, particle_pusher="boris", current_deposition=deposition,
+                          current_filter="none", shape_factor=shape_factor, guard_cells=2, tile_shape=(n_local,) * 3,
+                          particle_tile_capacity_factor=1.25, pml_active=False, boundary_conditions=(0, 0, 0),
+                          particle_boundary_conditions=(0, 0, 0), field_mesh=tuple(mesh))
+    dp = DynamicParameters(dt=cfg["dt"], dx=dx, dy=dx, dz=dx, Nx=N[0], Ny=N[1], Nz=N[2], x_wind=cfg["wind"][0], y_wind=cfg["wind"][1],
+                           z_wind=cfg["wind"][2], C=C_LIGHT, eps=EPS0, mu=MU0, kb=1.380649e-23, alpha=1.0,
+                           grids=GridParameters((), (), (), ()))
+    center, vertex = build_yee_grid(dp)
+    dp = dp._replace(grids=GridParameters(vertex=vertex, center=center, tiled_vertex_grid=(), tiled_center_grid=()))
+    return sp, dp
+
+
+# ------------------------------------------------------------------------------------------------ clocks sampler
+class ClockSampler(threading.Thread):
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index=0):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([v.strip() for v in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = sorted(float(s[1]) for s in self.samples if s[1].replace(".", "").isdigit())
+        reasons = set()
+        for s in self.samples:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.samples[0][2]), "reasons": sorted(reasons),
+                "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm (oracle)
+def cpu_reference(steps, warmup, shape_factor, n=16, ppc=16, seed=1234):
+    """The reference's algorithm on the host cores: NumPy float64 restatement (oracle/), bounded sample n^3 x ppc."""
+    from oracle import fixtures as fx, evolve as oevolve
+    cfg = physical_setup(n, (1, 1, 1), ppc, shape_factor, "f64")
+    sp, dp = fx.kernel_parameters(Nx=n, Ny=n, Nz=n, x_wind=cfg["wind"][0], y_wind=cfg["wind"][1], z_wind=cfg["wind"][2], dt=cfg["dt"],
+                                  shape_factor=shape_factor, current_deposition="esirkepov", C=C_LIGHT, eps=EPS0, mu=MU0)
+    tp, sc = fx.thermal_plasma(sp, dp, ppc_per_species=ppc // 2, vth=(0.05, 0.05 * math.sqrt(ME / MP)), seed=seed,
+                               charge=cfg["charge"], mass=cfg["mass"], weight=cfg["weight"])
+    z = fx.empty_tiled_vector
+    fields = (z(sp, dp), z(sp, dp), z(sp, dp), fx.empty_tiled_scalar(sp, dp), fx.empty_tiled_scalar(sp, dp), (z(sp, dp), z(sp, dp)), None, False)
+    npart = int(tp.active.sum())
+    for _ in range(warmup):
+        tp, fields = oevolve.time_loop_electrodynamic(tp, sc, fields, sp, dp)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        tp, fields = oevolve.time_loop_electrodynamic(tp, sc, fields, sp, dp)
+    el = time.perf_counter() - t0
+    return {"value": npart * steps / el, "unit": "particle-steps/s", "cores": 1, "kind": "port",
+            "sample": f"{n}^3 cells x {ppc} ppc ({npart} particles), {steps} steps, NumPy float64 restatement of the reference "
+                      f"(jax is not installable here); NumPy scatter-add is single-threaded"}, el / max(steps, 1)
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    base, ms = cpu_reference(args.steps, args.warmup, args.shape_factor, n=args.cpu_n)
+    line = {"impl": "reference", "metric": "particle-steps/sec (push+deposit+Yee)", "value": base["value"], "unit": "particle-steps/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args, args.gpus), "cpu_baseline": base,
+            "e2e": {"value": base["value"], "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def workload_config(args, n_gpus):
+    mesh = mesh_for(n_gpus)
+    return {"workload": f"synthetic 3D periodic thermal plasma, {args.n}^3 cells per GPU x {args.ppc} ppc (2 species), "
+                        f"Esirkepov + first-order Yee, shape_factor={args.shape_factor}, relativistic Boris, g=2",
+            "cells_per_gpu": args.n ** 3, "ppc": args.ppc, "mesh": list(mesh), "sort_interval": args.sort_interval,
+            "cache": "inputs >> L2 (particles 6.4 GB f32 at 256^3 x 16 ppc); no L2 flush needed"}
+
+
+def mesh_for(n):
+    return {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}.get(n, (n, 1, 1))
+
+
+# ------------------------------------------------------------------------------------------------ device workload
+def device_plasma(cfg, sp, dp, n_local, moff, ppc, dtype, device, seed):
+    """Synthetic thermal plasma generated directly on the device in the reference TiledParticles layout (one tile)."""
+    import torch
+    import pypic3d_b200 as pp
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    n_per = n_local ** 3 * (ppc // 2)
+    x = torch.empty((1, 1, 1, 2, n_per, 3), dtype=dtype, device=device)
+    u = torch.empty_like(x)
+    for s in range(2):
+        for a in range(3):
+            lo = -cfg["wind"][a] / 2 + moff[a] * n_local * cfg["dx"]
+            x[0, 0, 0, s, :, a] = (lo + torch.rand(n_per, generator=g, device=device, dtype=torch.float64) * (n_local * cfg["dx"])).to(dtype)
+            u[0, 0, 0, s, :, a] = (torch.randn(n_per, generator=g, device=device, dtype=torch.float32) * cfg["vth"][s]).to(dtype)
+    # keep positions strictly inside the local box after rounding to dtype
+    for a in range(3):
+        lo = -cfg["wind"][a] / 2 + moff[a] * n_local * cfg["dx"]
+        hi = lo + n_local * cfg["dx"]
+        x[..., a].clamp_(min=lo, max=float(np.nextafter(np.float32(hi), np.float32(lo))) if dtype == torch.float32 else float(np.nextafter(hi, lo)))
+    active = torch.ones((1, 1, 1, 2, n_per), dtype=torch.bool, device=device)
+    species = pp.SpeciesConfig(charge=np.array(cfg["charge"]), mass=np.array(cfg["mass"]), weight=np.array([cfg["weight"]] * 2),
+                               update_x=np.ones((2, 3), bool), update_u=np.ones((2, 3), bool))
+    return pp.TiledParticles(x=x, u=u, active=active), species
+
+
+def zero_fields(n_local, dtype, device):
+    import torch
+    L = n_local + 4
+    z = lambda: torch.zeros((1, 1, 1, L, L, L), dtype=dtype, device=device)
+    v = lambda: (z(), z(), z())
+    return (v(), v(), v(), z(), z(), (v(), v()), None, torch.tensor(False, device=device))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=("ours", "reference"))
+    ap.add_argument("--n", type=int, default=256, help="cells per axis per GPU")
+    ap.add_argument("--ppc", type=int, default=16)
+    ap.add_argument("--shape-factor", type=int, default=1)
+    ap.add_argument("--dtype", default="f32", choices=("f32", "f64"))
+    ap.add_argument("--sort-interval", type=int, default=10)
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--cpu-n", type=int, default=16)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--check", action="store_true", help="also verify charge conservation at full size after the timed run")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import torch
+    import torch.distributed as dist
+    from pypic3d_b200 import _lib, ops
+    from pypic3d_b200.simulation import Simulation
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; pypic3d_b200 has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    n_gpus = world
+    mesh = mesh_for(n_gpus)
+    dtype = torch.float32 if args.dtype == "f32" else torch.float64
+    cfg = physical_setup(args.n, mesh, args.ppc, args.shape_factor, args.dtype)
+    sp, dp = make_params(cfg, args.n, mesh, args.shape_factor)
+    moff = (rank // (mesh[1] * mesh[2]), (rank // mesh[2]) % mesh[1], rank % mesh[2])
+    particles, species = device_plasma(cfg, sp, dp, args.n, moff, args.ppc, dtype, device, seed=1234 + rank)
+    fields = zero_fields(args.n, dtype, device)
+    if world > 1:
+        from pypic3d_b200.distributed import DistributedHalo
+        halo_factory = lambda p: DistributedHalo(p, dist.group.WORLD, device)
+    else:
+        halo_factory = None
+    sim = Simulation(particles, species, fields, sp, dp, sort_interval=args.sort_interval, gmesh=mesh, moff=moff,
+                     halo=halo_factory, capacity_factor=1.25 if world > 1 else 1.02)
+    n_local_particles = sim.n_particles()
+    del particles
+    torch.cuda.empty_cache()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        sim.step(1)
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    sim.k1_events = []
+    _lib.LAUNCHES = 0
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    sim.step(args.steps)
+    ev1.record()
+    barrier()
+    ms_total = ev0.elapsed_time(ev1)
+    launches = _lib.LAUNCHES
+    k1_ms = [a.elapsed_time(b) for a, b in sim.k1_events]
+    sim.k1_events = None
+    if sampler:
+        sampler.stop_flag = True
+        sampler.join(timeout=2)
+    t = torch.tensor([ms_total], dtype=torch.float64, device=device)
+    npart = torch.tensor([float(sim.n_particles())], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(npart, op=dist.ReduceOp.SUM)
+    ms_total = float(t.item())
+    total_particles = float(npart.item())
+    value = total_particles * args.steps / (ms_total * 1e-3)
+    overflow = sim.overflow()
+
+    # ---- roofline of the dominant kernel (K1, one launch per species per step) and of the whole step
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    real = 4 if args.dtype == "f32" else 8
+    k1_bytes_pp = 12 * real + (9.0 / args.ppc) * real        # r/w x,u + gather E,B (6) + J write (3) per cell
+    step_bytes_pp = 12 * real + 1 + (24.0 / args.ppc) * real  # 55 B (f32) / 109 B (f64) at 16 ppc
+    k1_avg_ms = float(np.mean(k1_ms)) if k1_ms else None
+    per_launch_particles = n_local_particles / 2
+    roof = None
+    if k1_avg_ms:
+        achieved = k1_bytes_pp * per_launch_particles / (k1_avg_ms * 1e-3) / 1e9
+        roof = {"bound": "hbm", "kernel": "k_fused (K1: gather+push+deposit+move+BC, one species per launch)", "achieved": achieved,
+                "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_particle": k1_bytes_pp, "avg_launch_ms": k1_avg_ms,
+                "k1_share_of_step": float(np.sum(k1_ms)) / ms_total if ms_total else None}
+    step_achieved = step_bytes_pp * (total_particles / n_gpus) * args.steps / (ms_total * 1e-3) / 1e9
+    roof_step = {"bytes_per_particle_step": step_bytes_pp, "achieved": step_achieved, "peak": peak, "unit": "GB/s", "frac": step_achieved / peak}
+
+    # ---- end-to-end through the public API with HOST buffers (rank-local): H2D -> load_state -> step -> export -> D2H
+    e2e = None
+    if not args.no_e2e:
+        e2e = run_e2e(sim, args, device, world, dist if world > 1 else None)
+
+    cpu_base = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu_base, _ = cpu_reference(3, 1, args.shape_factor, n=args.cpu_n, ppc=args.ppc)
+
+    check = None
+    if args.check:
+        check = conservation_check(sim, sp, dp, species)
+
+    if rank == 0:
+        line = {"metric": "particle-steps/sec (push+deposit+Yee)", "value": value, "unit": "particle-steps/s", "n_gpus": n_gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+                "config": workload_config(args, n_gpus), "particles": total_particles, "overflow": overflow,
+                "roofline": roof, "roofline_step": roof_step, "cpu_baseline": cpu_base, "e2e": e2e, "gpu_launches": launches,
+                "clocks": sampler.summary() if sampler else None}
+        if check is not None:
+            line["check"] = check
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_e2e(sim, args, device, world, dist):
+    """Same metric through the reference-facing API with host buffers: every step copies the TiledParticles + E,B,J pytrees
+    from pinned host memory, runs `load_state -> sort -> step -> export_state`, and copies the result pytrees back."""
+    import torch
+    parts, fields = sim.export_state()
+    host = {"x": parts.x.cpu().pin_memory(), "u": parts.u.cpu().pin_memory(), "a": parts.active.cpu().pin_memory(),
+            "F": [[c.cpu().pin_memory() for c in fields[k]] for k in range(3)]}
+    dev = {"x": parts.x, "u": parts.u, "a": parts.active, "F": [[c for c in fields[k]] for k in range(3)]}
+    h2d = host["x"].numel() * host["x"].element_size() * 2 + host["a"].numel() + sum(c.numel() * c.element_size() for k in host["F"] for c in k)
+    d2h = h2d
+    import pypic3d_b200 as pp
+
+    def one():
+        dev["x"].copy_(host["x"], non_blocking=True); dev["u"].copy_(host["u"], non_blocking=True); dev["a"].copy_(host["a"], non_blocking=True)
+        for k in range(3):
+            for c in range(3):
+                dev["F"][k][c].copy_(host["F"][k][c], non_blocking=True)
+        sim.load_state(pp.TiledParticles(dev["x"], dev["u"], dev["a"]), (tuple(dev["F"][0]), tuple(dev["F"][1]), tuple(dev["F"][2])))
+        sim.step(1)
+        p2, f2 = sim.export_state(out=(dev["x"], dev["u"], dev["a"]))
+        host["x"].copy_(p2.x, non_blocking=True); host["u"].copy_(p2.u, non_blocking=True); host["a"].copy_(p2.active, non_blocking=True)
+        for k in range(3):
+            for c in range(3):
+                host["F"][k][c].copy_(f2[k][c], non_blocking=True)
+    one()
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.e2e_steps):
+        one()
+    torch.cuda.synchronize()
+    el = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=device)
+    npart = torch.tensor([float(sim.n_particles())], dtype=torch.float64, device=device)
+    if dist is not None:
+        dist.all_reduce(el, op=dist.ReduceOp.MAX)
+        dist.all_reduce(npart, op=dist.ReduceOp.SUM)
+    return {"value": float(npart.item()) * args.e2e_steps / float(el.item()), "unit": "particle-steps/s", "h2d_bytes_per_step": int(h2d),
+            "d2h_bytes_per_step": int(d2h), "steps": args.e2e_steps, "ms_per_step": float(el.item()) / args.e2e_steps * 1e3,
+            "path": "pinned host TiledParticles+E,B,J -> H2D -> Simulation.load_state -> sort -> step -> export_state -> D2H"}
+
+
+def conservation_check(sim, sp, dp, species):
+    """Size-independent property at the benchmark size: discrete continuity residual of one more step (single GPU)."""
+    import torch
+    from pypic3d_b200.deposition.rho import compute_rho
+    p0, f0 = sim.export_state()
+    zero = torch.zeros_like(f0[0][0])
+    rho0 = compute_rho(p0, species, zero, sp, dp)
+    sim.step(1)
+    p1, f1 = sim.export_state()
+    rho1 = compute_rho(p1, species, zero, sp, dp)
+    I = (0, 0, 0, slice(2, -2), slice(2, -2), slice(2, -2))
+    bx = (0, 0, 0, slice(1, -3), slice(2, -2), slice(2, -2)); by = (0, 0, 0, slice(2, -2), slice(1, -3), slice(2, -2)); bz = (0, 0, 0, slice(2, -2), slice(2, -2), slice(1, -3))
+    J = f1[2]
+    div = (J[0][I] - J[0][bx]) / dp.dx + (J[1][I] - J[1][by]) / dp.dy + (J[2][I] - J[2][bz]) / dp.dz
+    drho = (rho1[I] - rho0[I]) / dp.dt
+    res = float((drho + div).abs().max())
+    scale = float(drho.abs().max())
+    return {"continuity_residual_max": res, "scale": scale, "relative": res / scale if scale else None,
+            "active_particles": int(p1.active.sum())}
+
+
+if __name__ == "__main__":
+    main()

@@ -66,6 +66,25 @@ def build(force=False, verbose=False):
 
 
 _LIB = None
+LAUNCHES = 0   # kernels launched through the C ABI since last reset (bench.py "gpu_launches")
+KERNELS_PER_CALL = {"pic_halo_fold_axis": 2, "pic_sort_scan": 3, "pic_retile": 2, "pic_microbench": 0, "pic_params_size": 0,
+                    "pic_version": 0}
+
+
+class _Counted:
+    __slots__ = ("fn", "k")
+
+    def __init__(self, fn, k):
+        self.fn, self.k = fn, k
+
+    def __call__(self, *args):
+        global LAUNCHES
+        LAUNCHES += self.k
+        return self.fn(*args)
+
+
+class _Namespace:
+    pass
 
 _VP = ctypes.c_void_p
 _PP = ctypes.POINTER(PicParams)
@@ -117,14 +136,17 @@ def lib():
         L = ctypes.CDLL(LIB_PATH)
     except OSError as exc:  # pragma: no cover
         raise RuntimeError(f"pypic3d_b200: cannot load {LIB_PATH}: {exc}; the CUDA extension is mandatory") from exc
+    ns = _Namespace()
     for name, argtypes in SIGNATURES.items():
         fn = getattr(L, name)
         fn.argtypes = argtypes
         fn.restype = ctypes.c_char_p if name == "pic_version" else ctypes.c_int
+        setattr(ns, name, _Counted(fn, KERNELS_PER_CALL.get(name, 1)))
     if L.pic_params_size() != ctypes.sizeof(PicParams):
         raise RuntimeError("pypic3d_b200: PicParams layout mismatch between Python and libpic_b200.so")
-    _LIB = L
-    return L
+    ns._cdll = L
+    _LIB = ns
+    return ns
 
 
 class PicError(RuntimeError):

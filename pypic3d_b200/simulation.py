@@ -66,7 +66,11 @@ class Simulation:
             raise ValueError("guard_cells must be >= 1")
         self.sort_interval = int(sort_interval)
         self.step_count = 0
-        self.halo = halo if halo is not None else LocalHalo(self.p)
+        if halo is None:
+            self.halo = LocalHalo(self.p)
+        else:
+            self.halo = halo(self.p) if callable(halo) and not hasattr(halo, "refresh_") else halo
+        self.k1_events = None   # set to [] to record (start, end) CUDA events around every K1 launch (bench.py roofline)
         self.distributed = any(self.p.gmesh[a] != self.p.mesh[a] for a in range(3))
         E, B, J, rho, phi, ext, pml_state, overflow = fields
         if pml_state is not None:
@@ -113,23 +117,40 @@ class Simulation:
 
     def _import(self, particles, capacity_factor):
         L = _lib.lib()
-        x, u, a = particles.x, ops._chk(particles.u, "particles.u", self.dtype), ops._chk(particles.active, "particles.active")
+        x, u, a = ops._chk(particles.x, "particles.x", self.dtype), ops._chk(particles.u, "particles.u", self.dtype), ops._chk(particles.active, "particles.active")
+        if tuple(x.shape[:4]) != (1, 1, 1, self.S) or int(x.shape[4]) != self.cap_ref:
+            raise ValueError(f"particle layout {tuple(x.shape)} does not match (1,1,1,{self.S},{self.cap_ref},3)")
         counts = a.reshape(self.S, -1).sum(dim=1).tolist() if a.numel() else [0] * self.S
-        self.species = []
+        first = not hasattr(self, "species")
+        if first:
+            self.species = []
         st = ops._stream()
         self._counter.zero_()
         for s in range(self.S):
-            sp_ = _Species()
-            sp_.cap = max(16, int(np.ceil(counts[s] * float(capacity_factor))) + 16)
-            sp_.buf = [torch.empty((6, sp_.cap), dtype=self.dtype, device=self.device) for _ in range(2)]
-            sp_.ids = [torch.empty(sp_.cap, dtype=torch.int32, device=self.device) for _ in range(2)] if self.track_ids else None
+            if first:
+                sp_ = _Species()
+                sp_.cap = max(16, int(np.ceil(counts[s] * float(capacity_factor))) + 16)
+                sp_.buf = [torch.empty((6, sp_.cap), dtype=self.dtype, device=self.device) for _ in range(2)]
+                sp_.ids = [torch.empty(sp_.cap, dtype=torch.int32, device=self.device) for _ in range(2)] if self.track_ids else None
+                self.species.append(sp_)
+            sp_ = self.species[s]
+            if counts[s] > sp_.cap:
+                raise PicError(f"species {s}: {counts[s]} particles exceed the resident capacity {sp_.cap}")
             sp_.cur = 0
             sp_.n = 0
             soa = self._soa(sp_)
             check(L.pic_soa_import(ctypes.byref(self.p), s, ops._p(x), ops._p(u), ops._p(a), self.cap_ref, ctypes.byref(soa),
                                    ops._p(self._counter[s:s + 1]), st), "pic_soa_import")
             sp_.n = int(counts[s])
-            self.species.append(sp_)
+
+    def load_state(self, particles, fields3=None):
+        """Replace the resident state from reference-layout pytrees (same shapes as at construction); re-sorts."""
+        self._import(particles, 1.0)
+        if fields3 is not None:
+            for dst, src in zip((self.E, self.B, self.J), fields3):
+                for d, s_ in zip(dst, src):
+                    d.copy_(ops._chk(s_, "field", self.dtype))
+        self.sort()
 
     def sort(self):
         """K2: counting sort of every species by local cell; also compacts dead (absorbed / migrated) slots away."""
@@ -174,10 +195,16 @@ class Simulation:
             if sp_.n == 0:
                 continue
             soa = self._soa(sp_)
+            if self.k1_events is not None:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
             check(L.pic_fused_push_deposit(ctypes.byref(p), s, self.deposition, ctypes.byref(soa), ops._v(self.E), ops._v(self.B),
                                            extE, extB, ops._v(self.J), ops._p(self.leave) if self.leave is not None else None,
                                            self.leave_cap, ops._p(self.leave_count) if self.leave_count is not None else None,
                                            ops._p(self.flags), st), "pic_fused_push_deposit")
+            if self.k1_events is not None:
+                e1.record()
+                self.k1_events.append((e0, e1))
         self.halo.migrate(self)
         # J: fold ghost deposits to their owners, then refresh (Esirkepov.py:357-359 / J_from_rhov.py:226-228)
         self.halo.fold_(self.J, pbc)
@@ -220,16 +247,24 @@ class Simulation:
     def n_particles(self):
         return sum(s.n for s in self.species)
 
-    def export_state(self, cap_ref=None):
-        """Reference pytrees: (TiledParticles, fields 8-tuple).  Slots are restored by id on a single GPU."""
+    def export_state(self, cap_ref=None, out=None):
+        """Reference pytrees: (TiledParticles, fields 8-tuple).  Slots are restored by id on a single GPU.
+        `out=(x, u, active)` reuses caller-owned tensors of the reference shape."""
         L = _lib.lib()
         st = ops._stream()
         cap = self.cap_ref if cap_ref is None else int(cap_ref)
         if not (self.track_ids and not self.distributed):
             cap = max(cap, max((s.n for s in self.species), default=0))
-        x = torch.zeros((1, 1, 1, self.S, cap, 3), dtype=self.dtype, device=self.device)
-        u = torch.zeros_like(x)
-        a = torch.zeros((1, 1, 1, self.S, cap), dtype=torch.bool, device=self.device)
+        if out is not None:
+            x, u, a = out
+            if int(x.shape[4]) < cap:
+                raise PicError("export_state(out=...): capacity too small")
+            cap = int(x.shape[4])
+            x.zero_(); u.zero_(); a.zero_()
+        else:
+            x = torch.zeros((1, 1, 1, self.S, cap, 3), dtype=self.dtype, device=self.device)
+            u = torch.zeros_like(x)
+            a = torch.zeros((1, 1, 1, self.S, cap), dtype=torch.bool, device=self.device)
         self._counter.zero_()
         for s, sp_ in enumerate(self.species):
             soa = self._soa(sp_)
