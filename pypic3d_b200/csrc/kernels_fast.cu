@@ -3,6 +3,8 @@
 //                      particle memory: reads x,y,z,vx,vy,vz once, writes them once (48 B f32 / 96 B f64 per particle)
 //   K2  k_sort_*       counting sort by local cell (histogram, exclusive scan, scatter), run every few steps
 //   import / export    TiledParticles (reference AoS + active mask) <-> compact SoA
+#include <stdlib.h>
+
 #include "pic_common.cuh"
 
 namespace pic {
@@ -146,6 +148,100 @@ __global__ void __launch_bounds__(256) k_fused(const __grid_constant__ PicParams
         fused_particle<T, SF, DEP, ALL3D>(p, species, gm, i, s, F, X, has_ext, sink, leave, distributed, flags);
 }
 
+// K1 v3: specialised 3-D Esirkepov kernel (bodies: fast3d_advance / union_deposit in pic_slots.cuh).
+//  * geometry and per-species constants are computed on the host and live in the constant bank;
+//  * particles are cell-sorted, so neighbouring lanes usually deposit to the SAME nodes: the same-cell current values are
+//    combined with a segmented warp scan (key = stencil base index) and only the last lane of each run issues the global
+//    RED -- measured on B200, global fp32 RED sustains ~0.7 lane-ops/clk/SM (profiles/r01_microbench_atomics.jsonl), which
+//    made the un-aggregated kernel L2-atomic-bound (profiles/r01_k1_versions.md);
+//  * the few particles that change anchor cell are queued in shared memory and deposited by full warps through the
+//    union-stencil body, so the common path stays branch-free.
+template <typename T, int SF, int PUSHER>
+__global__ void __launch_bounds__(256, 2) k_fused3d(const __grid_constant__ PicParams p, int species, const __grid_constant__ Geom<T> gm,
+                                                    const __grid_constant__ FastConst<T> k, SoAView<T> s, Field6<T> F, Field3W<T> J,
+                                                    LeaveBuf leave, int distributed, int32_t* flags) {
+    constexpr int NV = SameCell<SF>::NV, NN = SameCell<SF>::NN;
+    constexpr int STEPS = (SF == 1) ? 5 : 3;          // segmented-scan depth: runs are cut at groups of 1 << STEPS lanes
+    constexpr int G = 1 << STEPS;
+    constexpr int QCAP = 512;
+    __shared__ T q_old[3][QCAP];
+    __shared__ T q_new[3][QCAP];
+    __shared__ int q_count;
+    TileSink<T> sink;
+    for (int c = 0; c < 3; ++c) { sink.J[c] = J.f[c]; sink.L[c] = gm.L[c]; }
+    sink.off = 0;
+    Field6<T> X;
+    for (int c = 0; c < 6; ++c) X.f[c] = nullptr;
+    if (threadIdx.x == 0) q_count = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int gl = lane & (G - 1);
+    for (int64_t base = (int64_t)blockIdx.x * blockDim.x; base < s.n; base += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = base + threadIdx.x;
+        T vals[NV], po[3], xn[3], v[3];
+        int key = 0, kind = 0;
+        if (i < s.n) kind = fast3d_advance<T, SF, PUSHER, false>(p, species, k, i, s, F, X, leave, distributed != 0, flags, po, xn, v, key, vals);
+        if (kind == 2) {
+            const int slot = atomicAdd(&q_count, 1);
+#pragma unroll
+            for (int a = 0; a < 3; ++a) { q_old[a][slot] = po[a]; q_new[a][slot] = xn[a]; }
+        }
+        if (kind != 1) {
+            key = -1 - lane;
+#pragma unroll
+            for (int n = 0; n < NV; ++n) vals[n] = (T)0;
+        }
+        // ---- segmented inclusive scan over lanes with equal key (flag = "a segment head lies in (lane-d, lane]")
+        const int key_prev = __shfl_up_sync(0xffffffffu, key, 1);
+        const bool head = (gl == 0) || (key != key_prev);
+        int flag = head ? 1 : 0;
+#pragma unroll
+        for (int d = 1; d < G; d <<= 1) {
+            const int fo = __shfl_up_sync(0xffffffffu, flag, d);
+            const bool take = (gl >= d) && (flag == 0);
+#pragma unroll
+            for (int n = 0; n < NV; ++n) {
+                const T o = __shfl_up_sync(0xffffffffu, vals[n], d);
+                vals[n] += take ? o : (T)0;
+            }
+            if (take) flag |= fo;
+        }
+        const int head_next = __shfl_down_sync(0xffffffffu, head ? 1 : 0, 1);
+        const bool tail = (gl == G - 1) || (head_next != 0);
+        if (tail && key >= 0) {
+            int n = 0;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                T* Jc = sink.J[c] + key;
+#pragma unroll
+                for (int f = 0; f < NN - 1; ++f)
+#pragma unroll
+                    for (int m1 = 0; m1 < NN; ++m1)
+#pragma unroll
+                        for (int m2 = 0; m2 < NN; ++m2) {
+                            const T val = vals[n++];
+                            if (val != (T)0) atomicAdd(Jc + SameCell<SF>::offset(c, f, m1, m2, k.sx, k.sy), val);
+                        }
+            }
+        }
+        // ---- deferred anchor-changing particles: flush when the queue could overflow on the next iteration
+        __syncthreads();
+        const int qn = q_count;
+        const bool last = (base + (int64_t)gridDim.x * blockDim.x >= s.n);
+        if (qn >= QCAP - 256 || (last && qn > 0)) {
+            for (int e = threadIdx.x; e < qn; e += blockDim.x) {
+                const T o3[3] = {q_old[0][e], q_old[1][e], q_old[2][e]};
+                const T n3[3] = {q_new[0][e], q_new[1][e], q_new[2][e]};
+                const T v3[3] = {(T)0, (T)0, (T)0};   // velocities only enter the deposit on inactive axes (none here)
+                union_deposit<T, SF>(p, species, gm, k, o3, n3, v3, sink);
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) q_count = 0;
+        }
+        __syncthreads();
+    }
+}
+
 // Append the migrated particles of `species` (packet rows [x,y,z,vx,vy,vz,species]) at the SoA tail; the number appended is
 // accumulated in d_count so the host can advance soa.n.
 template <typename T>
@@ -205,6 +301,19 @@ static int launch_fused(const PicParams* p, int species, int deposition, const P
     const bool all3d = (p->gmesh[0] * p->tile[0] > 1) && (p->gmesh[1] * p->tile[1] > 1) && (p->gmesh[2] * p->tile[2] > 1) && p->g >= 2;
     const int grid = grid_for(soa->n, 256, 8);
     const SoAView<T> sv = view_of<T>(soa);
+    if (all3d && deposition == 0 && !has_ext && p->pusher != PIC_PUSHER_HC && !getenv("PIC_K1_GENERIC")) {
+        Geom<T> gm;
+        make_geom<T>(*p, 0, 0, 0, gm);
+        FastConst<T> k;
+        make_fast_const<T>(*p, species, gm, k);
+        int distributed = 0;
+        for (int c = 0; c < 3; ++c) distributed |= (p->gmesh[c] != p->mesh[c]);
+        if (p->pusher == PIC_PUSHER_BORIS)
+            k_fused3d<T, SF, PIC_PUSHER_BORIS><<<grid, 256, 0, st>>>(*p, species, gm, k, sv, F, Jw, lb, distributed, flags);
+        else
+            k_fused3d<T, SF, PIC_PUSHER_BORIS_REL><<<grid, 256, 0, st>>>(*p, species, gm, k, sv, F, Jw, lb, distributed, flags);
+        PIC_LAUNCH_RET();
+    }
     if (deposition == 0) {
         if (all3d) k_fused<T, SF, 0, true><<<grid, 256, 0, st>>>(*p, species, sv, F, X, has_ext, Jw, lb, flags);
         else k_fused<T, SF, 0, false><<<grid, 256, 0, st>>>(*p, species, sv, F, X, has_ext, Jw, lb, flags);

@@ -234,6 +234,13 @@ struct TileSink {
         *ptr += val;
 #endif
     }
+    PIC_HD void add_unchecked(T* ptr, T val) const {
+#if defined(__CUDA_ARCH__)
+        atomicAdd(ptr, val);
+#else
+        *ptr += val;
+#endif
+    }
 };
 
 // ------------------------------------------------------------------------------------------------ Esirkepov

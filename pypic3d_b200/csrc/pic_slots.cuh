@@ -326,4 +326,398 @@ PIC_HD void fused_particle(const PicParams& p, int species, const Geom<T>& gm, i
     for (int c = 0; c < 3; ++c) { s.c[c][i] = pos[c]; s.c[3 + c][i] = v[c]; }
 }
 
+
+// ================================================================ K1 v2: specialised 3-D Esirkepov body
+// Same arithmetic as fused_particle<T,SF,0,true> (gather6_fast + push_velocity + esirkepov_deposit + move + BC), restructured
+// for instruction count: reciprocal multiplies instead of IEEE divisions, the old-position stencil shared between the gather
+// and the deposit, a branch-free union stencil of NS = SF+2 nodes per axis based at b = min(a_old, a_new) (- 1 for TSC), and
+// the transverse Esirkepov factor written as T[j][k] = P_j * S1_k + Q_j * S0_k with P = S1/3 + S0/6, Q = S0/3 + S1/6.
+// Requirements (checked by the launcher): all three axes active, g >= 2, periodic-or-any particle BCs, Esirkepov deposition.
+template <typename T>
+struct FastConst {
+    T oc[3], sc[3], inv_sc[3], ov[3], sv[3], inv_sv[3], d[3], inv_d[3], wind[3];
+    T dJ[3];          // -(q w / (d_a d_b)) / dt per axis
+    T h;              // q dt / (2 m)
+    T dt, C2, inv_C2;
+    int L[3];
+    int sx, sy;       // element strides of the x and y axes
+    int pbc[3];
+    int upd_x[3], upd_u[3];
+};
+
+template <typename T>
+PIC_HD void make_fast_const(const PicParams& p, int species, const Geom<T>& gm, FastConst<T>& k) {
+    for (int a = 0; a < 3; ++a) {
+        k.oc[a] = gm.oc[a]; k.sc[a] = gm.sc[a]; k.inv_sc[a] = (T)1 / gm.sc[a];
+        k.ov[a] = gm.ov[a]; k.sv[a] = gm.sv[a]; k.inv_sv[a] = (T)1 / gm.sv[a];
+        k.d[a] = gm.d[a]; k.inv_d[a] = (T)1 / gm.d[a];
+        k.wind[a] = (T)p.wind[a];
+        k.L[a] = gm.L[a];
+        k.pbc[a] = p.particle_bc[a];
+        k.upd_x[a] = p.update_x[species][a];
+        k.upd_u[a] = p.update_u[species][a];
+    }
+    const T qw = (T)(p.charge[species] * p.weight[species]);
+    const T dt = (T)p.dt;
+    k.dJ[0] = -(qw / (gm.d[1] * gm.d[2])) / dt;
+    k.dJ[1] = -(qw / (gm.d[2] * gm.d[0])) / dt;
+    k.dJ[2] = -(qw / (gm.d[0] * gm.d[1])) / dt;
+    k.h = (T)p.charge[species] * dt / ((T)2 * (T)p.mass[species]);
+    k.dt = dt;
+    k.C2 = (T)p.C * (T)p.C;
+    k.inv_C2 = (T)1 / k.C2;
+    k.sx = gm.L[1] * gm.L[2];
+    k.sy = gm.L[2];
+}
+
+// anchor + the three shape weights with reciprocal multiplies (<= 1 ulp from axis_stencil)
+template <typename T, int SF>
+PIC_HD void axis_stencil_rcp(T pos, T o, T s, T inv_s, T inv_d, int& a, T w[3]) {
+    const T q = (pos - o) * inv_s;
+    const T fa = (SF == 1) ? pic_floor(q) : pic_rint(q);
+    a = (int)fa;
+    const T r = (pos - (fa * s + o)) * inv_d;
+    if (SF == 1) {
+        w[0] = (T)0; w[1] = (T)1 - r; w[2] = r;
+    } else {
+        const T hm = (T)0.5 - r, hp = (T)0.5 + r;
+        w[0] = (T)0.5 * hm * hm; w[1] = (T)0.75 - r * r; w[2] = (T)0.5 * hp * hp;
+    }
+}
+
+template <typename T>
+PIC_HD T wrap_periodic_fast(T x, T wind) {
+    // bit-identical to wrap_periodic for -wind <= x + h < 2 wind (fmod is exact there); general fallback otherwise
+    const T h = (T)0.5 * wind;
+    T t = x + h;
+    if (t >= wind) { if (t >= (T)2 * wind) return wrap_periodic(x, wind); t -= wind; }
+    else if (t < (T)0) { if (t < -wind) return wrap_periodic(x, wind); t += wind; if (t >= wind) t -= wind; }
+    T w = t - h;
+    if (w == -h && x >= h) w = h;
+    return w;
+}
+
+// Esirkepov deposit on the union stencil of NS = SF+2 nodes per axis based at min(a_old, a_new) (- 1 for TSC): handles any
+// anchor shift in {-1, 0, +1}; anything else (or a stencil leaving the ghosted tile) goes to the bounds-checked general body.
+template <typename T, int SF>
+PIC_HD void union_deposit(const PicParams& p, int species, const Geom<T>& gm, const FastConst<T>& k, const T pos[3], const T xn[3],
+                          const T v[3], const TileSink<T>& sink) {
+    constexpr int NS = SF + 2;
+    constexpr int K0 = (SF == 1) ? 1 : 0;
+    T S0[3][NS], S1[3][NS];
+    int b[3];
+    bool ok = true;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        int an, ao;
+        T wn[3], wo[3];
+        axis_stencil_rcp<T, SF>(xn[a], k.oc[a], k.sc[a], k.inv_sc[a], k.inv_d[a], an, wn);
+        axis_stencil_rcp<T, SF>(pos[a], k.oc[a], k.sc[a], k.inv_sc[a], k.inv_d[a], ao, wo);
+        const int sh = an - ao;
+        ok = ok && (sh >= -1) && (sh <= 1);
+        const int lo = (sh < 0 ? an : ao) - (SF == 1 ? 0 : 1);   // first node of the union stencil
+        b[a] = lo;
+        ok = ok && (lo >= 0) && (lo + NS - 1 < k.L[a]);
+        const bool old_first = (sh >= 0);   // old stencil starts at the union base
+        const bool new_first = (sh <= 0);
+        // CIC: weights (w[1], w[2]) at nodes (a, a+1); TSC: (w[0], w[1], w[2]) at (a-1, a, a+1)
+#pragma unroll
+        for (int m = 0; m < NS; ++m) {
+            const int k0 = m + K0, k1 = m + K0 - 1;     // weight index if the stencil starts at the base / one node later
+            const T o_a = (k0 <= 2) ? wo[k0] : (T)0;
+            const T o_b = (k1 >= K0 && k1 <= 2) ? wo[k1] : (T)0;
+            const T n_a = (k0 <= 2) ? wn[k0] : (T)0;
+            const T n_b = (k1 >= K0 && k1 <= 2) ? wn[k1] : (T)0;
+            S0[a][m] = old_first ? o_a : o_b;
+            S1[a][m] = new_first ? n_a : n_b;
+        }
+    }
+    if (!ok) {
+        const T qw = (T)(p.charge[species] * p.weight[species]);
+        esirkepov_deposit<T, SF>(gm, pos, xn, v, qw, k.dt, sink);
+        return;
+    }
+    const T third = (T)(1.0 / 3.0), sixth = (T)(1.0 / 6.0);
+    T P[2][NS], Q[2][NS];
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int m = 0; m < NS; ++m) {
+            P[a][m] = third * S1[a][m] + sixth * S0[a][m];
+            Q[a][m] = third * S0[a][m] + sixth * S1[a][m];
+        }
+    const int base = b[0] * k.sx + b[1] * k.sy + b[2];
+    {   // Jx: cumsum over i of (S1x - S0x); T_yz[j][k] = P_y[j] S1z[k] + Q_y[j] S0z[k]
+        T* J = sink.J[0] + base;
+        T cum = (T)0;
+#pragma unroll
+        for (int ii = 0; ii < NS - 1; ++ii) {
+            cum += S1[0][ii] - S0[0][ii];
+            const T fc = k.dJ[0] * cum;
+#pragma unroll
+            for (int jj = 0; jj < NS; ++jj)
+#pragma unroll
+                for (int kk = 0; kk < NS; ++kk) {
+                    const T val = fc * (P[1][jj] * S1[2][kk] + Q[1][jj] * S0[2][kk]);
+                    if (val != (T)0) sink.add_unchecked(J + ii * k.sx + jj * k.sy + kk, val);
+                }
+        }
+    }
+    {   // Jy: cumsum over j; T_xz[i][k] = P_x[i] S1z[k] + Q_x[i] S0z[k]
+        T* J = sink.J[1] + base;
+        T cum = (T)0;
+#pragma unroll
+        for (int jj = 0; jj < NS - 1; ++jj) {
+            cum += S1[1][jj] - S0[1][jj];
+            const T fc = k.dJ[1] * cum;
+#pragma unroll
+            for (int ii = 0; ii < NS; ++ii)
+#pragma unroll
+                for (int kk = 0; kk < NS; ++kk) {
+                    const T val = fc * (P[0][ii] * S1[2][kk] + Q[0][ii] * S0[2][kk]);
+                    if (val != (T)0) sink.add_unchecked(J + ii * k.sx + jj * k.sy + kk, val);
+                }
+        }
+    }
+    {   // Jz: cumsum over k; T_xy[i][j] = P_x[i] S1y[j] + Q_x[i] S0y[j]
+        T* J = sink.J[2] + base;
+        T cum = (T)0;
+#pragma unroll
+        for (int kk = 0; kk < NS - 1; ++kk) {
+            cum += S1[2][kk] - S0[2][kk];
+            const T fc = k.dJ[2] * cum;
+#pragma unroll
+            for (int ii = 0; ii < NS; ++ii)
+#pragma unroll
+                for (int jj = 0; jj < NS; ++jj) {
+                    const T val = fc * (P[0][ii] * S1[1][jj] + Q[0][ii] * S0[1][jj]);
+                    if (val != (T)0) sink.add_unchecked(J + ii * k.sx + jj * k.sy + kk, val);
+                }
+        }
+    }
+}
+
+// Number of per-particle current values of the same-cell (no anchor shift) Esirkepov stencil: 3 components x (NN-1) faces x
+// NN x NN transverse nodes, NN = SF + 1 nodes per axis.  CIC: 12, TSC: 54.
+template <int SF>
+struct SameCell {
+    static constexpr int NN = SF + 1;
+    static constexpr int NV = 3 * (NN - 1) * NN * NN;
+    // element offset of value (c, f, m1, m2) relative to the stencil base node
+    PIC_HD static int offset(int c, int f, int m1, int m2, int sx, int sy) {
+        return c == 0 ? f * sx + m1 * sy + m2 : (c == 1 ? m1 * sx + f * sy + m2 : m1 * sx + m2 * sy + f);
+    }
+};
+
+// K1 v3 per-particle body: load -> stencils -> gather -> push -> new position -> store (move + BC + ownership).
+// Returns kind: 0 = nothing to deposit (dead slot), 1 = same-cell deposit: `vals` (SameCell<SF>::NV values) to be added at
+// J_c[key + offset(c, f, m1, m2)] -- these are what the kernel reduces across lanes of the same cell before the RED;
+// 2 = the particle changed anchor on some axis (or its stencil leaves the tile): deposit through union_deposit(old, new).
+template <typename T, int SF, int PUSHER, bool HAS_EXT>
+PIC_HD int fast3d_advance(const PicParams& p, int species, const FastConst<T>& k, int64_t i, const SoAView<T>& s, const Field6<T>& F,
+                          const Field6<T>& X, const LeaveBuf& leave, bool distributed, int32_t* flags, T pos_old[3], T xn[3], T vout[3],
+                          int& key, T* vals) {
+    constexpr int NN = SF + 1;
+    constexpr int K0 = (SF == 1) ? 1 : 0;
+    T pos[3] = {s.c[0][i], s.c[1][i], s.c[2][i]};
+    if (pic_isnan(pos[0])) return 0;
+    T v[3] = {s.c[3][i], s.c[4][i], s.c[5][i]};
+    // ---- stencils of the old position on the center and vertex lines
+    int ac[3], av[3];
+    T wc[3][3], wv[3][3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        axis_stencil_rcp<T, SF>(pos[a], k.oc[a], k.sc[a], k.inv_sc[a], k.inv_d[a], ac[a], wc[a]);
+        axis_stencil_rcp<T, SF>(pos[a], k.ov[a], k.sv[a], k.inv_sv[a], k.inv_d[a], av[a], wv[a]);
+    }
+    // ---- gather: Ex(v,c,c) Ey(c,v,c) Ez(c,c,v) Bx(c,v,v) By(v,c,v) Bz(v,v,c)
+    T EB[6];
+    {
+        int bc_[3], bv_[3];   // clamped first stencil index (memory safety only; owned particles never clamp for g >= 2)
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            int c0 = ac[a] - 1, v0 = av[a] - 1;
+            bc_[a] = c0 < 0 ? 0 : (c0 > k.L[a] - 3 ? k.L[a] - 3 : c0);
+            bv_[a] = v0 < 0 ? 0 : (v0 > k.L[a] - 3 ? k.L[a] - 3 : v0);
+        }
+        const int GT[6][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}, {0, 1, 1}, {1, 0, 1}, {1, 1, 0}};
+#pragma unroll
+        for (int c = 0; c < 6; ++c) {
+            const int gx = GT[c][0], gy = GT[c][1], gz = GT[c][2];
+            const T* wx = gx ? wv[0] : wc[0];
+            const T* wy = gy ? wv[1] : wc[1];
+            const T* wz = gz ? wv[2] : wc[2];
+            const int base = ((gx ? bv_[0] : bc_[0]) * k.sx) + ((gy ? bv_[1] : bc_[1]) * k.sy) + (gz ? bv_[2] : bc_[2]);
+            const T* f = F.f[c] + base;
+            const T* fx = HAS_EXT ? X.f[c] + base : nullptr;
+            T acc = (T)0;
+#pragma unroll
+            for (int a_ = K0; a_ < 3; ++a_) {
+                T ai = (T)0;
+#pragma unroll
+                for (int b_ = K0; b_ < 3; ++b_) {
+                    const int row = a_ * k.sx + b_ * k.sy;
+                    T aj = (T)0;
+#pragma unroll
+                    for (int c_ = K0; c_ < 3; ++c_) {
+                        T val = ld_ro(f + row + c_);
+                        if (HAS_EXT) val += ld_ro(fx + row + c_);
+                        aj += val * wz[c_];
+                    }
+                    ai += aj * wy[b_];
+                }
+                acc += ai * wx[a_];
+            }
+            EB[c] = acc;
+        }
+    }
+    // ---- push (same formulas as push_velocity; reciprocals hoisted)
+    {
+        const T h = k.h;
+        T um[3], t[3], cr[3], up[3], nu[3];
+        if (PUSHER == PIC_PUSHER_BORIS) {
+            for (int c = 0; c < 3; ++c) { um[c] = v[c] + h * EB[c]; t[c] = h * EB[3 + c]; }
+            cross3(um, t, cr);
+            for (int c = 0; c < 3; ++c) up[c] = um[c] + cr[c];
+            const T f2 = (T)2 / ((T)1 + t[0] * t[0] + t[1] * t[1] + t[2] * t[2]);
+            T sv_[3] = {t[0] * f2, t[1] * f2, t[2] * f2};
+            cross3(up, sv_, cr);
+            for (int c = 0; c < 3; ++c) nu[c] = (um[c] + cr[c]) + h * EB[c];
+        } else if (PUSHER == PIC_PUSHER_BORIS_REL) {
+            const T gamma = (T)1 / pic_sqrt((T)1 - (v[0] * v[0] + v[1] * v[1] + v[2] * v[2]) * k.inv_C2);
+            for (int c = 0; c < 3; ++c) um[c] = v[c] * gamma + h * EB[c];
+            const T inv_gm = (T)1 / pic_sqrt((T)1 + (um[0] * um[0] + um[1] * um[1] + um[2] * um[2]) * k.inv_C2);
+            for (int c = 0; c < 3; ++c) t[c] = h * EB[3 + c] * inv_gm;
+            cross3(um, t, cr);
+            for (int c = 0; c < 3; ++c) up[c] = um[c] + cr[c];
+            const T f2 = (T)2 / ((T)1 + t[0] * t[0] + t[1] * t[1] + t[2] * t[2]);
+            T sv_[3] = {t[0] * f2, t[1] * f2, t[2] * f2};
+            cross3(up, sv_, cr);
+            for (int c = 0; c < 3; ++c) nu[c] = (um[c] + cr[c]) + h * EB[c];
+            const T inv_ng = (T)1 / pic_sqrt((T)1 + (nu[0] * nu[0] + nu[1] * nu[1] + nu[2] * nu[2]) * k.inv_C2);
+            for (int c = 0; c < 3; ++c) nu[c] *= inv_ng;
+        } else {
+            push_velocity<T>(PIC_PUSHER_HC, v, EB, EB + 3, (T)p.charge[species], (T)p.mass[species], k.dt, (T)p.C, nu);
+        }
+        for (int c = 0; c < 3; ++c)
+            if (k.upd_u[c]) v[c] = nu[c];
+    }
+    // ---- new position and its stencil; same-cell test
+    bool same = true;
+    T wn[3][3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        xn[a] = pos[a] + (k.upd_x[a] ? v[a] * k.dt : (T)0);
+        int an;
+        axis_stencil_rcp<T, SF>(xn[a], k.oc[a], k.sc[a], k.inv_sc[a], k.inv_d[a], an, wn[a]);
+        const int lo = ac[a] - (SF == 1 ? 0 : 1);
+        same = same && (an == ac[a]) && (lo >= 0) && (lo + NN - 1 < k.L[a]);
+        pos_old[a] = pos[a];
+        vout[a] = v[a];
+    }
+    int kind = 2;
+    if (same) {
+        kind = 1;
+        key = (ac[0] - (SF == 1 ? 0 : 1)) * k.sx + (ac[1] - (SF == 1 ? 0 : 1)) * k.sy + (ac[2] - (SF == 1 ? 0 : 1));
+        const T third = (T)(1.0 / 3.0), sixth = (T)(1.0 / 6.0);
+        T P[2][NN], Q[2][NN], cum[3][NN - 1];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            T run = (T)0;
+#pragma unroll
+            for (int m = 0; m < NN - 1; ++m) {
+                run += wn[a][m + K0] - wc[a][m + K0];
+                cum[a][m] = k.dJ[a] * run;
+            }
+            if (a < 2) {
+#pragma unroll
+                for (int m = 0; m < NN; ++m) {
+                    P[a][m] = third * wn[a][m + K0] + sixth * wc[a][m + K0];
+                    Q[a][m] = third * wc[a][m + K0] + sixth * wn[a][m + K0];
+                }
+            }
+        }
+        int n = 0;
+        // component x: transverse (y, z); y: (x, z); z: (x, y) -- order matches SameCell<SF>::offset(c, f, m1, m2)
+#pragma unroll
+        for (int f = 0; f < NN - 1; ++f)
+#pragma unroll
+            for (int m1 = 0; m1 < NN; ++m1)
+#pragma unroll
+                for (int m2 = 0; m2 < NN; ++m2) vals[n++] = cum[0][f] * (P[1][m1] * wn[2][m2 + K0] + Q[1][m1] * wc[2][m2 + K0]);
+#pragma unroll
+        for (int f = 0; f < NN - 1; ++f)
+#pragma unroll
+            for (int m1 = 0; m1 < NN; ++m1)
+#pragma unroll
+                for (int m2 = 0; m2 < NN; ++m2) vals[n++] = cum[1][f] * (P[0][m1] * wn[2][m2 + K0] + Q[0][m1] * wc[2][m2 + K0]);
+#pragma unroll
+        for (int f = 0; f < NN - 1; ++f)
+#pragma unroll
+            for (int m1 = 0; m1 < NN; ++m1)
+#pragma unroll
+                for (int m2 = 0; m2 < NN; ++m2) vals[n++] = cum[2][f] * (P[0][m1] * wn[1][m2 + K0] + Q[0][m1] * wc[1][m2 + K0]);
+    }
+    // ---- move + global particle BCs + ownership, then store
+    bool alive = true;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        pos[a] = xn[a];
+        if (k.pbc[a] == PIC_BC_PERIODIC) pos[a] = wrap_periodic_fast<T>(pos[a], k.wind[a]);
+        else alive = apply_axis_bc<T>(pos[a], v[a], k.wind[a], k.pbc[a]) && alive;
+    }
+    if (alive && distributed) {
+        int off[3];
+        bool invalid = false, nonlocal_ = false;
+        for (int c = 0; c < 3; ++c) {
+            const int N = p.gmesh[c] * p.tile[c];
+            const int dtile = dest_tile<T>(pos[c], k.wind[c], k.d[c], N, p.tile[c], p.gmesh[c]);
+            off[c] = adjacent_offset(dtile, p.moff[c], p.gmesh[c]);
+            invalid |= (off[c] > 1 || off[c] < -1);
+            nonlocal_ |= (off[c] != 0);
+        }
+        if (invalid) { atomic_or_i32(flags, 1); alive = false; }
+        else if (nonlocal_) {
+            const int dir = ((1 - off[0]) * 3 + (1 - off[1])) * 3 + (1 - off[2]);
+            const int64_t slot = atomic_add_i32(&leave.count[dir], 1);
+            if (slot < leave.cap) {
+                T* pk = (T*)leave.buf + ((int64_t)dir * leave.cap + slot) * 7;
+                for (int c = 0; c < 3; ++c) { pk[c] = pos[c]; pk[3 + c] = v[c]; }
+                pk[6] = (T)species;
+            } else {
+                atomic_or_i32(flags, 2);
+            }
+            alive = false;
+        }
+    }
+    if (!alive) pos[0] = pic_nan<T>();
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { s.c[c][i] = pos[c]; s.c[3 + c][i] = v[c]; }
+    return kind;
+}
+
+// Scalar composition of the K1 v3 body (what one lane does when nothing is shared with its neighbours); used by the host
+// check and as the specification of the kernel's warp-aggregated deposit.
+template <typename T, int SF, int PUSHER, bool HAS_EXT>
+PIC_HD void fused_particle_fast3d(const PicParams& p, int species, const Geom<T>& gm, const FastConst<T>& k, int64_t i,
+                                  const SoAView<T>& s, const Field6<T>& F, const Field6<T>& X, const TileSink<T>& sink,
+                                  const LeaveBuf& leave, bool distributed, int32_t* flags) {
+    constexpr int NN = SameCell<SF>::NN;
+    T po[3], xn[3], v[3], vals[SameCell<SF>::NV];
+    int key = 0;
+    const int kind = fast3d_advance<T, SF, PUSHER, HAS_EXT>(p, species, k, i, s, F, X, leave, distributed, flags, po, xn, v, key, vals);
+    if (kind == 1) {
+        int n = 0;
+        for (int c = 0; c < 3; ++c)
+            for (int f = 0; f < NN - 1; ++f)
+                for (int m1 = 0; m1 < NN; ++m1)
+                    for (int m2 = 0; m2 < NN; ++m2) {
+                        const T val = vals[n++];
+                        if (val != (T)0) sink.add_unchecked(sink.J[c] + key + SameCell<SF>::offset(c, f, m1, m2, k.sx, k.sy), val);
+                    }
+    } else if (kind == 2) {
+        union_deposit<T, SF>(p, species, gm, k, po, xn, v, sink);
+    }
+}
+
 }  // namespace pic

@@ -54,6 +54,30 @@ static void t_fused(const PicParams* p, int species, int dep, void* const comp[6
     }
 }
 
+template <typename T, int SF>
+static void t_fused3d(const PicParams* p, int species, void* const comp[6], int64_t n, const void* const E[3], const void* const B[3],
+                      void* const J[3], void* leave, int64_t leave_cap, int32_t* leave_count, int32_t* flags) {
+    Field6<T> F, X;
+    SoAView<T> s;
+    for (int c = 0; c < 6; ++c) { s.c[c] = (T*)comp[c]; X.f[c] = nullptr; }
+    s.id = nullptr; s.cap = n; s.n = n;
+    for (int c = 0; c < 3; ++c) { F.f[c] = (const T*)E[c]; F.f[3 + c] = (const T*)B[c]; }
+    Geom<T> gm;
+    make_geom<T>(*p, 0, 0, 0, gm);
+    FastConst<T> k;
+    make_fast_const<T>(*p, species, gm, k);
+    TileSink<T> sink;
+    for (int c = 0; c < 3; ++c) { sink.J[c] = (T*)J[c]; sink.L[c] = gm.L[c]; }
+    sink.off = 0;
+    LeaveBuf lb{leave, leave_cap, leave_count};
+    bool distributed = false;
+    for (int c = 0; c < 3; ++c) distributed |= (p->gmesh[c] != p->mesh[c]);
+    for (int64_t i = 0; i < n; ++i) {
+        if (p->pusher == PIC_PUSHER_BORIS) fused_particle_fast3d<T, SF, PIC_PUSHER_BORIS, false>(*p, species, gm, k, i, s, F, X, sink, lb, distributed, flags);
+        else fused_particle_fast3d<T, SF, PIC_PUSHER_BORIS_REL, false>(*p, species, gm, k, i, s, F, X, sink, lb, distributed, flags);
+    }
+}
+
 #define HC_DISPATCH(p, FN, ...)                                                   \
     do {                                                                          \
         if ((p)->dtype == PIC_F32) {                                              \
@@ -77,6 +101,10 @@ void hc_retile_classify(const PicParams* p, const void* x_in, const void* u_in, 
         if (p->dtype == PIC_F32) slot_retile_classify<float>(*p, i, (const float*)x_in, (const float*)u_in, a_in, (float*)x_out, (float*)u_out, a_out, cap, code, overflow);
         else slot_retile_classify<double>(*p, i, (const double*)x_in, (const double*)u_in, a_in, (double*)x_out, (double*)u_out, a_out, cap, code, overflow);
     }
+}
+void hc_fused3d(const PicParams* p, int species, void* const comp[6], int64_t n, const void* const E[3], const void* const B[3],
+                void* const J[3], void* leave, int64_t leave_cap, int32_t* leave_count, int32_t* flags) {
+    HC_DISPATCH(p, t_fused3d, p, species, comp, n, E, B, J, leave, leave_cap, leave_count, flags);
 }
 void hc_fused(const PicParams* p, int species, int dep, void* const comp[6], int64_t n, const void* const E[3],
               const void* const B[3], void* const J[3], void* leave, int64_t leave_cap, int32_t* leave_count, int32_t* flags) {
