@@ -156,12 +156,12 @@ __global__ void __launch_bounds__(256) k_fused(const __grid_constant__ PicParams
 //    made the un-aggregated kernel L2-atomic-bound (profiles/r01_k1_versions.md);
 //  * the few particles that change anchor cell are queued in shared memory and deposited by full warps through the
 //    union-stencil body, so the common path stays branch-free.
-template <typename T, int SF, int PUSHER>
-__global__ void __launch_bounds__(256, 2) k_fused3d(const __grid_constant__ PicParams p, int species, const __grid_constant__ Geom<T> gm,
+template <typename T, int SF, int PUSHER, int STEPS>
+__global__ void __launch_bounds__(256, (SF == 1 ? 3 : 2)) k_fused3d(const __grid_constant__ PicParams p, int species, const __grid_constant__ Geom<T> gm,
                                                     const __grid_constant__ FastConst<T> k, SoAView<T> s, Field6<T> F, Field3W<T> J,
                                                     LeaveBuf leave, int distributed, int32_t* flags) {
     constexpr int NV = SameCell<SF>::NV, NN = SameCell<SF>::NN;
-    constexpr int STEPS = (SF == 1) ? 5 : 3;          // segmented-scan depth: runs are cut at groups of 1 << STEPS lanes
+    // STEPS = segmented-scan depth: runs are cut at groups of 1 << STEPS lanes (fewer steps = fewer shuffles, more REDs)
     constexpr int G = 1 << STEPS;
     constexpr int QCAP = 512;
     __shared__ T q_old[3][QCAP];
@@ -219,8 +219,7 @@ __global__ void __launch_bounds__(256, 2) k_fused3d(const __grid_constant__ PicP
                     for (int m1 = 0; m1 < NN; ++m1)
 #pragma unroll
                         for (int m2 = 0; m2 < NN; ++m2) {
-                            const T val = vals[n++];
-                            if (val != (T)0) atomicAdd(Jc + SameCell<SF>::offset(c, f, m1, m2, k.sx, k.sy), val);
+                            atomicAdd(Jc + SameCell<SF>::offset(c, f, m1, m2, k.sx, k.sy), vals[n++]);
                         }
             }
         }
@@ -308,10 +307,22 @@ static int launch_fused(const PicParams* p, int species, int deposition, const P
         make_fast_const<T>(*p, species, gm, k);
         int distributed = 0;
         for (int c = 0; c < 3; ++c) distributed |= (p->gmesh[c] != p->mesh[c]);
-        if (p->pusher == PIC_PUSHER_BORIS)
-            k_fused3d<T, SF, PIC_PUSHER_BORIS><<<grid, 256, 0, st>>>(*p, species, gm, k, sv, F, Jw, lb, distributed, flags);
-        else
-            k_fused3d<T, SF, PIC_PUSHER_BORIS_REL><<<grid, 256, 0, st>>>(*p, species, gm, k, sv, F, Jw, lb, distributed, flags);
+        static int steps = 0;
+        if (!steps) {
+            const char* e = getenv("PIC_K1_SCAN_STEPS");
+            steps = e ? atoi(e) : 3;   // measured best on B200 (profiles/r01_k1_versions.md)
+            if (steps < 3 || steps > 5) steps = 3;
+        }
+        const int gridk = grid_for(soa->n, 256, SF == 1 ? 9 : 8);
+#define PIC_LAUNCH_K1(PUSH, ST) k_fused3d<T, SF, PUSH, ST><<<gridk, 256, 0, st>>>(*p, species, gm, k, sv, F, Jw, lb, distributed, flags)
+        if (SF == 2 || steps == 3) {
+            if (p->pusher == PIC_PUSHER_BORIS) PIC_LAUNCH_K1(PIC_PUSHER_BORIS, 3); else PIC_LAUNCH_K1(PIC_PUSHER_BORIS_REL, 3);
+        } else if (steps == 4) {
+            if (p->pusher == PIC_PUSHER_BORIS) PIC_LAUNCH_K1(PIC_PUSHER_BORIS, 4); else PIC_LAUNCH_K1(PIC_PUSHER_BORIS_REL, 4);
+        } else {
+            if (p->pusher == PIC_PUSHER_BORIS) PIC_LAUNCH_K1(PIC_PUSHER_BORIS, 5); else PIC_LAUNCH_K1(PIC_PUSHER_BORIS_REL, 5);
+        }
+#undef PIC_LAUNCH_K1
         PIC_LAUNCH_RET();
     }
     if (deposition == 0) {

@@ -390,10 +390,11 @@ PIC_HD T wrap_periodic_fast(T x, T wind) {
     // bit-identical to wrap_periodic for -wind <= x + h < 2 wind (fmod is exact there); general fallback otherwise
     const T h = (T)0.5 * wind;
     T t = x + h;
-    if (t >= wind) { if (t >= (T)2 * wind) return wrap_periodic(x, wind); t -= wind; }
-    else if (t < (T)0) { if (t < -wind) return wrap_periodic(x, wind); t += wind; if (t >= wind) t -= wind; }
+    if (t >= (T)2 * wind || t < -wind) return wrap_periodic(x, wind);   // never taken for |v| dt < wind
+    const T up = t - wind, dn = t + wind;
+    t = (t >= wind) ? up : ((t < (T)0) ? ((dn >= wind) ? dn - wind : dn) : t);
     T w = t - h;
-    if (w == -h && x >= h) w = h;
+    w = (w == -h && x >= h) ? h : w;
     return w;
 }
 

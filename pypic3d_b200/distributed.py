@@ -1,0 +1,235 @@
+"""Multi-GPU domain decomposition: one process per GPU, one reference tile per rank (the reference's one-tile-per-device
+mesh, ghost_cells.py:98-116 / particle_tile_communication.py:292-426), NCCL over NVLink via `torch.distributed` P2P.
+
+Two exchange steps per time step, nearest neighbours only:
+  * guard cells: `refresh_` / `fold_` walk the axes x -> y -> z exactly like the reference (`_local_refresh_scalar_tile`,
+    `_local_fold_scalar_tile`), sending FULL-transverse-extent faces so edges and corners propagate through the sequence;
+    on an axis that is not split across ranks the single-GPU kernel runs instead (periodic self-exchange / walls);
+  * particles: the fused kernel writes leavers into 27 per-direction packet buffers; `migrate` exchanges the counts,
+    then the packets (the reference's 26 dense streams `_send_particle_stream` become <= 26 compact messages), and appends.
+Rank layout: rank = (cx * my + cy) * mz + cz.
+
+`kernels` abstracts pack/unpack/local passes so the protocol can be exercised on CPU tensors under the gloo backend in
+the test-suite; the product always uses `CudaHaloKernels` (hand-written CUDA behind the C ABI) -- there is no CPU product path.
+"""
+import ctypes
+
+import torch
+import torch.distributed as dist
+
+from . import _lib, ops
+
+HALO_SET, HALO_ADD, HALO_SUB = 0, 1, 2
+
+
+class CudaHaloKernels:
+    def pack(self, p, axis, start, nplanes, fields, buf):
+        ops.pack_planes(p, axis, start, nplanes, fields, buf)
+
+    def unpack(self, p, axis, start, nplanes, fields, buf, mode):
+        ops.unpack_planes_(p, axis, start, nplanes, fields, buf, mode)
+
+    def refresh_axis(self, p, axis, bc, fields):
+        ops.halo_refresh_axis_(p, axis, bc, fields)
+
+    def fold_axis(self, p, axis, bc, fields):
+        ops.halo_fold_axis_(p, axis, bc, fields)
+
+
+def rank_of(coords, mesh):
+    return (coords[0] * mesh[1] + coords[1]) * mesh[2] + coords[2]
+
+
+def coords_of(rank, mesh):
+    return (rank // (mesh[1] * mesh[2]), (rank // mesh[2]) % mesh[1], rank % mesh[2])
+
+
+def neighbor(coords, mesh, axis, step, periodic):
+    """Rank of the neighbour `step` (+1/-1) along `axis`, or None at an open chain end (ghost_cells.py:72-83)."""
+    c = list(coords)
+    c[axis] += step
+    if c[axis] < 0 or c[axis] >= mesh[axis]:
+        if not periodic:
+            return None
+        c[axis] %= mesh[axis]
+    return rank_of(c, mesh)
+
+
+DIRS = [(1 - sx, 1 - sy, 1 - sz) for sx in range(3) for sy in range(3) for sz in range(3)]   # dir code -> offset (ox,oy,oz)
+
+
+class DistributedHalo:
+    def __init__(self, params, group=None, device=None, kernels=None):
+        self.p = params
+        self.group = group
+        self.device = device
+        self.k = kernels if kernels is not None else CudaHaloKernels()
+        self.mesh = tuple(int(v) for v in params.gmesh)
+        self.coords = tuple(int(v) for v in params.moff)
+        self.rank = rank_of(self.coords, self.mesh)
+        self.L = tuple(int(params.tile[a]) + 2 * int(params.g) for a in range(3))
+        self.g = int(params.g)
+        self._bufs = {}
+
+    # ------------------------------------------------------------------ helpers
+    def _is_split(self, axis):
+        return self.mesh[axis] > 1
+
+    def _buf(self, key, n, like):
+        b = self._bufs.get((key, like.dtype))
+        if b is None or b.numel() < n:
+            b = torch.empty(n, dtype=like.dtype, device=like.device)
+            self._bufs[(key, like.dtype)] = b
+        return b[:n]
+
+    def _plane_elems(self, axis, ncomp):
+        u, v = [a for a in range(3) if a != axis]
+        return ncomp * self.g * self.L[u] * self.L[v]
+
+    def _exchange(self, sends, recvs):
+        """sends/recvs: lists of (peer_rank, tensor) in matching order on both sides."""
+        reqs = []
+        opl = []
+        for peer, t in sends:
+            opl.append(dist.P2POp(dist.isend, t, peer, group=self.group))
+        for peer, t in recvs:
+            opl.append(dist.P2POp(dist.irecv, t, peer, group=self.group))
+        if opl:
+            reqs = dist.batch_isend_irecv(opl)
+            for r in reqs:
+                r.wait()
+
+    # ------------------------------------------------------------------ guard cells
+    def refresh_(self, fields, bcs):
+        """In-place refresh x -> y -> z (ghost_cells.py:181-215)."""
+        g, p = self.g, self.p
+        for axis in range(3):
+            bc = int(bcs[axis])
+            if not self._is_split(axis):
+                self.k.refresh_axis(p, axis, bc, fields)
+                continue
+            n = self._plane_elems(axis, len(fields))
+            L = self.L[axis]
+            up = neighbor(self.coords, self.mesh, axis, +1, bc == 0)
+            dn = neighbor(self.coords, self.mesh, axis, -1, bc == 0)
+            s_up, s_dn = self._buf(("s_up", axis), n, fields[0]), self._buf(("s_dn", axis), n, fields[0])
+            r_lo, r_hi = self._buf(("r_lo", axis), n, fields[0]), self._buf(("r_hi", axis), n, fields[0])
+            self.k.pack(p, axis, L - 2 * g, g, fields, s_up)     # upper interior -> +1 neighbour's lower ghost (:187)
+            self.k.pack(p, axis, g, g, fields, s_dn)             # lower interior -> -1 neighbour's upper ghost (:191)
+            sends, recvs = [], []
+            if up is not None:
+                sends.append((up, s_up))
+            if dn is not None:
+                sends.append((dn, s_dn))
+            # receive order must mirror the peers' send order: first what their "+1 send" delivers (from my -1 side)
+            if dn is not None:
+                recvs.append((dn, r_lo))
+            else:
+                r_lo.zero_()                                     # open chain end: zeros (:189-191)
+            if up is not None:
+                recvs.append((up, r_hi))
+            else:
+                r_hi.zero_()
+            self._exchange(sends, recvs)
+            self.k.unpack(p, axis, 0, g, fields, r_lo, HALO_SET)
+            self.k.unpack(p, axis, L - g, g, fields, r_hi, HALO_SET)
+
+    def fold_(self, fields, bcs):
+        """In-place fold-add of ghost deposits to their owners, then zero ghosts (ghost_cells.py:263-316)."""
+        g, p = self.g, self.p
+        for axis in range(3):
+            bc = int(bcs[axis])
+            if not self._is_split(axis):
+                self.k.fold_axis(p, axis, bc, fields)
+                continue
+            n = self._plane_elems(axis, len(fields))
+            L = self.L[axis]
+            up = neighbor(self.coords, self.mesh, axis, +1, bc == 0)
+            dn = neighbor(self.coords, self.mesh, axis, -1, bc == 0)
+            s_lo, s_hi = self._buf(("s_up", axis), n, fields[0]), self._buf(("s_dn", axis), n, fields[0])
+            r_from_up, r_from_dn = self._buf(("r_lo", axis), n, fields[0]), self._buf(("r_hi", axis), n, fields[0])
+            self.k.pack(p, axis, 0, g, fields, s_lo)             # lower ghost belongs to the -1 neighbour's upper interior (:271)
+            self.k.pack(p, axis, L - g, g, fields, s_hi)         # upper ghost belongs to the +1 neighbour's lower interior (:272)
+            sends, recvs = [], []
+            if up is not None:
+                sends.append((up, s_hi))
+            if dn is not None:
+                sends.append((dn, s_lo))
+            if dn is not None:
+                recvs.append((dn, r_from_dn))                    # their upper ghost -> my lower interior
+            if up is not None:
+                recvs.append((up, r_from_up))                    # their lower ghost -> my upper interior
+            self._exchange(sends, recvs)
+            if up is not None:
+                self.k.unpack(p, axis, L - 2 * g, g, fields, r_from_up, HALO_ADD)
+            if dn is not None:
+                self.k.unpack(p, axis, g, g, fields, r_from_dn, HALO_ADD)
+            if bc == 1:                                          # conducting wall ranks (:238-260)
+                if self.coords[axis] == 0:
+                    self.k.unpack(p, axis, g, g, fields, s_lo, HALO_SUB)
+                if self.coords[axis] == self.mesh[axis] - 1:
+                    self.k.unpack(p, axis, L - 2 * g, g, fields, s_hi, HALO_SUB)
+            z = self._buf(("zero", axis), n, fields[0])
+            z.zero_()
+            self.k.unpack(p, axis, 0, g, fields, z, HALO_SET)
+            self.k.unpack(p, axis, L - g, g, fields, z, HALO_SET)
+
+    # ------------------------------------------------------------------ particles
+    def active_dirs(self, particle_bcs):
+        """Direction codes that can carry leavers: offsets only along split axes, existing neighbour on every offset axis."""
+        out = []
+        for d, off in enumerate(DIRS):
+            if off == (0, 0, 0) or any(off[a] != 0 and not self._is_split(a) for a in range(3)):
+                continue
+            dst, src = list(self.coords), list(self.coords)
+            ok = True
+            for a in range(3):
+                if off[a] == 0:
+                    continue
+                per = int(particle_bcs[a]) == 0
+                dst[a] += off[a]; src[a] -= off[a]
+                if per:
+                    dst[a] %= self.mesh[a]; src[a] %= self.mesh[a]
+            dst_ok = all(0 <= dst[a] < self.mesh[a] for a in range(3))
+            src_ok = all(0 <= src[a] < self.mesh[a] for a in range(3))
+            out.append((d, rank_of(dst, self.mesh) if dst_ok else None, rank_of(src, self.mesh) if src_ok else None))
+        return out
+
+    def exchange_packets(self, counts, packets, particle_bcs, like):
+        """counts[d] / packets[d] ([counts[d], 7] tensors) for every direction code d -> list of received [n, 7] tensors."""
+        dirs = self.active_dirs(particle_bcs)
+        dev = like.device
+        c_send = [torch.tensor([int(counts[d])], dtype=torch.int64, device=dev) for d, _, _ in dirs]
+        c_recv = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in dirs]
+        self._exchange([(dst, c_send[i]) for i, (d, dst, src) in enumerate(dirs) if dst is not None],
+                       [(src, c_recv[i]) for i, (d, dst, src) in enumerate(dirs) if src is not None])
+        n_in = [int(c.item()) for c in c_recv]
+        recv = [torch.empty((n_in[i], 7), dtype=like.dtype, device=dev) for i in range(len(dirs))]
+        self._exchange([(dst, packets[d]) for i, (d, dst, src) in enumerate(dirs) if dst is not None and int(counts[d]) > 0],
+                       [(src, recv[i]) for i, (d, dst, src) in enumerate(dirs) if src is not None and n_in[i] > 0])
+        return [r for r in recv if r.shape[0] > 0]
+
+    def migrate(self, sim):
+        """Exchange the leavers written by K1 and append the arrivals to the resident SoA (K3/K4 of SURVEY.md section 7)."""
+        counts = sim.leave_count.cpu().tolist()
+        cap = sim.leave_cap
+        if any(c > cap for c in counts):
+            sim.flags[0:1] |= 2                      # leave-packet overflow: surfaced by Simulation.overflow()
+            counts = [min(c, cap) for c in counts]
+        view = sim.leave.view(27, cap, 7)
+        packets = {d: view[d, :counts[d]] for d in range(27)}
+        incoming = self.exchange_packets(counts, packets, tuple(self.p.particle_bc), sim.leave)
+        if not incoming:
+            return
+        pk = torch.cat(incoming, dim=0).contiguous() if len(incoming) > 1 else incoming[0].contiguous()
+        n_in = int(pk.shape[0])
+        L = _lib.lib()
+        st = ops._stream()
+        sim._counter.zero_()
+        for s, sp_ in enumerate(sim.species):
+            soa = sim._soa(sp_)
+            _lib.check(L.pic_soa_append(ctypes.byref(self.p), ctypes.byref(soa), ops._p(pk), n_in, s, ops._p(sim._counter[s:s + 1]),
+                                        ops._p(sim.flags), st), "pic_soa_append")
+        added = sim._counter[:sim.S].cpu().tolist()
+        for s, sp_ in enumerate(sim.species):
+            sp_.n = min(sp_.cap, sp_.n + int(added[s]))

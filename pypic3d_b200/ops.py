@@ -141,6 +141,14 @@ def halo_refresh_(p, fields, bcs):
         check(L.pic_halo_refresh_axis(ctypes.byref(p), axis, int(bcs[axis]), len(fields), ptrs, _stream()), "pic_halo_refresh_axis")
 
 
+def halo_refresh_axis_(p, axis, bc, fields):
+    check(_lib.lib().pic_halo_refresh_axis(ctypes.byref(p), int(axis), int(bc), len(fields), _v(fields), _stream()), "pic_halo_refresh_axis")
+
+
+def halo_fold_axis_(p, axis, bc, fields):
+    check(_lib.lib().pic_halo_fold_axis(ctypes.byref(p), int(axis), int(bc), len(fields), _v(fields), _stream()), "pic_halo_fold_axis")
+
+
 def halo_fold_(p, fields, bcs):
     L = _lib.lib()
     ptrs = _v(fields)

@@ -1,0 +1,172 @@
+"""world_size-2 gloo tests (CPU) of the multi-GPU host logic in pypic3d_b200/distributed.py: neighbour topology, message
+order, face extents and fold/refresh sequencing of the guard-cell exchange, and the particle-packet exchange.
+
+The CUDA pack/unpack kernels are replaced by a NumPy test double with the same contract (buffer layout
+[comp][plane][u][v]); what is verified is the protocol -- compared against the oracle's in-process tile-mesh emulation
+(oracle/halo.py), i.e. against the reference's ppermute semantics (ghost_cells.py:181-316)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import halo as ohalo
+from pypic3d_b200 import _lib
+from pypic3d_b200.distributed import DistributedHalo, coords_of, rank_of, neighbor, DIRS
+
+
+class NumpyHaloKernels:
+    """Test double for CudaHaloKernels operating on torch CPU tensors of shape (1,1,1,Lx,Ly,Lz)."""
+
+    @staticmethod
+    def _planes(f, axis, start, n):
+        idx = [0, 0, 0, slice(None), slice(None), slice(None)]
+        idx[3 + axis] = slice(start, start + n)
+        return f[tuple(idx)].movedim(axis, 0)
+
+    def pack(self, p, axis, start, nplanes, fields, buf):
+        out = torch.stack([self._planes(f, axis, start, nplanes).contiguous() for f in fields], 0)
+        buf.copy_(out.reshape(-1))
+
+    def unpack(self, p, axis, start, nplanes, fields, buf, mode):
+        shp = (len(fields),) + tuple(self._planes(fields[0], axis, start, nplanes).shape)
+        b = buf.reshape(shp)
+        for c, f in enumerate(fields):
+            v = self._planes(f, axis, start, nplanes)
+            if mode == 0:
+                v.copy_(b[c])
+            elif mode == 1:
+                v.add_(b[c])
+            else:
+                v.sub_(b[c])
+
+    def refresh_axis(self, p, axis, bc, fields):
+        tile = tuple(int(p.tile[a]) for a in range(3))
+        bcs = [0, 0, 0]; bcs[axis] = bc
+        for f in fields:
+            f.copy_(torch.from_numpy(_one_axis(ohalo.refresh, f.numpy(), tile, axis, bc, int(p.g))))
+
+    def fold_axis(self, p, axis, bc, fields):
+        tile = tuple(int(p.tile[a]) for a in range(3))
+        for f in fields:
+            f.copy_(torch.from_numpy(_one_axis(ohalo.fold, f.numpy(), tile, axis, bc, int(p.g))))
+
+
+def _one_axis(fn, arr, tile, axis, bc, g):
+    """Apply the oracle's x->y->z pass for ONE axis only (the other two made no-ops by a transposed single-axis call)."""
+    # move `axis` to position 0, run with only axis 0 'real' by giving the others identity via separate 1-axis emulation
+    a = np.array(arr, dtype=np.float64, copy=True)
+    lo_g = [slice(None)] * 6; hi_g = [slice(None)] * 6; lo_i = [slice(None)] * 6; hi_i = [slice(None)] * 6
+    lo_g[3 + axis] = slice(0, g); hi_g[3 + axis] = slice(-g, None); lo_i[3 + axis] = slice(g, 2 * g); hi_i[3 + axis] = slice(-2 * g, -g)
+    lo_g, hi_g, lo_i, hi_i = map(tuple, (lo_g, hi_g, lo_i, hi_i))
+    reduced = tile[axis] == 1
+    if fn is ohalo.refresh:
+        if reduced:
+            mid = [slice(None)] * 6; mid[3 + axis] = slice(g, g + 1)
+            a[lo_g] = a[tuple(mid)] if bc == 0 else 0.0
+            a[hi_g] = a[tuple(mid)] if bc == 0 else 0.0
+        else:
+            lo, hi = a[hi_i].copy(), a[lo_i].copy()
+            a[lo_g] = lo if bc == 0 else 0.0
+            a[hi_g] = hi if bc == 0 else 0.0
+    else:
+        if reduced:
+            mid = [slice(None)] * 6; mid[3 + axis] = slice(g, g + 1)
+            gs = a[lo_g].sum(axis=3 + axis, keepdims=True) + a[hi_g].sum(axis=3 + axis, keepdims=True)
+            if bc == 0:
+                a[tuple(mid)] += gs
+            elif bc == 1:
+                a[tuple(mid)] -= gs
+        else:
+            lo, hi = a[lo_g].copy(), a[hi_g].copy()
+            if bc == 0:
+                a[hi_i] += lo; a[lo_i] += hi
+            elif bc == 1:
+                a[lo_i] -= lo; a[hi_i] -= hi
+        a[lo_g] = 0.0; a[hi_g] = 0.0
+    return a
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _params(mesh, tile, g, coords, pbc=(0, 0, 0)):
+    p = _lib.PicParams()
+    p.dtype = 1
+    p.g = g
+    for a in range(3):
+        p.mesh[a] = 1; p.gmesh[a] = mesh[a]; p.moff[a] = coords[a]; p.tile[a] = tile[a]; p.particle_bc[a] = pbc[a]
+    return p
+
+
+def _worker(rank, world, port, mesh, tile, g, bcs, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        coords = coords_of(rank, mesh)
+        rng = np.random.default_rng(42)
+        full = [rng.normal(size=tuple(mesh) + tuple(w + 2 * g for w in tile)) for _ in range(3)]
+        mine = lambda arrs: [torch.from_numpy(a[coords][None, None, None].copy()) for a in arrs]
+        halo = DistributedHalo(_params(mesh, tile, g, coords), None, torch.device("cpu"), kernels=NumpyHaloKernels())
+        out = {}
+        f = mine(full); halo.refresh_(f, bcs)
+        ref = [ohalo.refresh(a, tile, bcs, g) for a in full]
+        out["refresh"] = max(float(np.abs(f[c].numpy()[0, 0, 0] - ref[c][coords]).max()) for c in range(3))
+        f = mine(full); halo.fold_(f, bcs)
+        ref = [ohalo.fold(a, tile, bcs, g) for a in full]
+        out["fold"] = max(float(np.abs(f[c].numpy()[0, 0, 0] - ref[c][coords]).max()) for c in range(3))
+        # particle packets: every active direction carries (rank, d) tagged rows; the receiver checks provenance
+        dirs = halo.active_dirs((0, 0, 0))
+        counts = [0] * 27; packets = {}
+        for d, dst, src in dirs:
+            counts[d] = 1 + (d % 3)
+            packets[d] = torch.full((counts[d], 7), float(100 * rank + d), dtype=torch.float64)
+        for d in range(27):
+            packets.setdefault(d, torch.zeros((0, 7), dtype=torch.float64))
+        got = halo.exchange_packets(counts, packets, (0, 0, 0), torch.zeros(1, dtype=torch.float64))
+        expect = sorted(float(100 * src + d) for d, dst, src in dirs if src is not None for _ in range(1 + (d % 3)))
+        have = sorted(float(v) for t in got for v in t[:, 0].tolist())
+        out["packets_ok"] = (expect == have)
+        q.put((rank, out))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("mesh,tile,g", [((2, 1, 1), (4, 3, 2), 2), ((1, 2, 1), (3, 4, 1), 2), ((1, 1, 2), (2, 2, 5), 1)])
+@pytest.mark.parametrize("bcs", [(0, 0, 0), (1, 1, 1), (2, 0, 1)])
+def test_two_rank_halo_and_packets(mesh, tile, g, bcs):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, mesh, tile, g, bcs, q)) for r in range(2)]
+    for pr in procs:
+        pr.start()
+    res = [q.get(timeout=120) for _ in range(2)]
+    for pr in procs:
+        pr.join(timeout=60)
+        assert pr.exitcode == 0
+    for rank, out in res:
+        assert out["refresh"] < 1e-13, (rank, out)
+        assert out["fold"] < 1e-13, (rank, out)
+        assert out["packets_ok"], (rank, out)
+
+
+def test_topology_helpers():
+    mesh = (2, 2, 2)
+    for r in range(8):
+        assert rank_of(coords_of(r, mesh), mesh) == r
+    assert neighbor((1, 0, 0), mesh, 0, +1, True) == rank_of((0, 0, 0), mesh)
+    assert neighbor((1, 0, 0), mesh, 0, +1, False) is None
+    assert DIRS[0] == (1, 1, 1) and DIRS[13] == (0, 0, 0) and DIRS[26] == (-1, -1, -1)
+    halo = DistributedHalo(_params((4, 1, 1), (4, 4, 4), 2, (0, 0, 0)), None, torch.device("cpu"), kernels=NumpyHaloKernels())
+    dirs = halo.active_dirs((0, 0, 0))
+    assert [(d, dst, src) for d, dst, src in dirs] == [(4, 1, 3), (22, 3, 1)]     # +x and -x only on a slab mesh
+    dirs = halo.active_dirs((2, 0, 0))                                           # absorbing walls: no wrap-around peers
+    assert [(d, dst, src) for d, dst, src in dirs] == [(4, 1, None), (22, None, 1)]
