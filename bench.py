@@ -147,26 +147,28 @@ def mesh_for(n):
 
 
 # ------------------------------------------------------------------------------------------------ device workload
-def device_plasma(cfg, sp, dp, n_local, moff, ppc, dtype, device, seed):
+def device_plasma(cfg, sp, dp, n_local, moff, ppc, dtype, device, seed, cap_factor=1.0):
     """Synthetic thermal plasma generated directly on the device in the reference TiledParticles layout (one tile)."""
     import torch
     import pypic3d_b200 as pp
     g = torch.Generator(device=device)
     g.manual_seed(seed)
     n_per = n_local ** 3 * (ppc // 2)
-    x = torch.empty((1, 1, 1, 2, n_per, 3), dtype=dtype, device=device)
-    u = torch.empty_like(x)
+    cap = int(math.ceil(n_per * cap_factor))          # reference layout: fixed slot capacity, inactive tail (particle_class.py:17-31)
+    x = torch.zeros((1, 1, 1, 2, cap, 3), dtype=dtype, device=device)
+    u = torch.zeros_like(x)
     for s in range(2):
         for a in range(3):
             lo = -cfg["wind"][a] / 2 + moff[a] * n_local * cfg["dx"]
-            x[0, 0, 0, s, :, a] = (lo + torch.rand(n_per, generator=g, device=device, dtype=torch.float64) * (n_local * cfg["dx"])).to(dtype)
-            u[0, 0, 0, s, :, a] = (torch.randn(n_per, generator=g, device=device, dtype=torch.float32) * cfg["vth"][s]).to(dtype)
+            x[0, 0, 0, s, :n_per, a] = (lo + torch.rand(n_per, generator=g, device=device, dtype=torch.float64) * (n_local * cfg["dx"])).to(dtype)
+            u[0, 0, 0, s, :n_per, a] = (torch.randn(n_per, generator=g, device=device, dtype=torch.float32) * cfg["vth"][s]).to(dtype)
     # keep positions strictly inside the local box after rounding to dtype
     for a in range(3):
         lo = -cfg["wind"][a] / 2 + moff[a] * n_local * cfg["dx"]
         hi = lo + n_local * cfg["dx"]
-        x[..., a].clamp_(min=lo, max=float(np.nextafter(np.float32(hi), np.float32(lo))) if dtype == torch.float32 else float(np.nextafter(hi, lo)))
-    active = torch.ones((1, 1, 1, 2, n_per), dtype=torch.bool, device=device)
+        x[..., :n_per, a].clamp_(min=lo, max=float(np.nextafter(np.float32(hi), np.float32(lo))) if dtype == torch.float32 else float(np.nextafter(hi, lo)))
+    active = torch.zeros((1, 1, 1, 2, cap), dtype=torch.bool, device=device)
+    active[..., :n_per] = True
     species = pp.SpeciesConfig(charge=np.array(cfg["charge"]), mass=np.array(cfg["mass"]), weight=np.array([cfg["weight"]] * 2),
                                update_x=np.ones((2, 3), bool), update_u=np.ones((2, 3), bool))
     return pp.TiledParticles(x=x, u=u, active=active), species
@@ -220,7 +222,8 @@ def main():
     cfg = physical_setup(args.n, mesh, args.ppc, args.shape_factor, args.dtype)
     sp, dp = make_params(cfg, args.n, mesh, args.shape_factor)
     moff = (rank // (mesh[1] * mesh[2]), (rank // mesh[2]) % mesh[1], rank % mesh[2])
-    particles, species = device_plasma(cfg, sp, dp, args.n, moff, args.ppc, dtype, device, seed=1234 + rank)
+    particles, species = device_plasma(cfg, sp, dp, args.n, moff, args.ppc, dtype, device, seed=1234 + rank,
+                                       cap_factor=1.02 if world > 1 else 1.0)
     fields = zero_fields(args.n, dtype, device)
     if world > 1:
         from pypic3d_b200.distributed import DistributedHalo

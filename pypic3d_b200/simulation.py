@@ -253,8 +253,6 @@ class Simulation:
         L = _lib.lib()
         st = ops._stream()
         cap = self.cap_ref if cap_ref is None else int(cap_ref)
-        if not (self.track_ids and not self.distributed):
-            cap = max(cap, max((s.n for s in self.species), default=0))
         if out is not None:
             x, u, a = out
             if int(x.shape[4]) < cap:
@@ -272,6 +270,10 @@ class Simulation:
                 soa.id = None
             check(L.pic_soa_export(ctypes.byref(self.p), s, ctypes.byref(soa), ops._p(x), ops._p(u), ops._p(a), cap,
                                    ops._p(self._counter[s:s + 1]), st), "pic_soa_export")
+        if self.distributed or not self.track_ids:
+            live = self._counter[:self.S].cpu().tolist()
+            if any(int(n) > cap for n in live):          # fixed-capacity contract of the reference layout (:169-230)
+                self.flags[0:1] |= 2
         rho, phi, ext = self._passthrough
         overflow = torch.tensor(self.overflow(), device=self.device)
         fields = (tuple(c.clone() for c in self.E), tuple(c.clone() for c in self.B), tuple(c.clone() for c in self.J), rho, phi, ext,
