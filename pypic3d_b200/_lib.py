@@ -12,7 +12,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
-LIB_PATH = os.path.join(_HERE, "libpic_b200.so")
+LIB_PATH = os.environ.get("PIC_B200_LIB", os.path.join(_HERE, "libpic_b200.so"))   # override: A/B builds for profiling
 SOURCES = ["kernels_particles_ref.cu", "kernels_fields.cu", "kernels_fast.cu", "microbench.cu"]
 HEADERS = ["pic_common.cuh", "pic_math.cuh", "pic_slots.cuh"]
 MAX_SPECIES = 16
@@ -44,6 +44,8 @@ class PicSoA(ctypes.Structure):
 
 
 def needs_build():
+    if "PIC_B200_LIB" in os.environ:
+        return False
     if not os.path.exists(LIB_PATH):
         return True
     t = os.path.getmtime(LIB_PATH)

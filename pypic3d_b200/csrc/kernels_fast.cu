@@ -163,28 +163,40 @@ __global__ void __launch_bounds__(256, (SF == 1 ? 3 : 2)) k_fused3d(const __grid
     constexpr int NV = SameCell<SF>::NV, NN = SameCell<SF>::NN;
     // STEPS = segmented-scan depth: runs are cut at groups of 1 << STEPS lanes (fewer steps = fewer shuffles, more REDs)
     constexpr int G = 1 << STEPS;
-    constexpr int QCAP = 512;
-    __shared__ T q_old[3][QCAP];
-    __shared__ T q_new[3][QCAP];
-    __shared__ int q_count;
+    constexpr int QW = 64;                            // per-warp queue of anchor-changing particles (flushed at >= 32)
+    constexpr int NWARP = 8;
+    __shared__ T q_old[NWARP][3][QW];
+    __shared__ T q_new[NWARP][3][QW];
     TileSink<T> sink;
     for (int c = 0; c < 3; ++c) { sink.J[c] = J.f[c]; sink.L[c] = gm.L[c]; }
     sink.off = 0;
     Field6<T> X;
     for (int c = 0; c < 6; ++c) X.f[c] = nullptr;
-    if (threadIdx.x == 0) q_count = 0;
-    __syncthreads();
     const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
     const int gl = lane & (G - 1);
-    for (int64_t base = (int64_t)blockIdx.x * blockDim.x; base < s.n; base += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t i = base + threadIdx.x;
+    int qn = 0;                                       // warp-uniform queue fill
+    // Each CTA walks a CONTIGUOUS range of the cell-sorted particle stream, 256 particles (8 warps x 32) per iteration:
+    // consecutive iterations touch neighbouring cells, so the E/B stencil rows stay in L1 between iterations and across
+    // the warps of the CTA.  Warps never synchronise with each other (the deferred queue is warp-private).
+    const int64_t per_block = ((s.n + (int64_t)gridDim.x * 256 - 1) / ((int64_t)gridDim.x * 256)) * 256;
+    const int64_t b_begin = (int64_t)blockIdx.x * per_block;
+    const int64_t w_end = (b_begin + per_block < s.n) ? b_begin + per_block : s.n;
+    for (int64_t base = b_begin + warp * 32; base < w_end; base += 256) {
+        const int64_t i = base + lane;
         T vals[NV], po[3], xn[3], v[3];
         int key = 0, kind = 0;
-        if (i < s.n) kind = fast3d_advance<T, SF, PUSHER, false>(p, species, k, i, s, F, X, leave, distributed != 0, flags, po, xn, v, key, vals);
-        if (kind == 2) {
-            const int slot = atomicAdd(&q_count, 1);
+        if (i < w_end) kind = fast3d_advance<T, SF, PUSHER, false>(p, species, k, i, s, F, X, leave, distributed != 0, flags, po, xn, v, key, vals);
+        // ---- deferred anchor-changing particles: warp-private queue
+        const unsigned defer = __ballot_sync(0xffffffffu, kind == 2);
+        if (defer) {
+            if (kind == 2) {
+                const int slot = qn + __popc(defer & ((1u << lane) - 1u));
 #pragma unroll
-            for (int a = 0; a < 3; ++a) { q_old[a][slot] = po[a]; q_new[a][slot] = xn[a]; }
+                for (int a = 0; a < 3; ++a) { q_old[warp][a][slot] = po[a]; q_new[warp][a][slot] = xn[a]; }
+            }
+            qn += __popc(defer);
+            __syncwarp();
         }
         if (kind != 1) {
             key = -1 - lane;
@@ -218,26 +230,20 @@ __global__ void __launch_bounds__(256, (SF == 1 ? 3 : 2)) k_fused3d(const __grid
 #pragma unroll
                     for (int m1 = 0; m1 < NN; ++m1)
 #pragma unroll
-                        for (int m2 = 0; m2 < NN; ++m2) {
-                            atomicAdd(Jc + SameCell<SF>::offset(c, f, m1, m2, k.sx, k.sy), vals[n++]);
-                        }
+                        for (int m2 = 0; m2 < NN; ++m2) atomicAdd(Jc + SameCell<SF>::offset(c, f, m1, m2, k.sx, k.sy), vals[n++]);
             }
         }
-        // ---- deferred anchor-changing particles: flush when the queue could overflow on the next iteration
-        __syncthreads();
-        const int qn = q_count;
-        const bool last = (base + (int64_t)gridDim.x * blockDim.x >= s.n);
-        if (qn >= QCAP - 256 || (last && qn > 0)) {
-            for (int e = threadIdx.x; e < qn; e += blockDim.x) {
-                const T o3[3] = {q_old[0][e], q_old[1][e], q_old[2][e]};
-                const T n3[3] = {q_new[0][e], q_new[1][e], q_new[2][e]};
+        // ---- flush the warp queue with a (nearly) full warp
+        if (qn >= 32 || (base + 256 >= w_end && qn > 0)) {
+            for (int e = lane; e < qn; e += 32) {
+                const T o3[3] = {q_old[warp][0][e], q_old[warp][1][e], q_old[warp][2][e]};
+                const T n3[3] = {q_new[warp][0][e], q_new[warp][1][e], q_new[warp][2][e]};
                 const T v3[3] = {(T)0, (T)0, (T)0};   // velocities only enter the deposit on inactive axes (none here)
                 union_deposit<T, SF>(p, species, gm, k, o3, n3, v3, sink);
             }
-            __syncthreads();
-            if (threadIdx.x == 0) q_count = 0;
+            qn = 0;
+            __syncwarp();
         }
-        __syncthreads();
     }
 }
 

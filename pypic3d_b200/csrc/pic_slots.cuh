@@ -370,6 +370,31 @@ PIC_HD void make_fast_const(const PicParams& p, int species, const Geom<T>& gm, 
     k.sy = gm.L[2];
 }
 
+// 1/sqrt(x) and a/b for the push: f32 on the device uses the SFU approximations (<= 2 ulp; the f32 parity tolerance is
+// 2e-5), f64 and the host keep IEEE operations.
+#ifndef PIC_FASTMATH
+#define PIC_FASTMATH 0   /* measured slower on B200 (profiles/r01_k1_versions.md): the kernel is latency-, not issue-bound */
+#endif
+#ifndef PIC_GATHER_V
+#define PIC_GATHER_V 0   /* 0: pointer + int base (immediate offsets), 1: unsigned offsets; 0 measured faster */
+#endif
+PIC_HD float pic_rsqrt(float x) {
+#if defined(__CUDA_ARCH__) && PIC_FASTMATH
+    return rsqrtf(x);
+#else
+    return 1.0f / sqrtf(x);
+#endif
+}
+PIC_HD double pic_rsqrt(double x) { return 1.0 / sqrt(x); }
+PIC_HD float pic_fdiv(float a, float b) {
+#if defined(__CUDA_ARCH__) && PIC_FASTMATH
+    return __fdividef(a, b);
+#else
+    return a / b;
+#endif
+}
+PIC_HD double pic_fdiv(double a, double b) { return a / b; }
+
 // anchor + the three shape weights with reciprocal multiplies (<= 1 ulp from axis_stencil)
 template <typename T, int SF>
 PIC_HD void axis_stencil_rcp(T pos, T o, T s, T inv_s, T inv_d, int& a, T w[3]) {
@@ -531,6 +556,54 @@ PIC_HD int fast3d_advance(const PicParams& p, int species, const FastConst<T>& k
         axis_stencil_rcp<T, SF>(pos[a], k.oc[a], k.sc[a], k.inv_sc[a], k.inv_d[a], ac[a], wc[a]);
         axis_stencil_rcp<T, SF>(pos[a], k.ov[a], k.sv[a], k.inv_sv[a], k.inv_d[a], av[a], wv[a]);
     }
+#if PIC_GATHER_V == 1
+    // ---- gather: Ex(v,c,c) Ey(c,v,c) Ez(c,c,v) Bx(c,v,v) By(v,c,v) Bz(v,v,c)
+    // Offsets are unsigned 32-bit element indices from the component base pointers (which live in the constant bank), so
+    // each load is one "uniform base + 32-bit offset" LDG instead of a 64-bit address computation per row.
+    T EB[6];
+    {
+        unsigned oc_[3], ov_[3];   // clamped first stencil index (memory safety only; owned particles never clamp for g >= 2)
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            int c0 = ac[a] - 1, v0 = av[a] - 1;
+            c0 = c0 < 0 ? 0 : (c0 > k.L[a] - 3 ? k.L[a] - 3 : c0);
+            v0 = v0 < 0 ? 0 : (v0 > k.L[a] - 3 ? k.L[a] - 3 : v0);
+            const unsigned stride = a == 0 ? (unsigned)k.sx : (a == 1 ? (unsigned)k.sy : 1u);
+            oc_[a] = (unsigned)c0 * stride;
+            ov_[a] = (unsigned)v0 * stride;
+        }
+        const int GT[6][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}, {0, 1, 1}, {1, 0, 1}, {1, 1, 0}};
+#pragma unroll
+        for (int c = 0; c < 6; ++c) {
+            const int gx = GT[c][0], gy = GT[c][1], gz = GT[c][2];
+            const T* wx = gx ? wv[0] : wc[0];
+            const T* wy = gy ? wv[1] : wc[1];
+            const T* wz = gz ? wv[2] : wc[2];
+            const unsigned base = (gx ? ov_[0] : oc_[0]) + (gy ? ov_[1] : oc_[1]) + (gz ? ov_[2] : oc_[2]);
+            const T* f = F.f[c];
+            const T* fx = HAS_EXT ? X.f[c] : nullptr;
+            T acc = (T)0;
+#pragma unroll
+            for (int a_ = K0; a_ < 3; ++a_) {
+                T ai = (T)0;
+#pragma unroll
+                for (int b_ = K0; b_ < 3; ++b_) {
+                    const unsigned row = base + (unsigned)a_ * (unsigned)k.sx + (unsigned)b_ * (unsigned)k.sy;
+                    T aj = (T)0;
+#pragma unroll
+                    for (int c_ = K0; c_ < 3; ++c_) {
+                        T val = ld_ro(f + (row + (unsigned)c_));
+                        if (HAS_EXT) val += ld_ro(fx + (row + (unsigned)c_));
+                        aj += val * wz[c_];
+                    }
+                    ai += aj * wy[b_];
+                }
+                acc += ai * wx[a_];
+            }
+            EB[c] = acc;
+        }
+    }
+#else
     // ---- gather: Ex(v,c,c) Ey(c,v,c) Ez(c,c,v) Bx(c,v,v) By(v,c,v) Bz(v,v,c)
     T EB[6];
     {
@@ -572,6 +645,7 @@ PIC_HD int fast3d_advance(const PicParams& p, int species, const FastConst<T>& k
             EB[c] = acc;
         }
     }
+#endif
     // ---- push (same formulas as push_velocity; reciprocals hoisted)
     {
         const T h = k.h;
@@ -580,22 +654,22 @@ PIC_HD int fast3d_advance(const PicParams& p, int species, const FastConst<T>& k
             for (int c = 0; c < 3; ++c) { um[c] = v[c] + h * EB[c]; t[c] = h * EB[3 + c]; }
             cross3(um, t, cr);
             for (int c = 0; c < 3; ++c) up[c] = um[c] + cr[c];
-            const T f2 = (T)2 / ((T)1 + t[0] * t[0] + t[1] * t[1] + t[2] * t[2]);
+            const T f2 = pic_fdiv((T)2, (T)1 + t[0] * t[0] + t[1] * t[1] + t[2] * t[2]);
             T sv_[3] = {t[0] * f2, t[1] * f2, t[2] * f2};
             cross3(up, sv_, cr);
             for (int c = 0; c < 3; ++c) nu[c] = (um[c] + cr[c]) + h * EB[c];
         } else if (PUSHER == PIC_PUSHER_BORIS_REL) {
-            const T gamma = (T)1 / pic_sqrt((T)1 - (v[0] * v[0] + v[1] * v[1] + v[2] * v[2]) * k.inv_C2);
+            const T gamma = pic_rsqrt((T)1 - (v[0] * v[0] + v[1] * v[1] + v[2] * v[2]) * k.inv_C2);
             for (int c = 0; c < 3; ++c) um[c] = v[c] * gamma + h * EB[c];
-            const T inv_gm = (T)1 / pic_sqrt((T)1 + (um[0] * um[0] + um[1] * um[1] + um[2] * um[2]) * k.inv_C2);
+            const T inv_gm = pic_rsqrt((T)1 + (um[0] * um[0] + um[1] * um[1] + um[2] * um[2]) * k.inv_C2);
             for (int c = 0; c < 3; ++c) t[c] = h * EB[3 + c] * inv_gm;
             cross3(um, t, cr);
             for (int c = 0; c < 3; ++c) up[c] = um[c] + cr[c];
-            const T f2 = (T)2 / ((T)1 + t[0] * t[0] + t[1] * t[1] + t[2] * t[2]);
+            const T f2 = pic_fdiv((T)2, (T)1 + t[0] * t[0] + t[1] * t[1] + t[2] * t[2]);
             T sv_[3] = {t[0] * f2, t[1] * f2, t[2] * f2};
             cross3(up, sv_, cr);
             for (int c = 0; c < 3; ++c) nu[c] = (um[c] + cr[c]) + h * EB[c];
-            const T inv_ng = (T)1 / pic_sqrt((T)1 + (nu[0] * nu[0] + nu[1] * nu[1] + nu[2] * nu[2]) * k.inv_C2);
+            const T inv_ng = pic_rsqrt((T)1 + (nu[0] * nu[0] + nu[1] * nu[1] + nu[2] * nu[2]) * k.inv_C2);
             for (int c = 0; c < 3; ++c) nu[c] *= inv_ng;
         } else {
             push_velocity<T>(PIC_PUSHER_HC, v, EB, EB + 3, (T)p.charge[species], (T)p.mass[species], k.dt, (T)p.C, nu);
