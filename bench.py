@@ -284,11 +284,19 @@ def main():
     step_bytes_pp = 12 * real + 1 + (24.0 / args.ppc) * real  # 55 B (f32) / 109 B (f64) at 16 ppc
     k1_avg_ms = float(np.mean(k1_ms)) if k1_ms else None
     per_launch_particles = n_local_particles / 2
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r01_k1_traffic.json")
+    if os.path.exists(tpath):
+        tj = json.load(open(tpath))
+        c = tj["config"]
+        if (c["n"], c["ppc"], c["dtype"], c["shape_factor"]) == (args.n, args.ppc, args.dtype, args.shape_factor):
+            traffic = (tj["dram_bytes_read"] + tj["dram_bytes_write"]) * per_launch_particles / tj["particles_per_launch"]
     roof = None
     if k1_avg_ms:
         achieved = k1_bytes_pp * per_launch_particles / (k1_avg_ms * 1e-3) / 1e9
         roof = {"bound": "hbm", "kernel": "k_fused (K1: gather+push+deposit+move+BC, one species per launch)", "achieved": achieved,
-                "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": "profiles/r01_k1_traffic.json (ncu dram__bytes_read+write, bytes per launch)" if traffic else None,
+                "algorithmic_bytes_per_launch": k1_bytes_pp * per_launch_particles, "peak_source": peak_src,
                 "algorithmic_bytes_per_particle": k1_bytes_pp, "avg_launch_ms": k1_avg_ms,
                 "k1_share_of_step": float(np.sum(k1_ms)) / ms_total if ms_total else None}
     step_achieved = step_bytes_pp * (total_particles / n_gpus) * args.steps / (ms_total * 1e-3) / 1e9
