@@ -343,6 +343,7 @@ struct FastConst {
     int sx, sy;       // element strides of the x and y axes
     int pbc[3];
     int upd_x[3], upd_u[3];
+    T box_lo[3], box_hi[3];   // local subdomain [lo, hi) on axes split across ranks (+-inf elsewhere)
 };
 
 template <typename T>
@@ -356,6 +357,13 @@ PIC_HD void make_fast_const(const PicParams& p, int species, const Geom<T>& gm, 
         k.pbc[a] = p.particle_bc[a];
         k.upd_x[a] = p.update_x[species][a];
         k.upd_u[a] = p.update_u[species][a];
+    }
+    for (int a = 0; a < 3; ++a) {
+        const bool split = p.gmesh[a] != p.mesh[a];
+        const double lo = -0.5 * p.wind[a] + (double)(p.moff[a] * p.tile[a]) * (a == 0 ? p.dx : (a == 1 ? p.dy : p.dz));
+        const double hi = -0.5 * p.wind[a] + (double)((p.moff[a] + 1) * p.tile[a]) * (a == 0 ? p.dx : (a == 1 ? p.dy : p.dz));
+        k.box_lo[a] = split ? (T)lo : (T)(-INFINITY);
+        k.box_hi[a] = split ? (T)hi : (T)(INFINITY);
     }
     const T qw = (T)(p.charge[species] * p.weight[species]);
     const T dt = (T)p.dt;
@@ -734,36 +742,33 @@ PIC_HD int fast3d_advance(const PicParams& p, int species, const FastConst<T>& k
                 for (int m2 = 0; m2 < NN; ++m2) vals[n++] = cum[2][f] * (P[0][m1] * wn[1][m2 + K0] + Q[0][m1] * wc[1][m2 + K0]);
     }
     // ---- move + global particle BCs + ownership, then store
+    // Ownership on split axes is the physical crossing direction of the local box [lo, hi): taken BEFORE the periodic wrap
+    // (first -> last tile is -1, last -> first is +1, particle_tile_communication.py:145-165) and after reflect/absorb.
     bool alive = true;
+    int dir = 13;   // ((1-0)*3 + (1-0))*3 + (1-0): stays
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
         pos[a] = xn[a];
-        if (k.pbc[a] == PIC_BC_PERIODIC) pos[a] = wrap_periodic_fast<T>(pos[a], k.wind[a]);
-        else alive = apply_axis_bc<T>(pos[a], v[a], k.wind[a], k.pbc[a]) && alive;
+        int off;
+        if (k.pbc[a] == PIC_BC_PERIODIC) {
+            off = (pos[a] >= k.box_hi[a]) ? 1 : ((pos[a] < k.box_lo[a]) ? -1 : 0);
+            pos[a] = wrap_periodic_fast<T>(pos[a], k.wind[a]);
+        } else {
+            alive = apply_axis_bc<T>(pos[a], v[a], k.wind[a], k.pbc[a]) && alive;
+            off = (pos[a] >= k.box_hi[a]) ? 1 : ((pos[a] < k.box_lo[a]) ? -1 : 0);
+        }
+        dir -= off * (a == 0 ? 9 : (a == 1 ? 3 : 1));
     }
-    if (alive && distributed) {
-        int off[3];
-        bool invalid = false, nonlocal_ = false;
-        for (int c = 0; c < 3; ++c) {
-            const int N = p.gmesh[c] * p.tile[c];
-            const int dtile = dest_tile<T>(pos[c], k.wind[c], k.d[c], N, p.tile[c], p.gmesh[c]);
-            off[c] = adjacent_offset(dtile, p.moff[c], p.gmesh[c]);
-            invalid |= (off[c] > 1 || off[c] < -1);
-            nonlocal_ |= (off[c] != 0);
+    if (alive && distributed && dir != 13) {
+        const int64_t slot = atomic_add_i32(&leave.count[dir], 1);
+        if (slot < leave.cap) {
+            T* pk = (T*)leave.buf + ((int64_t)dir * leave.cap + slot) * 7;
+            for (int c = 0; c < 3; ++c) { pk[c] = pos[c]; pk[3 + c] = v[c]; }
+            pk[6] = (T)species;
+        } else {
+            atomic_or_i32(flags, 2);
         }
-        if (invalid) { atomic_or_i32(flags, 1); alive = false; }
-        else if (nonlocal_) {
-            const int dir = ((1 - off[0]) * 3 + (1 - off[1])) * 3 + (1 - off[2]);
-            const int64_t slot = atomic_add_i32(&leave.count[dir], 1);
-            if (slot < leave.cap) {
-                T* pk = (T*)leave.buf + ((int64_t)dir * leave.cap + slot) * 7;
-                for (int c = 0; c < 3; ++c) { pk[c] = pos[c]; pk[3 + c] = v[c]; }
-                pk[6] = (T)species;
-            } else {
-                atomic_or_i32(flags, 2);
-            }
-            alive = false;
-        }
+        alive = false;
     }
     if (!alive) pos[0] = pic_nan<T>();
 #pragma unroll

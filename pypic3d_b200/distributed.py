@@ -196,40 +196,47 @@ class DistributedHalo:
         return out
 
     def exchange_packets(self, counts, packets, particle_bcs, like):
-        """counts[d] / packets[d] ([counts[d], 7] tensors) for every direction code d -> list of received [n, 7] tensors."""
+        """counts[s][d] / packets[s][d] ([counts[s][d], 7] tensors) for every species s and direction code d ->
+        per-species lists of received [n, 7] tensors.  Two rounds: the counts (one small message per direction carrying all
+        species), then one payload message per non-empty (direction, species)."""
         dirs = self.active_dirs(particle_bcs)
+        S = len(counts)
         dev = like.device
-        c_send = [torch.tensor([int(counts[d])], dtype=torch.int64, device=dev) for d, _, _ in dirs]
-        c_recv = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in dirs]
+        c_send = [torch.tensor([int(counts[s][d]) for s in range(S)], dtype=torch.int64, device=dev) for d, _, _ in dirs]
+        c_recv = [torch.zeros(S, dtype=torch.int64, device=dev) for _ in dirs]
         self._exchange([(dst, c_send[i]) for i, (d, dst, src) in enumerate(dirs) if dst is not None],
                        [(src, c_recv[i]) for i, (d, dst, src) in enumerate(dirs) if src is not None])
-        n_in = [int(c.item()) for c in c_recv]
-        recv = [torch.empty((n_in[i], 7), dtype=like.dtype, device=dev) for i in range(len(dirs))]
-        self._exchange([(dst, packets[d]) for i, (d, dst, src) in enumerate(dirs) if dst is not None and int(counts[d]) > 0],
-                       [(src, recv[i]) for i, (d, dst, src) in enumerate(dirs) if src is not None and n_in[i] > 0])
-        return [r for r in recv if r.shape[0] > 0]
+        n_in = [c.tolist() for c in c_recv]
+        sends, recvs, out = [], [], [[] for _ in range(S)]
+        for i, (d, dst, src) in enumerate(dirs):
+            for s in range(S):
+                if dst is not None and int(counts[s][d]) > 0:
+                    sends.append((dst, packets[s][d]))
+                if src is not None and int(n_in[i][s]) > 0:
+                    t = torch.empty((int(n_in[i][s]), 7), dtype=like.dtype, device=dev)
+                    recvs.append((src, t))
+                    out[s].append(t)
+        self._exchange(sends, recvs)
+        return out
 
     def migrate(self, sim):
-        """Exchange the leavers written by K1 and append the arrivals to the resident SoA (K3/K4 of SURVEY.md section 7)."""
-        counts = sim.leave_count.cpu().tolist()
-        cap = sim.leave_cap
-        if any(c > cap for c in counts):
+        """Exchange the leavers written by K1 and append the arrivals to the resident SoA (K3/K4 of SURVEY.md section 7).
+        Two host syncs per step: the leave counts, then the arrival counts."""
+        S, cap = sim.S, sim.leave_cap
+        counts = sim.leave_count.view(S, 27).cpu().tolist()
+        if any(c > cap for row in counts for c in row):
             sim.flags[0:1] |= 2                      # leave-packet overflow: surfaced by Simulation.overflow()
-            counts = [min(c, cap) for c in counts]
-        view = sim.leave.view(27, cap, 7)
-        packets = {d: view[d, :counts[d]] for d in range(27)}
+            counts = [[min(c, cap) for c in row] for row in counts]
+        view = sim.leave.view(S, 27, cap, 7)
+        packets = [{d: view[s, d, :counts[s][d]] for d in range(27)} for s in range(S)]
         incoming = self.exchange_packets(counts, packets, tuple(self.p.particle_bc), sim.leave)
-        if not incoming:
-            return
-        pk = torch.cat(incoming, dim=0).contiguous() if len(incoming) > 1 else incoming[0].contiguous()
-        n_in = int(pk.shape[0])
         L = _lib.lib()
         st = ops._stream()
-        sim._counter.zero_()
         for s, sp_ in enumerate(sim.species):
-            soa = sim._soa(sp_)
-            _lib.check(L.pic_soa_append(ctypes.byref(self.p), ctypes.byref(soa), ops._p(pk), n_in, s, ops._p(sim._counter[s:s + 1]),
-                                        ops._p(sim.flags), st), "pic_soa_append")
-        added = sim._counter[:sim.S].cpu().tolist()
-        for s, sp_ in enumerate(sim.species):
-            sp_.n = min(sp_.cap, sp_.n + int(added[s]))
+            for pk in incoming[s]:
+                n_in = int(pk.shape[0])
+                soa = sim._soa(sp_)
+                sim._counter[s:s + 1].zero_()
+                _lib.check(L.pic_soa_append(ctypes.byref(self.p), ctypes.byref(soa), ops._p(pk), n_in, s, ops._p(sim._counter[s:s + 1]),
+                                            ops._p(sim.flags), st), "pic_soa_append")
+                sp_.n = min(sp_.cap, sp_.n + n_in)   # rows beyond capacity were dropped by the kernel and flagged

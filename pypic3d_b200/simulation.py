@@ -100,8 +100,8 @@ class Simulation:
         if self.distributed:
             ntot = max(1, sum(s.n for s in self.species))
             self.leave_cap = int(leave_capacity) if leave_capacity else max(1024, ntot // 8)
-            self.leave = torch.empty(27 * self.leave_cap * 7, dtype=self.dtype, device=self.device)
-            self.leave_count = torch.zeros(27, dtype=torch.int32, device=self.device)
+            self.leave = torch.empty(self.S * 27 * self.leave_cap * 7, dtype=self.dtype, device=self.device)
+            self.leave_count = torch.zeros(self.S * 27, dtype=torch.int32, device=self.device)
         self.sort()
 
     # ------------------------------------------------------------------------------------------ layout
@@ -198,10 +198,14 @@ class Simulation:
             if self.k1_events is not None:
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
+            if self.leave is not None:      # per-species packet buffers [27][leave_cap][7] and counters [27]
+                lv = ops._p(self.leave[s * 27 * self.leave_cap * 7:(s + 1) * 27 * self.leave_cap * 7])
+                lc = ops._p(self.leave_count[s * 27:(s + 1) * 27])
+            else:
+                lv = lc = None
             check(L.pic_fused_push_deposit(ctypes.byref(p), s, self.deposition, ctypes.byref(soa), ops._v(self.E), ops._v(self.B),
-                                           extE, extB, ops._v(self.J), ops._p(self.leave) if self.leave is not None else None,
-                                           self.leave_cap, ops._p(self.leave_count) if self.leave_count is not None else None,
-                                           ops._p(self.flags), st), "pic_fused_push_deposit")
+                                           extE, extB, ops._v(self.J), lv, self.leave_cap, lc, ops._p(self.flags), st),
+                  "pic_fused_push_deposit")
             if self.k1_events is not None:
                 e1.record()
                 self.k1_events.append((e0, e1))

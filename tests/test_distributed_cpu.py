@@ -124,16 +124,21 @@ def _worker(rank, world, port, mesh, tile, g, bcs, q):
         out["fold"] = max(float(np.abs(f[c].numpy()[0, 0, 0] - ref[c][coords]).max()) for c in range(3))
         # particle packets: every active direction carries (rank, d) tagged rows; the receiver checks provenance
         dirs = halo.active_dirs((0, 0, 0))
-        counts = [0] * 27; packets = {}
-        for d, dst, src in dirs:
-            counts[d] = 1 + (d % 3)
-            packets[d] = torch.full((counts[d], 7), float(100 * rank + d), dtype=torch.float64)
-        for d in range(27):
-            packets.setdefault(d, torch.zeros((0, 7), dtype=torch.float64))
+        S = 2
+        counts = [[0] * 27 for _ in range(S)]; packets = [dict() for _ in range(S)]
+        for s_ in range(S):
+            for d, dst, src in dirs:
+                counts[s_][d] = (d + s_) % 3          # includes empty messages
+                packets[s_][d] = torch.full((counts[s_][d], 7), float(1000 * s_ + 100 * rank + d), dtype=torch.float64)
+            for d in range(27):
+                packets[s_].setdefault(d, torch.zeros((0, 7), dtype=torch.float64))
         got = halo.exchange_packets(counts, packets, (0, 0, 0), torch.zeros(1, dtype=torch.float64))
-        expect = sorted(float(100 * src + d) for d, dst, src in dirs if src is not None for _ in range(1 + (d % 3)))
-        have = sorted(float(v) for t in got for v in t[:, 0].tolist())
-        out["packets_ok"] = (expect == have)
+        ok = True
+        for s_ in range(S):
+            expect = sorted(float(1000 * s_ + 100 * src + d) for d, dst, src in dirs if src is not None for _ in range((d + s_) % 3))
+            have = sorted(float(v) for t in got[s_] for v in t[:, 0].tolist())
+            ok = ok and (expect == have)
+        out["packets_ok"] = ok
         q.put((rank, out))
     finally:
         dist.destroy_process_group()
