@@ -131,7 +131,7 @@ def run_reference_arm(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(args, args.gpus), "cpu_baseline": base,
             "e2e": {"value": base["value"], "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    _emit(line)
 
 
 def workload_config(args, n_gpus):
@@ -182,7 +182,26 @@ def zero_fields(n_local, dtype, device):
     return (v(), v(), v(), z(), z(), (v(), v()), None, torch.tensor(False, device=device))
 
 
+_REAL_STDOUT = None
+
+
+def _capture_stdout():
+    """Route everything libraries print on fd 1 (e.g. the NCCL version banner) to stderr; the JSON line is written to the
+    real stdout at the end, so stdout carries exactly one line."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def _emit(line):
+    sys.stdout.flush()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, (json.dumps(line) + "\n").encode())
+
+
 def main():
+    _capture_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -215,6 +234,8 @@ def main():
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
     if world > 1:
+        # keep stdout to the single JSON line: NCCL's version/debug banner goes to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=device)
     n_gpus = world
     mesh = mesh_for(n_gpus)
@@ -324,7 +345,7 @@ def main():
                 "clocks": sampler.summary() if sampler else None}
         if check is not None:
             line["check"] = check
-        print(json.dumps(line))
+        _emit(line)
     if world > 1:
         dist.destroy_process_group()
 
