@@ -285,7 +285,9 @@ def main():
         sampler.stop_flag = True
         sampler.join(timeout=2)
     t = torch.tensor([ms_total], dtype=torch.float64, device=device)
-    npart = torch.tensor([float(sim.n_particles())], dtype=torch.float64, device=device)
+    # periodic boundaries conserve the global particle number, so the count taken right after construction (exact: freshly
+    # sorted, no holes) is the number of particles advanced in every timed step
+    npart = torch.tensor([float(n_local_particles)], dtype=torch.float64, device=device)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(npart, op=dist.ReduceOp.SUM)
@@ -383,7 +385,7 @@ def run_e2e(sim, args, device, world, dist):
         one()
     torch.cuda.synchronize()
     el = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=device)
-    npart = torch.tensor([float(sim.n_particles())], dtype=torch.float64, device=device)
+    npart = torch.tensor([float(parts.active.sum().item())], dtype=torch.float64, device=device)
     if dist is not None:
         dist.all_reduce(el, op=dist.ReduceOp.MAX)
         dist.all_reduce(npart, op=dist.ReduceOp.SUM)

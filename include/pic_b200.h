@@ -144,8 +144,20 @@ typedef struct PicSoA {
     void* comp[6];
     int32_t* id;        /* original reference slot (tile-major s*cap+slot) or -1; may be NULL */
     int64_t cap;
-    int64_t n;          /* slots in use (live + dead holes) */
+    int64_t n;          /* host-side upper bound of the slots in use (sizes the launch) */
+    int32_t* n_dev;     /* device counter of the slots in use (live + dead holes); when non-NULL the kernels read the
+                           count from here, so appends / sorts never need a host round trip */
 } PicSoA;
+
+/* Per-direction migration packets of one species (multi-GPU).  Packet d occupies rows row_off[d] .. row_off[d]+cap[d] of
+ * `buf` ([rows][7] reals): row row_off[d] is the header (its first 4 bytes are the int32 row count), the following
+ * cap[d] rows are x,y,z,vx,vy,vz,species.  Fixed sizes let ranks exchange packets without first exchanging counts.
+ * direction d = ((1-ox)*3 + (1-oy))*3 + (1-oz), cap[d] = 0 for directions that cannot occur. */
+typedef struct PicLeave {
+    void* buf;
+    int32_t row_off[27];
+    int32_t cap[27];
+} PicLeave;
 
 /* TiledParticles (reference layout, single local tile) -> compact SoA of species s.  d_count: int32 device counter
  * (zeroed by the caller) receiving the number of particles written. */
@@ -166,18 +178,17 @@ int pic_sort_scatter(const PicParams* p, const PicSoA* src, const PicSoA* dst, c
  *   gather E,B (+ext) -> Boris/HC -> deposit (Esirkepov: x -> x+v*dt ; direct: at x+v*dt/2) -> move -> particle BC
  * == evolve.py:33-79 for one local tile.  J is accumulated with atomics into the ghosted tile (fold afterwards).
  * deposition: 0 = esirkepov, 1 = direct.  ext_E/ext_B may be NULL (external fields absent).
- * Leavers (multi-GPU, distributed axes) go to `leave`: [27 directions][leave_cap][7] packets (x,y,z,vx,vy,vz,species),
- * direction = ((1-ox)*3 + (1-oy))*3 + (1-oz), with per-direction counters d_leave_count[27]; pass NULL when
- * mesh == gmesh.  flags[0] |= 1 on an invalid (>1 tile) jump, |= 2 when a packet / SoA capacity overflowed. */
+ * Leavers (multi-GPU, distributed axes) are written into the per-direction packets of `leave` (see PicLeave); pass NULL
+ * when mesh == gmesh.  flags[0] |= 1 on an invalid (>1 tile) jump, |= 2 when a packet / SoA capacity overflowed. */
 int pic_fused_push_deposit(const PicParams* p, int species, int deposition, const PicSoA* soa,
                            const void* const E[3], const void* const B[3], const void* const extE[3],
-                           const void* const extB[3], void* const J[3], void* leave, int64_t leave_cap,
-                           int32_t* d_leave_count, int32_t* flags, void* stream);
+                           const void* const extB[3], void* const J[3], const PicLeave* leave, int32_t* flags,
+                           void* stream);
 
-/* Append the particles of `species` among `n_in` migrated packets ([n_in][7] = x,y,z,vx,vy,vz,species as written by
- * the fused kernel) at the SoA tail; d_count (device int32) accumulates how many were appended. */
-int pic_soa_append(const PicParams* p, const PicSoA* soa, const void* packet, int64_t n_in, int species,
-                   int32_t* d_count, int32_t* flags, void* stream);
+/* Zero the 27 packet headers of `leave` (before K1 of a step). */
+int pic_packets_reset(const PicParams* p, const PicLeave* leave, void* stream);
+/* Append every received packet of `recv` (same layout as PicLeave) to the SoA tail, advancing soa->n_dev on the device. */
+int pic_soa_append_packets(const PicParams* p, const PicSoA* soa, const PicLeave* recv, int32_t* flags, void* stream);
 
 /* Microbenchmarks used for design evidence (profiles/): returns elapsed device ms for `iters` launches. */
 int pic_microbench(int which, int iters, float* ms_out);

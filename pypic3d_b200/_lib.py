@@ -40,7 +40,13 @@ class PicParams(ctypes.Structure):
 
 class PicSoA(ctypes.Structure):
     """Mirror of `struct PicSoA`."""
-    _fields_ = [("comp", ctypes.c_void_p * 6), ("id", ctypes.c_void_p), ("cap", ctypes.c_int64), ("n", ctypes.c_int64)]
+    _fields_ = [("comp", ctypes.c_void_p * 6), ("id", ctypes.c_void_p), ("cap", ctypes.c_int64), ("n", ctypes.c_int64),
+                ("n_dev", ctypes.c_void_p)]
+
+
+class PicLeave(ctypes.Structure):
+    """Mirror of `struct PicLeave`."""
+    _fields_ = [("buf", ctypes.c_void_p), ("row_off", ctypes.c_int32 * 27), ("cap", ctypes.c_int32 * 27)]
 
 
 def needs_build():
@@ -95,6 +101,7 @@ _INT = ctypes.c_int
 _DBL = ctypes.c_double
 _V3 = ctypes.POINTER(ctypes.c_void_p)
 _SOA = ctypes.POINTER(PicSoA)
+_LEAVE = ctypes.POINTER(PicLeave)
 
 # name -> argtypes; every symbol declared in include/pic_b200.h
 SIGNATURES = {
@@ -119,8 +126,9 @@ SIGNATURES = {
     "pic_sort_histogram": [_PP, _SOA, _VP, _VP],
     "pic_sort_scan": [_I64, _VP, _VP, _VP, _VP],
     "pic_sort_scatter": [_PP, _SOA, _SOA, _VP, _VP, _VP],
-    "pic_fused_push_deposit": [_PP, _INT, _INT, _SOA, _V3, _V3, _V3, _V3, _V3, _VP, _I64, _VP, _VP, _VP],
-    "pic_soa_append": [_PP, _SOA, _VP, _I64, _INT, _VP, _VP, _VP],
+    "pic_fused_push_deposit": [_PP, _INT, _INT, _SOA, _V3, _V3, _V3, _V3, _V3, _LEAVE, _VP, _VP],
+    "pic_packets_reset": [_PP, _LEAVE, _VP],
+    "pic_soa_append_packets": [_PP, _SOA, _LEAVE, _VP, _VP],
     "pic_microbench": [_INT, _INT, ctypes.POINTER(ctypes.c_float)],
     "pic_params_size": [],
     "pic_version": [],

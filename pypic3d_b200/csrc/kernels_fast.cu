@@ -26,7 +26,8 @@ __global__ void __launch_bounds__(256) k_import(int species, int n_species, cons
 template <typename T>
 __global__ void __launch_bounds__(256) k_export(int species, SoAView<T> s, T* __restrict__ x, T* __restrict__ u,
                                                 uint8_t* __restrict__ active, int64_t cap_ref, int32_t* count) {
-    for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < s.n; j += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t n = s.count();
+    for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x) {
         const T px = s.c[0][j];
         if (pic_isnan(px)) continue;
         int64_t slot;
@@ -42,14 +43,16 @@ __global__ void __launch_bounds__(256) k_export(int species, SoAView<T> s, T* __
 // ---------------------------------------------------------------- counting sort by local cell
 template <typename T>
 __global__ void __launch_bounds__(256) k_sort_hist(const __grid_constant__ PicParams p, SoAView<T> s, int32_t* __restrict__ count) {
-    for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < s.n; j += (int64_t)gridDim.x * blockDim.x)
+    const int64_t n = s.count();
+    for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x)
         atomicAdd(&count[local_cell<T>(p, s.c[0][j], s.c[1][j], s.c[2][j])], 1);
 }
 
 template <typename T>
 __global__ void __launch_bounds__(256) k_sort_scatter(const __grid_constant__ PicParams p, SoAView<T> s, SoAView<T> d,
                                                       const int32_t* __restrict__ offset, int32_t* __restrict__ cursor) {
-    for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < s.n; j += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t n = s.count();
+    for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x) {
         const T px = s.c[0][j], py = s.c[1][j], pz = s.c[2][j];
         const int cell = local_cell<T>(p, px, py, pz);
         const int64_t dst = (int64_t)offset[cell] + atomicAdd(&cursor[cell], 1);
@@ -144,7 +147,8 @@ __global__ void __launch_bounds__(256) k_fused(const __grid_constant__ PicParams
     sink.off = 0;
     bool distributed = false;
     for (int c = 0; c < 3; ++c) distributed |= (p.gmesh[c] != p.mesh[c]);
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < s.n; i += (int64_t)gridDim.x * blockDim.x)
+    const int64_t n = s.count();
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
         fused_particle<T, SF, DEP, ALL3D>(p, species, gm, i, s, F, X, has_ext, sink, leave, distributed, flags);
 }
 
@@ -179,9 +183,10 @@ __global__ void __launch_bounds__(256, (SF == 1 ? 3 : 2)) k_fused3d(const __grid
     // Each CTA walks a CONTIGUOUS range of the cell-sorted particle stream, 256 particles (8 warps x 32) per iteration:
     // consecutive iterations touch neighbouring cells, so the E/B stencil rows stay in L1 between iterations and across
     // the warps of the CTA.  Warps never synchronise with each other (the deferred queue is warp-private).
-    const int64_t per_block = ((s.n + (int64_t)gridDim.x * 256 - 1) / ((int64_t)gridDim.x * 256)) * 256;
+    const int64_t n_total = s.count();
+    const int64_t per_block = ((n_total + (int64_t)gridDim.x * 256 - 1) / ((int64_t)gridDim.x * 256)) * 256;
     const int64_t b_begin = (int64_t)blockIdx.x * per_block;
-    const int64_t w_end = (b_begin + per_block < s.n) ? b_begin + per_block : s.n;
+    const int64_t w_end = (b_begin + per_block < n_total) ? b_begin + per_block : n_total;
     for (int64_t base = b_begin + warp * 32; base < w_end; base += 256) {
         const int64_t i = base + lane;
         T vals[NV], po[3], xn[3], v[3];
@@ -247,19 +252,35 @@ __global__ void __launch_bounds__(256, (SF == 1 ? 3 : 2)) k_fused3d(const __grid
     }
 }
 
-// Append the migrated particles of `species` (packet rows [x,y,z,vx,vy,vz,species]) at the SoA tail; the number appended is
-// accumulated in d_count so the host can advance soa.n.
+// Append every received packet (PicLeave layout: header row with the int32 count, then rows x,y,z,vx,vy,vz,species) at the
+// SoA tail; the device counter n_dev advances atomically, so no host round trip is needed between exchange and append.
 template <typename T>
-__global__ void __launch_bounds__(256) k_append(SoAView<T> s, const T* __restrict__ packet, int64_t n_in, int species,
-                                                int32_t* d_count, int32_t* flags) {
-    for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < n_in; j += (int64_t)gridDim.x * blockDim.x) {
-        if ((int)packet[j * 7 + 6] != species) continue;
-        const int64_t dst = s.n + atomicAdd(d_count, 1);
-        if (dst >= s.cap) { atomicOr(flags, 2); continue; }
-        for (int c = 0; c < 6; ++c) s.c[c][dst] = packet[j * 7 + c];
-        if (s.id) s.id[dst] = -1;
+__global__ void __launch_bounds__(256) k_append_packets(SoAView<T> s, LeaveBuf recv, int32_t* flags) {
+    for (int d = 0; d < 27; ++d) {
+        const int cap = recv.cap[d];
+        if (cap == 0) continue;
+        const T* base = (const T*)recv.buf + (int64_t)recv.row_off[d] * 7;
+        int n_in = *(const int32_t*)base;
+        if (n_in > cap) n_in = cap;     // the sender flagged the overflow
+        for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n_in; j += gridDim.x * blockDim.x) {
+            const int64_t dst = atomicAdd(s.n_dev, 1);
+            if (dst >= s.cap) { atomicOr(flags, 2); continue; }
+            const T* pk = base + (int64_t)(1 + j) * 7;
+            for (int c = 0; c < 6; ++c) s.c[c][dst] = pk[c];
+            if (s.id) s.id[dst] = -1;
+        }
     }
 }
+
+__global__ void k_packets_reset(LeaveBuf l, int real_bytes) {
+    const int d = threadIdx.x;
+    if (d < 27 && l.cap[d] > 0) {
+        char* h = (char*)l.buf + (int64_t)l.row_off[d] * 7 * real_bytes;
+        for (int b = 0; b < 7 * real_bytes; ++b) h[b] = 0;
+    }
+}
+
+__global__ void k_set_count(int32_t* n_dev, const int32_t* src) { *n_dev = *src; }
 
 // ---------------------------------------------------------------- launchers
 template <typename T>
@@ -272,28 +293,30 @@ static int launch_import(const PicParams* p, int species, const void* x, const v
 template <typename T>
 static int launch_export(const PicParams* p, int species, const PicSoA* soa, void* x, void* u, uint8_t* active, int64_t cap_ref,
                          int32_t* count, cudaStream_t st) {
-    if (soa->n == 0) return 0;
+    if (soa->n == 0 && !soa->n_dev) return 0;
     k_export<T><<<grid_for(soa->n, 256), 256, 0, st>>>(species, view_of<T>(soa), (T*)x, (T*)u, active, cap_ref, count);
     PIC_LAUNCH_RET();
 }
 template <typename T>
 static int launch_hist(const PicParams* p, const PicSoA* src, int32_t* count, cudaStream_t st) {
-    if (src->n == 0) return 0;
+    if (src->n == 0 && !src->n_dev) return 0;
     k_sort_hist<T><<<grid_for(src->n, 256), 256, 0, st>>>(*p, view_of<T>(src), count);
     PIC_LAUNCH_RET();
 }
 template <typename T>
 static int launch_scatter(const PicParams* p, const PicSoA* src, const PicSoA* dst, const int32_t* offset, int32_t* cursor, cudaStream_t st) {
-    if (src->n == 0) return 0;
+    if (src->n == 0 && !src->n_dev) return 0;
     k_sort_scatter<T><<<grid_for(src->n, 256), 256, 0, st>>>(*p, view_of<T>(src), view_of<T>(dst), offset, cursor);
+    if (src->n_dev)   // live particles precede the trash bin: the new slot count is offset[ncells]
+        k_set_count<<<1, 1, 0, st>>>(src->n_dev, offset + (int64_t)p->tile[0] * p->tile[1] * p->tile[2]);
     PIC_LAUNCH_RET();
 }
 
 template <typename T, int SF>
 static int launch_fused(const PicParams* p, int species, int deposition, const PicSoA* soa, const void* const E[3],
                         const void* const B[3], const void* const extE[3], const void* const extB[3], void* const J[3],
-                        void* leave, int64_t leave_cap, int32_t* d_leave_count, int32_t* flags, cudaStream_t st) {
-    if (soa->n == 0) return 0;
+                        const PicLeave* leave, int32_t* flags, cudaStream_t st) {
+    if (soa->n == 0 && !soa->n_dev) return 0;
     Field6<T> F, X;
     Field3W<T> Jw;
     const int has_ext = (extE && extB) ? 1 : 0;
@@ -302,7 +325,7 @@ static int launch_fused(const PicParams* p, int species, int deposition, const P
         X.f[c] = has_ext ? (const T*)extE[c] : nullptr; X.f[3 + c] = has_ext ? (const T*)extB[c] : nullptr;
         Jw.f[c] = (T*)J[c];
     }
-    LeaveBuf lb{leave, leave_cap, d_leave_count};
+    const LeaveBuf lb = leave_of(leave);
     const bool all3d = (p->gmesh[0] * p->tile[0] > 1) && (p->gmesh[1] * p->tile[1] > 1) && (p->gmesh[2] * p->tile[2] > 1) && p->g >= 2;
     const int grid = grid_for(soa->n, 256, 8);
     const SoAView<T> sv = view_of<T>(soa);
@@ -342,10 +365,11 @@ static int launch_fused(const PicParams* p, int species, int deposition, const P
 }
 
 template <typename T>
-static int launch_append(const PicParams* p, const PicSoA* soa, const void* packet, int64_t n_in, int species, int32_t* d_count,
-                         int32_t* flags, cudaStream_t st) {
-    if (n_in == 0) return 0;
-    k_append<T><<<grid_for(n_in, 256), 256, 0, st>>>(view_of<T>(soa), (const T*)packet, n_in, species, d_count, flags);
+static int launch_append_packets(const PicParams* p, const PicSoA* soa, const PicLeave* recv, int32_t* flags, cudaStream_t st) {
+    int maxcap = 0;
+    for (int d = 0; d < 27; ++d) maxcap = recv->cap[d] > maxcap ? recv->cap[d] : maxcap;
+    if (maxcap == 0) return 0;
+    k_append_packets<T><<<grid_for(maxcap, 256, 2), 256, 0, st>>>(view_of<T>(soa), leave_of(recv), flags);
     PIC_LAUNCH_RET();
 }
 
@@ -394,23 +418,27 @@ int pic_sort_scatter(const PicParams* p, const PicSoA* src, const PicSoA* dst, c
 
 int pic_fused_push_deposit(const PicParams* p, int species, int deposition, const PicSoA* soa, const void* const E[3],
                            const void* const B[3], const void* const extE[3], const void* const extB[3], void* const J[3],
-                           void* leave, int64_t leave_cap, int32_t* d_leave_count, int32_t* flags, void* stream) {
+                           const PicLeave* leave, int32_t* flags, void* stream) {
     PIC_CHECK_ARG(p && soa && E && B && J && flags && species >= 0 && species < p->n_species && (deposition == 0 || deposition == 1));
     PIC_CHECK_ARG(p->mesh[0] == 1 && p->mesh[1] == 1 && p->mesh[2] == 1);
     bool distributed = false;
     for (int c = 0; c < 3; ++c) distributed |= (p->gmesh[c] != p->mesh[c]);
     if (distributed) {
-        PIC_CHECK_ARG(leave && d_leave_count && leave_cap > 0);
+        PIC_CHECK_ARG(leave && leave->buf);
         if (deposition == 1) return PIC_EUNSUPPORTED;  // centred deposit across ranks needs a mid-step migration
     }
-    PIC_DISPATCH_T_SF(p, launch_fused, p, species, deposition, soa, E, B, extE, extB, J, leave, leave_cap, d_leave_count, flags,
-                      (cudaStream_t)stream);
+    PIC_DISPATCH_T_SF(p, launch_fused, p, species, deposition, soa, E, B, extE, extB, J, leave, flags, (cudaStream_t)stream);
 }
 
-int pic_soa_append(const PicParams* p, const PicSoA* soa, const void* packet, int64_t n_in, int species, int32_t* d_count,
-                   int32_t* flags, void* stream) {
-    PIC_CHECK_ARG(p && soa && packet && flags && d_count && n_in >= 0 && species >= 0 && species < p->n_species);
-    PIC_DISPATCH_T(p, launch_append, p, soa, packet, n_in, species, d_count, flags, (cudaStream_t)stream);
+int pic_packets_reset(const PicParams* p, const PicLeave* leave, void* stream) {
+    PIC_CHECK_ARG(p && leave && leave->buf);
+    k_packets_reset<<<1, 32, 0, (cudaStream_t)stream>>>(leave_of(leave), p->dtype == PIC_F32 ? 4 : 8);
+    PIC_LAUNCH_RET();
+}
+
+int pic_soa_append_packets(const PicParams* p, const PicSoA* soa, const PicLeave* recv, int32_t* flags, void* stream) {
+    PIC_CHECK_ARG(p && soa && soa->n_dev && recv && recv->buf && flags);
+    PIC_DISPATCH_T(p, launch_append_packets, p, soa, recv, flags, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -174,6 +174,12 @@ struct SoAView {
     T* c[6];
     int32_t* id;
     int64_t cap, n;
+    int32_t* n_dev;
+    PIC_HD int64_t count() const {   // slots in use: device counter when present (clamped to the capacity), else the host value
+        if (!n_dev) return n;
+        const int64_t m = *n_dev;
+        return m < cap ? m : cap;
+    }
 };
 template <typename T>
 static inline SoAView<T> view_of(const PicSoA* s) {
@@ -182,14 +188,34 @@ static inline SoAView<T> view_of(const PicSoA* s) {
     v.id = s->id;
     v.cap = s->cap;
     v.n = s->n;
+    v.n_dev = s->n_dev;
     return v;
 }
 
+// Device view of PicLeave (include/pic_b200.h): per-direction packets with an int32 row count in the header row.
 struct LeaveBuf {
-    void* buf;        // [27][leave_cap][7]
-    int64_t cap;
-    int32_t* count;   // [27]
+    void* buf;
+    int32_t row_off[27];
+    int32_t cap[27];
+    template <typename T>
+    PIC_HD void push(int dir, const T pos[3], const T v[3], int species, int32_t* flags) const {
+        T* base = (T*)buf + (int64_t)row_off[dir] * 7;
+        const int slot = atomic_add_i32((int32_t*)base, 1);
+        if (slot < cap[dir]) {
+            T* pk = base + (int64_t)(1 + slot) * 7;
+            for (int c = 0; c < 3; ++c) { pk[c] = pos[c]; pk[3 + c] = v[c]; }
+            pk[6] = (T)species;
+        } else {
+            atomic_or_i32(flags, 2);
+        }
+    }
 };
+static inline LeaveBuf leave_of(const PicLeave* l) {
+    LeaveBuf b;
+    b.buf = l ? l->buf : nullptr;
+    for (int d = 0; d < 27; ++d) { b.row_off[d] = l ? l->row_off[d] : 0; b.cap[d] = l ? l->cap[d] : 0; }
+    return b;
+}
 
 template <typename T>
 PIC_HD int local_cell(const PicParams& p, T px, T py, T pz) {
@@ -311,14 +337,7 @@ PIC_HD void fused_particle(const PicParams& p, int species, const Geom<T>& gm, i
         if (invalid) { atomic_or_i32(flags, 1); alive = false; }
         else if (nonlocal_) {
             const int dir = ((1 - off[0]) * 3 + (1 - off[1])) * 3 + (1 - off[2]);
-            const int64_t slot = atomic_add_i32(&leave.count[dir], 1);
-            if (slot < leave.cap) {
-                T* pk = (T*)leave.buf + ((int64_t)dir * leave.cap + slot) * 7;
-                for (int c = 0; c < 3; ++c) { pk[c] = pos[c]; pk[3 + c] = v[c]; }
-                pk[6] = (T)species;
-            } else {
-                atomic_or_i32(flags, 2);
-            }
+            leave.push<T>(dir, pos, v, species, flags);
             alive = false;
         }
     }
@@ -760,14 +779,7 @@ PIC_HD int fast3d_advance(const PicParams& p, int species, const FastConst<T>& k
         dir -= off * (a == 0 ? 9 : (a == 1 ? 3 : 1));
     }
     if (alive && distributed && dir != 13) {
-        const int64_t slot = atomic_add_i32(&leave.count[dir], 1);
-        if (slot < leave.cap) {
-            T* pk = (T*)leave.buf + ((int64_t)dir * leave.cap + slot) * 7;
-            for (int c = 0; c < 3; ++c) { pk[c] = pos[c]; pk[3 + c] = v[c]; }
-            pk[6] = (T)species;
-        } else {
-            atomic_or_i32(flags, 2);
-        }
+        leave.push<T>(dir, pos, v, species, flags);
         alive = false;
     }
     if (!alive) pos[0] = pic_nan<T>();

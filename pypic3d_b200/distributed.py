@@ -195,48 +195,32 @@ class DistributedHalo:
             out.append((d, rank_of(dst, self.mesh) if dst_ok else None, rank_of(src, self.mesh) if src_ok else None))
         return out
 
-    def exchange_packets(self, counts, packets, particle_bcs, like):
-        """counts[s][d] / packets[s][d] ([counts[s][d], 7] tensors) for every species s and direction code d ->
-        per-species lists of received [n, 7] tensors.  Two rounds: the counts (one small message per direction carrying all
-        species), then one payload message per non-empty (direction, species)."""
+    def exchange_packets(self, leave_bufs, recv_bufs, leave, particle_bcs):
+        """One batched round: for every species and every active direction send the fixed-size packet (header + cap rows,
+        layout `PicLeave`) to the destination rank and receive the matching packet from the source rank.
+        leave_bufs / recv_bufs: per-species flat tensors; leave: per-species objects with row_off[27] / cap[27]."""
         dirs = self.active_dirs(particle_bcs)
-        S = len(counts)
-        dev = like.device
-        c_send = [torch.tensor([int(counts[s][d]) for s in range(S)], dtype=torch.int64, device=dev) for d, _, _ in dirs]
-        c_recv = [torch.zeros(S, dtype=torch.int64, device=dev) for _ in dirs]
-        self._exchange([(dst, c_send[i]) for i, (d, dst, src) in enumerate(dirs) if dst is not None],
-                       [(src, c_recv[i]) for i, (d, dst, src) in enumerate(dirs) if src is not None])
-        n_in = [c.tolist() for c in c_recv]
-        sends, recvs, out = [], [], [[] for _ in range(S)]
-        for i, (d, dst, src) in enumerate(dirs):
-            for s in range(S):
-                if dst is not None and int(counts[s][d]) > 0:
-                    sends.append((dst, packets[s][d]))
-                if src is not None and int(n_in[i][s]) > 0:
-                    t = torch.empty((int(n_in[i][s]), 7), dtype=like.dtype, device=dev)
-                    recvs.append((src, t))
-                    out[s].append(t)
+        sends, recvs = [], []
+        for s in range(len(leave_bufs)):
+            for d, dst, src in dirs:
+                cap = int(leave[s].cap[d])
+                if cap == 0:
+                    continue
+                lo, hi = int(leave[s].row_off[d]) * 7, (int(leave[s].row_off[d]) + cap + 1) * 7
+                if dst is not None:
+                    sends.append((dst, leave_bufs[s][lo:hi]))
+                if src is not None:
+                    recvs.append((src, recv_bufs[s][lo:hi]))
         self._exchange(sends, recvs)
-        return out
 
     def migrate(self, sim):
-        """Exchange the leavers written by K1 and append the arrivals to the resident SoA (K3/K4 of SURVEY.md section 7).
-        Two host syncs per step: the leave counts, then the arrival counts."""
-        S, cap = sim.S, sim.leave_cap
-        counts = sim.leave_count.view(S, 27).cpu().tolist()
-        if any(c > cap for row in counts for c in row):
-            sim.flags[0:1] |= 2                      # leave-packet overflow: surfaced by Simulation.overflow()
-            counts = [[min(c, cap) for c in row] for row in counts]
-        view = sim.leave.view(S, 27, cap, 7)
-        packets = [{d: view[s, d, :counts[s][d]] for d in range(27)} for s in range(S)]
-        incoming = self.exchange_packets(counts, packets, tuple(self.p.particle_bc), sim.leave)
+        """Exchange the leaver packets written by K1 and append the arrivals to the resident SoA (K3/K4 of SURVEY.md
+        section 7).  No host synchronisation: packet sizes are fixed and the row counts travel in the packet headers."""
         L = _lib.lib()
         st = ops._stream()
-        for s, sp_ in enumerate(sim.species):
-            for pk in incoming[s]:
-                n_in = int(pk.shape[0])
-                soa = sim._soa(sp_)
-                sim._counter[s:s + 1].zero_()
-                _lib.check(L.pic_soa_append(ctypes.byref(self.p), ctypes.byref(soa), ops._p(pk), n_in, s, ops._p(sim._counter[s:s + 1]),
-                                            ops._p(sim.flags), st), "pic_soa_append")
-                sp_.n = min(sp_.cap, sp_.n + n_in)   # rows beyond capacity were dropped by the kernel and flagged
+        self.exchange_packets([sp_.leave_buf for sp_ in sim.species], [sp_.recv_buf for sp_ in sim.species],
+                              [sp_.leave for sp_ in sim.species], tuple(self.p.particle_bc))
+        for sp_ in sim.species:
+            soa = sim._soa(sp_)
+            _lib.check(L.pic_soa_append_packets(ctypes.byref(self.p), ctypes.byref(soa), ctypes.byref(sp_.recv), ops._p(sim.flags), st),
+                       "pic_soa_append_packets")

@@ -17,13 +17,13 @@ import numpy as np
 import torch
 
 from . import _lib, ops
-from ._lib import PicSoA, PicError, check
+from ._lib import PicSoA, PicLeave, PicError, check
 from .particles.particle_class import TiledParticles
 from .boundary_conditions.grid_and_stencil import BC_CONDUCTING
 
 
 class _Species:
-    __slots__ = ("buf", "ids", "cur", "n", "cap")
+    __slots__ = ("buf", "ids", "cur", "n", "cap", "n_dev", "leave", "recv", "leave_buf", "recv_buf")
 
 
 class LocalHalo:
@@ -44,7 +44,7 @@ class LocalHalo:
 
 class Simulation:
     def __init__(self, particles, species_config, fields, static_parameters, dynamic_parameters, *, sort_interval=10,
-                 capacity_factor=1.25, track_ids=True, halo=None, gmesh=None, moff=(0, 0, 0), leave_capacity=None):
+                 capacity_factor=1.25, track_ids=True, halo=None, gmesh=None, moff=(0, 0, 0), leave_fraction=0.25):
         sp, dp = static_parameters, dynamic_parameters
         if getattr(sp, "pml_active", False):
             raise NotImplementedError("PML is outside the hot path of pypic3d_b200")
@@ -94,14 +94,9 @@ class Simulation:
         self.cap_ref = int(x.shape[4])
         self.track_ids = bool(track_ids)
         self._import(particles, capacity_factor)
-        self.leave_cap = 0
-        self.leave = None
-        self.leave_count = None
+        self.leave_fraction = float(leave_fraction)
         if self.distributed:
-            ntot = max(1, sum(s.n for s in self.species))
-            self.leave_cap = int(leave_capacity) if leave_capacity else max(1024, ntot // 8)
-            self.leave = torch.empty(self.S * 27 * self.leave_cap * 7, dtype=self.dtype, device=self.device)
-            self.leave_count = torch.zeros(self.S * 27, dtype=torch.int32, device=self.device)
+            self._alloc_packets()
         self.sort()
 
     # ------------------------------------------------------------------------------------------ layout
@@ -113,7 +108,38 @@ class Simulation:
         s.id = sp_.ids[k].data_ptr() if sp_.ids is not None else None
         s.cap = sp_.cap
         s.n = sp_.n
+        s.n_dev = sp_.n_dev.data_ptr()
         return s
+
+    def _alloc_packets(self):
+        """Fixed-size per-direction migration packets (PicLeave).  Capacity of a face packet = the particles that could
+        cross that face in one step at light speed from a uniform plasma x `leave_fraction` (thermal plasmas use ~1 % of it);
+        edges and corners scale with the product of the per-axis fractions.  Identical on every rank by construction."""
+        p = self.p
+        d = (p.dx, p.dy, p.dz)
+        frac = [min(1.0, p.C * p.dt / (p.tile[a] * d[a])) for a in range(3)]
+        split = [p.gmesh[a] != p.mesh[a] for a in range(3)]
+        real = 4 if self.dtype == torch.float32 else 8
+        for sp_ in self.species:
+            n0 = max(1, int(sp_.cap))
+            L, R = PicLeave(), PicLeave()
+            rows = 0
+            for dcode in range(27):
+                off = (1 - dcode // 9, 1 - (dcode // 3) % 3, 1 - dcode % 3)
+                cap = 0
+                if off != (0, 0, 0) and all(off[a] == 0 or split[a] for a in range(3)):
+                    f = 1.0
+                    for a in range(3):
+                        if off[a] != 0:
+                            f *= frac[a]
+                    cap = int(n0 * f * self.leave_fraction) + 1024
+                L.row_off[dcode] = R.row_off[dcode] = rows
+                L.cap[dcode] = R.cap[dcode] = cap
+                rows += (cap + 1) if cap else 0
+            sp_.leave_buf = torch.zeros(max(rows, 1) * 7, dtype=self.dtype, device=self.device)
+            sp_.recv_buf = torch.zeros(max(rows, 1) * 7, dtype=self.dtype, device=self.device)
+            L.buf, R.buf = sp_.leave_buf.data_ptr(), sp_.recv_buf.data_ptr()
+            sp_.leave, sp_.recv = L, R
 
     def _import(self, particles, capacity_factor):
         L = _lib.lib()
@@ -132,16 +158,19 @@ class Simulation:
                 sp_.cap = max(16, int(np.ceil(counts[s] * float(capacity_factor))) + 16)
                 sp_.buf = [torch.empty((6, sp_.cap), dtype=self.dtype, device=self.device) for _ in range(2)]
                 sp_.ids = [torch.empty(sp_.cap, dtype=torch.int32, device=self.device) for _ in range(2)] if self.track_ids else None
+                sp_.n_dev = torch.zeros(1, dtype=torch.int32, device=self.device)
+                sp_.leave = sp_.recv = sp_.leave_buf = sp_.recv_buf = None
                 self.species.append(sp_)
             sp_ = self.species[s]
             if counts[s] > sp_.cap:
                 raise PicError(f"species {s}: {counts[s]} particles exceed the resident capacity {sp_.cap}")
             sp_.cur = 0
-            sp_.n = 0
+            sp_.n = sp_.cap                       # host-side upper bound; the live count is sp_.n_dev on the device
+            sp_.n_dev.zero_()
             soa = self._soa(sp_)
+            soa.n_dev = None                      # the import kernel counts into n_dev itself
             check(L.pic_soa_import(ctypes.byref(self.p), s, ops._p(x), ops._p(u), ops._p(a), self.cap_ref, ctypes.byref(soa),
-                                   ops._p(self._counter[s:s + 1]), st), "pic_soa_import")
-            sp_.n = int(counts[s])
+                                   ops._p(sp_.n_dev), st), "pic_soa_import")
 
     def load_state(self, particles, fields3=None):
         """Replace the resident state from reference-layout pytrees (same shapes as at construction); re-sorts."""
@@ -158,8 +187,6 @@ class Simulation:
         st = ops._stream()
         n = self.ncells + 1
         for sp_ in self.species:
-            if sp_.n == 0:
-                continue
             src, dst = self._soa(sp_), self._soa(sp_, 1 - sp_.cur)
             self._cell_count.zero_()
             check(L.pic_sort_histogram(ctypes.byref(self.p), ctypes.byref(src), ops._p(self._cell_count), st), "pic_sort_histogram")
@@ -167,13 +194,7 @@ class Simulation:
             self._cell_count.zero_()
             check(L.pic_sort_scatter(ctypes.byref(self.p), ctypes.byref(src), ctypes.byref(dst), ops._p(self._cell_offset),
                                      ops._p(self._cell_count), st), "pic_sort_scatter")
-            sp_.cur = 1 - sp_.cur
-            if self._may_have_dead:
-                sp_.n = int(self._cell_offset[self.ncells].item())   # live particles precede the trash bin
-
-    @property
-    def _may_have_dead(self):
-        return self.distributed or any(int(b) == 2 for b in self.p.particle_bc)
+            sp_.cur = 1 - sp_.cur           # (the scatter also set n_dev = number of live particles, on the device)
 
     # ------------------------------------------------------------------------------------------ the step
     def step(self, n_steps=1):
@@ -188,24 +209,18 @@ class Simulation:
         for c in self.J:
             c.zero_()
         if self.distributed:
-            self.leave_count.zero_()
+            for sp_ in self.species:
+                check(L.pic_packets_reset(ctypes.byref(p), ctypes.byref(sp_.leave), st), "pic_packets_reset")
         extE = ops._v(self.ext_E) if self.ext_E is not None else None
         extB = ops._v(self.ext_B) if self.ext_B is not None else None
         for s, sp_ in enumerate(self.species):
-            if sp_.n == 0:
-                continue
             soa = self._soa(sp_)
             if self.k1_events is not None:
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
-            if self.leave is not None:      # per-species packet buffers [27][leave_cap][7] and counters [27]
-                lv = ops._p(self.leave[s * 27 * self.leave_cap * 7:(s + 1) * 27 * self.leave_cap * 7])
-                lc = ops._p(self.leave_count[s * 27:(s + 1) * 27])
-            else:
-                lv = lc = None
             check(L.pic_fused_push_deposit(ctypes.byref(p), s, self.deposition, ctypes.byref(soa), ops._v(self.E), ops._v(self.B),
-                                           extE, extB, ops._v(self.J), lv, self.leave_cap, lc, ops._p(self.flags), st),
-                  "pic_fused_push_deposit")
+                                           extE, extB, ops._v(self.J), ctypes.byref(sp_.leave) if sp_.leave is not None else None,
+                                           ops._p(self.flags), st), "pic_fused_push_deposit")
             if self.k1_events is not None:
                 e1.record()
                 self.k1_events.append((e0, e1))
@@ -249,7 +264,9 @@ class Simulation:
         return self.overflow_previous or bool((self.flags[0] != 0).item())
 
     def n_particles(self):
-        return sum(s.n for s in self.species)
+        """Slots in use (host sync).  Exact particle count on a single GPU; between sorts of a multi-GPU run it still
+        includes the holes left by migrated particles."""
+        return sum(min(int(s.n_dev.item()), s.cap) for s in self.species)
 
     def export_state(self, cap_ref=None, out=None):
         """Reference pytrees: (TiledParticles, fields 8-tuple).  Slots are restored by id on a single GPU.

@@ -32,14 +32,14 @@ static void t_fused(const PicParams* p, int species, int dep, void* const comp[6
     Field6<T> F, X;
     SoAView<T> s;
     for (int c = 0; c < 6; ++c) { s.c[c] = (T*)comp[c]; X.f[c] = nullptr; }
-    s.id = nullptr; s.cap = n; s.n = n;
+    s.id = nullptr; s.cap = n; s.n = n; s.n_dev = nullptr;
     for (int c = 0; c < 3; ++c) { F.f[c] = (const T*)E[c]; F.f[3 + c] = (const T*)B[c]; }
     Geom<T> gm;
     make_geom<T>(*p, 0, 0, 0, gm);
     TileSink<T> sink;
     for (int c = 0; c < 3; ++c) { sink.J[c] = (T*)J[c]; sink.L[c] = gm.L[c]; }
     sink.off = 0;
-    LeaveBuf lb{leave, leave_cap, leave_count};
+    LeaveBuf lb = leave_of(nullptr); (void)leave; (void)leave_cap; (void)leave_count;
     bool distributed = false;
     for (int c = 0; c < 3; ++c) distributed |= (p->gmesh[c] != p->mesh[c]);
     const bool all3d = (p->gmesh[0] * p->tile[0] > 1) && (p->gmesh[1] * p->tile[1] > 1) && (p->gmesh[2] * p->tile[2] > 1) && p->g >= 2;
@@ -60,7 +60,7 @@ static void t_fused3d(const PicParams* p, int species, void* const comp[6], int6
     Field6<T> F, X;
     SoAView<T> s;
     for (int c = 0; c < 6; ++c) { s.c[c] = (T*)comp[c]; X.f[c] = nullptr; }
-    s.id = nullptr; s.cap = n; s.n = n;
+    s.id = nullptr; s.cap = n; s.n = n; s.n_dev = nullptr;
     for (int c = 0; c < 3; ++c) { F.f[c] = (const T*)E[c]; F.f[3 + c] = (const T*)B[c]; }
     Geom<T> gm;
     make_geom<T>(*p, 0, 0, 0, gm);
@@ -69,7 +69,7 @@ static void t_fused3d(const PicParams* p, int species, void* const comp[6], int6
     TileSink<T> sink;
     for (int c = 0; c < 3; ++c) { sink.J[c] = (T*)J[c]; sink.L[c] = gm.L[c]; }
     sink.off = 0;
-    LeaveBuf lb{leave, leave_cap, leave_count};
+    LeaveBuf lb = leave_of(nullptr); (void)leave; (void)leave_cap; (void)leave_count;
     bool distributed = false;
     for (int c = 0; c < 3; ++c) distributed |= (p->gmesh[c] != p->mesh[c]);
     for (int64_t i = 0; i < n; ++i) {

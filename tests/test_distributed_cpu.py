@@ -122,22 +122,29 @@ def _worker(rank, world, port, mesh, tile, g, bcs, q):
         f = mine(full); halo.fold_(f, bcs)
         ref = [ohalo.fold(a, tile, bcs, g) for a in full]
         out["fold"] = max(float(np.abs(f[c].numpy()[0, 0, 0] - ref[c][coords]).max()) for c in range(3))
-        # particle packets: every active direction carries (rank, d) tagged rows; the receiver checks provenance
+        # particle packets: fixed-size packets (header row + cap rows) tagged with (species, rank, direction)
         dirs = halo.active_dirs((0, 0, 0))
         S = 2
-        counts = [[0] * 27 for _ in range(S)]; packets = [dict() for _ in range(S)]
+
+        class _L:
+            row_off = [0] * 27; cap = [0] * 27
+        lay = _L(); rows = 0
+        for d, dst, src in dirs:
+            lay.row_off[d] = rows; lay.cap[d] = 2 + d % 3; rows += lay.cap[d] + 1
+        send = [torch.zeros(rows * 7, dtype=torch.float64) for _ in range(S)]
+        recv = [torch.zeros(rows * 7, dtype=torch.float64) for _ in range(S)]
         for s_ in range(S):
+            v = send[s_].view(rows, 7)
             for d, dst, src in dirs:
-                counts[s_][d] = (d + s_) % 3          # includes empty messages
-                packets[s_][d] = torch.full((counts[s_][d], 7), float(1000 * s_ + 100 * rank + d), dtype=torch.float64)
-            for d in range(27):
-                packets[s_].setdefault(d, torch.zeros((0, 7), dtype=torch.float64))
-        got = halo.exchange_packets(counts, packets, (0, 0, 0), torch.zeros(1, dtype=torch.float64))
+                v[lay.row_off[d]:lay.row_off[d] + lay.cap[d] + 1] = float(1000 * s_ + 100 * rank + d)
+        halo.exchange_packets(send, recv, [lay] * S, (0, 0, 0))
         ok = True
         for s_ in range(S):
-            expect = sorted(float(1000 * s_ + 100 * src + d) for d, dst, src in dirs if src is not None for _ in range((d + s_) % 3))
-            have = sorted(float(v) for t in got[s_] for v in t[:, 0].tolist())
-            ok = ok and (expect == have)
+            v = recv[s_].view(rows, 7)
+            for d, dst, src in dirs:
+                blk = v[lay.row_off[d]:lay.row_off[d] + lay.cap[d] + 1]
+                want = float(1000 * s_ + 100 * src + d) if src is not None else 0.0
+                ok = ok and bool((blk == want).all())
         out["packets_ok"] = ok
         q.put((rank, out))
     finally:
