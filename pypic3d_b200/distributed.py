@@ -99,6 +99,12 @@ class DistributedHalo:
             for r in reqs:
                 r.wait()
 
+    def allreduce_max(self, values):
+        """Element-wise max over ranks of a short list of ints (set-up time only)."""
+        t = torch.tensor([int(v) for v in values], dtype=torch.int64, device=self.device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+        return [int(v) for v in t.tolist()]
+
     # ------------------------------------------------------------------ guard cells
     def refresh_(self, fields, bcs):
         """In-place refresh x -> y -> z (ghost_cells.py:181-215)."""

@@ -41,6 +41,9 @@ class LocalHalo:
     def migrate(self, sim):
         return None
 
+    def allreduce_max(self, values):
+        return list(values)
+
 
 class Simulation:
     def __init__(self, particles, species_config, fields, static_parameters, dynamic_parameters, *, sort_interval=10,
@@ -120,8 +123,9 @@ class Simulation:
         frac = [min(1.0, p.C * p.dt / (p.tile[a] * d[a])) for a in range(3)]
         split = [p.gmesh[a] != p.mesh[a] for a in range(3)]
         real = 4 if self.dtype == torch.float32 else 8
-        for sp_ in self.species:
-            n0 = max(1, int(sp_.cap))
+        # packet sizes must agree on every rank: base them on the largest per-species capacity of the whole job
+        n0s = self.halo.allreduce_max([max(1, int(sp_.cap)) for sp_ in self.species])
+        for sp_, n0 in zip(self.species, n0s):
             L, R = PicLeave(), PicLeave()
             rows = 0
             for dcode in range(27):

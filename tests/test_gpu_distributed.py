@@ -32,34 +32,39 @@ def _worker(rank, world, port, mesh, sf, pbc, steps, q):
     dev = torch.device("cuda", rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     try:
-        tile = (8, 6, 4)
-        N = tuple(mesh[a] * tile[a] for a in range(3))
-        sp, dp, tp, sc, E, B = make_case(N, tile, sf, current_deposition="esirkepov", particle_boundary_conditions=pbc, n=400,
-                                         capacity=4.0, vmax=0.3, dt=0.04)
-        fields = make_fields(sp, dp)
-        c = coords_of(rank, mesh)
-        sl = (slice(c[0], c[0] + 1), slice(c[1], c[1] + 1), slice(c[2], c[2] + 1))
-        ps, pd = gu.to_pkg_params(sp, dp)
-        t = lambda a: gu.tt(np.ascontiguousarray(a[sl]), dev=dev)
-        v = lambda F: tuple(t(x) for x in F)
-        parts = pp.TiledParticles(t(tp.x), t(tp.u), t(tp.active))
-        f8 = (v(fields[0]), v(fields[1]), v(fields[2]), t(fields[3]), t(fields[4]), (v(fields[5][0]), v(fields[5][1])), None,
-              torch.tensor(False, device=dev))
-        sim = Simulation(parts, gu.species_to_pkg(sc), f8, ps, pd, sort_interval=2, gmesh=mesh, moff=c, capacity_factor=4.0,
-                         halo=lambda p: DistributedHalo(p, None, dev))
-        for _ in range(steps):
-            tp, fields = oevolve.time_loop_electrodynamic(tp, sc, fields, sp, dp)
-        sim.step(steps)
-        gp, gf = sim.export_state()
-        err = 0.0
-        for k in range(3):
-            for a, b in zip(gf[k], fields[k]):
-                ref = b[sl]
-                err = max(err, float(np.abs(gu.npy(a) - ref).max()) / max(1.0, float(np.abs(ref).max())))
-        got = gu.sorted_active(gu.npy(gp.x), gu.npy(gp.u), gu.npy(gp.active))
-        want = gu.sorted_active(tp.x[sl], tp.u[sl], tp.active[sl])
-        perr = float(np.abs(got - want).max()) if got.shape == want.shape and got.size else (0.0 if got.shape == want.shape else 1e9)
-        q.put((rank, err, perr, got.shape[0], want.shape[0], sim.overflow(), bool(fields[7])))
+      try:
+          tile = (8, 6, 4)
+          N = tuple(mesh[a] * tile[a] for a in range(3))
+          sp, dp, tp, sc, E, B = make_case(N, tile, sf, current_deposition="esirkepov", particle_boundary_conditions=pbc, n=400,
+                                           capacity=4.0, vmax=0.3, dt=0.04)
+          fields = make_fields(sp, dp)
+          c = coords_of(rank, mesh)
+          sl = (slice(c[0], c[0] + 1), slice(c[1], c[1] + 1), slice(c[2], c[2] + 1))
+          ps, pd = gu.to_pkg_params(sp, dp)
+          t = lambda a: gu.tt(np.ascontiguousarray(a[sl]), dev=dev)
+          v = lambda F: tuple(t(x) for x in F)
+          parts = pp.TiledParticles(t(tp.x), t(tp.u), t(tp.active))
+          f8 = (v(fields[0]), v(fields[1]), v(fields[2]), t(fields[3]), t(fields[4]), (v(fields[5][0]), v(fields[5][1])), None,
+                torch.tensor(False, device=dev))
+          sim = Simulation(parts, gu.species_to_pkg(sc), f8, ps, pd, sort_interval=2, gmesh=mesh, moff=c, capacity_factor=4.0,
+                           halo=lambda p: DistributedHalo(p, None, dev))
+          for _ in range(steps):
+              tp, fields = oevolve.time_loop_electrodynamic(tp, sc, fields, sp, dp)
+          sim.step(steps)
+          gp, gf = sim.export_state()
+          err = 0.0
+          for k in range(3):
+              for a, b in zip(gf[k], fields[k]):
+                  ref = b[sl]
+                  err = max(err, float(np.abs(gu.npy(a) - ref).max()) / max(1.0, float(np.abs(ref).max())))
+          got = gu.sorted_active(gu.npy(gp.x), gu.npy(gp.u), gu.npy(gp.active))
+          want = gu.sorted_active(tp.x[sl], tp.u[sl], tp.active[sl])
+          perr = float(np.abs(got - want).max()) if got.shape == want.shape and got.size else (0.0 if got.shape == want.shape else 1e9)
+          q.put((rank, err, perr, got.shape[0], want.shape[0], sim.overflow(), bool(fields[7])))
+      except Exception:
+        import traceback
+        q.put((rank, traceback.format_exc()))
+        raise
     finally:
         dist.destroy_process_group()
 
@@ -79,7 +84,9 @@ def test_distributed_resident_matches_oracle(mesh, sf, pbc):
     procs = [ctx.Process(target=_worker, args=(r, world, port, mesh, sf, pbc, 4, q)) for r in range(world)]
     for pr in procs:
         pr.start()
-    res = [q.get(timeout=300) for _ in range(world)]
+    res = [q.get(timeout=90) for _ in range(world)]
+    for r in res:
+        assert len(r) == 7, r[1]
     for pr in procs:
         pr.join(timeout=120)
         assert pr.exitcode == 0
