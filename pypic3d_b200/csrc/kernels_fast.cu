@@ -160,8 +160,14 @@ __global__ void __launch_bounds__(256) k_fused(const __grid_constant__ PicParams
 //    made the un-aggregated kernel L2-atomic-bound (profiles/r01_k1_versions.md);
 //  * the few particles that change anchor cell are queued in shared memory and deposited by full warps through the
 //    union-stencil body, so the common path stays branch-free.
+#ifndef PIC_K1_CTAS
+#define PIC_K1_CTAS 4   /* 64 registers; measured 5.31 ms vs 5.56 (3 CTAs) vs 6.22 (5, spills) per launch */
+#endif
+#ifndef PIC_K1_PREFETCH
+#define PIC_K1_PREFETCH 0   /* software prefetch of the next particle measured neutral-to-worse (5.37 vs 5.31 ms) */
+#endif
 template <typename T, int SF, int PUSHER, int STEPS>
-__global__ void __launch_bounds__(256, (SF == 1 ? 3 : 2)) k_fused3d(const __grid_constant__ PicParams p, int species, const __grid_constant__ Geom<T> gm,
+__global__ void __launch_bounds__(256, (SF == 1 ? PIC_K1_CTAS : 2)) k_fused3d(const __grid_constant__ PicParams p, int species, const __grid_constant__ Geom<T> gm,
                                                     const __grid_constant__ FastConst<T> k, SoAView<T> s, Field6<T> F, Field3W<T> J,
                                                     LeaveBuf leave, int distributed, int32_t* flags) {
     constexpr int NV = SameCell<SF>::NV, NN = SameCell<SF>::NN;
@@ -187,11 +193,33 @@ __global__ void __launch_bounds__(256, (SF == 1 ? 3 : 2)) k_fused3d(const __grid
     const int64_t per_block = ((n_total + (int64_t)gridDim.x * 256 - 1) / ((int64_t)gridDim.x * 256)) * 256;
     const int64_t b_begin = (int64_t)blockIdx.x * per_block;
     const int64_t w_end = (b_begin + per_block < n_total) ? b_begin + per_block : n_total;
+#if PIC_K1_PREFETCH
+    // software prefetch: the six particle words of the NEXT iteration are requested before the current particle is
+    // processed, so their DRAM latency overlaps ~1000 instructions of work
+    T cur[6];
+    {
+        const int64_t i0 = b_begin + warp * 32 + lane;
+#pragma unroll
+        for (int c = 0; c < 6; ++c) cur[c] = (i0 < w_end) ? s.c[c][i0] : pic_nan<T>();
+    }
+#endif
     for (int64_t base = b_begin + warp * 32; base < w_end; base += 256) {
         const int64_t i = base + lane;
         T vals[NV], po[3], xn[3], v[3];
         int key = 0, kind = 0;
+#if PIC_K1_PREFETCH
+        T nxt[6];
+        {
+            const int64_t in = i + 256;
+#pragma unroll
+            for (int c = 0; c < 6; ++c) nxt[c] = (in < w_end) ? s.c[c][in] : pic_nan<T>();
+        }
+        if (i < w_end) kind = fast3d_advance<T, SF, PUSHER, false>(p, species, k, i, s, F, X, leave, distributed != 0, flags, po, xn, v, key, vals, cur);
+#pragma unroll
+        for (int c = 0; c < 6; ++c) cur[c] = nxt[c];
+#else
         if (i < w_end) kind = fast3d_advance<T, SF, PUSHER, false>(p, species, k, i, s, F, X, leave, distributed != 0, flags, po, xn, v, key, vals);
+#endif
         // ---- deferred anchor-changing particles: warp-private queue
         const unsigned defer = __ballot_sync(0xffffffffu, kind == 2);
         if (defer) {
@@ -208,6 +236,14 @@ __global__ void __launch_bounds__(256, (SF == 1 ? 3 : 2)) k_fused3d(const __grid
 #pragma unroll
             for (int n = 0; n < NV; ++n) vals[n] = (T)0;
         }
+#if defined(PIC_ABLATE) && PIC_ABLATE == 1   /* profiling build: no scan, no RED (keeps vals alive through one store) */
+        {
+            T acc = (T)0;
+            for (int n = 0; n < NV; ++n) acc += vals[n];
+            if (acc == (T)1.2345e30) sink.J[0][0] = acc;
+            continue;
+        }
+#endif
         // ---- segmented inclusive scan over lanes with equal key (flag = "a segment head lies in (lane-d, lane]")
         const int key_prev = __shfl_up_sync(0xffffffffu, key, 1);
         const bool head = (gl == 0) || (key != key_prev);
@@ -342,7 +378,7 @@ static int launch_fused(const PicParams* p, int species, int deposition, const P
             steps = e ? atoi(e) : 3;   // measured best on B200 (profiles/r01_k1_versions.md)
             if (steps < 3 || steps > 5) steps = 3;
         }
-        const int gridk = grid_for(soa->n, 256, SF == 1 ? 9 : 8);
+        const int gridk = grid_for(soa->n, 256, SF == 1 ? 3 * PIC_K1_CTAS : 8);
 #define PIC_LAUNCH_K1(PUSH, ST) k_fused3d<T, SF, PUSH, ST><<<gridk, 256, 0, st>>>(*p, species, gm, k, sv, F, Jw, lb, distributed, flags)
         if (SF == 2 || steps == 3) {
             if (p->pusher == PIC_PUSHER_BORIS) PIC_LAUNCH_K1(PIC_PUSHER_BORIS, 3); else PIC_LAUNCH_K1(PIC_PUSHER_BORIS_REL, 3);

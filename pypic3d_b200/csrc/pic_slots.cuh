@@ -217,6 +217,13 @@ static inline LeaveBuf leave_of(const PicLeave* l) {
     return b;
 }
 
+// Sort key of a particle.  PIC_SORT_BLOCK > 1 orders cells in B x B x B blocks (block-major, row-major inside a block) so that a
+// CTA's 256 consecutive particles span a compact 3-D neighbourhood and the E/B stencil is reused in all three directions from
+// L1/L2; requires every tile width to be a multiple of B, otherwise plain row-major (z fastest) order is used.  Both orders keep
+// all particles of one cell contiguous, which is all the deposit aggregation needs.
+#ifndef PIC_SORT_BLOCK
+#define PIC_SORT_BLOCK 4
+#endif
 template <typename T>
 PIC_HD int local_cell(const PicParams& p, T px, T py, T pz) {
     if (pic_isnan(px)) return p.tile[0] * p.tile[1] * p.tile[2];  // dead -> trash bin at the end
@@ -226,6 +233,12 @@ PIC_HD int local_cell(const PicParams& p, T px, T py, T pz) {
     for (int a = 0; a < 3; ++a) {
         int cell = (int)pic_floor((pos[a] + (T)0.5 * (T)p.wind[a]) / dd[a]) - p.moff[a] * p.tile[a];
         c[a] = cell < 0 ? 0 : (cell > p.tile[a] - 1 ? p.tile[a] - 1 : cell);
+    }
+    constexpr int B = PIC_SORT_BLOCK;
+    if (B > 1 && p.tile[0] % B == 0 && p.tile[1] % B == 0 && p.tile[2] % B == 0) {
+        const int nby = p.tile[1] / B, nbz = p.tile[2] / B;
+        const int blk = ((c[0] / B) * nby + (c[1] / B)) * nbz + (c[2] / B);
+        return blk * (B * B * B) + ((c[0] % B) * B + (c[1] % B)) * B + (c[2] % B);
     }
     return (c[0] * p.tile[1] + c[1]) * p.tile[2] + c[2];
 }
@@ -569,12 +582,13 @@ struct SameCell {
 template <typename T, int SF, int PUSHER, bool HAS_EXT>
 PIC_HD int fast3d_advance(const PicParams& p, int species, const FastConst<T>& k, int64_t i, const SoAView<T>& s, const Field6<T>& F,
                           const Field6<T>& X, const LeaveBuf& leave, bool distributed, int32_t* flags, T pos_old[3], T xn[3], T vout[3],
-                          int& key, T* vals) {
+                          int& key, T* vals, const T* pre = nullptr) {
     constexpr int NN = SF + 1;
     constexpr int K0 = (SF == 1) ? 1 : 0;
-    T pos[3] = {s.c[0][i], s.c[1][i], s.c[2][i]};
+    // `pre`: x,y,z,vx,vy,vz of particle i already loaded by the caller (software prefetch of the next iteration)
+    T pos[3] = {pre ? pre[0] : s.c[0][i], pre ? pre[1] : s.c[1][i], pre ? pre[2] : s.c[2][i]};
     if (pic_isnan(pos[0])) return 0;
-    T v[3] = {s.c[3][i], s.c[4][i], s.c[5][i]};
+    T v[3] = {pre ? pre[3] : s.c[3][i], pre ? pre[4] : s.c[4][i], pre ? pre[5] : s.c[5][i]};
     // ---- stencils of the old position on the center and vertex lines
     int ac[3], av[3];
     T wc[3][3], wv[3][3];
@@ -633,6 +647,10 @@ PIC_HD int fast3d_advance(const PicParams& p, int species, const FastConst<T>& k
 #else
     // ---- gather: Ex(v,c,c) Ey(c,v,c) Ez(c,c,v) Bx(c,v,v) By(v,c,v) Bz(v,v,c)
     T EB[6];
+#if defined(PIC_ABLATE) && PIC_ABLATE == 2   /* profiling build: no gather */
+    for (int c = 0; c < 6; ++c) EB[c] = (T)(ac[c % 3] + av[c % 3]) * wc[0][1];
+    if (false)
+#endif
     {
         int bc_[3], bv_[3];   // clamped first stencil index (memory safety only; owned particles never clamp for g >= 2)
 #pragma unroll
