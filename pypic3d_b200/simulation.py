@@ -97,6 +97,7 @@ class Simulation:
         self.cap_ref = int(x.shape[4])
         self.track_ids = bool(track_ids)
         self._import(particles, capacity_factor)
+        self.sort_every = self._sort_intervals(particles)
         self.leave_fraction = float(leave_fraction)
         if self.distributed:
             self._alloc_packets()
@@ -176,7 +177,22 @@ class Simulation:
             check(L.pic_soa_import(ctypes.byref(self.p), s, ops._p(x), ops._p(u), ops._p(a), self.cap_ref, ctypes.byref(soa),
                                    ops._p(sp_.n_dev), st), "pic_soa_import")
 
+    def _sort_intervals(self, particles):
+        """Per-species sort cadence: `sort_interval` for the fastest species, proportionally longer (up to 20x) for species
+        whose rms displacement per step is smaller -- a heavy, cold species stays cell-sorted far longer than electrons.
+        Sorting never changes results (only memory order), so this is purely a cost knob.  Multi-GPU runs keep the base
+        interval for every species because the sort is also what compacts migrated slots."""
+        base = max(1, self.sort_interval)
+        if self.sort_interval <= 0 or self.distributed or particles.x.shape[4] == 0:
+            return [base] * self.S
+        a = particles.active.reshape(self.S, -1)
+        v2 = (particles.u.to(torch.float64) ** 2).sum(-1).reshape(self.S, -1)
+        vrms = torch.sqrt((v2 * a).sum(1) / a.sum(1).clamp(min=1)).tolist()
+        vmax = max(vrms) if max(vrms) > 0 else 1.0
+        return [int(min(20 * base, max(base, round(base * vmax / v)))) if v > 0 else 20 * base for v in vrms]
+
     def load_state(self, particles, fields3=None):
+        self._J_ghosts_stale = False
         """Replace the resident state from reference-layout pytrees (same shapes as at construction); re-sorts."""
         self._import(particles, 1.0)
         if fields3 is not None:
@@ -185,12 +201,15 @@ class Simulation:
                     d.copy_(ops._chk(s_, "field", self.dtype))
         self.sort()
 
-    def sort(self):
-        """K2: counting sort of every species by local cell; also compacts dead (absorbed / migrated) slots away."""
+    def sort(self, which=None):
+        """K2: counting sort of the given species (default: all) by local cell; also compacts dead (absorbed / migrated)
+        slots away."""
         L = _lib.lib()
         st = ops._stream()
         n = self.ncells + 1
-        for sp_ in self.species:
+        for s, sp_ in enumerate(self.species):
+            if which is not None and s not in which:
+                continue
             src, dst = self._soa(sp_), self._soa(sp_, 1 - sp_.cur)
             self._cell_count.zero_()
             check(L.pic_sort_histogram(ctypes.byref(self.p), ctypes.byref(src), ops._p(self._cell_count), st), "pic_sort_histogram")
@@ -231,10 +250,13 @@ class Simulation:
         self.halo.migrate(self)
         # J: fold ghost deposits to their owners, then refresh (Esirkepov.py:357-359 / J_from_rhov.py:226-228)
         self.halo.fold_(self.J, pbc)
-        self.halo.refresh_(self.J, pbc)
         if self.current_filter in ("bilinear", "digital"):                       # J_from_rhov.py:234-255
-            self.J = [ops.filter27(p, self.current_filter, self.alpha, c) for c in self.J]
             self.halo.refresh_(self.J, pbc)
+            self.J = [ops.filter27(p, self.current_filter, self.alpha, c) for c in self.J]
+        # update_E reads J on the tile interior only, so the ghost refresh the reference performs here
+        # (Esirkepov.py:359 / J_from_rhov.py:228,246) is deferred until somebody looks at J (export_state): one guard-cell
+        # exchange less per step; the exported J is identical.
+        self._J_ghosts_stale = True
         # B half step from E_old (evolve.py:88); E halos are valid from the previous step
         ops.update_B_(p, self.B, self.E)
         self.halo.refresh_(self.B, fbc)
@@ -259,8 +281,10 @@ class Simulation:
             self.B = [ops.filter27(p, "digital", self.alpha, c) for c in self.B]
         self.halo.refresh_(self.B, fbc)
         self.step_count += 1
-        if self.sort_interval > 0 and self.step_count % self.sort_interval == 0:
-            self.sort()
+        if self.sort_interval > 0:
+            due = [s for s in range(self.S) if self.step_count % self.sort_every[s] == 0]
+            if due:
+                self.sort(due)
 
     # ------------------------------------------------------------------------------------------ results
     def overflow(self):
@@ -299,6 +323,9 @@ class Simulation:
             live = self._counter[:self.S].cpu().tolist()
             if any(int(n) > cap for n in live):          # fixed-capacity contract of the reference layout (:169-230)
                 self.flags[0:1] |= 2
+        if getattr(self, "_J_ghosts_stale", False):
+            self.halo.refresh_(self.J, tuple(self.p.particle_bc))
+            self._J_ghosts_stale = False
         rho, phi, ext = self._passthrough
         overflow = torch.tensor(self.overflow(), device=self.device)
         fields = (tuple(c.clone() for c in self.E), tuple(c.clone() for c in self.B), tuple(c.clone() for c in self.J), rho, phi, ext,
