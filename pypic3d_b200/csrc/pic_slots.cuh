@@ -376,6 +376,7 @@ struct FastConst {
     int pbc[3];
     int upd_x[3], upd_u[3];
     T box_lo[3], box_hi[3];   // local subdomain [lo, hi) on axes split across ranks (+-inf elsewhere)
+    long long rowoff[3][3];   // byte offset of stencil row (a, b): (a * sx + b * sy) * sizeof(T)
 };
 
 template <typename T>
@@ -408,6 +409,8 @@ PIC_HD void make_fast_const(const PicParams& p, int species, const Geom<T>& gm, 
     k.inv_C2 = (T)1 / k.C2;
     k.sx = gm.L[1] * gm.L[2];
     k.sy = gm.L[2];
+    for (int a = 0; a < 3; ++a)
+        for (int b = 0; b < 3; ++b) k.rowoff[a][b] = ((long long)a * k.sx + (long long)b * k.sy) * (long long)sizeof(T);
 }
 
 // 1/sqrt(x) and a/b for the push: f32 on the device uses the SFU approximations (<= 2 ulp; the f32 parity tolerance is
@@ -416,7 +419,7 @@ PIC_HD void make_fast_const(const PicParams& p, int species, const Geom<T>& gm, 
 #define PIC_FASTMATH 0   /* measured slower on B200 (profiles/r01_k1_versions.md): the kernel is latency-, not issue-bound */
 #endif
 #ifndef PIC_GATHER_V
-#define PIC_GATHER_V 0   /* 0: pointer + int base (immediate offsets), 1: unsigned offsets; 0 measured faster */
+#define PIC_GATHER_V 2   /* 2: 64-bit row offsets from the constant bank (4.88 ms); 0: pointer + int row (5.15 ms); 1: u32 offsets (slower) */
 #endif
 PIC_HD float pic_rsqrt(float x) {
 #if defined(__CUDA_ARCH__) && PIC_FASTMATH
@@ -450,17 +453,32 @@ PIC_HD void axis_stencil_rcp(T pos, T o, T s, T inv_s, T inv_d, int& a, T w[3]) 
     }
 }
 
+#ifndef PIC_WRAP_V
+#define PIC_WRAP_V 1   /* measured 5.15 vs 5.31 ms per K1 launch */
+#endif
 template <typename T>
 PIC_HD T wrap_periodic_fast(T x, T wind) {
     // bit-identical to wrap_periodic for -wind <= x + h < 2 wind (fmod is exact there); general fallback otherwise
     const T h = (T)0.5 * wind;
     T t = x + h;
+#if PIC_WRAP_V == 1
+    // one rarely-taken branch: interior particles only pay (x + h) - h, exactly what the reference's mod() leaves them with
+    if (t >= wind || t < (T)0) {
+        if (t >= (T)2 * wind || t < -wind) return wrap_periodic(x, wind);
+        t = (t >= wind) ? t - wind : t + wind;
+        if (t >= wind) t -= wind;
+        const T w = t - h;
+        return (w == -h && x >= h) ? h : w;
+    }
+    return t - h;
+#else
     if (t >= (T)2 * wind || t < -wind) return wrap_periodic(x, wind);   // never taken for |v| dt < wind
     const T up = t - wind, dn = t + wind;
     t = (t >= wind) ? up : ((t < (T)0) ? ((dn >= wind) ? dn - wind : dn) : t);
     T w = t - h;
     w = (w == -h && x >= h) ? h : w;
     return w;
+#endif
 }
 
 // Esirkepov deposit on the union stencil of NS = SF+2 nodes per axis based at min(a_old, a_new) (- 1 for TSC): handles any
@@ -597,7 +615,54 @@ PIC_HD int fast3d_advance(const PicParams& p, int species, const FastConst<T>& k
         axis_stencil_rcp<T, SF>(pos[a], k.oc[a], k.sc[a], k.inv_sc[a], k.inv_d[a], ac[a], wc[a]);
         axis_stencil_rcp<T, SF>(pos[a], k.ov[a], k.sv[a], k.inv_sv[a], k.inv_d[a], av[a], wv[a]);
     }
-#if PIC_GATHER_V == 1
+#if PIC_GATHER_V == 2
+    // ---- gather: Ex(v,c,c) Ey(c,v,c) Ez(c,c,v) Bx(c,v,v) By(v,c,v) Bz(v,v,c)
+    // One 64-bit base pointer per component; the 3x3 stencil rows are reached by adding 64-bit byte offsets that live in the
+    // constant bank (2 integer instructions per row), the z neighbours by immediate offsets.
+    T EB[6];
+    {
+        int bc_[3], bv_[3];   // clamped first stencil index (memory safety only; owned particles never clamp for g >= 2)
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            const int hi = k.L[a] - 3;
+            int c0 = ac[a] - 1, v0 = av[a] - 1;
+            c0 = c0 < hi ? c0 : hi; c0 = c0 > 0 ? c0 : 0;
+            v0 = v0 < hi ? v0 : hi; v0 = v0 > 0 ? v0 : 0;
+            bc_[a] = c0; bv_[a] = v0;
+        }
+        const int GT[6][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}, {0, 1, 1}, {1, 0, 1}, {1, 1, 0}};
+#pragma unroll
+        for (int c = 0; c < 6; ++c) {
+            const int gx = GT[c][0], gy = GT[c][1], gz = GT[c][2];
+            const T* wx = gx ? wv[0] : wc[0];
+            const T* wy = gy ? wv[1] : wc[1];
+            const T* wz = gz ? wv[2] : wc[2];
+            const int base = ((gx ? bv_[0] : bc_[0]) * k.sx) + ((gy ? bv_[1] : bc_[1]) * k.sy) + (gz ? bv_[2] : bc_[2]);
+            const char* f = (const char*)(F.f[c] + base);
+            const char* fx = HAS_EXT ? (const char*)(X.f[c] + base) : nullptr;
+            T acc = (T)0;
+#pragma unroll
+            for (int a_ = K0; a_ < 3; ++a_) {
+                T ai = (T)0;
+#pragma unroll
+                for (int b_ = K0; b_ < 3; ++b_) {
+                    const T* r = (const T*)(f + k.rowoff[a_][b_]);
+                    const T* rx = HAS_EXT ? (const T*)(fx + k.rowoff[a_][b_]) : nullptr;
+                    T aj = (T)0;
+#pragma unroll
+                    for (int c_ = K0; c_ < 3; ++c_) {
+                        T val = ld_ro(r + c_);
+                        if (HAS_EXT) val += ld_ro(rx + c_);
+                        aj += val * wz[c_];
+                    }
+                    ai += aj * wy[b_];
+                }
+                acc += ai * wx[a_];
+            }
+            EB[c] = acc;
+        }
+    }
+#elif PIC_GATHER_V == 1
     // ---- gather: Ex(v,c,c) Ey(c,v,c) Ez(c,c,v) Bx(c,v,v) By(v,c,v) Bz(v,v,c)
     // Offsets are unsigned 32-bit element indices from the component base pointers (which live in the constant bank), so
     // each load is one "uniform base + 32-bit offset" LDG instead of a 64-bit address computation per row.
