@@ -163,6 +163,9 @@ __global__ void __launch_bounds__(256) k_fused(const __grid_constant__ PicParams
 #ifndef PIC_K1_CTAS
 #define PIC_K1_CTAS 4   /* 64 registers; measured 5.31 ms vs 5.56 (3 CTAs) vs 6.22 (5, spills) per launch */
 #endif
+#ifndef PIC_DEPOSIT_V
+#define PIC_DEPOSIT_V 0   /* CIC same-cell deposit: 0 = segmented warp scan (4.88 ms); 1 = run-cooperative reduction through shared memory (9.0 ms: the per-run work split diverges badly when cell-changers cut the runs) */
+#endif
 #ifndef PIC_K1_PREFETCH
 #define PIC_K1_PREFETCH 0   /* software prefetch of the next particle measured neutral-to-worse (5.37 vs 5.31 ms) */
 #endif
@@ -177,6 +180,9 @@ __global__ void __launch_bounds__(256, (SF == 1 ? PIC_K1_CTAS : 2)) k_fused3d(co
     constexpr int NWARP = 8;
     __shared__ T q_old[NWARP][3][QW];
     __shared__ T q_new[NWARP][3][QW];
+    constexpr bool COOP = (SF == 1) && (PIC_DEPOSIT_V == 1) && (sizeof(T) == 4);   // f64 would exceed the 48 KB static smem
+    constexpr int NVP = NV + 1;                       // odd row stride: conflict-free for both the writes and the run reads
+    __shared__ T vbuf[COOP ? NWARP : 1][COOP ? 32 : 1][COOP ? NVP : 1];
     TileSink<T> sink;
     for (int c = 0; c < 3; ++c) { sink.J[c] = J.f[c]; sink.L[c] = gm.L[c]; }
     sink.off = 0;
@@ -244,34 +250,61 @@ __global__ void __launch_bounds__(256, (SF == 1 ? PIC_K1_CTAS : 2)) k_fused3d(co
             continue;
         }
 #endif
-        // ---- segmented inclusive scan over lanes with equal key (flag = "a segment head lies in (lane-d, lane]")
-        const int key_prev = __shfl_up_sync(0xffffffffu, key, 1);
-        const bool head = (gl == 0) || (key != key_prev);
-        int flag = head ? 1 : 0;
+        if (COOP) {
+            // ---- run-cooperative reduction: every lane parks its same-cell values in shared memory; the lanes of one run
+            // (consecutive particles of the same cell) then split the NV sums of that run between them: lane `pos` of a run of
+            // length `len` sums values pos, pos+len, ... over the run and issues those REDs.  ~NV loads+adds per lane whatever
+            // the run length, instead of 3 shuffle steps x NV values.
 #pragma unroll
-        for (int d = 1; d < G; d <<= 1) {
-            const int fo = __shfl_up_sync(0xffffffffu, flag, d);
-            const bool take = (gl >= d) && (flag == 0);
-#pragma unroll
-            for (int n = 0; n < NV; ++n) {
-                const T o = __shfl_up_sync(0xffffffffu, vals[n], d);
-                vals[n] += take ? o : (T)0;
+            for (int n = 0; n < NV; ++n) vbuf[warp][lane][n] = vals[n];
+            const int key_prev = __shfl_up_sync(0xffffffffu, key, 1);
+            const bool head = (lane == 0) || (key != key_prev);
+            const unsigned heads = __ballot_sync(0xffffffffu, head);
+            __syncwarp();
+            if (key >= 0) {
+                const int start = 31 - __clz(heads & (0xffffffffu >> (31 - lane)));
+                const unsigned above = (lane == 31) ? 0u : (heads >> (lane + 1));
+                const int end = above ? lane + __ffs(above) - 1 : 31;
+                const int len = end - start + 1;
+                for (int n = lane - start; n < NV; n += len) {
+                    T sum = (T)0;
+                    for (int l = start; l <= end; ++l) sum += vbuf[warp][l][n];
+                    const int c = n / (NV / 3), r = n % (NV / 3);
+                    const int f = r / (NN * NN), m1 = (r / NN) % NN, m2 = r % NN;
+                    atomicAdd(sink.J[c] + key + SameCell<SF>::offset(c, f, m1, m2, k.sx, k.sy), sum);
+                }
             }
-            if (take) flag |= fo;
-        }
-        const int head_next = __shfl_down_sync(0xffffffffu, head ? 1 : 0, 1);
-        const bool tail = (gl == G - 1) || (head_next != 0);
-        if (tail && key >= 0) {
-            int n = 0;
+            __syncwarp();
+        } else {
+        // ---- segmented inclusive scan over lanes with equal key (flag = "a segment head lies in (lane-d, lane]")
+            const int key_prev = __shfl_up_sync(0xffffffffu, key, 1);
+            const bool head = (gl == 0) || (key != key_prev);
+            int flag = head ? 1 : 0;
 #pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                T* Jc = sink.J[c] + key;
+            for (int d = 1; d < G; d <<= 1) {
+                const int fo = __shfl_up_sync(0xffffffffu, flag, d);
+                const bool take = (gl >= d) && (flag == 0);
 #pragma unroll
-                for (int f = 0; f < NN - 1; ++f)
+                for (int n = 0; n < NV; ++n) {
+                    const T o = __shfl_up_sync(0xffffffffu, vals[n], d);
+                    vals[n] += take ? o : (T)0;
+                }
+                if (take) flag |= fo;
+            }
+            const int head_next = __shfl_down_sync(0xffffffffu, head ? 1 : 0, 1);
+            const bool tail = (gl == G - 1) || (head_next != 0);
+            if (tail && key >= 0) {
+                int n = 0;
 #pragma unroll
-                    for (int m1 = 0; m1 < NN; ++m1)
+                for (int c = 0; c < 3; ++c) {
+                    T* Jc = sink.J[c] + key;
 #pragma unroll
-                        for (int m2 = 0; m2 < NN; ++m2) atomicAdd(Jc + SameCell<SF>::offset(c, f, m1, m2, k.sx, k.sy), vals[n++]);
+                    for (int f = 0; f < NN - 1; ++f)
+#pragma unroll
+                        for (int m1 = 0; m1 < NN; ++m1)
+#pragma unroll
+                            for (int m2 = 0; m2 < NN; ++m2) atomicAdd(Jc + SameCell<SF>::offset(c, f, m1, m2, k.sx, k.sy), vals[n++]);
+                }
             }
         }
         // ---- flush the warp queue with a (nearly) full warp
