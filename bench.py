@@ -251,8 +251,11 @@ def main():
         halo_factory = lambda p: DistributedHalo(p, dist.group.WORLD, device)
     else:
         halo_factory = None
+    # track_ids=False: exported particles come back compacted in cell order instead of their original slots (any slot
+    # order is a valid TiledParticles state; the reference itself re-slots particles when they migrate), so the state a
+    # caller feeds back in the e2e loop is already nearly sorted.
     sim = Simulation(particles, species, fields, sp, dp, sort_interval=args.sort_interval, gmesh=mesh, moff=moff,
-                     halo=halo_factory, capacity_factor=1.25 if world > 1 else 1.02)
+                     halo=halo_factory, capacity_factor=1.25 if world > 1 else 1.02, track_ids=False)
     n_local_particles = sim.n_particles()
     del particles
     torch.cuda.empty_cache()

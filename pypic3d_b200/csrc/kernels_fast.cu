@@ -287,7 +287,7 @@ __global__ void __launch_bounds__(256, (SF == 1 ? PIC_K1_CTAS : 2)) k_fused3d(co
 #pragma unroll
                 for (int n = 0; n < NV; ++n) {
                     const T o = __shfl_up_sync(0xffffffffu, vals[n], d);
-                    vals[n] += take ? o : (T)0;
+                    if (take) vals[n] += o;      // predicated add (one instruction instead of select + add)
                 }
                 if (take) flag |= fo;
             }

@@ -327,6 +327,31 @@ def test_resident_simulation_matches_oracle(c, dtype, sort_interval):
     assert sim.overflow() == bool(fields[7])
 
 
+@pytest.mark.parametrize("c", STEP_CASES[:3])
+def test_resident_without_slot_ids(c):
+    """track_ids=False (the bench configuration): particles come back compacted in cell order; same set of particles."""
+    from pypic3d_b200.simulation import Simulation
+    c = dict(c, tile=c["N"])
+    sp, dp, tp, sc, fields = _step_setup(c)
+    ps, pd = gu.to_pkg_params(sp, dp)
+    sim = Simulation(gu.particles_to_gpu(tp), gu.species_to_pkg(sc), gu.fields_to_gpu(fields), ps, pd, sort_interval=2, track_ids=False)
+    for _ in range(3):
+        tp, fields = oevolve.time_loop_electrodynamic(tp, sc, fields, sp, dp)
+    sim.step(3)
+    gp, gf = sim.export_state()
+    for s in range(tp.x.shape[3]):
+        got = gu.sorted_active(gu.npy(gp.x)[:, :, :, s], gu.npy(gp.u)[:, :, :, s], gu.npy(gp.active)[:, :, :, s])
+        want = gu.sorted_active(tp.x[:, :, :, s], tp.u[:, :, :, s], tp.active[:, :, :, s])
+        assert got.shape == want.shape and np.abs(got - want).max() < 1e-10
+    for k in range(3):
+        for a, b in zip(gf[k], fields[k]):
+            gu.assert_close(a, b, 1e-11, "EBJ"[k])
+    # and the exported state can be loaded back
+    sim.load_state(gp, (gf[0], gf[1], gf[2]))
+    sim.step(1)
+    assert not sim.overflow()
+
+
 @pytest.mark.parametrize("sf", (1, 2))
 def test_resident_with_external_fields(sf):
     from pypic3d_b200.simulation import Simulation
