@@ -315,12 +315,13 @@ def main():
     if os.path.exists(tpath):
         tj = json.load(open(tpath))
         c = tj["config"]
-        if (c["n"], c["ppc"], c["dtype"], c["shape_factor"]) == (args.n, args.ppc, args.dtype, args.shape_factor):
+        if (c["n"], c["ppc"], c["dtype"], c["shape_factor"], c.get("k1_variant", "global")) == (args.n, args.ppc, args.dtype, args.shape_factor, sim.k1_variant):
             traffic = (tj["dram_bytes_read"] + tj["dram_bytes_write"]) * per_launch_particles / tj["particles_per_launch"]
     roof = None
     if k1_avg_ms:
         achieved = k1_bytes_pp * per_launch_particles / (k1_avg_ms * 1e-3) / 1e9
-        roof = {"bound": "hbm", "kernel": "k_fused (K1: gather+push+deposit+move+BC, one species per launch)", "achieved": achieved,
+        kname = "k_tile3d (K1 v9: supercell E/B tiles in shared memory" if sim.k1_variant == "tile" else "k_fused3d (K1 v8: global gather"
+        roof = {"bound": "hbm", "kernel": kname + "; gather+push+deposit+move+BC, one species per launch)", "achieved": achieved,
                 "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": "profiles/r01_k1_traffic.json (ncu dram__bytes_read+write, bytes per launch)" if traffic else None,
                 "algorithmic_bytes_per_launch": k1_bytes_pp * per_launch_particles, "peak_source": peak_src,
                 "algorithmic_bytes_per_particle": k1_bytes_pp, "avg_launch_ms": k1_avg_ms,
@@ -347,6 +348,7 @@ def main():
                 "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
                 "config": workload_config(args, n_gpus), "particles": total_particles, "overflow": overflow,
                 "roofline": roof, "roofline_step": roof_step, "cpu_baseline": cpu_base, "e2e": e2e, "gpu_launches": launches,
+                "k1_variant": sim.k1_variant, "k1_global_fallback_particles": int(sim.flags[2].item()),
                 "clocks": sampler.summary() if sampler else None}
         if check is not None:
             line["check"] = check

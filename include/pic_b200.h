@@ -185,6 +185,19 @@ int pic_fused_push_deposit(const PicParams* p, int species, int deposition, cons
                            const void* const extB[3], void* const J[3], const PicLeave* leave, int32_t* flags,
                            void* stream);
 
+/* K1 v9, the supercell tile variant of pic_fused_push_deposit for the headline configuration (Esirkepov, CIC, all three axes
+ * active, g == 2, every tile width a multiple of 4, Boris or relativistic Boris, no external fields): same result, but each CTA
+ * stages the 8x8x8-node E/B neighbourhood of one 4x4x4-cell supercell in shared memory (cp.async, double-buffered) and the
+ * gather reads it from there.  blk_off: int32[nblk+1] device array, blk_off[b] = first slot of supercell b in the cell-sorted
+ * SoA = cell_offset[64*b] of the last pic_sort_scan (nblk = tile[0]*tile[1]*tile[2]/64); slots >= blk_off[nblk] (appended since
+ * the sort) and particles that drifted more than one cell out of their supercell take the global-memory body, so the result
+ * does not depend on how stale the sort is.  flags: int32[>=3]; flags[0] as for pic_fused_push_deposit, flags[2] counts the
+ * particles that took the global-memory body.  Returns PIC_EUNSUPPORTED for any other configuration (call
+ * pic_fused_push_deposit instead).  Replaces, like pic_fused_push_deposit, evolve.py:33-79. */
+int pic_fused_tile3d(const PicParams* p, int species, const PicSoA* soa, const int32_t* blk_off, int nblk,
+                     const void* const E[3], const void* const B[3], void* const J[3], const PicLeave* leave, int32_t* flags,
+                     void* stream);
+
 /* Zero the 27 packet headers of `leave` (before K1 of a step). */
 int pic_packets_reset(const PicParams* p, const PicLeave* leave, void* stream);
 /* Append every received packet of `recv` (same layout as PicLeave) to the SoA tail, advancing soa->n_dev on the device. */

@@ -321,6 +321,200 @@ __global__ void __launch_bounds__(256, (SF == 1 ? PIC_K1_CTAS : 2)) k_fused3d(co
     }
 }
 
+// ---------------------------------------------------------------- K1 v9: supercell tile kernel (CIC)
+// The blocked sort order keeps the particles of one 4x4x4-cell supercell contiguous; `blk_off` (from the last sort) delimits
+// them.  A CTA walks a contiguous range of supercells.  For each one it stages the 8x8x8-node E/B neighbourhood of all six
+// components in shared memory with 16-byte cp.async copies (double-buffered: the next supercell's tile is in flight while the
+// current one is processed), and the per-particle gather becomes 48 shared-memory loads with constant offsets from one
+// 32-bit base per component -- no 64-bit address arithmetic, no L1 misses on the critical path.  Particles drift between
+// sorts; the tile carries a one-cell margin, and a particle that left it (kind 3) takes the global-memory body, so the
+// result never depends on how well the stream is sorted.  Push, same-cell deposit (segmented warp scan + RED), deferred
+// cell-crossers, move, BCs and leaver packets are the v8 code.
+#ifndef PIC_K9_CTAS
+#define PIC_K9_CTAS 4
+#endif
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+
+// Segmented inclusive scan (depth STEPS) of the same-cell current values over lanes with equal key; the last lane of every run
+// issues the REDs.  (flag = "a segment head lies in (lane-d, lane]")
+template <typename T, int SF, int STEPS>
+__device__ __forceinline__ void same_cell_scan_red(T* vals, int key, int lane, const TileSink<T>& sink, int sx, int sy) {
+    constexpr int NV = SameCell<SF>::NV, NN = SameCell<SF>::NN;
+    constexpr int G = 1 << STEPS;
+    const int gl = lane & (G - 1);
+    const int key_prev = __shfl_up_sync(0xffffffffu, key, 1);
+    const bool head = (gl == 0) || (key != key_prev);
+    int flag = head ? 1 : 0;
+#pragma unroll
+    for (int d = 1; d < G; d <<= 1) {
+        const int fo = __shfl_up_sync(0xffffffffu, flag, d);
+        const bool take = (gl >= d) && (flag == 0);
+#pragma unroll
+        for (int n = 0; n < NV; ++n) {
+            const T o = __shfl_up_sync(0xffffffffu, vals[n], d);
+            if (take) vals[n] += o;      // predicated add (one instruction instead of select + add)
+        }
+        if (take) flag |= fo;
+    }
+    const int head_next = __shfl_down_sync(0xffffffffu, head ? 1 : 0, 1);
+    const bool tail = (gl == G - 1) || (head_next != 0);
+    if (tail && key >= 0) {
+        int n = 0;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            T* Jc = sink.J[c] + key;
+#pragma unroll
+            for (int f = 0; f < NN - 1; ++f)
+#pragma unroll
+                for (int m1 = 0; m1 < NN; ++m1)
+#pragma unroll
+                    for (int m2 = 0; m2 < NN; ++m2) atomicAdd(Jc + SameCell<SF>::offset(c, f, m1, m2, sx, sy), vals[n++]);
+        }
+    }
+}
+
+template <typename T, int PUSHER, int STEPS, int NW>
+__global__ void __launch_bounds__(NW * 32, (sizeof(T) == 8 ? 3 : PIC_K9_CTAS)) k_tile3d(const __grid_constant__ PicParams p, int species, const __grid_constant__ Geom<T> gm,
+                                                   const __grid_constant__ FastConst<T> k, SoAView<T> s, const __grid_constant__ Field6<T> F, Field3W<T> J,
+                                                   LeaveBuf leave, int distributed, int32_t* flags,
+                                                   const int32_t* __restrict__ blk_off, int nblk, int nby, int nbz) {
+    constexpr int SF = 1;
+    constexpr int NV = SameCell<SF>::NV;
+    constexpr int NT = NW * 32;
+    constexpr int QW = 64;                                   // per-warp queue of anchor-changing particles (flushed at >= 32)
+    constexpr int EPC = 16 / (int)sizeof(T);                 // elements per 16-byte copy
+    constexpr int CPR = TILE_N / EPC;                        // copies per z row: 2 (f32) / 4 (f64)
+    constexpr int CPC = TILE_N * TILE_N * CPR;               // copies per component
+    static_assert(NT % CPC == 0 && 6 % (NT / CPC) == 0, "a staging pass must cover whole components");
+    constexpr int CPP = NT / CPC;                            // components per pass
+    constexpr int PER_T = 6 / CPP;                           // copies per thread and tile: 3 (f32) / 6 (f64) with 256 threads
+    constexpr int TILE_ALL = 6 * TILE_ELEMS;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T* tiles = reinterpret_cast<T*>(smem_raw);               // [2][6][8][8][8]
+    T* q_old = tiles + 2 * TILE_ALL;                         // [NW][3][QW]
+    T* q_new = q_old + NW * 3 * QW;
+    TileSink<T> sink;
+    for (int c = 0; c < 3; ++c) { sink.J[c] = J.f[c]; sink.L[c] = gm.L[c]; }
+    sink.off = 0;
+    Field6<T> X;
+    for (int c = 0; c < 6; ++c) X.f[c] = nullptr;
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int warp = tid >> 5;
+    T* qo = q_old + warp * 3 * QW;
+    T* qn_ = q_new + warp * 3 * QW;
+    int qn = 0;                                              // warp-uniform queue fill
+    const int per_cta = (nblk + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int b0 = (int)blockIdx.x * per_cta;
+    int b1 = (b0 + per_cta < nblk) ? b0 + per_cta : nblk;
+    if (b1 < b0) b1 = b0;
+    // per-thread staging constants: the CTA copies CPP whole components per pass; this thread always moves the same 16-byte
+    // piece (row, part) of component c0 + j * CPP
+    const int c0 = tid / CPC;
+    int src_off, dst_off;
+    {
+        const int r = tid % CPC;
+        const int row = r / CPR, part = r % CPR;
+        src_off = ((row / TILE_N) * gm.L[1] + (row % TILE_N)) * gm.L[2] + part * EPC;
+        dst_off = c0 * TILE_ELEMS + row * TILE_N + part * EPC;
+    }
+    const int n_live = (int)s.count();
+    auto stage = [&](int bx, int by, int bz, int buf) {
+        // g == 2: the tile's first node is the supercell's first cell
+        const int64_t base = ((int64_t)(bx * TILE_B) * gm.L[1] + by * TILE_B) * gm.L[2] + bz * TILE_B + src_off;
+        T* dst = tiles + buf * TILE_ALL + dst_off;
+#pragma unroll
+        for (int j = 0; j < PER_T; ++j) cp_async16(dst + j * CPP * TILE_ELEMS, F.f[c0 + j * CPP] + base);
+        cp_async_commit();
+    };
+    int cz = b0 % nbz, cy = (b0 / nbz) % nby, cx = b0 / (nbz * nby);
+    int off_cur = 0, off_next = 0;
+    if (b0 < b1) {
+        stage(cx, cy, cz, 0);
+        off_cur = blk_off[b0]; off_next = blk_off[b0 + 1];
+    }
+    // iteration b == b1 is the tail pass: this CTA's share of the slots appended since the last sort (particles received from
+    // neighbour ranks, ~1e-4 of the stream per step).  They are not binned; an impossible tile origin sends them through
+    // the global-memory gather of the same body.
+    for (int b = b0; b <= b1; ++b) {
+        const bool tail_pass = (b == b1);
+        const int buf = (b - b0) & 1;
+        TileSrc<T> ts;
+        ts.t = tiles + buf * TILE_ALL;
+        int p_beg, p_end;
+        if (!tail_pass) {
+            int nx = cx, ny = cy, nz = cz + 1;
+            if (nz == nbz) { nz = 0; if (++ny == nby) { ny = 0; ++nx; } }
+            const int off_nn = (b + 2 <= nblk) ? blk_off[b + 2] : off_next;    // requested one supercell ahead of its use
+            if (b + 1 < b1) { stage(nx, ny, nz, buf ^ 1); cp_async_wait<1>(); }
+            else cp_async_wait<0>();
+            ts.o[0] = cx * TILE_B; ts.o[1] = cy * TILE_B; ts.o[2] = cz * TILE_B;
+            p_beg = off_cur;
+            p_end = (off_next < n_live) ? off_next : n_live;
+            off_cur = off_next; off_next = off_nn;
+            cx = nx; cy = ny; cz = nz;
+        } else {
+            const int tail0 = blk_off[nblk];
+            const int ntail = n_live > tail0 ? n_live - tail0 : 0;
+            const int per = ((ntail + (int)gridDim.x * 32 - 1) / ((int)gridDim.x * 32)) * 32;
+            ts.o[0] = ts.o[1] = ts.o[2] = -(1 << 24);
+            p_beg = tail0 + (int)blockIdx.x * per;
+            p_end = (p_beg + per < n_live) ? p_beg + per : n_live;
+        }
+        __syncthreads();
+        for (int base = p_beg + warp * 32; base < p_end; base += NT) {
+            const int i = base + lane;
+            T vals[NV], po[3], xn[3], v[3];
+            int key = 0, kind = 0;
+            if (i < p_end) kind = fast3d_advance<T, SF, PUSHER, false, true>(p, species, k, i, s, F, X, leave, distributed != 0, flags, po, xn, v, key, vals, nullptr, &ts);
+            // ---- deferred anchor-changing particles: warp-private queue
+            const unsigned defer = __ballot_sync(0xffffffffu, kind == 2);
+            if (defer) {
+                if (kind == 2) {
+                    const int slot = qn + __popc(defer & ((1u << lane) - 1u));
+#pragma unroll
+                    for (int a = 0; a < 3; ++a) { qo[a * QW + slot] = po[a]; qn_[a * QW + slot] = xn[a]; }
+                }
+                qn += __popc(defer);
+                __syncwarp();
+            }
+            if (kind != 1) {
+                key = -1 - lane;
+#pragma unroll
+                for (int n = 0; n < NV; ++n) vals[n] = (T)0;
+            }
+            same_cell_scan_red<T, SF, STEPS>(vals, key, lane, sink, k.sx, k.sy);
+            // ---- flush the warp queue with a (nearly) full warp
+            if (qn >= 32 || (tail_pass && base + NT >= p_end && qn > 0)) {
+                for (int e = lane; e < qn; e += 32) {
+                    const T o3[3] = {qo[e], qo[QW + e], qo[2 * QW + e]};
+                    const T n3[3] = {qn_[e], qn_[QW + e], qn_[2 * QW + e]};
+                    const T v3[3] = {(T)0, (T)0, (T)0};   // velocities only enter the deposit on inactive axes (none here)
+                    union_deposit<T, SF>(p, species, gm, k, o3, n3, v3, sink);
+                }
+                qn = 0;
+                __syncwarp();
+            }
+        }
+        __syncthreads();     // everybody is done with tile `buf` before iteration b+1 prefetches into it
+    }
+    if (qn > 0) {            // (only reached with a non-empty queue when the tail pass had no iteration for this warp)
+        for (int e = lane; e < qn; e += 32) {
+            const T o3[3] = {qo[e], qo[QW + e], qo[2 * QW + e]};
+            const T n3[3] = {qn_[e], qn_[QW + e], qn_[2 * QW + e]};
+            const T v3[3] = {(T)0, (T)0, (T)0};
+            union_deposit<T, SF>(p, species, gm, k, o3, n3, v3, sink);
+        }
+    }
+}
+
 // Append every received packet (PicLeave layout: header row with the int32 count, then rows x,y,z,vx,vy,vz,species) at the
 // SoA tail; the device counter n_dev advances atomically, so no host round trip is needed between exchange and append.
 template <typename T>
@@ -433,6 +627,50 @@ static int launch_fused(const PicParams* p, int species, int deposition, const P
     PIC_LAUNCH_RET();
 }
 
+// K1 v9 launcher: returns PIC_EUNSUPPORTED when the configuration is outside what the tile kernel was built for (the caller then
+// uses pic_fused_push_deposit).
+template <typename T>
+static int launch_tile3d(const PicParams* p, int species, const PicSoA* soa, const int32_t* blk_off, int nblk, const void* const E[3],
+                         const void* const B[3], void* const J[3], const PicLeave* leave, int32_t* flags, cudaStream_t st) {
+    static_assert(PIC_SORT_BLOCK == TILE_B, "the tile kernel walks the supercells of the blocked sort order");
+    if (p->shape_factor != 1 || p->g != 2 || (p->pusher != PIC_PUSHER_BORIS && p->pusher != PIC_PUSHER_BORIS_REL)) return PIC_EUNSUPPORTED;
+    for (int a = 0; a < 3; ++a)
+        if (p->tile[a] % TILE_B != 0 || p->gmesh[a] * p->tile[a] <= 1) return PIC_EUNSUPPORTED;
+    const int nbx = p->tile[0] / TILE_B, nby = p->tile[1] / TILE_B, nbz = p->tile[2] / TILE_B;
+    if (nblk != nbx * nby * nbz) return PIC_EINVAL;
+    for (int c = 0; c < 3; ++c)
+        if (((uintptr_t)E[c] | (uintptr_t)B[c]) & 15) return PIC_EUNSUPPORTED;     // 16-byte cp.async rows
+    if (soa->n == 0 && !soa->n_dev) return 0;
+    Field6<T> F;
+    Field3W<T> Jw;
+    for (int c = 0; c < 3; ++c) { F.f[c] = (const T*)E[c]; F.f[3 + c] = (const T*)B[c]; Jw.f[c] = (T*)J[c]; }
+    Geom<T> gm;
+    make_geom<T>(*p, 0, 0, 0, gm);
+    FastConst<T> k;
+    make_fast_const<T>(*p, species, gm, k);
+    int distributed = 0;
+    for (int c = 0; c < 3; ++c) distributed |= (p->gmesh[c] != p->mesh[c]);
+    constexpr int NW = 8, QW = 64;
+    const size_t smem = (size_t)(2 * 6 * TILE_ELEMS + 2 * NW * 3 * QW) * sizeof(T);
+    int grid = num_sms() * (sizeof(T) == 8 ? 3 : PIC_K9_CTAS);
+    if (grid > nblk) grid = nblk;
+    const SoAView<T> sv = view_of<T>(soa);
+    const LeaveBuf lb = leave_of(leave);
+#define PIC_LAUNCH_K9(PUSH)                                                                                              \
+    do {                                                                                                                 \
+        static bool attr_set = false;                                                                                    \
+        if (!attr_set) {                                                                                                 \
+            cudaError_t e = cudaFuncSetAttribute(k_tile3d<T, PUSH, 3, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+            if (e != cudaSuccess) return (int)e;                                                                         \
+            attr_set = true;                                                                                             \
+        }                                                                                                                \
+        k_tile3d<T, PUSH, 3, NW><<<grid, NW * 32, smem, st>>>(*p, species, gm, k, sv, F, Jw, lb, distributed, flags, blk_off, nblk, nby, nbz); \
+    } while (0)
+    if (p->pusher == PIC_PUSHER_BORIS) PIC_LAUNCH_K9(PIC_PUSHER_BORIS); else PIC_LAUNCH_K9(PIC_PUSHER_BORIS_REL);
+#undef PIC_LAUNCH_K9
+    PIC_LAUNCH_RET();
+}
+
 template <typename T>
 static int launch_append_packets(const PicParams* p, const PicSoA* soa, const PicLeave* recv, int32_t* flags, cudaStream_t st) {
     int maxcap = 0;
@@ -497,6 +735,16 @@ int pic_fused_push_deposit(const PicParams* p, int species, int deposition, cons
         if (deposition == 1) return PIC_EUNSUPPORTED;  // centred deposit across ranks needs a mid-step migration
     }
     PIC_DISPATCH_T_SF(p, launch_fused, p, species, deposition, soa, E, B, extE, extB, J, leave, flags, (cudaStream_t)stream);
+}
+
+int pic_fused_tile3d(const PicParams* p, int species, const PicSoA* soa, const int32_t* blk_off, int nblk, const void* const E[3],
+                     const void* const B[3], void* const J[3], const PicLeave* leave, int32_t* flags, void* stream) {
+    PIC_CHECK_ARG(p && soa && blk_off && E && B && J && flags && species >= 0 && species < p->n_species && nblk > 0);
+    PIC_CHECK_ARG(p->mesh[0] == 1 && p->mesh[1] == 1 && p->mesh[2] == 1);
+    bool distributed = false;
+    for (int c = 0; c < 3; ++c) distributed |= (p->gmesh[c] != p->mesh[c]);
+    if (distributed) PIC_CHECK_ARG(leave && leave->buf);
+    PIC_DISPATCH_T(p, launch_tile3d, p, species, soa, blk_off, nblk, E, B, J, leave, flags, (cudaStream_t)stream);
 }
 
 int pic_packets_reset(const PicParams* p, const PicLeave* leave, void* stream) {

@@ -593,34 +593,13 @@ struct SameCell {
     }
 };
 
-// K1 v3 per-particle body: load -> stencils -> gather -> push -> new position -> store (move + BC + ownership).
-// Returns kind: 0 = nothing to deposit (dead slot), 1 = same-cell deposit: `vals` (SameCell<SF>::NV values) to be added at
-// J_c[key + offset(c, f, m1, m2)] -- these are what the kernel reduces across lanes of the same cell before the RED;
-// 2 = the particle changed anchor on some axis (or its stencil leaves the tile): deposit through union_deposit(old, new).
-template <typename T, int SF, int PUSHER, bool HAS_EXT>
-PIC_HD int fast3d_advance(const PicParams& p, int species, const FastConst<T>& k, int64_t i, const SoAView<T>& s, const Field6<T>& F,
-                          const Field6<T>& X, const LeaveBuf& leave, bool distributed, int32_t* flags, T pos_old[3], T xn[3], T vout[3],
-                          int& key, T* vals, const T* pre = nullptr) {
-    constexpr int NN = SF + 1;
+// Global-memory gather: Ex(v,c,c) Ey(c,v,c) Ez(c,c,v) Bx(c,v,v) By(v,c,v) Bz(v,v,c).
+// One 64-bit base pointer per component; the 3x3 stencil rows are reached by adding 64-bit byte offsets that live in the
+// constant bank (2 integer instructions per row), the z neighbours by immediate offsets.
+template <typename T, int SF, bool HAS_EXT>
+PIC_HD void gather_rows(const FastConst<T>& k, const Field6<T>& F, const Field6<T>& X, const int ac[3], const int av[3],
+                        const T wc[3][3], const T wv[3][3], T EB[6]) {
     constexpr int K0 = (SF == 1) ? 1 : 0;
-    // `pre`: x,y,z,vx,vy,vz of particle i already loaded by the caller (software prefetch of the next iteration)
-    T pos[3] = {pre ? pre[0] : s.c[0][i], pre ? pre[1] : s.c[1][i], pre ? pre[2] : s.c[2][i]};
-    if (pic_isnan(pos[0])) return 0;
-    T v[3] = {pre ? pre[3] : s.c[3][i], pre ? pre[4] : s.c[4][i], pre ? pre[5] : s.c[5][i]};
-    // ---- stencils of the old position on the center and vertex lines
-    int ac[3], av[3];
-    T wc[3][3], wv[3][3];
-#pragma unroll
-    for (int a = 0; a < 3; ++a) {
-        axis_stencil_rcp<T, SF>(pos[a], k.oc[a], k.sc[a], k.inv_sc[a], k.inv_d[a], ac[a], wc[a]);
-        axis_stencil_rcp<T, SF>(pos[a], k.ov[a], k.sv[a], k.inv_sv[a], k.inv_d[a], av[a], wv[a]);
-    }
-#if PIC_GATHER_V == 2
-    // ---- gather: Ex(v,c,c) Ey(c,v,c) Ez(c,c,v) Bx(c,v,v) By(v,c,v) Bz(v,v,c)
-    // One 64-bit base pointer per component; the 3x3 stencil rows are reached by adding 64-bit byte offsets that live in the
-    // constant bank (2 integer instructions per row), the z neighbours by immediate offsets.
-    T EB[6];
-    {
         int bc_[3], bv_[3];   // clamped first stencil index (memory safety only; owned particles never clamp for g >= 2)
 #pragma unroll
         for (int a = 0; a < 3; ++a) {
@@ -661,12 +640,91 @@ PIC_HD int fast3d_advance(const PicParams& p, int species, const FastConst<T>& k
             }
             EB[c] = acc;
         }
+}
+
+// K1 v9: shared-memory E/B tile of one supercell (TILE_B^3 cells of the blocked sort order).  TILE_N = 8 nodes per axis starting
+// at array index o[a] = (first cell of the supercell) + g - 2 cover both Yee lines of every CIC particle that sits in the supercell
+// or at most one cell outside it: centre anchors o+1 .. o+6 and vertex anchors o .. o+6, each reading nodes (a, a+1).
+constexpr int TILE_B = 4;
+constexpr int TILE_N = 8;
+constexpr int TILE_ELEMS = TILE_N * TILE_N * TILE_N;     // per component
+template <typename T>
+struct TileSrc {
+    const T* t;      // [6][TILE_N][TILE_N][TILE_N], z fastest -- same component order as Field6
+    int o[3];        // array index of the tile's first node on each axis
+};
+
+// K1 v3 per-particle body: load -> stencils -> gather -> push -> new position -> store (move + BC + ownership).
+// Returns kind: 0 = nothing to deposit (dead slot), 1 = same-cell deposit: `vals` (SameCell<SF>::NV values) to be added at
+// J_c[key + offset(c, f, m1, m2)] -- these are what the kernel reduces across lanes of the same cell before the RED;
+// 2 = the particle changed anchor on some axis (or its stencil leaves the tile): deposit through union_deposit(old, new).
+// TILE = true (K1 v9, CIC only): E and B are read from the supercell tile `ts` instead of global memory; a particle whose stencil
+// is not covered by the tile (it drifted more than one cell out of its supercell since the last sort) gathers from global
+// memory with the same arithmetic, so the result never depends on how stale the sort is.
+template <typename T, int SF, int PUSHER, bool HAS_EXT, bool TILE = false>
+PIC_HD int fast3d_advance(const PicParams& p, int species, const FastConst<T>& k, int64_t i, const SoAView<T>& s, const Field6<T>& F,
+                          const Field6<T>& X, const LeaveBuf& leave, bool distributed, int32_t* flags, T pos_old[3], T xn[3], T vout[3],
+                          int& key, T* vals, const T* pre = nullptr, const TileSrc<T>* ts = nullptr) {
+    static_assert(!TILE || (SF == 1 && !HAS_EXT), "the tile gather is built for CIC without external fields");
+    constexpr int NN = SF + 1;
+    constexpr int K0 = (SF == 1) ? 1 : 0;
+    // `pre`: x,y,z,vx,vy,vz of particle i already loaded by the caller (software prefetch of the next iteration)
+    T pos[3] = {pre ? pre[0] : s.c[0][i], pre ? pre[1] : s.c[1][i], pre ? pre[2] : s.c[2][i]};
+    if (pic_isnan(pos[0])) return 0;
+    T v[3] = {pre ? pre[3] : s.c[3][i], pre ? pre[4] : s.c[4][i], pre ? pre[5] : s.c[5][i]};
+    // ---- stencils of the old position on the center and vertex lines
+    int ac[3], av[3];
+    T wc[3][3], wv[3][3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        axis_stencil_rcp<T, SF>(pos[a], k.oc[a], k.sc[a], k.inv_sc[a], k.inv_d[a], ac[a], wc[a]);
+        axis_stencil_rcp<T, SF>(pos[a], k.ov[a], k.sv[a], k.inv_sv[a], k.inv_d[a], av[a], wv[a]);
     }
+    T EB[6];
+    if (TILE) {
+        // ---- gather from the supercell tile: one 32-bit element offset per component, the 8 corners by constant offsets
+        int rc[3], rv[3];
+        bool in_tile = true;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            rc[a] = ac[a] - ts->o[a];
+            rv[a] = av[a] - ts->o[a];
+            in_tile = in_tile && ((unsigned)rc[a] <= (unsigned)(TILE_N - 2)) && ((unsigned)rv[a] <= (unsigned)(TILE_N - 2));
+        }
+        if (!in_tile) {      // drifted out of the tile's one-cell margin (rare): same arithmetic from global memory
+            gather_rows<T, SF, HAS_EXT>(k, F, X, ac, av, wc, wv, EB);
+            atomic_add_i32(flags + 2, 1);    // diagnostic: flags[2] counts the particles that took this path
+        } else {
+        const int GT[6][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}, {0, 1, 1}, {1, 0, 1}, {1, 1, 0}};
+#pragma unroll
+        for (int c = 0; c < 6; ++c) {
+            const int gx = GT[c][0], gy = GT[c][1], gz = GT[c][2];
+            const T* wx = gx ? wv[0] : wc[0];
+            const T* wy = gy ? wv[1] : wc[1];
+            const T* wz = gz ? wv[2] : wc[2];
+            const T* f = ts->t + c * TILE_ELEMS + ((gx ? rv[0] : rc[0]) * (TILE_N * TILE_N) + (gy ? rv[1] : rc[1]) * TILE_N + (gz ? rv[2] : rc[2]));
+            T acc = (T)0;
+#pragma unroll
+            for (int a_ = 0; a_ < 2; ++a_) {
+                T ai = (T)0;
+#pragma unroll
+                for (int b_ = 0; b_ < 2; ++b_) {
+                    const T* r = f + a_ * (TILE_N * TILE_N) + b_ * TILE_N;
+                    const T aj = r[0] * wz[1] + r[1] * wz[2];
+                    ai += aj * wy[1 + b_];
+                }
+                acc += ai * wx[1 + a_];
+            }
+            EB[c] = acc;
+        }
+        }
+    } else
+#if PIC_GATHER_V == 2
+    { gather_rows<T, SF, HAS_EXT>(k, F, X, ac, av, wc, wv, EB); }
 #elif PIC_GATHER_V == 1
     // ---- gather: Ex(v,c,c) Ey(c,v,c) Ez(c,c,v) Bx(c,v,v) By(v,c,v) Bz(v,v,c)
     // Offsets are unsigned 32-bit element indices from the component base pointers (which live in the constant bank), so
     // each load is one "uniform base + 32-bit offset" LDG instead of a 64-bit address computation per row.
-    T EB[6];
     {
         unsigned oc_[3], ov_[3];   // clamped first stencil index (memory safety only; owned particles never clamp for g >= 2)
 #pragma unroll
@@ -711,7 +769,6 @@ PIC_HD int fast3d_advance(const PicParams& p, int species, const FastConst<T>& k
     }
 #else
     // ---- gather: Ex(v,c,c) Ey(c,v,c) Ez(c,c,v) Bx(c,v,v) By(v,c,v) Bz(v,v,c)
-    T EB[6];
 #if defined(PIC_ABLATE) && PIC_ABLATE == 2   /* profiling build: no gather */
     for (int c = 0; c < 6; ++c) EB[c] = (T)(ac[c % 3] + av[c % 3]) * wc[0][1];
     if (false)

@@ -23,7 +23,7 @@ from .boundary_conditions.grid_and_stencil import BC_CONDUCTING
 
 
 class _Species:
-    __slots__ = ("buf", "ids", "cur", "n", "cap", "n_dev", "leave", "recv", "leave_buf", "recv_buf")
+    __slots__ = ("buf", "ids", "cur", "n", "cap", "n_dev", "leave", "recv", "leave_buf", "recv_buf", "blk_off")
 
 
 class LocalHalo:
@@ -96,6 +96,7 @@ class Simulation:
         self._counter = torch.zeros(max(self.S, 1) + 27, dtype=torch.int32, device=self.device)
         self.cap_ref = int(x.shape[4])
         self.track_ids = bool(track_ids)
+        self.k1_variant = self._pick_k1_variant(sp)
         self._import(particles, capacity_factor)
         self.sort_every = self._sort_intervals(particles)
         self.leave_fraction = float(leave_fraction)
@@ -104,6 +105,20 @@ class Simulation:
         self.sort()
 
     # ------------------------------------------------------------------------------------------ layout
+    def _pick_k1_variant(self, sp):
+        """"tile": K1 v9 (pic_fused_tile3d, supercell E/B tiles in shared memory) when the configuration is the one it was
+        built for; "global": pic_fused_push_deposit (every other configuration).  PIC_K1_VARIANT=global forces the latter
+        (A/B measurements); both give the same result."""
+        import os
+        p = self.p
+        ok = (self.deposition == 0 and int(p.shape_factor) == 1 and int(p.g) == 2
+              and int(p.pusher) in (0, 1)   # PIC_PUSHER_BORIS, PIC_PUSHER_BORIS_REL
+              and all(int(p.tile[a]) % 4 == 0 and int(p.gmesh[a]) * int(p.tile[a]) > 1 for a in range(3))
+              and self.ext_E is None)
+        if os.environ.get("PIC_K1_VARIANT", "tile") != "tile":
+            ok = False
+        return "tile" if ok else "global"
+
     def _soa(self, sp_, which=None):
         k = sp_.cur if which is None else which
         s = PicSoA()
@@ -165,6 +180,7 @@ class Simulation:
                 sp_.ids = [torch.empty(sp_.cap, dtype=torch.int32, device=self.device) for _ in range(2)] if self.track_ids else None
                 sp_.n_dev = torch.zeros(1, dtype=torch.int32, device=self.device)
                 sp_.leave = sp_.recv = sp_.leave_buf = sp_.recv_buf = None
+                sp_.blk_off = torch.zeros(self.ncells // 64 + 1, dtype=torch.int32, device=self.device)
                 self.species.append(sp_)
             sp_ = self.species[s]
             if counts[s] > sp_.cap:
@@ -218,6 +234,8 @@ class Simulation:
             check(L.pic_sort_scatter(ctypes.byref(self.p), ctypes.byref(src), ctypes.byref(dst), ops._p(self._cell_offset),
                                      ops._p(self._cell_count), st), "pic_sort_scatter")
             sp_.cur = 1 - sp_.cur           # (the scatter also set n_dev = number of live particles, on the device)
+            if self.k1_variant == "tile":   # first slot of every 4x4x4-cell supercell of the blocked sort order (K1 v9)
+                sp_.blk_off.copy_(self._cell_offset[::64])
 
     # ------------------------------------------------------------------------------------------ the step
     def step(self, n_steps=1):
@@ -241,9 +259,14 @@ class Simulation:
             if self.k1_events is not None:
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
-            check(L.pic_fused_push_deposit(ctypes.byref(p), s, self.deposition, ctypes.byref(soa), ops._v(self.E), ops._v(self.B),
-                                           extE, extB, ops._v(self.J), ctypes.byref(sp_.leave) if sp_.leave is not None else None,
-                                           ops._p(self.flags), st), "pic_fused_push_deposit")
+            leave = ctypes.byref(sp_.leave) if sp_.leave is not None else None
+            if self.k1_variant == "tile":
+                check(L.pic_fused_tile3d(ctypes.byref(p), s, ctypes.byref(soa), ops._p(sp_.blk_off), self.ncells // 64,
+                                         ops._v(self.E), ops._v(self.B), ops._v(self.J), leave, ops._p(self.flags), st),
+                      "pic_fused_tile3d")
+            else:
+                check(L.pic_fused_push_deposit(ctypes.byref(p), s, self.deposition, ctypes.byref(soa), ops._v(self.E), ops._v(self.B),
+                                               extE, extB, ops._v(self.J), leave, ops._p(self.flags), st), "pic_fused_push_deposit")
             if self.k1_events is not None:
                 e1.record()
                 self.k1_events.append((e0, e1))

@@ -369,6 +369,69 @@ def test_resident_with_external_fields(sf):
         gu.assert_close(a, b, 1e-11, "E")
 
 
+# ------------------------------------------------------------------------------------------------ K1 v9 (supercell tiles)
+TILE_CASES = [
+    dict(N=(8, 8, 4), pbc=(0, 0, 0), rel=True),
+    dict(N=(12, 8, 8), pbc=(2, 0, 1), rel=True),
+    dict(N=(4, 8, 16), pbc=(0, 0, 0), rel=False),
+]
+
+
+@pytest.mark.parametrize("c", TILE_CASES)
+@pytest.mark.parametrize("dtype", (F64, F32))
+@pytest.mark.parametrize("sort_interval", (1, 4, 0))
+def test_resident_tile_kernel_matches_oracle(c, dtype, sort_interval):
+    """K1 v9 (pic_fused_tile3d): E/B gathered from shared-memory supercell tiles.  Fast particles (up to 0.2 dx per step) and
+    sort_interval 4 / never let particles drift into the tile margin and beyond it, so the tile gather, its global-memory
+    fallback and the deferred cell-crossers are all exercised; 8 steps, slot-exact against the oracle."""
+    from pypic3d_b200.simulation import Simulation
+    N = c["N"]
+    sp, dp, tp, sc, E, B = make_case(N, N, 1, current_deposition="esirkepov", relativistic=c["rel"],
+                                     particle_boundary_conditions=c["pbc"], capacity=3.0, vmax=2.0, C=10.0, dt=0.05, n=200)
+    fields = make_fields(sp, dp)
+    ps, pd = gu.to_pkg_params(sp, dp)
+    sim = Simulation(gu.particles_to_gpu(tp, dtype), gu.species_to_pkg(sc), gu.fields_to_gpu(fields, dtype), ps, pd, sort_interval=sort_interval)
+    assert sim.k1_variant == "tile"
+    for _ in range(8):
+        tp, fields = oevolve.time_loop_electrodynamic(tp, sc, fields, sp, dp)
+    sim.step(8)
+    gp, gf = sim.export_state()
+    tol = TOL[dtype] * (10 if dtype == F64 else 5)
+    assert np.array_equal(gu.npy(gp.active), tp.active)
+    gu.assert_close(gp.x, tp.x, tol, "x"); gu.assert_close(gp.u, tp.u, tol, "u")
+    for k in range(3):
+        for a, b in zip(gf[k], fields[k]):
+            gu.assert_close(a, b, tol, "EBJ"[k])
+    assert sim.overflow() == bool(fields[7])
+
+
+@pytest.mark.parametrize("dtype,tol", [(F64, 1e-11), (F32, 2e-4)])
+def test_tile_and_global_k1_variants_agree(dtype, tol, monkeypatch):
+    """Same 32^3 x 16 ppc thermal plasma, 12 steps with a sort every 5: the supercell-tile K1 and the global-gather K1 differ only
+    by the order of the floating-point atomics."""
+    from pypic3d_b200.simulation import Simulation
+    n = 32
+    sp, dp = fx.kernel_parameters(Nx=n, Ny=n, Nz=n, x_wind=float(n), y_wind=float(n), z_wind=float(n), shape_factor=1, dt=0.3,
+                                  current_deposition="esirkepov", particle_tile_capacity_factor=1.0)
+    tp, sc = fx.thermal_plasma(sp, dp, ppc_per_species=8, vth=(0.15, 0.02), seed=5)
+    fields = make_fields(sp, dp, scale=0.02)
+    ps, pd = gu.to_pkg_params(sp, dp)
+    out = {}
+    for variant in ("tile", "global"):
+        monkeypatch.setenv("PIC_K1_VARIANT", variant)
+        sim = Simulation(gu.particles_to_gpu(tp, dtype), gu.species_to_pkg(sc), gu.fields_to_gpu(fields, dtype), ps, pd, sort_interval=5)
+        assert sim.k1_variant == variant
+        sim.step(12)
+        out[variant] = sim.export_state()
+        assert not sim.overflow()
+    (pa, fa), (pb, fb) = out["tile"], out["global"]
+    assert torch.equal(pa.active, pb.active)
+    gu.assert_close(pa.x, gu.npy(pb.x), tol, "x"); gu.assert_close(pa.u, gu.npy(pb.u), tol, "u")
+    for k in range(3):
+        for a, b in zip(fa[k], fb[k]):
+            gu.assert_close(a, gu.npy(b), tol, "EBJ"[k])
+
+
 # ------------------------------------------------------------------------------------------------ conservation at size
 @pytest.mark.parametrize("sf", (1, 2))
 @pytest.mark.parametrize("dtype,tol", [(F64, 1e-11), (F32, 5e-4)])

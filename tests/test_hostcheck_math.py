@@ -182,3 +182,42 @@ def test_fused3d_fast_body_matches_oracle_step(hc, sf, rel, dtype, tol, pbc, vma
     for c in range(3):
         assert np.allclose(J[c], Jref[c][0, 0, 0], rtol=tol, atol=tol * scale), ("J", c)
     assert flags[0] == 0
+
+
+@pytest.mark.parametrize("rel", (True, False))
+@pytest.mark.parametrize("dtype,tol", [(np.float64, 1e-12), (np.float32, 3e-5)])
+@pytest.mark.parametrize("pbc", [(0, 0, 0), (1, 0, 2)])
+@pytest.mark.parametrize("shift", (0, 1, -1))
+def test_tile3d_body_matches_oracle_step(hc, rel, dtype, tol, pbc, shift):
+    """K1 v9 body (E/B gathered from a supercell tile, global-memory fallback outside it) == oracle step on one tile.
+    shift != 0 hands every particle the tile of a neighbouring supercell along one axis, so particles land in the tile's
+    one-cell margin or outside it: the tile gather and the fallback must give the same numbers."""
+    from tests.cases import make_case
+    N = (8, 8, 4)
+    sp, dp, tp, sc, E, B = make_case(N, N, 1, current_deposition="esirkepov", relativistic=rel, particle_boundary_conditions=pbc,
+                                     vmax=3.0, C=10.0, n=120)
+    assert int(sp.guard_cells) == 2
+    pushed = pusher.particle_push(tp, sc, E, B, sp, dp)
+    z = fx.empty_tiled_vector(sp, dp)
+    Jref = dep.Esirkepov_current(pushed, sc, z, sp, dp, fold=False)
+    moved, _ = opart.refresh_tiled_particle_tiles(opart.update_tiled_particle_positions(pushed, sc, dp.dt), sp, dp)
+    p = _lib.make_params(sp, dp, sc, dtype)
+    Ec = [np.ascontiguousarray(c[0, 0, 0], dtype=dtype) for c in E]; Bc = [np.ascontiguousarray(c[0, 0, 0], dtype=dtype) for c in B]
+    J = [np.zeros_like(Ec[0]) for _ in range(3)]
+    flags = np.zeros(4, dtype=np.int32)
+    for s in range(2):
+        act = tp.active[0, 0, 0, s]
+        comp = [np.ascontiguousarray(tp.x[0, 0, 0, s][act][:, c], dtype=dtype) for c in range(3)] + \
+               [np.ascontiguousarray(tp.u[0, 0, 0, s][act][:, c], dtype=dtype) for c in range(3)]
+        cp = (ctypes.c_void_p * 6)(*[a.ctypes.data for a in comp])
+        hc.hc_tile3d(ctypes.byref(p), s, cp, ctypes.c_int64(int(act.sum())), _v3(Ec), _v3(Bc), _v3(J), ctypes.c_int(shift), _ptr(flags))
+        alive = moved.active[0, 0, 0, s][act]
+        xr = moved.x[0, 0, 0, s][act]; ur = moved.u[0, 0, 0, s][act]
+        assert np.array_equal(~np.isnan(comp[0]), alive)
+        for c in range(3):
+            assert np.allclose(comp[c][alive], xr[alive][:, c], rtol=tol, atol=tol * 4), ("x", s, c)
+            assert np.allclose(comp[3 + c][alive], ur[alive][:, c], rtol=tol, atol=tol * 10), ("u", s, c)
+    scale = max(np.abs(r).max() for r in Jref)
+    for c in range(3):
+        assert np.allclose(J[c], Jref[c][0, 0, 0], rtol=tol, atol=tol * scale), ("J", c)
+    assert flags[0] == 0
