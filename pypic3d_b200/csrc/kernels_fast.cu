@@ -334,13 +334,30 @@ __global__ void __launch_bounds__(256, (SF == 1 ? PIC_K1_CTAS : 2)) k_fused3d(co
 #define PIC_K9_CTAS 4
 #endif
 
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
-    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gmem_src) : "memory");
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+// mbarrier (shared::cta) helpers for the tile pipeline
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("{\n .reg .b64 st;\n mbarrier.arrive.shared::cta.b64 st, [%0];\n}\n" ::"r"(smem_u32(bar)) : "memory");
+}
+// arrive on `bar` once all cp.async copies this thread issued so far have landed (counts against the init count)
+__device__ __forceinline__ void mbar_arrive_on_copies(uint64_t* bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, int parity) {
+    asm volatile(
+        "{\n .reg .pred p;\n"
+        "MBAR_WAIT:\n"
+        " mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        " @p bra MBAR_DONE;\n"
+        " bra MBAR_WAIT;\n"
+        "MBAR_DONE:\n}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
 
 // Segmented inclusive scan (depth STEPS) of the same-cell current values over lanes with equal key; the last lane of every run
 // issues the REDs.  (flag = "a segment head lies in (lane-d, lane]")
@@ -381,7 +398,7 @@ __device__ __forceinline__ void same_cell_scan_red(T* vals, int key, int lane, c
 }
 
 template <typename T, int PUSHER, int STEPS, int NW>
-__global__ void __launch_bounds__(NW * 32, (sizeof(T) == 8 ? 3 : PIC_K9_CTAS)) k_tile3d(const __grid_constant__ PicParams p, int species, const __grid_constant__ Geom<T> gm,
+__global__ void __launch_bounds__(NW * 32, (sizeof(T) == 8 ? 2 : PIC_K9_CTAS)) k_tile3d(const __grid_constant__ PicParams p, int species, const __grid_constant__ Geom<T> gm,
                                                    const __grid_constant__ FastConst<T> k, SoAView<T> s, const __grid_constant__ Field6<T> F, Field3W<T> J,
                                                    LeaveBuf leave, int distributed, int32_t* flags,
                                                    const int32_t* __restrict__ blk_off, int nblk, int nby, int nbz) {
@@ -389,6 +406,7 @@ __global__ void __launch_bounds__(NW * 32, (sizeof(T) == 8 ? 3 : PIC_K9_CTAS)) k
     constexpr int NV = SameCell<SF>::NV;
     constexpr int NT = NW * 32;
     constexpr int QW = 64;                                   // per-warp queue of anchor-changing particles (flushed at >= 32)
+    constexpr int NSTAGE = 3;                                // tile ring: two supercells in flight ahead of the one being processed
     constexpr int EPC = 16 / (int)sizeof(T);                 // elements per 16-byte copy
     constexpr int CPR = TILE_N / EPC;                        // copies per z row: 2 (f32) / 4 (f64)
     constexpr int CPC = TILE_N * TILE_N * CPR;               // copies per component
@@ -397,9 +415,12 @@ __global__ void __launch_bounds__(NW * 32, (sizeof(T) == 8 ? 3 : PIC_K9_CTAS)) k
     constexpr int PER_T = 6 / CPP;                           // copies per thread and tile: 3 (f32) / 6 (f64) with 256 threads
     constexpr int TILE_ALL = 6 * TILE_ELEMS;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    T* tiles = reinterpret_cast<T*>(smem_raw);               // [2][6][8][8][8]
-    T* q_old = tiles + 2 * TILE_ALL;                         // [NW][3][QW]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);  // full[NSTAGE], empty[NSTAGE]
+    T* tiles = reinterpret_cast<T*>(smem_raw + 64);          // [NSTAGE][6][TILE_N x TILE_SX]
+    T* q_old = tiles + NSTAGE * TILE_ALL;                    // [NW][3][QW]
     T* q_new = q_old + NW * 3 * QW;
+    uint64_t* full = bars;
+    uint64_t* empty = bars + NSTAGE;
     TileSink<T> sink;
     for (int c = 0; c < 3; ++c) { sink.J[c] = J.f[c]; sink.L[c] = gm.L[c]; }
     sink.off = 0;
@@ -408,6 +429,11 @@ __global__ void __launch_bounds__(NW * 32, (sizeof(T) == 8 ? 3 : PIC_K9_CTAS)) k
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int warp = tid >> 5;
+    if (tid == 0) {
+        for (int i = 0; i < NSTAGE; ++i) { mbar_init(full + i, NT); mbar_init(empty + i, NW); }
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    __syncthreads();
     T* qo = q_old + warp * 3 * QW;
     T* qn_ = q_new + warp * 3 * QW;
     int qn = 0;                                              // warp-uniform queue fill
@@ -423,43 +449,53 @@ __global__ void __launch_bounds__(NW * 32, (sizeof(T) == 8 ? 3 : PIC_K9_CTAS)) k
         const int r = tid % CPC;
         const int row = r / CPR, part = r % CPR;
         src_off = ((row / TILE_N) * gm.L[1] + (row % TILE_N)) * gm.L[2] + part * EPC;
-        dst_off = c0 * TILE_ELEMS + row * TILE_N + part * EPC;
+        dst_off = c0 * TILE_ELEMS + (row / TILE_N) * TILE_SX + (row % TILE_N) * TILE_N + part * EPC;
     }
     const int n_live = (int)s.count();
-    auto stage = [&](int bx, int by, int bz, int buf) {
+    // supercell coordinates of the next tile to be requested (runs two supercells ahead of the one being processed)
+    int sx_ = b0 / (nbz * nby), sy_ = (b0 / nbz) % nby, sz_ = b0 % nbz;
+    int stage_slot = 0;
+    auto stage_next = [&]() {
         // g == 2: the tile's first node is the supercell's first cell
-        const int64_t base = ((int64_t)(bx * TILE_B) * gm.L[1] + by * TILE_B) * gm.L[2] + bz * TILE_B + src_off;
-        T* dst = tiles + buf * TILE_ALL + dst_off;
+        const int64_t base = ((int64_t)(sx_ * TILE_B) * gm.L[1] + sy_ * TILE_B) * gm.L[2] + sz_ * TILE_B + src_off;
+        T* dst = tiles + stage_slot * TILE_ALL + dst_off;
 #pragma unroll
         for (int j = 0; j < PER_T; ++j) cp_async16(dst + j * CPP * TILE_ELEMS, F.f[c0 + j * CPP] + base);
-        cp_async_commit();
+        mbar_arrive_on_copies(full + stage_slot);
+        if (++sz_ == nbz) { sz_ = 0; if (++sy_ == nby) { sy_ = 0; ++sx_; } }
+        if (++stage_slot == NSTAGE) stage_slot = 0;
     };
-    int cz = b0 % nbz, cy = (b0 / nbz) % nby, cx = b0 / (nbz * nby);
+    // coordinates of the supercell being processed
+    int cx = sx_, cy = sy_, cz = sz_;
     int off_cur = 0, off_next = 0;
-    if (b0 < b1) {
-        stage(cx, cy, cz, 0);
-        off_cur = blk_off[b0]; off_next = blk_off[b0 + 1];
-    }
+    if (b0 < b1) { off_cur = blk_off[b0]; off_next = blk_off[b0 + 1]; }
+#pragma unroll
+    for (int j = 0; j < NSTAGE - 1; ++j)
+        if (b0 + j < b1) stage_next();
+    int slot = 0, par = 0;       // ring slot of the supercell being processed and the parity of its use count
+    int rot = 0;                 // 32-particle chunks are dealt to the warps round-robin, continuing across supercells, so every
+                                 // warp gets the same number of chunks (+-1) whatever the supercell populations are
     // iteration b == b1 is the tail pass: this CTA's share of the slots appended since the last sort (particles received from
     // neighbour ranks, ~1e-4 of the stream per step).  They are not binned; an impossible tile origin sends them through
     // the global-memory gather of the same body.
     for (int b = b0; b <= b1; ++b) {
         const bool tail_pass = (b == b1);
-        const int buf = (b - b0) & 1;
         TileSrc<T> ts;
-        ts.t = tiles + buf * TILE_ALL;
+        ts.t = tiles + slot * TILE_ALL;
         int p_beg, p_end;
         if (!tail_pass) {
-            int nx = cx, ny = cy, nz = cz + 1;
-            if (nz == nbz) { nz = 0; if (++ny == nby) { ny = 0; ++nx; } }
             const int off_nn = (b + 2 <= nblk) ? blk_off[b + 2] : off_next;    // requested one supercell ahead of its use
-            if (b + 1 < b1) { stage(nx, ny, nz, buf ^ 1); cp_async_wait<1>(); }
-            else cp_async_wait<0>();
+            if (b + NSTAGE - 1 < b1) {
+                // the ring slot two ahead last held supercell b-1: wait until every warp is done with it
+                if (b > b0) mbar_wait(empty + stage_slot, par ^ (slot == 0 ? 1 : 0));
+                stage_next();
+            }
+            mbar_wait(full + slot, par);
             ts.o[0] = cx * TILE_B; ts.o[1] = cy * TILE_B; ts.o[2] = cz * TILE_B;
             p_beg = off_cur;
             p_end = (off_next < n_live) ? off_next : n_live;
             off_cur = off_next; off_next = off_nn;
-            cx = nx; cy = ny; cz = nz;
+            if (++cz == nbz) { cz = 0; if (++cy == nby) { cy = 0; ++cx; } }
         } else {
             const int tail0 = blk_off[nblk];
             const int ntail = n_live > tail0 ? n_live - tail0 : 0;
@@ -468,9 +504,9 @@ __global__ void __launch_bounds__(NW * 32, (sizeof(T) == 8 ? 3 : PIC_K9_CTAS)) k
             p_beg = tail0 + (int)blockIdx.x * per;
             p_end = (p_beg + per < n_live) ? p_beg + per : n_live;
         }
-        __syncthreads();
-        for (int base = p_beg + warp * 32; base < p_end; base += NT) {
-            const int i = base + lane;
+        const int nchunk = p_end > p_beg ? (p_end - p_beg + 31) >> 5 : 0;
+        for (int ch = (warp - rot) & (NW - 1); ch < nchunk; ch += NW) {
+            const int i = p_beg + ch * 32 + lane;
             T vals[NV], po[3], xn[3], v[3];
             int key = 0, kind = 0;
             if (i < p_end) kind = fast3d_advance<T, SF, PUSHER, false, true>(p, species, k, i, s, F, X, leave, distributed != 0, flags, po, xn, v, key, vals, nullptr, &ts);
@@ -478,9 +514,9 @@ __global__ void __launch_bounds__(NW * 32, (sizeof(T) == 8 ? 3 : PIC_K9_CTAS)) k
             const unsigned defer = __ballot_sync(0xffffffffu, kind == 2);
             if (defer) {
                 if (kind == 2) {
-                    const int slot = qn + __popc(defer & ((1u << lane) - 1u));
+                    const int slot_q = qn + __popc(defer & ((1u << lane) - 1u));
 #pragma unroll
-                    for (int a = 0; a < 3; ++a) { qo[a * QW + slot] = po[a]; qn_[a * QW + slot] = xn[a]; }
+                    for (int a = 0; a < 3; ++a) { qo[a * QW + slot_q] = po[a]; qn_[a * QW + slot_q] = xn[a]; }
                 }
                 qn += __popc(defer);
                 __syncwarp();
@@ -492,7 +528,7 @@ __global__ void __launch_bounds__(NW * 32, (sizeof(T) == 8 ? 3 : PIC_K9_CTAS)) k
             }
             same_cell_scan_red<T, SF, STEPS>(vals, key, lane, sink, k.sx, k.sy);
             // ---- flush the warp queue with a (nearly) full warp
-            if (qn >= 32 || (tail_pass && base + NT >= p_end && qn > 0)) {
+            if (qn >= 32) {
                 for (int e = lane; e < qn; e += 32) {
                     const T o3[3] = {qo[e], qo[QW + e], qo[2 * QW + e]};
                     const T n3[3] = {qn_[e], qn_[QW + e], qn_[2 * QW + e]};
@@ -503,9 +539,14 @@ __global__ void __launch_bounds__(NW * 32, (sizeof(T) == 8 ? 3 : PIC_K9_CTAS)) k
                 __syncwarp();
             }
         }
-        __syncthreads();     // everybody is done with tile `buf` before iteration b+1 prefetches into it
+        rot = (rot + nchunk) & (NW - 1);
+        if (!tail_pass) {
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty + slot);        // this warp no longer reads the tile in `slot`
+            if (++slot == NSTAGE) { slot = 0; par ^= 1; }
+        }
     }
-    if (qn > 0) {            // (only reached with a non-empty queue when the tail pass had no iteration for this warp)
+    if (qn > 0) {
         for (int e = lane; e < qn; e += 32) {
             const T o3[3] = {qo[e], qo[QW + e], qo[2 * QW + e]};
             const T n3[3] = {qn_[e], qn_[QW + e], qn_[2 * QW + e]};
@@ -651,8 +692,8 @@ static int launch_tile3d(const PicParams* p, int species, const PicSoA* soa, con
     int distributed = 0;
     for (int c = 0; c < 3; ++c) distributed |= (p->gmesh[c] != p->mesh[c]);
     constexpr int NW = 8, QW = 64;
-    const size_t smem = (size_t)(2 * 6 * TILE_ELEMS + 2 * NW * 3 * QW) * sizeof(T);
-    int grid = num_sms() * (sizeof(T) == 8 ? 3 : PIC_K9_CTAS);
+    const size_t smem = 64 + (size_t)(3 * 6 * TILE_ELEMS + 2 * NW * 3 * QW) * sizeof(T);
+    int grid = num_sms() * (sizeof(T) == 8 ? 2 : PIC_K9_CTAS);
     if (grid > nblk) grid = nblk;
     const SoAView<T> sv = view_of<T>(soa);
     const LeaveBuf lb = leave_of(leave);

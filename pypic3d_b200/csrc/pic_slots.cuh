@@ -647,10 +647,12 @@ PIC_HD void gather_rows(const FastConst<T>& k, const Field6<T>& F, const Field6<
 // or at most one cell outside it: centre anchors o+1 .. o+6 and vertex anchors o .. o+6, each reading nodes (a, a+1).
 constexpr int TILE_B = 4;
 constexpr int TILE_N = 8;
-constexpr int TILE_ELEMS = TILE_N * TILE_N * TILE_N;     // per component
+constexpr int TILE_SX = TILE_N * TILE_N + 4;             // x-plane stride, padded: the centre / vertex anchors of one cell differ by one
+                                                         // plane, which would otherwise fall into the same shared-memory bank
+constexpr int TILE_ELEMS = TILE_N * TILE_SX;             // per component
 template <typename T>
 struct TileSrc {
-    const T* t;      // [6][TILE_N][TILE_N][TILE_N], z fastest -- same component order as Field6
+    const T* t;      // [6][TILE_N] planes of stride TILE_SX, each [TILE_N][TILE_N], z fastest -- same component order as Field6
     int o[3];        // array index of the tile's first node on each axis
 };
 
@@ -702,14 +704,14 @@ PIC_HD int fast3d_advance(const PicParams& p, int species, const FastConst<T>& k
             const T* wx = gx ? wv[0] : wc[0];
             const T* wy = gy ? wv[1] : wc[1];
             const T* wz = gz ? wv[2] : wc[2];
-            const T* f = ts->t + c * TILE_ELEMS + ((gx ? rv[0] : rc[0]) * (TILE_N * TILE_N) + (gy ? rv[1] : rc[1]) * TILE_N + (gz ? rv[2] : rc[2]));
+            const T* f = ts->t + c * TILE_ELEMS + ((gx ? rv[0] : rc[0]) * TILE_SX + (gy ? rv[1] : rc[1]) * TILE_N + (gz ? rv[2] : rc[2]));
             T acc = (T)0;
 #pragma unroll
             for (int a_ = 0; a_ < 2; ++a_) {
                 T ai = (T)0;
 #pragma unroll
                 for (int b_ = 0; b_ < 2; ++b_) {
-                    const T* r = f + a_ * (TILE_N * TILE_N) + b_ * TILE_N;
+                    const T* r = f + a_ * TILE_SX + b_ * TILE_N;
                     const T aj = r[0] * wz[1] + r[1] * wz[2];
                     ai += aj * wy[1 + b_];
                 }

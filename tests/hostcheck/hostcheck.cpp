@@ -127,7 +127,7 @@ static void t_tile3d(const PicParams* p, int species, void* const comp[6], int64
                 for (int x = 0; x < TILE_N; ++x)
                     for (int y = 0; y < TILE_N; ++y)
                         for (int z = 0; z < TILE_N; ++z)
-                            tile[((c * TILE_N + x) * TILE_N + y) * TILE_N + z] =
+                            tile[c * TILE_ELEMS + x * TILE_SX + y * TILE_N + z] =
                                 F.f[c][((size_t)(ts.o[0] + x) * gm.L[1] + (ts.o[1] + y)) * gm.L[2] + (ts.o[2] + z)];
         T po[3], xn[3], v[3], vals[SameCell<1>::NV];
         int key = 0, kind;

@@ -373,28 +373,30 @@ def test_resident_with_external_fields(sf):
 TILE_CASES = [
     dict(N=(8, 8, 4), pbc=(0, 0, 0), rel=True),
     dict(N=(12, 8, 8), pbc=(2, 0, 1), rel=True),
-    dict(N=(4, 8, 16), pbc=(0, 0, 0), rel=False),
+    dict(N=(4, 8, 8), pbc=(0, 0, 0), rel=False),
 ]
 
 
 @pytest.mark.parametrize("c", TILE_CASES)
 @pytest.mark.parametrize("dtype", (F64, F32))
-@pytest.mark.parametrize("sort_interval", (1, 4, 0))
+@pytest.mark.parametrize("sort_interval", (1, 5, 0))
 def test_resident_tile_kernel_matches_oracle(c, dtype, sort_interval):
-    """K1 v9 (pic_fused_tile3d): E/B gathered from shared-memory supercell tiles.  Fast particles (up to 0.2 dx per step) and
-    sort_interval 4 / never let particles drift into the tile margin and beyond it, so the tile gather, its global-memory
-    fallback and the deferred cell-crossers are all exercised; 8 steps, slot-exact against the oracle."""
+    """K1 v9 (pic_fused_tile3d): E/B gathered from shared-memory supercell tiles.  Fast particles (up to 0.16 cells per step)
+    and sort_interval 5 / never let particles drift into the tile margin and beyond it, so the tile gather, its global-memory
+    fallback and the deferred cell-crossers are all exercised; 12 steps (dt inside the Yee CFL limit), slot-exact against the
+    oracle."""
     from pypic3d_b200.simulation import Simulation
     N = c["N"]
     sp, dp, tp, sc, E, B = make_case(N, N, 1, current_deposition="esirkepov", relativistic=c["rel"],
-                                     particle_boundary_conditions=c["pbc"], capacity=3.0, vmax=2.0, C=10.0, dt=0.05, n=200)
+                                     particle_boundary_conditions=c["pbc"], capacity=3.0, vmax=4.0, C=10.0, dt=0.015, n=200)
     fields = make_fields(sp, dp)
     ps, pd = gu.to_pkg_params(sp, dp)
     sim = Simulation(gu.particles_to_gpu(tp, dtype), gu.species_to_pkg(sc), gu.fields_to_gpu(fields, dtype), ps, pd, sort_interval=sort_interval)
     assert sim.k1_variant == "tile"
-    for _ in range(8):
+    for _ in range(12):
         tp, fields = oevolve.time_loop_electrodynamic(tp, sc, fields, sp, dp)
-    sim.step(8)
+    assert np.isfinite(tp.x[tp.active]).all()
+    sim.step(12)
     gp, gf = sim.export_state()
     tol = TOL[dtype] * (10 if dtype == F64 else 5)
     assert np.array_equal(gu.npy(gp.active), tp.active)
@@ -403,6 +405,8 @@ def test_resident_tile_kernel_matches_oracle(c, dtype, sort_interval):
         for a, b in zip(gf[k], fields[k]):
             gu.assert_close(a, b, tol, "EBJ"[k])
     assert sim.overflow() == bool(fields[7])
+    if sort_interval == 0:      # never re-sorted: some particles must have left their tile and taken the global-memory gather
+        assert int(sim.flags[2].item()) > 0
 
 
 @pytest.mark.parametrize("dtype,tol", [(F64, 1e-11), (F32, 2e-4)])
