@@ -4,6 +4,7 @@
 //   K2  k_sort_*       counting sort by local cell (histogram, exclusive scan, scatter), run every few steps
 //   import / export    TiledParticles (reference AoS + active mask) <-> compact SoA
 #include <stdlib.h>
+#include <cuda.h>
 
 #include "pic_common.cuh"
 
@@ -335,19 +336,15 @@ __global__ void __launch_bounds__(256, (SF == 1 ? PIC_K1_CTAS : 2)) k_fused3d(co
 #endif
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
-}
-// mbarrier (shared::cta) helpers for the tile pipeline
+// mbarrier (shared::cta) + TMA helpers for the tile pipeline
 __device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("{\n .reg .b64 st;\n mbarrier.arrive.shared::cta.b64 st, [%0];\n}\n" ::"r"(smem_u32(bar)) : "memory");
 }
-// arrive on `bar` once all cp.async copies this thread issued so far have landed (counts against the init count)
-__device__ __forceinline__ void mbar_arrive_on_copies(uint64_t* bar) {
-    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, int bytes) {
+    asm volatile("{\n .reg .b64 st;\n mbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n}\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, int parity) {
     asm volatile(
@@ -358,6 +355,15 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, int parity) {
         " bra MBAR_WAIT;\n"
         "MBAR_DONE:\n}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
+// TMA: one [x 8][y 9][z 8] box of a field component -> shared memory, completion signalled on `bar` (complete_tx)
+__device__ __forceinline__ void tma_load_box(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int z, int y, int x) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];\n"
+                 ::"r"(smem_u32(smem_dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(z), "r"(y), "r"(x)
+                 : "memory");
+}
+struct TileMaps {
+    CUtensorMap m[6];      // Ex Ey Ez Bx By Bz, each the ghosted (Lx, Ly, Lz) tile with an 8 x 9 x 8 box
+};
 
 // Segmented inclusive scan (depth STEPS) of the same-cell current values over lanes with equal key; the last lane of every run
 // issues the REDs.  (flag = "a segment head lies in (lane-d, lane]")
@@ -400,27 +406,21 @@ __device__ __forceinline__ void same_cell_scan_red(T* vals, int key, int lane, c
 template <typename T, int PUSHER, int STEPS, int NW>
 __global__ void __launch_bounds__(NW * 32, (sizeof(T) == 8 ? 2 : PIC_K9_CTAS)) k_tile3d(const __grid_constant__ PicParams p, int species, const __grid_constant__ Geom<T> gm,
                                                    const __grid_constant__ FastConst<T> k, SoAView<T> s, const __grid_constant__ Field6<T> F, Field3W<T> J,
-                                                   LeaveBuf leave, int distributed, int32_t* flags,
+                                                   LeaveBuf leave, int distributed, int32_t* flags, const __grid_constant__ TileMaps tm,
                                                    const int32_t* __restrict__ blk_off, int nblk, int nby, int nbz) {
     constexpr int SF = 1;
     constexpr int NV = SameCell<SF>::NV;
-    constexpr int NT = NW * 32;
     constexpr int QW = 64;                                   // per-warp queue of anchor-changing particles (flushed at >= 32)
-    constexpr int NSTAGE = 3;                                // tile ring: two supercells in flight ahead of the one being processed
-    constexpr int EPC = 16 / (int)sizeof(T);                 // elements per 16-byte copy
-    constexpr int CPR = TILE_N / EPC;                        // copies per z row: 2 (f32) / 4 (f64)
-    constexpr int CPC = TILE_N * TILE_N * CPR;               // copies per component
-    static_assert(NT % CPC == 0 && 6 % (NT / CPC) == 0, "a staging pass must cover whole components");
-    constexpr int CPP = NT / CPC;                            // components per pass
-    constexpr int PER_T = 6 / CPP;                           // copies per thread and tile: 3 (f32) / 6 (f64) with 256 threads
+    constexpr int NSTAGE = 3;                                // tile ring: the next supercell's tile is in flight while the current
+                                                             // one is processed, and a warp may run one supercell ahead of the slowest
     constexpr int TILE_ALL = 6 * TILE_ELEMS;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);  // full[NSTAGE], empty[NSTAGE]
-    T* tiles = reinterpret_cast<T*>(smem_raw + 64);          // [NSTAGE][6][TILE_N x TILE_SX]
+    constexpr int TILE_BYTES = TILE_ALL * (int)sizeof(T);
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);  // full[NSTAGE]: the tile has landed (TMA complete_tx)
+    uint64_t* empty = full + NSTAGE;                         // empty[NSTAGE]: every warp is done reading the tile
+    T* tiles = reinterpret_cast<T*>(smem_raw + 128);         // [NSTAGE][6][8][9][8]
     T* q_old = tiles + NSTAGE * TILE_ALL;                    // [NW][3][QW]
     T* q_new = q_old + NW * 3 * QW;
-    uint64_t* full = bars;
-    uint64_t* empty = bars + NSTAGE;
     TileSink<T> sink;
     for (int c = 0; c < 3; ++c) { sink.J[c] = J.f[c]; sink.L[c] = gm.L[c]; }
     sink.off = 0;
@@ -430,7 +430,7 @@ __global__ void __launch_bounds__(NW * 32, (sizeof(T) == 8 ? 2 : PIC_K9_CTAS)) k
     const int lane = tid & 31;
     const int warp = tid >> 5;
     if (tid == 0) {
-        for (int i = 0; i < NSTAGE; ++i) { mbar_init(full + i, NT); mbar_init(empty + i, NW); }
+        for (int i = 0; i < NSTAGE; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, NW); }
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
     __syncthreads();
@@ -441,37 +441,21 @@ __global__ void __launch_bounds__(NW * 32, (sizeof(T) == 8 ? 2 : PIC_K9_CTAS)) k
     const int b0 = (int)blockIdx.x * per_cta;
     int b1 = (b0 + per_cta < nblk) ? b0 + per_cta : nblk;
     if (b1 < b0) b1 = b0;
-    // per-thread staging constants: the CTA copies CPP whole components per pass; this thread always moves the same 16-byte
-    // piece (row, part) of component c0 + j * CPP
-    const int c0 = tid / CPC;
-    int src_off, dst_off;
-    {
-        const int r = tid % CPC;
-        const int row = r / CPR, part = r % CPR;
-        src_off = ((row / TILE_N) * gm.L[1] + (row % TILE_N)) * gm.L[2] + part * EPC;
-        dst_off = c0 * TILE_ELEMS + (row / TILE_N) * TILE_SX + (row % TILE_N) * TILE_N + part * EPC;
-    }
     const int n_live = (int)s.count();
-    // supercell coordinates of the next tile to be requested (runs two supercells ahead of the one being processed)
-    int sx_ = b0 / (nbz * nby), sy_ = (b0 / nbz) % nby, sz_ = b0 % nbz;
-    int stage_slot = 0;
-    auto stage_next = [&]() {
-        // g == 2: the tile's first node is the supercell's first cell
-        const int64_t base = ((int64_t)(sx_ * TILE_B) * gm.L[1] + sy_ * TILE_B) * gm.L[2] + sz_ * TILE_B + src_off;
-        T* dst = tiles + stage_slot * TILE_ALL + dst_off;
+    // one elected thread feeds the ring: six TMA box copies per supercell (g == 2: the tile's first node is the supercell's
+    // first cell; the 9th y row of the last supercell row lies outside the array and is zero-filled, it is never read)
+    auto request_tile = [&](int bx, int by, int bz, int dst_slot) {
+        mbar_arrive_expect_tx(full + dst_slot, TILE_BYTES);
 #pragma unroll
-        for (int j = 0; j < PER_T; ++j) cp_async16(dst + j * CPP * TILE_ELEMS, F.f[c0 + j * CPP] + base);
-        mbar_arrive_on_copies(full + stage_slot);
-        if (++sz_ == nbz) { sz_ = 0; if (++sy_ == nby) { sy_ = 0; ++sx_; } }
-        if (++stage_slot == NSTAGE) stage_slot = 0;
+        for (int c = 0; c < 6; ++c)
+            tma_load_box(tiles + dst_slot * TILE_ALL + c * TILE_ELEMS, &tm.m[c], full + dst_slot, bz * TILE_B, by * TILE_B, bx * TILE_B);
     };
-    // coordinates of the supercell being processed
-    int cx = sx_, cy = sy_, cz = sz_;
+    int cx = b0 / (nbz * nby), cy = (b0 / nbz) % nby, cz = b0 % nbz;    // supercell being processed
     int off_cur = 0, off_next = 0;
-    if (b0 < b1) { off_cur = blk_off[b0]; off_next = blk_off[b0 + 1]; }
-#pragma unroll
-    for (int j = 0; j < NSTAGE - 1; ++j)
-        if (b0 + j < b1) stage_next();
+    if (b0 < b1) {
+        off_cur = blk_off[b0]; off_next = blk_off[b0 + 1];
+        if (tid == 0) request_tile(cx, cy, cz, 0);
+    }
     int slot = 0, par = 0;       // ring slot of the supercell being processed and the parity of its use count
     int rot = 0;                 // 32-particle chunks are dealt to the warps round-robin, continuing across supercells, so every
                                  // warp gets the same number of chunks (+-1) whatever the supercell populations are
@@ -485,17 +469,19 @@ __global__ void __launch_bounds__(NW * 32, (sizeof(T) == 8 ? 2 : PIC_K9_CTAS)) k
         int p_beg, p_end;
         if (!tail_pass) {
             const int off_nn = (b + 2 <= nblk) ? blk_off[b + 2] : off_next;    // requested one supercell ahead of its use
-            if (b + NSTAGE - 1 < b1) {
-                // the ring slot two ahead last held supercell b-1: wait until every warp is done with it
-                if (b > b0) mbar_wait(empty + stage_slot, par ^ (slot == 0 ? 1 : 0));
-                stage_next();
-            }
-            mbar_wait(full + slot, par);
             ts.o[0] = cx * TILE_B; ts.o[1] = cy * TILE_B; ts.o[2] = cz * TILE_B;
+            if (++cz == nbz) { cz = 0; if (++cy == nby) { cy = 0; ++cx; } }      // now the coordinates of supercell b + 1
+            if (tid == 0 && b + 1 < b1) {
+                const int ns = (slot == NSTAGE - 1) ? 0 : slot + 1;
+                // ring slot `ns` last held supercell b - 2: wait until every warp has released it
+                if (b - b0 >= 2) mbar_wait(empty + ns, slot == NSTAGE - 1 ? par : par ^ 1);
+                request_tile(cx, cy, cz, ns);
+            }
+            __syncwarp();
+            mbar_wait(full + slot, par);
             p_beg = off_cur;
             p_end = (off_next < n_live) ? off_next : n_live;
             off_cur = off_next; off_next = off_nn;
-            if (++cz == nbz) { cz = 0; if (++cy == nby) { cy = 0; ++cx; } }
         } else {
             const int tail0 = blk_off[nblk];
             const int ntail = n_live > tail0 ? n_live - tail0 : 0;
@@ -668,6 +654,10 @@ static int launch_fused(const PicParams* p, int species, int deposition, const P
     PIC_LAUNCH_RET();
 }
 
+typedef CUresult (*PFN_tensorMapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                             const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                             CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
 // K1 v9 launcher: returns PIC_EUNSUPPORTED when the configuration is outside what the tile kernel was built for (the caller then
 // uses pic_fused_push_deposit).
 template <typename T>
@@ -680,7 +670,7 @@ static int launch_tile3d(const PicParams* p, int species, const PicSoA* soa, con
     const int nbx = p->tile[0] / TILE_B, nby = p->tile[1] / TILE_B, nbz = p->tile[2] / TILE_B;
     if (nblk != nbx * nby * nbz) return PIC_EINVAL;
     for (int c = 0; c < 3; ++c)
-        if (((uintptr_t)E[c] | (uintptr_t)B[c]) & 15) return PIC_EUNSUPPORTED;     // 16-byte cp.async rows
+        if (((uintptr_t)E[c] | (uintptr_t)B[c]) & 15) return PIC_EUNSUPPORTED;     // TMA global addresses are 16-byte aligned
     if (soa->n == 0 && !soa->n_dev) return 0;
     Field6<T> F;
     Field3W<T> Jw;
@@ -692,11 +682,33 @@ static int launch_tile3d(const PicParams* p, int species, const PicSoA* soa, con
     int distributed = 0;
     for (int c = 0; c < 3; ++c) distributed |= (p->gmesh[c] != p->mesh[c]);
     constexpr int NW = 8, QW = 64;
-    const size_t smem = 64 + (size_t)(3 * 6 * TILE_ELEMS + 2 * NW * 3 * QW) * sizeof(T);
+    const size_t smem = 128 + (size_t)(3 * 6 * TILE_ELEMS + 2 * NW * 3 * QW) * sizeof(T);
     int grid = num_sms() * (sizeof(T) == 8 ? 2 : PIC_K9_CTAS);
     if (grid > nblk) grid = nblk;
     const SoAView<T> sv = view_of<T>(soa);
     const LeaveBuf lb = leave_of(leave);
+    // TMA descriptors of the six ghosted field tiles: dims (z, y, x) = (Lz, Ly, Lx), box 8 x 9 x 8
+    static PFN_tensorMapEncodeTiled encode = nullptr;
+    if (!encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn)
+            return PIC_EUNSUPPORTED;
+        encode = (PFN_tensorMapEncodeTiled)fn;
+    }
+    TileMaps tm;
+    {
+        const cuuint64_t dims[3] = {(cuuint64_t)gm.L[2], (cuuint64_t)gm.L[1], (cuuint64_t)gm.L[0]};
+        const cuuint64_t strides[2] = {(cuuint64_t)gm.L[2] * sizeof(T), (cuuint64_t)gm.L[2] * gm.L[1] * sizeof(T)};
+        const cuuint32_t box[3] = {(cuuint32_t)TILE_N, (cuuint32_t)TILE_NY, (cuuint32_t)TILE_N};
+        const cuuint32_t estr[3] = {1, 1, 1};
+        for (int c = 0; c < 6; ++c) {
+            const CUresult r = encode(&tm.m[c], sizeof(T) == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3,
+                                      const_cast<T*>(F.f[c]), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                      CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) return PIC_EUNSUPPORTED;
+        }
+    }
 #define PIC_LAUNCH_K9(PUSH)                                                                                              \
     do {                                                                                                                 \
         static bool attr_set = false;                                                                                    \
@@ -705,7 +717,7 @@ static int launch_tile3d(const PicParams* p, int species, const PicSoA* soa, con
             if (e != cudaSuccess) return (int)e;                                                                         \
             attr_set = true;                                                                                             \
         }                                                                                                                \
-        k_tile3d<T, PUSH, 3, NW><<<grid, NW * 32, smem, st>>>(*p, species, gm, k, sv, F, Jw, lb, distributed, flags, blk_off, nblk, nby, nbz); \
+        k_tile3d<T, PUSH, 3, NW><<<grid, NW * 32, smem, st>>>(*p, species, gm, k, sv, F, Jw, lb, distributed, flags, tm, blk_off, nblk, nby, nbz); \
     } while (0)
     if (p->pusher == PIC_PUSHER_BORIS) PIC_LAUNCH_K9(PIC_PUSHER_BORIS); else PIC_LAUNCH_K9(PIC_PUSHER_BORIS_REL);
 #undef PIC_LAUNCH_K9

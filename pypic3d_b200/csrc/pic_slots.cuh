@@ -647,12 +647,13 @@ PIC_HD void gather_rows(const FastConst<T>& k, const Field6<T>& F, const Field6<
 // or at most one cell outside it: centre anchors o+1 .. o+6 and vertex anchors o .. o+6, each reading nodes (a, a+1).
 constexpr int TILE_B = 4;
 constexpr int TILE_N = 8;
-constexpr int TILE_SX = TILE_N * TILE_N + 4;             // x-plane stride, padded: the centre / vertex anchors of one cell differ by one
-                                                         // plane, which would otherwise fall into the same shared-memory bank
+constexpr int TILE_NY = TILE_N + 1;                      // one spare y row per x plane: with a plane stride of 72 words the centre and
+                                                         // vertex anchors of one cell (one plane apart) fall into different banks
+constexpr int TILE_SX = TILE_NY * TILE_N;                // x-plane stride (the tile is the dense TMA box [x 8][y 9][z 8])
 constexpr int TILE_ELEMS = TILE_N * TILE_SX;             // per component
 template <typename T>
 struct TileSrc {
-    const T* t;      // [6][TILE_N] planes of stride TILE_SX, each [TILE_N][TILE_N], z fastest -- same component order as Field6
+    const T* t;      // [6][TILE_N][TILE_NY][TILE_N], z fastest -- same component order as Field6
     int o[3];        // array index of the tile's first node on each axis
 };
 
