@@ -334,6 +334,9 @@ __global__ void __launch_bounds__(256, (SF == 1 ? PIC_K1_CTAS : 2)) k_fused3d(co
 #ifndef PIC_K9_CTAS
 #define PIC_K9_CTAS 4
 #endif
+#ifndef PIC_K9_PREFETCH
+#define PIC_K9_PREFETCH 1
+#endif
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 // mbarrier (shared::cta) + TMA helpers for the tile pipeline
@@ -403,7 +406,7 @@ __device__ __forceinline__ void same_cell_scan_red(T* vals, int key, int lane, c
     }
 }
 
-template <typename T, int PUSHER, int STEPS, int NW>
+template <typename T, int PUSHER, int STEPS, int NW, bool PER1>
 __global__ void __launch_bounds__(NW * 32, (sizeof(T) == 8 ? 2 : PIC_K9_CTAS)) k_tile3d(const __grid_constant__ PicParams p, int species, const __grid_constant__ Geom<T> gm,
                                                    const __grid_constant__ FastConst<T> k, SoAView<T> s, const __grid_constant__ Field6<T> F, Field3W<T> J,
                                                    LeaveBuf leave, int distributed, int32_t* flags, const __grid_constant__ TileMaps tm,
@@ -418,6 +421,7 @@ __global__ void __launch_bounds__(NW * 32, (sizeof(T) == 8 ? 2 : PIC_K9_CTAS)) k
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);  // full[NSTAGE]: the tile has landed (TMA complete_tx)
     uint64_t* empty = full + NSTAGE;                         // empty[NSTAGE]: every warp is done reading the tile
+    int* requested = reinterpret_cast<int*>(empty + NSTAGE); // last supercell whose tile has been requested
     T* tiles = reinterpret_cast<T*>(smem_raw + 128);         // [NSTAGE][6][8][9][8]
     T* q_old = tiles + NSTAGE * TILE_ALL;                    // [NW][3][QW]
     T* q_new = q_old + NW * 3 * QW;
@@ -432,6 +436,7 @@ __global__ void __launch_bounds__(NW * 32, (sizeof(T) == 8 ? 2 : PIC_K9_CTAS)) k
     if (tid == 0) {
         for (int i = 0; i < NSTAGE; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, NW); }
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+        *requested = (int)blockIdx.x * ((nblk + (int)gridDim.x - 1) / (int)gridDim.x);
     }
     __syncthreads();
     T* qo = q_old + warp * 3 * QW;
@@ -442,8 +447,10 @@ __global__ void __launch_bounds__(NW * 32, (sizeof(T) == 8 ? 2 : PIC_K9_CTAS)) k
     int b1 = (b0 + per_cta < nblk) ? b0 + per_cta : nblk;
     if (b1 < b0) b1 = b0;
     const int n_live = (int)s.count();
-    // one elected thread feeds the ring: six TMA box copies per supercell (g == 2: the tile's first node is the supercell's
-    // first cell; the 9th y row of the last supercell row lies outside the array and is zero-filled, it is never read)
+    // One thread feeds the ring with six TMA box copies per supercell (g == 2: the tile's first node is the supercell's first
+    // cell; the 9th y row of the last supercell row lies outside the array and is zero-filled, it is never read).  The tile of
+    // supercell b + 1 is requested by whichever warp enters supercell b FIRST (compare-and-swap on `requested`), so the
+    // request leads its first use by a full supercell of work even when some warp lags.
     auto request_tile = [&](int bx, int by, int bz, int dst_slot) {
         mbar_arrive_expect_tx(full + dst_slot, TILE_BYTES);
 #pragma unroll
@@ -471,7 +478,7 @@ __global__ void __launch_bounds__(NW * 32, (sizeof(T) == 8 ? 2 : PIC_K9_CTAS)) k
             const int off_nn = (b + 2 <= nblk) ? blk_off[b + 2] : off_next;    // requested one supercell ahead of its use
             ts.o[0] = cx * TILE_B; ts.o[1] = cy * TILE_B; ts.o[2] = cz * TILE_B;
             if (++cz == nbz) { cz = 0; if (++cy == nby) { cy = 0; ++cx; } }      // now the coordinates of supercell b + 1
-            if (tid == 0 && b + 1 < b1) {
+            if (lane == 0 && b + 1 < b1 && atomicCAS(requested, b, b + 1) == b) {
                 const int ns = (slot == NSTAGE - 1) ? 0 : slot + 1;
                 // ring slot `ns` last held supercell b - 2: wait until every warp has released it
                 if (b - b0 >= 2) mbar_wait(empty + ns, slot == NSTAGE - 1 ? par : par ^ 1);
@@ -493,9 +500,17 @@ __global__ void __launch_bounds__(NW * 32, (sizeof(T) == 8 ? 2 : PIC_K9_CTAS)) k
         const int nchunk = p_end > p_beg ? (p_end - p_beg + 31) >> 5 : 0;
         for (int ch = (warp - rot) & (NW - 1); ch < nchunk; ch += NW) {
             const int i = p_beg + ch * 32 + lane;
+#if PIC_K9_PREFETCH
+            // the warp's next chunk lies NW * 32 particles further along the stream (supercells are contiguous): pull its six
+            // lines towards L2 now, so the loads of the next iteration do not wait for DRAM
+            if (i + NW * 32 < n_live) {
+#pragma unroll
+                for (int c = 0; c < 6; ++c) asm volatile("prefetch.global.L2 [%0];\n" ::"l"(s.c[c] + i + NW * 32));
+            }
+#endif
             T vals[NV], po[3], xn[3], v[3];
             int key = 0, kind = 0;
-            if (i < p_end) kind = fast3d_advance<T, SF, PUSHER, false, true>(p, species, k, i, s, F, X, leave, distributed != 0, flags, po, xn, v, key, vals, nullptr, &ts);
+            if (i < p_end) kind = fast3d_advance<T, SF, PUSHER, false, true, PER1>(p, species, k, i, s, F, X, leave, distributed != 0, flags, po, xn, v, key, vals, nullptr, &ts);
             // ---- deferred anchor-changing particles: warp-private queue
             const unsigned defer = __ballot_sync(0xffffffffu, kind == 2);
             if (defer) {
@@ -709,17 +724,20 @@ static int launch_tile3d(const PicParams* p, int species, const PicSoA* soa, con
             if (r != CUDA_SUCCESS) return PIC_EUNSUPPORTED;
         }
     }
-#define PIC_LAUNCH_K9(PUSH)                                                                                              \
+    bool per1 = !distributed;
+    for (int a = 0; a < 3; ++a) per1 = per1 && (p->particle_bc[a] == PIC_BC_PERIODIC);
+#define PIC_LAUNCH_K9(PUSH, PER)                                                                                         \
     do {                                                                                                                 \
         static bool attr_set = false;                                                                                    \
         if (!attr_set) {                                                                                                 \
-            cudaError_t e = cudaFuncSetAttribute(k_tile3d<T, PUSH, 3, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+            cudaError_t e = cudaFuncSetAttribute(k_tile3d<T, PUSH, 3, NW, PER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
             if (e != cudaSuccess) return (int)e;                                                                         \
             attr_set = true;                                                                                             \
         }                                                                                                                \
-        k_tile3d<T, PUSH, 3, NW><<<grid, NW * 32, smem, st>>>(*p, species, gm, k, sv, F, Jw, lb, distributed, flags, tm, blk_off, nblk, nby, nbz); \
+        k_tile3d<T, PUSH, 3, NW, PER><<<grid, NW * 32, smem, st>>>(*p, species, gm, k, sv, F, Jw, lb, distributed, flags, tm, blk_off, nblk, nby, nbz); \
     } while (0)
-    if (p->pusher == PIC_PUSHER_BORIS) PIC_LAUNCH_K9(PIC_PUSHER_BORIS); else PIC_LAUNCH_K9(PIC_PUSHER_BORIS_REL);
+    if (p->pusher == PIC_PUSHER_BORIS) { if (per1) PIC_LAUNCH_K9(PIC_PUSHER_BORIS, true); else PIC_LAUNCH_K9(PIC_PUSHER_BORIS, false); }
+    else { if (per1) PIC_LAUNCH_K9(PIC_PUSHER_BORIS_REL, true); else PIC_LAUNCH_K9(PIC_PUSHER_BORIS_REL, false); }
 #undef PIC_LAUNCH_K9
     PIC_LAUNCH_RET();
 }

@@ -664,7 +664,8 @@ struct TileSrc {
 // TILE = true (K1 v9, CIC only): E and B are read from the supercell tile `ts` instead of global memory; a particle whose stencil
 // is not covered by the tile (it drifted more than one cell out of its supercell since the last sort) gathers from global
 // memory with the same arithmetic, so the result never depends on how stale the sort is.
-template <typename T, int SF, int PUSHER, bool HAS_EXT, bool TILE = false>
+// PERIODIC1 = true: all three particle BCs periodic on a single rank (the launcher checks) -- the move is just the wrap.
+template <typename T, int SF, int PUSHER, bool HAS_EXT, bool TILE = false, bool PERIODIC1 = false>
 PIC_HD int fast3d_advance(const PicParams& p, int species, const FastConst<T>& k, int64_t i, const SoAView<T>& s, const Field6<T>& F,
                           const Field6<T>& X, const LeaveBuf& leave, bool distributed, int32_t* flags, T pos_old[3], T xn[3], T vout[3],
                           int& key, T* vals, const T* pre = nullptr, const TileSrc<T>* ts = nullptr) {
@@ -906,6 +907,11 @@ PIC_HD int fast3d_advance(const PicParams& p, int species, const FastConst<T>& k
     // ---- move + global particle BCs + ownership, then store
     // Ownership on split axes is the physical crossing direction of the local box [lo, hi): taken BEFORE the periodic wrap
     // (first -> last tile is -1, last -> first is +1, particle_tile_communication.py:145-165) and after reflect/absorb.
+    if (PERIODIC1) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) { s.c[c][i] = wrap_periodic_fast<T>(xn[c], k.wind[c]); s.c[3 + c][i] = v[c]; }
+        return kind;
+    }
     bool alive = true;
     int dir = 13;   // ((1-0)*3 + (1-0))*3 + (1-0): stays
 #pragma unroll
