@@ -325,7 +325,8 @@ def main():
                 "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": "profiles/r01_k1_traffic.json (ncu dram__bytes_read+write, bytes per launch)" if traffic else None,
                 "algorithmic_bytes_per_launch": k1_bytes_pp * per_launch_particles, "peak_source": peak_src,
                 "algorithmic_bytes_per_particle": k1_bytes_pp, "avg_launch_ms": k1_avg_ms,
-                "k1_share_of_step": float(np.sum(k1_ms)) / ms_total if ms_total else None}
+                "k1_share_of_step": float(np.sum(k1_ms)) / ms_total if ms_total else None,
+                "avg_launch_ms_by_species": [float(np.mean(k1_ms[i::sim.S])) for i in range(sim.S)]}
     step_achieved = step_bytes_pp * (total_particles / n_gpus) * args.steps / (ms_total * 1e-3) / 1e9
     roof_step = {"bytes_per_particle_step": step_bytes_pp, "achieved": step_achieved, "peak": peak, "unit": "GB/s", "frac": step_achieved / peak}
 

@@ -332,10 +332,13 @@ __global__ void __launch_bounds__(256, (SF == 1 ? PIC_K1_CTAS : 2)) k_fused3d(co
 // result never depends on how well the stream is sorted.  Push, same-cell deposit (segmented warp scan + RED), deferred
 // cell-crossers, move, BCs and leaver packets are the v8 code.
 #ifndef PIC_K9_CTAS
-#define PIC_K9_CTAS 4
+#define PIC_K9_CTAS 3       /* 80 registers: measured 4.67 ms vs 5.08 with 4 CTAs/SM (64 registers spill the per-supercell state) */
+#endif
+#ifndef PIC_K9_NW
+#define PIC_K9_NW 8         /* warps per CTA */
 #endif
 #ifndef PIC_K9_PREFETCH
-#define PIC_K9_PREFETCH 1
+#define PIC_K9_PREFETCH 0   /* L2 prefetch of the particles NW chunks ahead: measured 5.08 vs 5.00 ms without */
 #endif
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -352,7 +355,10 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, int bytes) 
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, int parity) {
     asm volatile(
         "{\n .reg .pred p;\n"
+        " mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        " @p bra MBAR_DONE;\n"
         "MBAR_WAIT:\n"
+        " nanosleep.u32 128;\n"          // a waiting warp should not compete for issue slots
         " mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
         " @p bra MBAR_DONE;\n"
         " bra MBAR_WAIT;\n"
@@ -422,6 +428,8 @@ __global__ void __launch_bounds__(NW * 32, (sizeof(T) == 8 ? 2 : PIC_K9_CTAS)) k
     uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);  // full[NSTAGE]: the tile has landed (TMA complete_tx)
     uint64_t* empty = full + NSTAGE;                         // empty[NSTAGE]: every warp is done reading the tile
     int* requested = reinterpret_cast<int*>(empty + NSTAGE); // last supercell whose tile has been requested
+    int* chunk_ctr = requested + 1;                          // [NSTAGE + 1]: next undealt 32-particle chunk of the supercell in each
+                                                             // ring slot (+ one counter for the tail pass)
     T* tiles = reinterpret_cast<T*>(smem_raw + 128);         // [NSTAGE][6][8][9][8]
     T* q_old = tiles + NSTAGE * TILE_ALL;                    // [NW][3][QW]
     T* q_new = q_old + NW * 3 * QW;
@@ -437,6 +445,7 @@ __global__ void __launch_bounds__(NW * 32, (sizeof(T) == 8 ? 2 : PIC_K9_CTAS)) k
         for (int i = 0; i < NSTAGE; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, NW); }
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
         *requested = (int)blockIdx.x * ((nblk + (int)gridDim.x - 1) / (int)gridDim.x);
+        for (int i = 0; i <= NSTAGE; ++i) chunk_ctr[i] = 0;
     }
     __syncthreads();
     T* qo = q_old + warp * 3 * QW;
@@ -464,8 +473,8 @@ __global__ void __launch_bounds__(NW * 32, (sizeof(T) == 8 ? 2 : PIC_K9_CTAS)) k
         if (tid == 0) request_tile(cx, cy, cz, 0);
     }
     int slot = 0, par = 0;       // ring slot of the supercell being processed and the parity of its use count
-    int rot = 0;                 // 32-particle chunks are dealt to the warps round-robin, continuing across supercells, so every
-                                 // warp gets the same number of chunks (+-1) whatever the supercell populations are
+    // The 32-particle chunks of a supercell are dealt to the warps dynamically (shared-memory counter): a warp that finishes
+    // early takes the next chunk, or moves on to the next supercell, so nobody waits for a straggler.
     // iteration b == b1 is the tail pass: this CTA's share of the slots appended since the last sort (particles received from
     // neighbour ranks, ~1e-4 of the stream per step).  They are not binned; an impossible tile origin sends them through
     // the global-memory gather of the same body.
@@ -482,6 +491,7 @@ __global__ void __launch_bounds__(NW * 32, (sizeof(T) == 8 ? 2 : PIC_K9_CTAS)) k
                 const int ns = (slot == NSTAGE - 1) ? 0 : slot + 1;
                 // ring slot `ns` last held supercell b - 2: wait until every warp has released it
                 if (b - b0 >= 2) mbar_wait(empty + ns, slot == NSTAGE - 1 ? par : par ^ 1);
+                chunk_ctr[ns] = 0;       // (published to the other warps by the release of the expect_tx arrive below)
                 request_tile(cx, cy, cz, ns);
             }
             __syncwarp();
@@ -498,7 +508,12 @@ __global__ void __launch_bounds__(NW * 32, (sizeof(T) == 8 ? 2 : PIC_K9_CTAS)) k
             p_end = (p_beg + per < n_live) ? p_beg + per : n_live;
         }
         const int nchunk = p_end > p_beg ? (p_end - p_beg + 31) >> 5 : 0;
-        for (int ch = (warp - rot) & (NW - 1); ch < nchunk; ch += NW) {
+        int* ctr = chunk_ctr + (tail_pass ? NSTAGE : slot);
+        for (;;) {
+            int ch = 0;
+            if (lane == 0) ch = atomicAdd(ctr, 1);
+            ch = __shfl_sync(0xffffffffu, ch, 0);
+            if (ch >= nchunk) break;
             const int i = p_beg + ch * 32 + lane;
 #if PIC_K9_PREFETCH
             // the warp's next chunk lies NW * 32 particles further along the stream (supercells are contiguous): pull its six
@@ -540,7 +555,6 @@ __global__ void __launch_bounds__(NW * 32, (sizeof(T) == 8 ? 2 : PIC_K9_CTAS)) k
                 __syncwarp();
             }
         }
-        rot = (rot + nchunk) & (NW - 1);
         if (!tail_pass) {
             __syncwarp();
             if (lane == 0) mbar_arrive(empty + slot);        // this warp no longer reads the tile in `slot`
@@ -696,7 +710,7 @@ static int launch_tile3d(const PicParams* p, int species, const PicSoA* soa, con
     make_fast_const<T>(*p, species, gm, k);
     int distributed = 0;
     for (int c = 0; c < 3; ++c) distributed |= (p->gmesh[c] != p->mesh[c]);
-    constexpr int NW = 8, QW = 64;
+    constexpr int NW = PIC_K9_NW, QW = 64;
     const size_t smem = 128 + (size_t)(3 * 6 * TILE_ELEMS + 2 * NW * 3 * QW) * sizeof(T);
     int grid = num_sms() * (sizeof(T) == 8 ? 2 : PIC_K9_CTAS);
     if (grid > nblk) grid = nblk;
