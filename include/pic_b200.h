@@ -186,14 +186,17 @@ int pic_fused_push_deposit(const PicParams* p, int species, int deposition, cons
                            void* stream);
 
 /* K1 v9, the supercell tile variant of pic_fused_push_deposit for the headline configuration (Esirkepov, CIC, all three axes
- * active, g == 2, every tile width a multiple of 4, Boris or relativistic Boris, no external fields): same result, but each CTA
- * stages the 8x8x8-node E/B neighbourhood of one 4x4x4-cell supercell in shared memory (cp.async, double-buffered) and the
- * gather reads it from there.  blk_off: int32[nblk+1] device array, blk_off[b] = first slot of supercell b in the cell-sorted
- * SoA = cell_offset[64*b] of the last pic_sort_scan (nblk = tile[0]*tile[1]*tile[2]/64); slots >= blk_off[nblk] (appended since
- * the sort) and particles that drifted more than one cell out of their supercell take the global-memory body, so the result
- * does not depend on how stale the sort is.  flags: int32[>=3]; flags[0] as for pic_fused_push_deposit, flags[2] counts the
- * particles that took the global-memory body.  Returns PIC_EUNSUPPORTED for any other configuration (call
- * pic_fused_push_deposit instead).  Replaces, like pic_fused_push_deposit, evolve.py:33-79. */
+ * active, g == 2, every tile width a multiple of 4, Boris or relativistic Boris, no external fields): same result, different
+ * data path.  The blocked sort order keeps the particles of one 4x4x4-cell supercell contiguous; per supercell one thread issues
+ * TMA copies of the 8x9x8-node E/B neighbourhood of all six components and of the supercell's slice of the six particle
+ * arrays into a three-stage shared-memory ring (mbarrier complete_tx), and the CTA's warps gather, push and deposit from
+ * shared memory.  blk_off: int32[nblk+1] device array, blk_off[b] = first slot of supercell b in the cell-sorted SoA =
+ * cell_offset[64*b] of the last pic_sort_scan (nblk = tile[0]*tile[1]*tile[2]/64); slots >= blk_off[nblk] (appended since
+ * the sort) and particles that drifted more than one cell out of their supercell gather from global memory, so the result
+ * does not depend on how stale the sort is.  The SoA rows should be 16-byte aligned (cap a multiple of 4 reals); otherwise
+ * particles are read from global memory.  flags: int32[>=3]; flags[0] as for pic_fused_push_deposit, flags[2] counts the
+ * particles that took the global-memory gather.  Returns PIC_EUNSUPPORTED for any other configuration or when the driver has
+ * no cuTensorMapEncodeTiled (call pic_fused_push_deposit instead).  Replaces, like pic_fused_push_deposit, evolve.py:33-79. */
 int pic_fused_tile3d(const PicParams* p, int species, const PicSoA* soa, const int32_t* blk_off, int nblk,
                      const void* const E[3], const void* const B[3], void* const J[3], const PicLeave* leave, int32_t* flags,
                      void* stream);

@@ -164,6 +164,9 @@ class PicError(RuntimeError):
     pass
 
 
+PIC_EINVAL, PIC_EUNSUPPORTED = -1, -2
+
+
 def check(code, what):
     if code != 0:
         kind = {-1: "invalid argument", -2: "unsupported configuration"}.get(code, f"CUDA error {code}")

@@ -332,10 +332,10 @@ __global__ void __launch_bounds__(256, (SF == 1 ? PIC_K1_CTAS : 2)) k_fused3d(co
 // result never depends on how well the stream is sorted.  Push, same-cell deposit (segmented warp scan + RED), deferred
 // cell-crossers, move, BCs and leaver packets are the v8 code.
 #ifndef PIC_K9_CTAS
-#define PIC_K9_CTAS 3       /* 80 registers: measured 4.67 ms vs 5.08 with 4 CTAs/SM (64 registers spill the per-supercell state) */
+#define PIC_K9_CTAS 2       /* CTAs per SM (sets the register cap): 2 x 12 warps at 80 registers; 64 registers spill the per-supercell state */
 #endif
 #ifndef PIC_K9_NW
-#define PIC_K9_NW 8         /* warps per CTA */
+#define PIC_K9_NW 12        /* warps per CTA */
 #endif
 #ifndef PIC_K9_PREFETCH
 #define PIC_K9_PREFETCH 0   /* L2 prefetch of the particles NW chunks ahead: measured 5.08 vs 5.00 ms without */
@@ -355,10 +355,7 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, int bytes) 
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, int parity) {
     asm volatile(
         "{\n .reg .pred p;\n"
-        " mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        " @p bra MBAR_DONE;\n"
         "MBAR_WAIT:\n"
-        " nanosleep.u32 128;\n"          // a waiting warp should not compete for issue slots
         " mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
         " @p bra MBAR_DONE;\n"
         " bra MBAR_WAIT;\n"
@@ -368,6 +365,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, int parity) {
 __device__ __forceinline__ void tma_load_box(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int z, int y, int x) {
     asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];\n"
                  ::"r"(smem_u32(smem_dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(z), "r"(y), "r"(x)
+                 : "memory");
+}
+// TMA bulk copy of `bytes` contiguous bytes (16-byte aligned, multiple of 16) global -> shared, completion on `bar`
+__device__ __forceinline__ void tma_load_bytes(void* smem_dst, const void* gmem_src, int bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+                 ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
 struct TileMaps {
@@ -412,26 +415,32 @@ __device__ __forceinline__ void same_cell_scan_red(T* vals, int key, int lane, c
     }
 }
 
+// Particle staging: the elected thread also bulk-copies the supercell's slice of the six particle arrays (TMA 1-D copies on the
+// same barrier as the field tile), so the hot loop reads x,y,z,vx,vy,vz from shared memory and no warp ever waits for DRAM on
+// its critical path.  PCAP slots per stage cover a supercell of up to ~PCAP particles (mean 512 at 8 ppc per species); the
+// slots beyond it, and arrays that are not 16-byte aligned, are read from global memory as before.
+constexpr int K9_PCAP = 640;
 template <typename T, int PUSHER, int STEPS, int NW, bool PER1>
-__global__ void __launch_bounds__(NW * 32, (sizeof(T) == 8 ? 2 : PIC_K9_CTAS)) k_tile3d(const __grid_constant__ PicParams p, int species, const __grid_constant__ Geom<T> gm,
-                                                   const __grid_constant__ FastConst<T> k, SoAView<T> s, const __grid_constant__ Field6<T> F, Field3W<T> J,
+__global__ void __launch_bounds__(NW * 32, (sizeof(T) == 8 ? 1 : PIC_K9_CTAS)) k_tile3d(const __grid_constant__ PicParams p, int species, const __grid_constant__ Geom<T> gm,
+                                                   const __grid_constant__ FastConst<T> k, const __grid_constant__ SoAView<T> s, const __grid_constant__ Field6<T> F, Field3W<T> J,
                                                    LeaveBuf leave, int distributed, int32_t* flags, const __grid_constant__ TileMaps tm,
-                                                   const int32_t* __restrict__ blk_off, int nblk, int nby, int nbz) {
+                                                   const int32_t* __restrict__ blk_off, int nblk, int nby, int nbz, int stage_particles) {
     constexpr int SF = 1;
     constexpr int NV = SameCell<SF>::NV;
     constexpr int QW = 64;                                   // per-warp queue of anchor-changing particles (flushed at >= 32)
-    constexpr int NSTAGE = 3;                                // tile ring: the next supercell's tile is in flight while the current
-                                                             // one is processed, and a warp may run one supercell ahead of the slowest
+    constexpr int NSTAGE = 3;                                // ring: the next supercell is in flight while the current one is
+                                                             // processed, and a warp may run one supercell ahead of the slowest
+    constexpr int PCAP = K9_PCAP;
     constexpr int TILE_ALL = 6 * TILE_ELEMS;
+    constexpr int STAGE_ELEMS = TILE_ALL + 6 * PCAP;         // field tile + particle slice
     constexpr int TILE_BYTES = TILE_ALL * (int)sizeof(T);
+    constexpr int AL = 16 / (int)sizeof(T);                  // elements per 16 bytes
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);  // full[NSTAGE]: the tile has landed (TMA complete_tx)
-    uint64_t* empty = full + NSTAGE;                         // empty[NSTAGE]: every warp is done reading the tile
-    int* requested = reinterpret_cast<int*>(empty + NSTAGE); // last supercell whose tile has been requested
-    int* chunk_ctr = requested + 1;                          // [NSTAGE + 1]: next undealt 32-particle chunk of the supercell in each
-                                                             // ring slot (+ one counter for the tail pass)
-    T* tiles = reinterpret_cast<T*>(smem_raw + 128);         // [NSTAGE][6][8][9][8]
-    T* q_old = tiles + NSTAGE * TILE_ALL;                    // [NW][3][QW]
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);  // full[NSTAGE]: tile + particles have landed (TMA complete_tx)
+    uint64_t* empty = full + NSTAGE;                         // empty[NSTAGE]: every warp is done reading the stage
+    int* requested = reinterpret_cast<int*>(empty + NSTAGE); // last supercell whose stage has been requested
+    T* stages = reinterpret_cast<T*>(smem_raw + 128);        // [NSTAGE][6][8][9][8] + [6][PCAP]
+    T* q_old = stages + NSTAGE * STAGE_ELEMS;                // [NW][3][QW]
     T* q_new = q_old + NW * 3 * QW;
     TileSink<T> sink;
     for (int c = 0; c < 3; ++c) { sink.J[c] = J.f[c]; sink.L[c] = gm.L[c]; }
@@ -441,64 +450,82 @@ __global__ void __launch_bounds__(NW * 32, (sizeof(T) == 8 ? 2 : PIC_K9_CTAS)) k
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int warp = tid >> 5;
+    const int per_cta = (nblk + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int b0 = (int)blockIdx.x * per_cta;
+    int b1 = (b0 + per_cta < nblk) ? b0 + per_cta : nblk;
+    if (b1 < b0) b1 = b0;
     if (tid == 0) {
         for (int i = 0; i < NSTAGE; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, NW); }
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
-        *requested = (int)blockIdx.x * ((nblk + (int)gridDim.x - 1) / (int)gridDim.x);
-        for (int i = 0; i <= NSTAGE; ++i) chunk_ctr[i] = 0;
+        *requested = b0;
     }
     __syncthreads();
     T* qo = q_old + warp * 3 * QW;
     T* qn_ = q_new + warp * 3 * QW;
     int qn = 0;                                              // warp-uniform queue fill
-    const int per_cta = (nblk + (int)gridDim.x - 1) / (int)gridDim.x;
-    const int b0 = (int)blockIdx.x * per_cta;
-    int b1 = (b0 + per_cta < nblk) ? b0 + per_cta : nblk;
-    if (b1 < b0) b1 = b0;
     const int n_live = (int)s.count();
-    // One thread feeds the ring with six TMA box copies per supercell (g == 2: the tile's first node is the supercell's first
-    // cell; the 9th y row of the last supercell row lies outside the array and is zero-filled, it is never read).  The tile of
-    // supercell b + 1 is requested by whichever warp enters supercell b FIRST (compare-and-swap on `requested`), so the
-    // request leads its first use by a full supercell of work even when some warp lags.
-    auto request_tile = [&](int bx, int by, int bz, int dst_slot) {
-        mbar_arrive_expect_tx(full + dst_slot, TILE_BYTES);
+    const int cap_al = (int)(s.cap < 0x7fffffff ? s.cap : 0x7fffffff) & ~(AL - 1);
+    // staged slice of supercell [beg, end): slots [beg_al, beg_al + n) with beg_al = beg rounded down to 16 bytes
+    auto slice_len = [&](int beg, int end) {
+        if (!stage_particles || end <= beg) return 0;
+        const int beg_al = beg & ~(AL - 1);
+        int n = (end - beg_al + AL - 1) & ~(AL - 1);
+        if (n > PCAP) n = PCAP;
+        if (beg_al + n > cap_al) n = cap_al - beg_al;
+        return n > 0 ? n : 0;
+    };
+    // One thread feeds the ring: six TMA box copies (g == 2: the tile's first node is the supercell's first cell; the 9th y
+    // row of the last supercell row lies outside the array and is zero-filled, it is never read) and six bulk copies of the
+    // particle slice per supercell.  The stage of supercell b + 1 is requested by whichever warp enters supercell b FIRST
+    // (compare-and-swap on `requested`), so the request leads its first use by a full supercell of work.
+    auto request_stage = [&](int bx, int by, int bz, int dst_slot, int beg, int end) {
+        const int n = slice_len(beg, end);
+        T* st = stages + dst_slot * STAGE_ELEMS;
+        mbar_arrive_expect_tx(full + dst_slot, TILE_BYTES + 6 * n * (int)sizeof(T));
 #pragma unroll
         for (int c = 0; c < 6; ++c)
-            tma_load_box(tiles + dst_slot * TILE_ALL + c * TILE_ELEMS, &tm.m[c], full + dst_slot, bz * TILE_B, by * TILE_B, bx * TILE_B);
+            tma_load_box(st + c * TILE_ELEMS, &tm.m[c], full + dst_slot, bz * TILE_B, by * TILE_B, bx * TILE_B);
+        if (n > 0) {
+            const int beg_al = beg & ~(AL - 1);
+#pragma unroll
+            for (int c = 0; c < 6; ++c) tma_load_bytes(st + TILE_ALL + c * PCAP, s.c[c] + beg_al, n * (int)sizeof(T), full + dst_slot);
+        }
     };
     int cx = b0 / (nbz * nby), cy = (b0 / nbz) % nby, cz = b0 % nbz;    // supercell being processed
-    int off_cur = 0, off_next = 0;
+    int off_cur = 0, off_next = 0, off_nn = 0;                           // blk_off[b], [b+1], [b+2]
     if (b0 < b1) {
         off_cur = blk_off[b0]; off_next = blk_off[b0 + 1];
-        if (tid == 0) request_tile(cx, cy, cz, 0);
+        off_nn = (b0 + 2 <= nblk) ? blk_off[b0 + 2] : off_next;
+        if (tid == 0) request_stage(cx, cy, cz, 0, off_cur, off_next < n_live ? off_next : n_live);
     }
     int slot = 0, par = 0;       // ring slot of the supercell being processed and the parity of its use count
-    // The 32-particle chunks of a supercell are dealt to the warps dynamically (shared-memory counter): a warp that finishes
-    // early takes the next chunk, or moves on to the next supercell, so nobody waits for a straggler.
+    int rot = 0;                 // 32-particle chunks are dealt to the warps round-robin, continuing across supercells, so every
+                                 // warp gets the same number of chunks (+-1) whatever the supercell populations are
     // iteration b == b1 is the tail pass: this CTA's share of the slots appended since the last sort (particles received from
     // neighbour ranks, ~1e-4 of the stream per step).  They are not binned; an impossible tile origin sends them through
     // the global-memory gather of the same body.
     for (int b = b0; b <= b1; ++b) {
         const bool tail_pass = (b == b1);
+        const T* st = stages + slot * STAGE_ELEMS;
         TileSrc<T> ts;
-        ts.t = tiles + slot * TILE_ALL;
-        int p_beg, p_end;
+        ts.t = st;
+        int p_beg, p_end, n_staged = 0;
         if (!tail_pass) {
-            const int off_nn = (b + 2 <= nblk) ? blk_off[b + 2] : off_next;    // requested one supercell ahead of its use
+            const int off_n3 = (b + 3 <= nblk) ? blk_off[b + 3] : off_nn;    // read two supercells ahead of its first use
             ts.o[0] = cx * TILE_B; ts.o[1] = cy * TILE_B; ts.o[2] = cz * TILE_B;
             if (++cz == nbz) { cz = 0; if (++cy == nby) { cy = 0; ++cx; } }      // now the coordinates of supercell b + 1
             if (lane == 0 && b + 1 < b1 && atomicCAS(requested, b, b + 1) == b) {
                 const int ns = (slot == NSTAGE - 1) ? 0 : slot + 1;
                 // ring slot `ns` last held supercell b - 2: wait until every warp has released it
                 if (b - b0 >= 2) mbar_wait(empty + ns, slot == NSTAGE - 1 ? par : par ^ 1);
-                chunk_ctr[ns] = 0;       // (published to the other warps by the release of the expect_tx arrive below)
-                request_tile(cx, cy, cz, ns);
+                request_stage(cx, cy, cz, ns, off_next, off_nn < n_live ? off_nn : n_live);
             }
             __syncwarp();
-            mbar_wait(full + slot, par);
             p_beg = off_cur;
             p_end = (off_next < n_live) ? off_next : n_live;
-            off_cur = off_next; off_next = off_nn;
+            n_staged = slice_len(p_beg, p_end);
+            off_cur = off_next; off_next = off_nn; off_nn = off_n3;
+            mbar_wait(full + slot, par);
         } else {
             const int tail0 = blk_off[nblk];
             const int ntail = n_live > tail0 ? n_live - tail0 : 0;
@@ -508,24 +535,22 @@ __global__ void __launch_bounds__(NW * 32, (sizeof(T) == 8 ? 2 : PIC_K9_CTAS)) k
             p_end = (p_beg + per < n_live) ? p_beg + per : n_live;
         }
         const int nchunk = p_end > p_beg ? (p_end - p_beg + 31) >> 5 : 0;
-        int* ctr = chunk_ctr + (tail_pass ? NSTAGE : slot);
-        for (;;) {
-            int ch = 0;
-            if (lane == 0) ch = atomicAdd(ctr, 1);
-            ch = __shfl_sync(0xffffffffu, ch, 0);
-            if (ch >= nchunk) break;
+        const T* pst = st + TILE_ALL - (p_beg & ~(AL - 1));      // staged particle i of array c sits at pst[c * PCAP + i]
+        const int i_staged_end = (p_beg & ~(AL - 1)) + n_staged;
+        for (int ch = (warp - rot + NW * 64) % NW; ch < nchunk; ch += NW) {
             const int i = p_beg + ch * 32 + lane;
-#if PIC_K9_PREFETCH
-            // the warp's next chunk lies NW * 32 particles further along the stream (supercells are contiguous): pull its six
-            // lines towards L2 now, so the loads of the next iteration do not wait for DRAM
-            if (i + NW * 32 < n_live) {
-#pragma unroll
-                for (int c = 0; c < 6; ++c) asm volatile("prefetch.global.L2 [%0];\n" ::"l"(s.c[c] + i + NW * 32));
-            }
-#endif
-            T vals[NV], po[3], xn[3], v[3];
+            T vals[NV], po[3], xn[3], v[3], cur[6];
             int key = 0, kind = 0;
-            if (i < p_end) kind = fast3d_advance<T, SF, PUSHER, false, true, PER1>(p, species, k, i, s, F, X, leave, distributed != 0, flags, po, xn, v, key, vals, nullptr, &ts);
+            if (i < p_end) {
+                if (i < i_staged_end) {
+#pragma unroll
+                    for (int c = 0; c < 6; ++c) cur[c] = pst[c * PCAP + i];
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 6; ++c) cur[c] = s.c[c][i];
+                }
+                kind = fast3d_advance<T, SF, PUSHER, false, true, PER1>(p, species, k, i, s, F, X, leave, distributed != 0, flags, po, xn, v, key, vals, cur, &ts);
+            }
             // ---- deferred anchor-changing particles: warp-private queue
             const unsigned defer = __ballot_sync(0xffffffffu, kind == 2);
             if (defer) {
@@ -555,9 +580,10 @@ __global__ void __launch_bounds__(NW * 32, (sizeof(T) == 8 ? 2 : PIC_K9_CTAS)) k
                 __syncwarp();
             }
         }
+        rot = (rot + nchunk) % NW;
         if (!tail_pass) {
             __syncwarp();
-            if (lane == 0) mbar_arrive(empty + slot);        // this warp no longer reads the tile in `slot`
+            if (lane == 0) mbar_arrive(empty + slot);        // this warp no longer reads the stage in `slot`
             if (++slot == NSTAGE) { slot = 0; par ^= 1; }
         }
     }
@@ -711,8 +737,12 @@ static int launch_tile3d(const PicParams* p, int species, const PicSoA* soa, con
     int distributed = 0;
     for (int c = 0; c < 3; ++c) distributed |= (p->gmesh[c] != p->mesh[c]);
     constexpr int NW = PIC_K9_NW, QW = 64;
-    const size_t smem = 128 + (size_t)(3 * 6 * TILE_ELEMS + 2 * NW * 3 * QW) * sizeof(T);
-    int grid = num_sms() * (sizeof(T) == 8 ? 2 : PIC_K9_CTAS);
+    const size_t smem = 128 + (size_t)(3 * (6 * TILE_ELEMS + 6 * K9_PCAP) + 2 * NW * 3 * QW) * sizeof(T);
+    if (smem > 227 * 1024) return PIC_EUNSUPPORTED;
+    int grid = num_sms() * (sizeof(T) == 8 ? 1 : PIC_K9_CTAS);
+    int stage_particles = 1;     // TMA bulk copies need 16-byte aligned sources
+    for (int c = 0; c < 6; ++c)
+        if ((uintptr_t)soa->comp[c] & 15) stage_particles = 0;
     if (grid > nblk) grid = nblk;
     const SoAView<T> sv = view_of<T>(soa);
     const LeaveBuf lb = leave_of(leave);
@@ -748,7 +778,7 @@ static int launch_tile3d(const PicParams* p, int species, const PicSoA* soa, con
             if (e != cudaSuccess) return (int)e;                                                                         \
             attr_set = true;                                                                                             \
         }                                                                                                                \
-        k_tile3d<T, PUSH, 3, NW, PER><<<grid, NW * 32, smem, st>>>(*p, species, gm, k, sv, F, Jw, lb, distributed, flags, tm, blk_off, nblk, nby, nbz); \
+        k_tile3d<T, PUSH, 3, NW, PER><<<grid, NW * 32, smem, st>>>(*p, species, gm, k, sv, F, Jw, lb, distributed, flags, tm, blk_off, nblk, nby, nbz, stage_particles); \
     } while (0)
     if (p->pusher == PIC_PUSHER_BORIS) { if (per1) PIC_LAUNCH_K9(PIC_PUSHER_BORIS, true); else PIC_LAUNCH_K9(PIC_PUSHER_BORIS, false); }
     else { if (per1) PIC_LAUNCH_K9(PIC_PUSHER_BORIS_REL, true); else PIC_LAUNCH_K9(PIC_PUSHER_BORIS_REL, false); }

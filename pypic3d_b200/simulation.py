@@ -175,7 +175,8 @@ class Simulation:
         for s in range(self.S):
             if first:
                 sp_ = _Species()
-                sp_.cap = max(16, int(np.ceil(counts[s] * float(capacity_factor))) + 16)
+                # a multiple of 64 slots keeps every row of the (6, cap) SoA 16-byte aligned (TMA bulk copies in K1 v9)
+                sp_.cap = (max(16, int(np.ceil(counts[s] * float(capacity_factor))) + 16) + 63) // 64 * 64
                 sp_.buf = [torch.empty((6, sp_.cap), dtype=self.dtype, device=self.device) for _ in range(2)]
                 sp_.ids = [torch.empty(sp_.cap, dtype=torch.int32, device=self.device) for _ in range(2)] if self.track_ids else None
                 sp_.n_dev = torch.zeros(1, dtype=torch.int32, device=self.device)
@@ -260,11 +261,15 @@ class Simulation:
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
             leave = ctypes.byref(sp_.leave) if sp_.leave is not None else None
+            rc = _lib.PIC_EUNSUPPORTED
             if self.k1_variant == "tile":
-                check(L.pic_fused_tile3d(ctypes.byref(p), s, ctypes.byref(soa), ops._p(sp_.blk_off), self.ncells // 64,
-                                         ops._v(self.E), ops._v(self.B), ops._v(self.J), leave, ops._p(self.flags), st),
-                      "pic_fused_tile3d")
-            else:
+                rc = L.pic_fused_tile3d(ctypes.byref(p), s, ctypes.byref(soa), ops._p(sp_.blk_off), self.ncells // 64,
+                                        ops._v(self.E), ops._v(self.B), ops._v(self.J), leave, ops._p(self.flags), st)
+                if rc == _lib.PIC_EUNSUPPORTED:     # e.g. no TMA driver entry point: the global-gather K1 computes the same step
+                    self.k1_variant = "global"
+                else:
+                    check(rc, "pic_fused_tile3d")
+            if self.k1_variant != "tile":
                 check(L.pic_fused_push_deposit(ctypes.byref(p), s, self.deposition, ctypes.byref(soa), ops._v(self.E), ops._v(self.B),
                                                extE, extB, ops._v(self.J), leave, ops._p(self.flags), st), "pic_fused_push_deposit")
             if self.k1_events is not None:
