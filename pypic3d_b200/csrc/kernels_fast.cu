@@ -361,6 +361,24 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, int parity) {
         " bra MBAR_WAIT;\n"
         "MBAR_DONE:\n}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
+// one bounded wait: true once the phase with `parity` has completed; otherwise the hardware may suspend the thread for up to
+// `hint_ns` before returning false (no issue slots burnt while waiting)
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, int parity, int hint_ns) {
+    unsigned ok;
+    asm volatile(
+        "{\n .reg .pred p;\n"
+        " mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+        " selp.u32 %0, 1, 0, p;\n}\n" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity), "r"(hint_ns) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, int parity) {
+    unsigned ok;
+    asm volatile(
+        "{\n .reg .pred p;\n"
+        " mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        " selp.u32 %0, 1, 0, p;\n}\n" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
 // TMA: one [x 8][y 9][z 8] box of a field component -> shared memory, completion signalled on `bar` (complete_tx)
 __device__ __forceinline__ void tma_load_box(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int z, int y, int x) {
     asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];\n"
@@ -457,7 +475,7 @@ __global__ void __launch_bounds__(NW * 32, (sizeof(T) == 8 ? 1 : PIC_K9_CTAS)) k
     if (tid == 0) {
         for (int i = 0; i < NSTAGE; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, NW); }
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
-        *requested = b0;
+        *requested = b0 - 1;
     }
     __syncthreads();
     T* qo = q_old + warp * 3 * QW;
@@ -474,30 +492,38 @@ __global__ void __launch_bounds__(NW * 32, (sizeof(T) == 8 ? 1 : PIC_K9_CTAS)) k
         if (beg_al + n > cap_al) n = cap_al - beg_al;
         return n > 0 ? n : 0;
     };
-    // One thread feeds the ring: six TMA box copies (g == 2: the tile's first node is the supercell's first cell; the 9th y
-    // row of the last supercell row lies outside the array and is zero-filled, it is never read) and six bulk copies of the
-    // particle slice per supercell.  The stage of supercell b + 1 is requested by whichever warp enters supercell b FIRST
-    // (compare-and-swap on `requested`), so the request leads its first use by a full supercell of work.
-    auto request_stage = [&](int bx, int by, int bz, int dst_slot, int beg, int end) {
+    // The ring is fed by single threads: six TMA box copies (g == 2: the tile's first node is the supercell's first cell; the
+    // 9th y row of the last supercell row lies outside the array and is zero-filled, it is never read) and six bulk copies of
+    // the particle slice per supercell.  Requests are made in order; `requested` is the last supercell asked for.  Any warp's
+    // lane 0 may make the next one (compare-and-swap) as soon as the ring slot it needs has been released by every warp --
+    // it never blocks for that: if the slot is still in use the attempt is dropped and repeated by the next warp that enters
+    // a supercell or waits for a stage, so a straggler delays nobody but the warps that actually need its slot.
+    auto try_request = [&](int upto) {
+        const int r = *reinterpret_cast<volatile int*>(requested) + 1;
+        if (r > upto || r >= b1) return;
+        const int jr = r - b0;
+        const int sr = jr % NSTAGE;
+        if (jr >= NSTAGE && !mbar_test(empty + sr, (jr / NSTAGE - 1) & 1)) return;     // previous occupant: supercell r - NSTAGE
+        if (atomicCAS(requested, r - 1, r) != r - 1) return;
+        const int bz = r % nbz, by = (r / nbz) % nby, bx = r / (nbz * nby);
+        const int beg = blk_off[r];
+        int end = blk_off[r + 1];
+        if (end > n_live) end = n_live;
         const int n = slice_len(beg, end);
-        T* st = stages + dst_slot * STAGE_ELEMS;
-        mbar_arrive_expect_tx(full + dst_slot, TILE_BYTES + 6 * n * (int)sizeof(T));
+        T* st = stages + sr * STAGE_ELEMS;
+        mbar_arrive_expect_tx(full + sr, TILE_BYTES + 6 * n * (int)sizeof(T));
 #pragma unroll
         for (int c = 0; c < 6; ++c)
-            tma_load_box(st + c * TILE_ELEMS, &tm.m[c], full + dst_slot, bz * TILE_B, by * TILE_B, bx * TILE_B);
+            tma_load_box(st + c * TILE_ELEMS, &tm.m[c], full + sr, bz * TILE_B, by * TILE_B, bx * TILE_B);
         if (n > 0) {
             const int beg_al = beg & ~(AL - 1);
 #pragma unroll
-            for (int c = 0; c < 6; ++c) tma_load_bytes(st + TILE_ALL + c * PCAP, s.c[c] + beg_al, n * (int)sizeof(T), full + dst_slot);
+            for (int c = 0; c < 6; ++c) tma_load_bytes(st + TILE_ALL + c * PCAP, s.c[c] + beg_al, n * (int)sizeof(T), full + sr);
         }
     };
     int cx = b0 / (nbz * nby), cy = (b0 / nbz) % nby, cz = b0 % nbz;    // supercell being processed
-    int off_cur = 0, off_next = 0, off_nn = 0;                           // blk_off[b], [b+1], [b+2]
-    if (b0 < b1) {
-        off_cur = blk_off[b0]; off_next = blk_off[b0 + 1];
-        off_nn = (b0 + 2 <= nblk) ? blk_off[b0 + 2] : off_next;
-        if (tid == 0) request_stage(cx, cy, cz, 0, off_cur, off_next < n_live ? off_next : n_live);
-    }
+    int off_cur = 0, off_next = 0;                                       // blk_off[b], [b+1]
+    if (b0 < b1) { off_cur = blk_off[b0]; off_next = blk_off[b0 + 1]; }
     int slot = 0, par = 0;       // ring slot of the supercell being processed and the parity of its use count
     int rot = 0;                 // 32-particle chunks are dealt to the warps round-robin, continuing across supercells, so every
                                  // warp gets the same number of chunks (+-1) whatever the supercell populations are
@@ -511,21 +537,18 @@ __global__ void __launch_bounds__(NW * 32, (sizeof(T) == 8 ? 1 : PIC_K9_CTAS)) k
         ts.t = st;
         int p_beg, p_end, n_staged = 0;
         if (!tail_pass) {
-            const int off_n3 = (b + 3 <= nblk) ? blk_off[b + 3] : off_nn;    // read two supercells ahead of its first use
+            const int off_nn = (b + 2 <= nblk) ? blk_off[b + 2] : off_next;    // read one supercell ahead of its use
             ts.o[0] = cx * TILE_B; ts.o[1] = cy * TILE_B; ts.o[2] = cz * TILE_B;
             if (++cz == nbz) { cz = 0; if (++cy == nby) { cy = 0; ++cx; } }      // now the coordinates of supercell b + 1
-            if (lane == 0 && b + 1 < b1 && atomicCAS(requested, b, b + 1) == b) {
-                const int ns = (slot == NSTAGE - 1) ? 0 : slot + 1;
-                // ring slot `ns` last held supercell b - 2: wait until every warp has released it
-                if (b - b0 >= 2) mbar_wait(empty + ns, slot == NSTAGE - 1 ? par : par ^ 1);
-                request_stage(cx, cy, cz, ns, off_next, off_nn < n_live ? off_nn : n_live);
-            }
-            __syncwarp();
+            if (lane == 0) try_request(b + 1);
             p_beg = off_cur;
             p_end = (off_next < n_live) ? off_next : n_live;
             n_staged = slice_len(p_beg, p_end);
-            off_cur = off_next; off_next = off_nn; off_nn = off_n3;
-            mbar_wait(full + slot, par);
+            off_cur = off_next; off_next = off_nn;
+            while (!mbar_try_wait(full + slot, par, 1000)) {
+                if (lane == 0) try_request(b + 1);       // the stage we wait for may not even have been requested yet
+            }
+            __syncwarp();
         } else {
             const int tail0 = blk_off[nblk];
             const int ntail = n_live > tail0 ? n_live - tail0 : 0;
