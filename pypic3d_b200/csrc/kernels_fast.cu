@@ -337,6 +337,9 @@ __global__ void __launch_bounds__(256, (SF == 1 ? PIC_K1_CTAS : 2)) k_fused3d(co
 #ifndef PIC_K9_NW
 #define PIC_K9_NW 12        /* warps per CTA */
 #endif
+#ifndef PIC_K9_DEAL
+#define PIC_K9_DEAL 1       /* how a supercell's 32-particle chunks reach the warps: 0 = static round-robin, 1 = shared-memory counter */
+#endif
 #ifndef PIC_K9_PREFETCH
 #define PIC_K9_PREFETCH 0   /* L2 prefetch of the particles NW chunks ahead: measured 5.08 vs 5.00 ms without */
 #endif
@@ -457,6 +460,7 @@ __global__ void __launch_bounds__(NW * 32, (sizeof(T) == 8 ? 1 : PIC_K9_CTAS)) k
     uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);  // full[NSTAGE]: tile + particles have landed (TMA complete_tx)
     uint64_t* empty = full + NSTAGE;                         // empty[NSTAGE]: every warp is done reading the stage
     int* requested = reinterpret_cast<int*>(empty + NSTAGE); // last supercell whose stage has been requested
+    int* chunk_ctr = requested + 1;                          // [NSTAGE + 1] next undealt chunk of the supercell in each ring slot (+ tail pass)
     T* stages = reinterpret_cast<T*>(smem_raw + 128);        // [NSTAGE][6][8][9][8] + [6][PCAP]
     T* q_old = stages + NSTAGE * STAGE_ELEMS;                // [NW][3][QW]
     T* q_new = q_old + NW * 3 * QW;
@@ -476,6 +480,7 @@ __global__ void __launch_bounds__(NW * 32, (sizeof(T) == 8 ? 1 : PIC_K9_CTAS)) k
         for (int i = 0; i < NSTAGE; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, NW); }
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
         *requested = b0 - 1;
+        for (int i = 0; i <= NSTAGE; ++i) chunk_ctr[i] = 0;
     }
     __syncthreads();
     T* qo = q_old + warp * 3 * QW;
@@ -511,6 +516,7 @@ __global__ void __launch_bounds__(NW * 32, (sizeof(T) == 8 ? 1 : PIC_K9_CTAS)) k
         if (end > n_live) end = n_live;
         const int n = slice_len(beg, end);
         T* st = stages + sr * STAGE_ELEMS;
+        chunk_ctr[sr] = 0;           // (published to the other warps by the release of the expect_tx arrive)
         mbar_arrive_expect_tx(full + sr, TILE_BYTES + 6 * n * (int)sizeof(T));
 #pragma unroll
         for (int c = 0; c < 6; ++c)
@@ -560,7 +566,18 @@ __global__ void __launch_bounds__(NW * 32, (sizeof(T) == 8 ? 1 : PIC_K9_CTAS)) k
         const int nchunk = p_end > p_beg ? (p_end - p_beg + 31) >> 5 : 0;
         const T* pst = st + TILE_ALL - (p_beg & ~(AL - 1));      // staged particle i of array c sits at pst[c * PCAP + i]
         const int i_staged_end = (p_beg & ~(AL - 1)) + n_staged;
+#if PIC_K9_DEAL == 1
+        // a warp that finishes early takes the next undealt chunk, or moves on to the next supercell: the warps stay within
+        // one chunk of each other, so ring slots are released promptly
+        int* ctr = chunk_ctr + (tail_pass ? NSTAGE : slot);
+        for (;;) {
+            int ch = 0;
+            if (lane == 0) ch = atomicAdd(ctr, 1);
+            ch = __shfl_sync(0xffffffffu, ch, 0);
+            if (ch >= nchunk) break;
+#else
         for (int ch = (warp - rot + NW * 64) % NW; ch < nchunk; ch += NW) {
+#endif
             const int i = p_beg + ch * 32 + lane;
             T vals[NV], po[3], xn[3], v[3], cur[6];
             int key = 0, kind = 0;
