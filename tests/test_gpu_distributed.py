@@ -18,7 +18,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, mesh, sf, pbc, steps, q):
+def _worker(rank, world, port, mesh, sf, pbc, steps, q, tile=(8, 6, 4), expect_variant=None):
     import torch.distributed as dist
     from oracle import evolve as oevolve
     from tests import gpu_util as gu
@@ -33,7 +33,6 @@ def _worker(rank, world, port, mesh, sf, pbc, steps, q):
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     try:
       try:
-          tile = (8, 6, 4)
           N = tuple(mesh[a] * tile[a] for a in range(3))
           sp, dp, tp, sc, E, B = make_case(N, tile, sf, current_deposition="esirkepov", particle_boundary_conditions=pbc, n=400,
                                            capacity=4.0, vmax=0.3, dt=0.04)
@@ -48,6 +47,8 @@ def _worker(rank, world, port, mesh, sf, pbc, steps, q):
                 torch.tensor(False, device=dev))
           sim = Simulation(parts, gu.species_to_pkg(sc), f8, ps, pd, sort_interval=2, gmesh=mesh, moff=c, capacity_factor=4.0,
                            halo=lambda p: DistributedHalo(p, None, dev))
+          if expect_variant is not None:
+              assert sim.k1_variant == expect_variant, sim.k1_variant
           for _ in range(steps):
               tp, fields = oevolve.time_loop_electrodynamic(tp, sc, fields, sp, dp)
           sim.step(steps)
@@ -82,6 +83,34 @@ def test_distributed_resident_matches_oracle(mesh, sf, pbc):
     q = ctx.Queue()
     port = _free_port()
     procs = [ctx.Process(target=_worker, args=(r, world, port, mesh, sf, pbc, 4, q)) for r in range(world)]
+    for pr in procs:
+        pr.start()
+    res = [q.get(timeout=90) for _ in range(world)]
+    for r in res:
+        assert len(r) == 7, r[1]
+    for pr in procs:
+        pr.join(timeout=120)
+        assert pr.exitcode == 0
+    for rank, err, perr, n_got, n_want, ovf, oovf in res:
+        assert n_got == n_want, (rank, n_got, n_want)
+        assert err < 1e-11, (rank, err)
+        assert perr < 1e-11, (rank, perr)
+        assert ovf == oovf
+
+
+@pytest.mark.parametrize("mesh", [(2, 1, 1), (1, 1, 2)])
+@pytest.mark.parametrize("pbc", [(0, 0, 0), (2, 0, 1)])
+def test_distributed_tile_kernel_matches_oracle(mesh, pbc):
+    """K1 v9 (supercell tiles) on a split domain: leaver packets, the appended-slot tail pass and the non-periodic move."""
+    world = mesh[0] * mesh[1] * mesh[2]
+    if not torch.cuda.is_available():
+        pytest.fail("-m gpu tests need a CUDA device")
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs, found {torch.cuda.device_count()}")
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, mesh, 1, pbc, 5, q, (8, 8, 4), "tile")) for r in range(world)]
     for pr in procs:
         pr.start()
     res = [q.get(timeout=90) for _ in range(world)]
