@@ -132,6 +132,21 @@ int pic_pack_planes(const PicParams* p, int axis, int start, int nplanes, int nc
 int pic_unpack_planes(const PicParams* p, int axis, int start, int nplanes, int ncomp, void* const* fields,
                       const void* buf, int mode, void* stream);
 
+/* ---- electrostatic field solve, one ghosted tile (mesh == 1,1,1) ----
+ * solvers/electrostatic_yee.py:71-156 solve_poisson_with_conjugate_gradient: matrix-free CG for -lapl(phi) = rho/eps with the
+ * reference's update order and stopping rule (k < max_iter && sum r^2 > tol^2); phi is the initial guess on entry and the
+ * solution (ghosts filled per field_bc: periodic refresh / constant-potential conducting walls) on return.
+ * work_r, work_p, work_lp: scratch arrays of the tile's ghosted size; scal: double[8] device scratch (scal[4] = iterations);
+ * the host looks at the device-side "done" flag every `check_every` iterations; *iters_out (host, may be NULL) = iterations. */
+int pic_poisson_cg(const PicParams* p, const void* rho, void* phi, void* work_r, void* work_p, void* work_lp, double* scal,
+                   double tol, int max_iter, int check_every, int* iters_out, void* stream);
+/* solvers/electrostatic_yee.py:20-37 _apply_tiled_phi_constant_boundaries on one tile (in place). */
+int pic_phi_boundaries(const PicParams* p, void* field, void* stream);
+/* boundary_conditions/ghost_cells.py:365-386: exterior ghost planes of `axis` := adjacent interior plane (in place). */
+int pic_constant_wall(const PicParams* p, int axis, void* field, void* stream);
+/* solvers/electrostatic_yee.py:212-246: E_c = -(phi[+1] - phi[-1]) / (2 d_c) on the tile interior (ghosts untouched). */
+int pic_gradient_neg(const PicParams* p, const void* phi, void* const E[3], void* stream);
+
 /* utils.py:160-187 compute_energy pieces: out[0] += sum over interiors of f^2 (double accumulate). */
 int pic_sum_squares_interior(const PicParams* p, const void* field, double* out, void* stream);
 /* out[0] += sum active*(sqrt(p^2C^2+m^2C^4)-mC^2), out[1] += sum active*|v|*m  (utils.py:170-202). */

@@ -36,3 +36,17 @@ def time_loop_electrodynamic(particles, species_config, fields, static_parameter
     E = update_E(E, B, J, sp, dp)                                                     # :92
     B = update_B(E, B, sp, dp, do_filter=True)                                        # :96
     return particles, (E, B, J, rho, phi, external_fields, pml_state, overflow)
+
+
+def time_loop_electrostatic(particles, species_config, fields, static_parameters, dynamic_parameters):
+    """PyPIC3D/evolve.py:106-161."""
+    from .electrostatic import calculate_tiled_electrostatic_fields
+    E, B, J, rho, phi, external_fields, pml_state, overflow_previous = fields                          # :122
+    sp, dp = static_parameters, dynamic_parameters
+    push_E, push_B = add_external_fields(E, B, external_fields)                                       # :128
+    particles = particle_push(particles, species_config, push_E, push_B, sp, dp)                      # :131
+    particles = update_tiled_particle_positions(particles, species_config, dp.dt)                     # :141
+    particles, overflow = refresh_tiled_particle_tiles(particles, sp, dp)                             # :144
+    overflow = bool(overflow_previous) | overflow
+    E, phi, rho = calculate_tiled_electrostatic_fields(sp, dp, particles, species_config, rho, phi)   # :148
+    return particles, (E, B, J, rho, phi, external_fields, pml_state, overflow)

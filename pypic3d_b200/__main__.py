@@ -32,6 +32,7 @@ def run_PyPIC3D(config_file, dtype=torch.float64, resident=None, verbose=True):
     dt, Nt, out = dp.dt, sp.Nt, sp.output_dir
     single_tile = tuple(particles.x.shape[:3]) == (1, 1, 1)
     resident = single_tile if resident is None else (resident and single_tile)
+    resident = resident and not sp.electrostatic       # the resident fused path is the electrodynamic step
     sim = Simulation(particles, species, fields, sp, dp) if resident else None
 
     def energies(particles, fields):

@@ -13,7 +13,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
 LIB_PATH = os.environ.get("PIC_B200_LIB", os.path.join(_HERE, "libpic_b200.so"))   # override: A/B builds for profiling
-SOURCES = ["kernels_particles_ref.cu", "kernels_fields.cu", "kernels_fast.cu", "microbench.cu"]
+SOURCES = ["kernels_particles_ref.cu", "kernels_fields.cu", "kernels_fast.cu", "kernels_poisson.cu", "microbench.cu"]
 HEADERS = ["pic_common.cuh", "pic_math.cuh", "pic_slots.cuh"]
 MAX_SPECIES = 16
 
@@ -75,7 +75,7 @@ def build(force=False, verbose=False):
 
 _LIB = None
 LAUNCHES = 0   # kernels launched through the C ABI since last reset (bench.py "gpu_launches")
-KERNELS_PER_CALL = {"pic_halo_fold_axis": 2, "pic_sort_scan": 3, "pic_retile": 2, "pic_microbench": 0, "pic_params_size": 0,
+KERNELS_PER_CALL = {"pic_poisson_cg": 0, "pic_phi_boundaries": 3, "pic_halo_fold_axis": 2, "pic_sort_scan": 3, "pic_retile": 2, "pic_microbench": 0, "pic_params_size": 0,
                     "pic_version": 0}
 
 
@@ -117,6 +117,10 @@ SIGNATURES = {
     "pic_halo_refresh_axis": [_PP, _INT, _INT, _INT, _V3, _VP],
     "pic_halo_fold_axis": [_PP, _INT, _INT, _INT, _V3, _VP],
     "pic_zero_wall": [_PP, _INT, _VP, _VP],
+    "pic_poisson_cg": [_PP, _VP, _VP, _VP, _VP, _VP, _VP, _DBL, _INT, _INT, ctypes.POINTER(ctypes.c_int), _VP],
+    "pic_phi_boundaries": [_PP, _VP, _VP],
+    "pic_constant_wall": [_PP, _INT, _VP, _VP],
+    "pic_gradient_neg": [_PP, _VP, _V3, _VP],
     "pic_pack_planes": [_PP, _INT, _INT, _INT, _INT, _V3, _VP, _VP],
     "pic_unpack_planes": [_PP, _INT, _INT, _INT, _INT, _V3, _VP, _INT, _VP],
     "pic_sum_squares_interior": [_PP, _VP, _VP, _VP],

@@ -1,6 +1,6 @@
 """`initialize_simulation(config)` with the reference's TOML schema, defaults and return tuple
 (PyPIC3D/initialization.py:138-488, utils.py:621-653, :540-618).  Host-side NumPy set-up; the returned particles / fields
-are torch CUDA tensors.  Not reproduced (outside the hot path): PML, the electrostatic solver,
+are torch CUDA tensors.  Not reproduced (outside the hot path): PML,
 openPMD / matplotlib output -- the corresponding keys are accepted and ignored with a notice."""
 import os
 from types import SimpleNamespace
@@ -10,11 +10,11 @@ import torch
 
 from .boundary_conditions.grid_and_stencil import BC_CONDUCTING, BC_PERIODIC
 from .boundary_conditions.ghost_cells import update_tiled_vector_ghost_cells
-from .evolve import time_loop_electrodynamic
+from .evolve import time_loop_electrodynamic, time_loop_electrostatic
 from .parameters import build_dynamic_parameters, build_static_parameters, make_field_mesh
 from .particles.particle_class import SpeciesConfig, TiledParticles
 from .particles.particle_initialization import load_particles_from_toml
-from .utilities.grids import build_tiled_yee_grids, build_yee_grid
+from .utilities.grids import build_collocated_grid, build_tiled_yee_grids, build_yee_grid
 from .utils import courant_condition
 
 
@@ -73,8 +73,6 @@ def _validate(static_config, dynamic_config):
     """initialization.py:42-124."""
     if static_config["solver"] not in ("electrodynamic_yee", "electrostatic"):
         raise ValueError(f"Unsupported solver: {static_config['solver']}. Use 'electrodynamic_yee' or 'electrostatic'.")
-    if static_config["solver"] == "electrostatic":
-        raise NotImplementedError("the electrostatic solver is outside the hot path of pypic3d_b200 (SURVEY.md section 8 f3)")
     if static_config["current_calculation"] not in ("j_from_rhov", "esirkepov"):
         raise ValueError("Unsupported current_calculation. Use 'j_from_rhov' or 'esirkepov'.")
     if static_config["current_calculation"] == "esirkepov" and static_config["filter_j"] != "none":
@@ -132,8 +130,9 @@ def initialize_simulation(toml_file, device=None, dtype=torch.float64, verbose=T
     if config.get("pml"):
         raise NotImplementedError("[pml] is outside the hot path of pypic3d_b200 (SURVEY.md section 2 row 15)")
     Nx, Ny, Nz = dynamic_config["Nx"], dynamic_config["Ny"], dynamic_config["Nz"]
+    electrostatic = static_config.get("solver") == "electrostatic"
     for n, w in zip((Nx, Ny, Nz), ("particle_tile_nx", "particle_tile_ny", "particle_tile_nz")):
-        if static_config[w] is None:
+        if static_config[w] is None or electrostatic:                                        # :243-254: one tile when electrostatic
             static_config[w] = int(n)
     static_config["guard_cells"] = max(int(static_config["guard_cells"]), 2)                  # :256
     _validate(static_config, dynamic_config)
@@ -144,7 +143,7 @@ def initialize_simulation(toml_file, device=None, dtype=torch.float64, verbose=T
         dynamic_config["dt"] = courant_condition(static_config["cfl"], dx, dy, dz, SimpleNamespace(**dynamic_config))
     dt = dynamic_config["dt"]
     static_config["Nt"] = int(static_config["Nt"]) if static_config["Nt"] is not None else int(dynamic_config["t_wind"] / dt)
-    static_config["electrostatic"] = False
+    static_config["electrostatic"] = electrostatic                                            # :237-238
     static_config["current_deposition"] = "esirkepov" if static_config["current_calculation"] == "esirkepov" else "direct"
     static_config["current_filter"] = static_config["filter_j"]
     static_config["boundary_conditions"] = {a: _encode_field_bc(static_config[f"{a}_bc"]) for a in "xyz"}
@@ -154,7 +153,7 @@ def initialize_simulation(toml_file, device=None, dtype=torch.float64, verbose=T
     static_config["field_mesh"] = make_field_mesh((Nx // static_config["particle_tile_nx"], Ny // static_config["particle_tile_ny"],
                                                    Nz // static_config["particle_tile_nz"]))
     ns = SimpleNamespace(**dynamic_config)
-    center, vertex = build_yee_grid(ns)
+    center, vertex = build_collocated_grid(ns) if electrostatic else build_yee_grid(ns)      # :310-313
     dynamic_config["grids"] = {"center": center, "vertex": vertex, "tiled_center_grid": (), "tiled_vertex_grid": ()}
     sp = build_static_parameters(static_config)
     dp = build_dynamic_parameters(dynamic_config)
@@ -185,4 +184,5 @@ def initialize_simulation(toml_file, device=None, dtype=torch.float64, verbose=T
     plasma_parameters = {"species": meta}
     if verbose:
         print(f"Initializing Simulation: {sp.name}\nUsing tiled Yee storage with tile shape: {sp.tile_shape}; dt = {dt}; Nt = {sp.Nt}")
-    return time_loop_electrodynamic, particles, fields, sp, dp, plotting, plasma_parameters, species_np
+    loop = time_loop_electrostatic if electrostatic else time_loop_electrodynamic             # :466-470
+    return loop, particles, fields, sp, dp, plotting, plasma_parameters, species_np

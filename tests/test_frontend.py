@@ -88,3 +88,40 @@ def test_two_stream_config_matches_oracle(tmp_path, tile_nx, dep):
     # energy history file written with the reference's row format, and it matches the oracle's energies at t=0
     rows = open(os.path.join(str(tmp_path), "data", "total_energy.txt")).read().strip().splitlines()
     assert len(rows) == 3 and rows[0].startswith("0.0, ")
+
+
+@pytest.mark.gpu
+def test_electrostatic_config_matches_oracle(tmp_path):
+    """solver = "electrostatic" (two-stream style plasma on 16x4x4): one tile, collocated grids (initialization.py:251-254,
+    310-313), evolve.time_loop_electrostatic selected; 5 steps from the identical initial state against the oracle."""
+    from tests import gpu_util as gu
+    gu.require_cuda()
+    from pypic3d_b200.initialization import initialize_simulation
+    from pypic3d_b200.evolve import time_loop_electrostatic
+    from pypic3d_b200.__main__ import run_PyPIC3D
+    from oracle import evolve as oevolve
+    from oracle.params import StaticParameters as OS, DynamicParameters as OD, GridParameters as OG, TiledParticles as OT, SpeciesConfig as OC
+    cfg = {k: dict(v) for k, v in TWO_STREAM.items()}
+    cfg["simulation_parameters"].update(output_dir=str(tmp_path), solver="electrostatic", Nx=16, Ny=4, Nz=4, particle_tile_nx=8,
+                                        particle_tile_ny=4, particle_tile_nz=4, particle_tile_capacity_factor=1.5, Nt=5, shape_factor=1)
+    for k in ("particle1", "particle2", "particle3"):
+        cfg[k]["N_particles"] = cfg[k]["N_particles"] // 5
+    np.random.seed(0)
+    loop, particles, fields, sp, dp, plotting, plasma, species = initialize_simulation(cfg, verbose=False)
+    assert loop is time_loop_electrostatic and sp.electrostatic and tuple(sp.tile_shape) == (16, 4, 4)
+    assert np.array_equal(np.asarray(dp.grids.center[0]), np.asarray(dp.grids.vertex[0]))
+    osp = OS(**sp._asdict()); odp = OD(**{**dp._asdict(), "grids": OG(**dp.grids._asdict())})
+    otp = OT(gu.npy(particles.x), gu.npy(particles.u), gu.npy(particles.active))
+    osc = OC(*[np.asarray(v) for v in species])
+    n = lambda F: tuple(gu.npy(c) for c in F)
+    of = (n(fields[0]), n(fields[1]), n(fields[2]), gu.npy(fields[3]), gu.npy(fields[4]), (n(fields[5][0]), n(fields[5][1])), None, False)
+    for _ in range(5):
+        otp, of = oevolve.time_loop_electrostatic(otp, osc, of, osp, odp)
+    np.random.seed(0)
+    sp2, dp2, plotting2, plasma2, gp, gf, species2 = run_PyPIC3D(cfg, verbose=False)
+    assert np.array_equal(gu.npy(gp.active), otp.active)
+    gu.assert_close(gp.x, otp.x, 1e-9, "x")
+    assert np.abs(gu.npy(gp.u) - otp.u).max() <= 1e-8 * np.abs(otp.u).max()
+    scale = max(np.abs(np.asarray(c)).max() for c in of[0])
+    for a, b in zip(gf[0], of[0]):
+        assert np.abs(gu.npy(a) - np.asarray(b)).max() <= 1e-7 * scale
