@@ -106,6 +106,11 @@ def test_electrostatic_config_matches_oracle(tmp_path):
                                         particle_tile_ny=4, particle_tile_nz=4, particle_tile_capacity_factor=1.5, Nt=5, shape_factor=1)
     for k in ("particle1", "particle2", "particle3"):
         cfg[k]["N_particles"] = cfg[k]["N_particles"] // 5
+    # The reference's stopping rule is absolute (sum r^2 <= 1e-24 with r = rho/eps0 in SI units).  At laboratory densities it is
+    # unreachable: every solve then runs its 5000 iterations at round-off stagnation, the constant null-space mode of the
+    # periodic operator drifts and the result depends on the summation order at the 1e-8..1e-3 level -- nothing to pin.  A
+    # tenuous plasma keeps the rule reachable (a dozen iterations), so the comparison is meaningful.
+    cfg["particle1"]["number_density"] = 1.0e-3
     np.random.seed(0)
     loop, particles, fields, sp, dp, plotting, plasma, species = initialize_simulation(cfg, verbose=False)
     assert loop is time_loop_electrostatic and sp.electrostatic and tuple(sp.tile_shape) == (16, 4, 4)
@@ -119,12 +124,10 @@ def test_electrostatic_config_matches_oracle(tmp_path):
         otp, of = oevolve.time_loop_electrostatic(otp, osc, of, osp, odp)
     np.random.seed(0)
     sp2, dp2, plotting2, plasma2, gp, gf, species2 = run_PyPIC3D(cfg, verbose=False)
-    # In SI units the reference's absolute stopping rule (sum r^2 <= 1e-24 with r ~ rho/eps0 ~ 1e7) is unreachable, so every
-    # solve runs its 5000 iterations at round-off stagnation: two summation orders then differ by ~1e-6 of E, not by 1e-15.
-    # (The tight comparison of the same step in normalised units is tests/test_gpu_electrostatic.py.)
     assert np.array_equal(gu.npy(gp.active), otp.active)
-    gu.assert_close(gp.x, otp.x, 1e-6, "x")
-    assert np.abs(gu.npy(gp.u) - otp.u).max() <= 1e-5 * np.abs(otp.u).max()
+    gu.assert_close(gp.x, otp.x, 1e-10, "x")
+    assert np.abs(gu.npy(gp.u) - otp.u).max() <= 1e-9 * np.abs(otp.u).max()
     scale = max(np.abs(np.asarray(c)).max() for c in of[0])
-    for a, b in zip(gf[0], of[0]):
-        assert np.abs(gu.npy(a) - np.asarray(b)).max() <= 1e-4 * scale
+    assert scale > 0
+    for a, b in zip(gf[0], of[0]):       # (a one-iteration difference at the stopping threshold moves E by ~1e-3 of its scale)
+        assert np.abs(gu.npy(a) - np.asarray(b)).max() <= 1e-2 * scale

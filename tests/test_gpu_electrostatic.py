@@ -78,9 +78,13 @@ def test_phi_boundaries_and_gradient_match_oracle(bcs):
         gu.assert_close(a, np.asarray(b), 1e-13, "E")
 
 
-@pytest.mark.parametrize("sf,alpha,bcs,pbc", [(1, 1.0, (0, 0, 0), (0, 0, 0)), (2, 0.9, (0, 0, 0), (0, 0, 0)), (1, 1.0, (1, 0, 0), (1, 0, 0))])
+@pytest.mark.parametrize("sf,alpha,bcs,pbc", [(1, 1.0, (0, 0, 0), (0, 0, 0)), (2, 0.9, (0, 0, 0), (0, 0, 0)), (2, 1.0, (0, 0, 0), (0, 0, 0))])
 def test_time_loop_electrostatic_matches_oracle(sf, alpha, bcs, pbc):
-    """Drop-in evolve.time_loop_electrostatic, 3 steps, slot-exact particles and fields against the oracle (f64)."""
+    """Drop-in evolve.time_loop_electrostatic, 3 steps, slot-exact particles and fields against the oracle (f64).
+    Periodic only: with a conducting wall the reference's rho deposit leaves a net interior charge (the wall node's share is
+    not folded back), the constant-potential Poisson problem is then inconsistent and its CG diverges (phi ~ 1e16 after the
+    5000 iterations) -- there is nothing meaningful to compare; the wall treatment itself is covered on consistent right-hand
+    sides by test_cg_matches_oracle and test_phi_boundaries_and_gradient_match_oracle."""
     from pypic3d_b200.evolve import time_loop_electrostatic
     n = 8
     sp, dp = fx.kernel_parameters(Nx=n, Ny=n, Nz=n, x_wind=float(n), y_wind=float(n), z_wind=float(n), tile_shape=(n, n, n), dt=0.1,
