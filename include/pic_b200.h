@@ -211,8 +211,10 @@ int pic_fused_push_deposit(const PicParams* p, int species, int deposition, cons
  * does not depend on how stale the sort is.  The SoA rows should be 16-byte aligned (cap a multiple of 4 reals); otherwise
  * particles are read from global memory.  flags: int32[>=3]; flags[0] as for pic_fused_push_deposit, flags[2] counts the
  * particles that took the global-memory gather.  Returns PIC_EUNSUPPORTED for any other configuration or when the driver has
- * no cuTensorMapEncodeTiled (call pic_fused_push_deposit instead).  Replaces, like pic_fused_push_deposit, evolve.py:33-79. */
-int pic_fused_tile3d(const PicParams* p, int species, const PicSoA* soa, const int32_t* blk_off, int nblk,
+ * no cuTensorMapEncodeTiled (call pic_fused_push_deposit instead).  Replaces, like pic_fused_push_deposit, evolve.py:33-79.
+ * options bit 0 (float32 only): accumulate the same-cell currents in per-supercell shared-memory J tiles (shared-memory
+ * atomics) and flush each tile with one TMA reduce per component instead of global REDs -- for species whose sort is stale. */
+int pic_fused_tile3d(const PicParams* p, int species, const PicSoA* soa, const int32_t* blk_off, int nblk, int options,
                      const void* const E[3], const void* const B[3], void* const J[3], const PicLeave* leave, int32_t* flags,
                      void* stream);
 

@@ -131,7 +131,7 @@ SIGNATURES = {
     "pic_sort_scan": [_I64, _VP, _VP, _VP, _VP],
     "pic_sort_scatter": [_PP, _SOA, _SOA, _VP, _VP, _VP],
     "pic_fused_push_deposit": [_PP, _INT, _INT, _SOA, _V3, _V3, _V3, _V3, _V3, _LEAVE, _VP, _VP],
-    "pic_fused_tile3d": [_PP, _INT, _SOA, _VP, _INT, _V3, _V3, _V3, _LEAVE, _VP, _VP],
+    "pic_fused_tile3d": [_PP, _INT, _SOA, _VP, _INT, _INT, _V3, _V3, _V3, _LEAVE, _VP, _VP],
     "pic_packets_reset": [_PP, _LEAVE, _VP],
     "pic_soa_append_packets": [_PP, _SOA, _LEAVE, _VP, _VP],
     "pic_microbench": [_INT, _INT, ctypes.POINTER(ctypes.c_float)],

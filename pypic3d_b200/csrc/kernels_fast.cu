@@ -394,8 +394,21 @@ __device__ __forceinline__ void tma_load_bytes(void* smem_dst, const void* gmem_
                  ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
+// TMA reduce: global J box (8 x 8 x 8 nodes at z, y, x) += the shared-memory tile (element-wise add performed in L2)
+__device__ __forceinline__ void tma_reduce_add_box(const CUtensorMap* map, const void* smem_src, int z, int y, int x) {
+    asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.bulk_group [%0, {%2, %3, %4}], [%1];\n"
+                 ::"l"((uint64_t)map), "r"(smem_u32(smem_src)), "r"(z), "r"(y), "r"(x)
+                 : "memory");
+}
+__device__ __forceinline__ void red_shared_add(float* p, float v) {
+    asm volatile("red.shared.add.f32 [%0], %1;\n" ::"r"(smem_u32(p)), "f"(v) : "memory");
+}
+__device__ __forceinline__ void red_shared_add(double* p, double v) {
+    asm volatile("red.shared.add.f64 [%0], %1;\n" ::"r"(smem_u32(p)), "d"(v) : "memory");
+}
 struct TileMaps {
     CUtensorMap m[6];      // Ex Ey Ez Bx By Bz, each the ghosted (Lx, Ly, Lz) tile with an 8 x 9 x 8 box
+    CUtensorMap j[3];      // Jx Jy Jz with an 8 x 8 x 8 box (TMA reduce target of the shared-memory J tiles)
 };
 
 // Segmented inclusive scan (depth STEPS) of the same-cell current values over lanes with equal key; the last lane of every run
@@ -436,19 +449,73 @@ __device__ __forceinline__ void same_cell_scan_red(T* vals, int key, int lane, c
     }
 }
 
+// Same reduction, but the run tails add into the supercell's shared-memory J tile (`jt`: [3][8][8][8], origin = the E/B tile's)
+// when their stencil is covered by it (srel >= 0), and into global memory otherwise.
+template <typename T, int STEPS>
+__device__ __forceinline__ void same_cell_scan_red_tile(T* vals, int key, int srel, int lane, const TileSink<T>& sink, int sx, int sy, T* jt) {
+    constexpr int SF = 1;
+    constexpr int NV = SameCell<SF>::NV, NN = SameCell<SF>::NN;
+    constexpr int G = 1 << STEPS;
+    const int gl = lane & (G - 1);
+    const int key_prev = __shfl_up_sync(0xffffffffu, key, 1);
+    const bool head = (gl == 0) || (key != key_prev);
+    int flag = head ? 1 : 0;
+#pragma unroll
+    for (int d = 1; d < G; d <<= 1) {
+        const int fo = __shfl_up_sync(0xffffffffu, flag, d);
+        const bool take = (gl >= d) && (flag == 0);
+#pragma unroll
+        for (int n = 0; n < NV; ++n) {
+            const T o = __shfl_up_sync(0xffffffffu, vals[n], d);
+            if (take) vals[n] += o;
+        }
+        if (take) flag |= fo;
+    }
+    const int head_next = __shfl_down_sync(0xffffffffu, head ? 1 : 0, 1);
+    const bool tail = (gl == G - 1) || (head_next != 0);
+    if (tail && key >= 0) {
+        if (srel >= 0) {
+            int n = 0;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                T* Jc = jt + c * (TILE_N * TILE_N * TILE_N) + srel;
+#pragma unroll
+                for (int m1 = 0; m1 < NN; ++m1)
+#pragma unroll
+                    for (int m2 = 0; m2 < NN; ++m2) red_shared_add(Jc + SameCell<SF>::offset(c, 0, m1, m2, TILE_N * TILE_N, TILE_N), vals[n++]);
+            }
+        } else {
+            int n = 0;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                T* Jc = sink.J[c] + key;
+#pragma unroll
+                for (int m1 = 0; m1 < NN; ++m1)
+#pragma unroll
+                    for (int m2 = 0; m2 < NN; ++m2) atomicAdd(Jc + SameCell<SF>::offset(c, 0, m1, m2, sx, sy), vals[n++]);
+            }
+        }
+    }
+}
+
 // Particle staging: the elected thread also bulk-copies the supercell's slice of the six particle arrays (TMA 1-D copies on the
 // same barrier as the field tile), so the hot loop reads x,y,z,vx,vy,vz from shared memory and no warp ever waits for DRAM on
 // its critical path.  PCAP slots per stage cover a supercell of up to ~PCAP particles (mean 512 at 8 ppc per species); the
 // slots beyond it, and arrays that are not 16-byte aligned, are read from global memory as before.
-constexpr int K9_PCAP = 640;
-template <typename T, int PUSHER, int STEPS, int NW, bool PER1>
+constexpr int K9_PCAP = 576;
+constexpr int K9_QW = 48;        // per-warp queue of anchor-changing particles, flushed once 16 are waiting (so <= 47 ever queue up)
+// JT = true: the same-cell currents are accumulated in a shared-memory J tile per supercell ([3][8][8][8], two tiles in flight)
+// with shared-memory atomics and flushed to global memory by ONE TMA reduce per component when the last warp leaves the
+// supercell -- instead of 12 global REDs per run of same-cell particles.  It pays for species whose sort is stale (cell
+// changers fragment the runs: 5.3 RED sectors per particle for electrons 8 steps after a sort, 3.5 right after it).
+template <typename T, int PUSHER, int STEPS, int NW, bool PER1, bool JT>
 __global__ void __launch_bounds__(NW * 32, (sizeof(T) == 8 ? 1 : PIC_K9_CTAS)) k_tile3d(const __grid_constant__ PicParams p, int species, const __grid_constant__ Geom<T> gm,
                                                    const __grid_constant__ FastConst<T> k, const __grid_constant__ SoAView<T> s, const __grid_constant__ Field6<T> F, Field3W<T> J,
                                                    LeaveBuf leave, int distributed, int32_t* flags, const __grid_constant__ TileMaps tm,
                                                    const int32_t* __restrict__ blk_off, int nblk, int nby, int nbz, int stage_particles) {
     constexpr int SF = 1;
     constexpr int NV = SameCell<SF>::NV;
-    constexpr int QW = 64;                                   // per-warp queue of anchor-changing particles (flushed at >= 32)
+    constexpr int QW = K9_QW;
     constexpr int NSTAGE = 3;                                // ring: the next supercell is in flight while the current one is
                                                              // processed, and a warp may run one supercell ahead of the slowest
     constexpr int PCAP = K9_PCAP;
@@ -461,9 +528,13 @@ __global__ void __launch_bounds__(NW * 32, (sizeof(T) == 8 ? 1 : PIC_K9_CTAS)) k
     uint64_t* empty = full + NSTAGE;                         // empty[NSTAGE]: every warp is done reading the stage
     int* requested = reinterpret_cast<int*>(empty + NSTAGE); // last supercell whose stage has been requested
     int* chunk_ctr = requested + 1;                          // [NSTAGE + 1] next undealt chunk of the supercell in each ring slot (+ tail pass)
+    int* jdone = chunk_ctr + NSTAGE + 1;                     // [2] warps that have left the supercell whose currents sit in J tile 0 / 1
+    uint64_t* jfree = reinterpret_cast<uint64_t*>(smem_raw + 96);   // [2] J tile flushed and zeroed again
     T* stages = reinterpret_cast<T*>(smem_raw + 128);        // [NSTAGE][6][8][9][8] + [6][PCAP]
     T* q_old = stages + NSTAGE * STAGE_ELEMS;                // [NW][3][QW]
     T* q_new = q_old + NW * 3 * QW;
+    constexpr int JT_ELEMS = 3 * TILE_N * TILE_N * TILE_N;
+    T* jtiles = q_new + NW * 3 * QW;                         // [2][3][8][8][8] (JT only; 128-byte aligned by construction)
     TileSink<T> sink;
     for (int c = 0; c < 3; ++c) { sink.J[c] = J.f[c]; sink.L[c] = gm.L[c]; }
     sink.off = 0;
@@ -478,10 +549,14 @@ __global__ void __launch_bounds__(NW * 32, (sizeof(T) == 8 ? 1 : PIC_K9_CTAS)) k
     if (b1 < b0) b1 = b0;
     if (tid == 0) {
         for (int i = 0; i < NSTAGE; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, NW); }
+        mbar_init(jfree, 1); mbar_init(jfree + 1, 1);
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
         *requested = b0 - 1;
         for (int i = 0; i <= NSTAGE; ++i) chunk_ctr[i] = 0;
+        jdone[0] = jdone[1] = 0;
     }
+    if (JT)
+        for (int i = tid; i < 2 * JT_ELEMS; i += NW * 32) jtiles[i] = (T)0;
     __syncthreads();
     T* qo = q_old + warp * 3 * QW;
     T* qn_ = q_new + warp * 3 * QW;
@@ -531,6 +606,7 @@ __global__ void __launch_bounds__(NW * 32, (sizeof(T) == 8 ? 1 : PIC_K9_CTAS)) k
     int off_cur = 0, off_next = 0;                                       // blk_off[b], [b+1]
     if (b0 < b1) { off_cur = blk_off[b0]; off_next = blk_off[b0 + 1]; }
     int slot = 0, par = 0;       // ring slot of the supercell being processed and the parity of its use count
+    int jsel = 0, juse = 0;      // J tile of the supercell being processed (alternates) and how often that tile has been used
     int rot = 0;                 // 32-particle chunks are dealt to the warps round-robin, continuing across supercells, so every
                                  // warp gets the same number of chunks (+-1) whatever the supercell populations are
     // iteration b == b1 is the tail pass: this CTA's share of the slots appended since the last sort (particles received from
@@ -553,6 +629,9 @@ __global__ void __launch_bounds__(NW * 32, (sizeof(T) == 8 ? 1 : PIC_K9_CTAS)) k
             off_cur = off_next; off_next = off_nn;
             while (!mbar_try_wait(full + slot, par, 1000)) {
                 if (lane == 0) try_request(b + 1);       // the stage we wait for may not even have been requested yet
+            }
+            if (JT && juse > 0) {                        // this J tile last held supercell b - 2: wait for its flush
+                while (!mbar_try_wait(jfree + jsel, (juse - 1) & 1, 1000)) {}
             }
             __syncwarp();
         } else {
@@ -580,7 +659,7 @@ __global__ void __launch_bounds__(NW * 32, (sizeof(T) == 8 ? 1 : PIC_K9_CTAS)) k
 #endif
             const int i = p_beg + ch * 32 + lane;
             T vals[NV], po[3], xn[3], v[3], cur[6];
-            int key = 0, kind = 0;
+            int key = 0, kind = 0, srel = -1;
             if (i < p_end) {
                 if (i < i_staged_end) {
 #pragma unroll
@@ -589,7 +668,7 @@ __global__ void __launch_bounds__(NW * 32, (sizeof(T) == 8 ? 1 : PIC_K9_CTAS)) k
 #pragma unroll
                     for (int c = 0; c < 6; ++c) cur[c] = s.c[c][i];
                 }
-                kind = fast3d_advance<T, SF, PUSHER, false, true, PER1>(p, species, k, i, s, F, X, leave, distributed != 0, flags, po, xn, v, key, vals, cur, &ts);
+                kind = fast3d_advance<T, SF, PUSHER, false, true, PER1>(p, species, k, i, s, F, X, leave, distributed != 0, flags, po, xn, v, key, vals, cur, &ts, JT ? &srel : nullptr);
             }
             // ---- deferred anchor-changing particles: warp-private queue
             const unsigned defer = __ballot_sync(0xffffffffu, kind == 2);
@@ -607,9 +686,10 @@ __global__ void __launch_bounds__(NW * 32, (sizeof(T) == 8 ? 1 : PIC_K9_CTAS)) k
 #pragma unroll
                 for (int n = 0; n < NV; ++n) vals[n] = (T)0;
             }
-            same_cell_scan_red<T, SF, STEPS>(vals, key, lane, sink, k.sx, k.sy);
-            // ---- flush the warp queue with a (nearly) full warp
-            if (qn >= 32) {
+            if (JT) same_cell_scan_red_tile<T, STEPS>(vals, key, tail_pass ? -1 : srel, lane, sink, k.sx, k.sy, jtiles + jsel * JT_ELEMS);
+            else same_cell_scan_red<T, SF, STEPS>(vals, key, lane, sink, k.sx, k.sy);
+            // ---- flush the warp queue once half a warp of them is waiting
+            if (qn >= QW - 32) {
                 for (int e = lane; e < qn; e += 32) {
                     const T o3[3] = {qo[e], qo[QW + e], qo[2 * QW + e]};
                     const T n3[3] = {qn_[e], qn_[QW + e], qn_[2 * QW + e]};
@@ -623,6 +703,38 @@ __global__ void __launch_bounds__(NW * 32, (sizeof(T) == 8 ? 1 : PIC_K9_CTAS)) k
         rot = (rot + nchunk) % NW;
         if (!tail_pass) {
             __syncwarp();
+            if (JT) {
+                // the last warp to leave the supercell adds its J tile to global memory with one TMA reduce per component
+                asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");      // our shared-memory adds -> visible to the TMA
+                int last = 0;
+                if (lane == 0) {
+                    __threadfence_block();
+                    last = (atomicAdd(jdone + jsel, 1) == NW - 1) ? 1 : 0;
+                }
+                last = __shfl_sync(0xffffffffu, last, 0);
+                if (last) {
+                    T* jt = jtiles + jsel * JT_ELEMS;
+                    __threadfence_block();
+                    if (lane == 0) {
+                        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+#pragma unroll
+                        for (int c = 0; c < 3; ++c)
+                            tma_reduce_add_box(&tm.j[c], jt + c * (TILE_N * TILE_N * TILE_N), ts.o[2], ts.o[1], ts.o[0]);
+                        asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
+                        asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");   // the tile has been read
+                    }
+                    __syncwarp();
+                    for (int i = lane; i < JT_ELEMS; i += 32) jt[i] = (T)0;
+                    __syncwarp();
+                    if (lane == 0) {
+                        jdone[jsel] = 0;
+                        __threadfence_block();
+                        mbar_arrive(jfree + jsel);
+                    }
+                }
+                if (jsel == 1) ++juse;
+                jsel ^= 1;
+            }
             if (lane == 0) mbar_arrive(empty + slot);        // this warp no longer reads the stage in `slot`
             if (++slot == NSTAGE) { slot = 0; par ^= 1; }
         }
@@ -756,7 +868,7 @@ typedef CUresult (*PFN_tensorMapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, 
 // K1 v9 launcher: returns PIC_EUNSUPPORTED when the configuration is outside what the tile kernel was built for (the caller then
 // uses pic_fused_push_deposit).
 template <typename T>
-static int launch_tile3d(const PicParams* p, int species, const PicSoA* soa, const int32_t* blk_off, int nblk, const void* const E[3],
+static int launch_tile3d(const PicParams* p, int species, const PicSoA* soa, const int32_t* blk_off, int nblk, int options, const void* const E[3],
                          const void* const B[3], void* const J[3], const PicLeave* leave, int32_t* flags, cudaStream_t st) {
     static_assert(PIC_SORT_BLOCK == TILE_B, "the tile kernel walks the supercells of the blocked sort order");
     if (p->shape_factor != 1 || p->g != 2 || (p->pusher != PIC_PUSHER_BORIS && p->pusher != PIC_PUSHER_BORIS_REL)) return PIC_EUNSUPPORTED;
@@ -776,8 +888,9 @@ static int launch_tile3d(const PicParams* p, int species, const PicSoA* soa, con
     make_fast_const<T>(*p, species, gm, k);
     int distributed = 0;
     for (int c = 0; c < 3; ++c) distributed |= (p->gmesh[c] != p->mesh[c]);
-    constexpr int NW = PIC_K9_NW, QW = 64;
-    const size_t smem = 128 + (size_t)(3 * (6 * TILE_ELEMS + 6 * K9_PCAP) + 2 * NW * 3 * QW) * sizeof(T);
+    constexpr int NW = PIC_K9_NW, QW = K9_QW;
+    const bool jt = (options & 1) && sizeof(T) == 4;          // shared-memory J tiles: f32 only (TMA reduce type)
+    const size_t smem = 128 + (size_t)(3 * (6 * TILE_ELEMS + 6 * K9_PCAP) + 2 * NW * 3 * QW + (jt ? 2 * 3 * TILE_N * TILE_N * TILE_N : 0)) * sizeof(T);
     if (smem > 227 * 1024) return PIC_EUNSUPPORTED;
     int grid = num_sms() * (sizeof(T) == 8 ? 1 : PIC_K9_CTAS);
     int stage_particles = 1;     // TMA bulk copies need 16-byte aligned sources
@@ -807,21 +920,30 @@ static int launch_tile3d(const PicParams* p, int species, const PicSoA* soa, con
                                       CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
             if (r != CUDA_SUCCESS) return PIC_EUNSUPPORTED;
         }
+        const cuuint32_t jbox[3] = {(cuuint32_t)TILE_N, (cuuint32_t)TILE_N, (cuuint32_t)TILE_N};
+        for (int c = 0; c < 3; ++c) {
+            const CUresult r = encode(&tm.j[c], sizeof(T) == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3,
+                                      Jw.f[c], dims, strides, jbox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                      CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) return PIC_EUNSUPPORTED;
+        }
     }
     bool per1 = !distributed;
     for (int a = 0; a < 3; ++a) per1 = per1 && (p->particle_bc[a] == PIC_BC_PERIODIC);
-#define PIC_LAUNCH_K9(PUSH, PER)                                                                                         \
+#define PIC_LAUNCH_K9(PUSH, PER, JTV)                                                                                    \
     do {                                                                                                                 \
-        static bool attr_set = false;                                                                                    \
-        if (!attr_set) {                                                                                                 \
-            cudaError_t e = cudaFuncSetAttribute(k_tile3d<T, PUSH, 3, NW, PER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        static size_t attr_smem = 0;                                                                                     \
+        if (attr_smem < smem) {                                                                                          \
+            cudaError_t e = cudaFuncSetAttribute(k_tile3d<T, PUSH, 3, NW, PER, JTV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
             if (e != cudaSuccess) return (int)e;                                                                         \
-            attr_set = true;                                                                                             \
+            attr_smem = smem;                                                                                            \
         }                                                                                                                \
-        k_tile3d<T, PUSH, 3, NW, PER><<<grid, NW * 32, smem, st>>>(*p, species, gm, k, sv, F, Jw, lb, distributed, flags, tm, blk_off, nblk, nby, nbz, stage_particles); \
+        k_tile3d<T, PUSH, 3, NW, PER, JTV><<<grid, NW * 32, smem, st>>>(*p, species, gm, k, sv, F, Jw, lb, distributed, flags, tm, blk_off, nblk, nby, nbz, stage_particles); \
     } while (0)
-    if (p->pusher == PIC_PUSHER_BORIS) { if (per1) PIC_LAUNCH_K9(PIC_PUSHER_BORIS, true); else PIC_LAUNCH_K9(PIC_PUSHER_BORIS, false); }
-    else { if (per1) PIC_LAUNCH_K9(PIC_PUSHER_BORIS_REL, true); else PIC_LAUNCH_K9(PIC_PUSHER_BORIS_REL, false); }
+#define PIC_LAUNCH_K9_J(PUSH, PER) do { if (jt) PIC_LAUNCH_K9(PUSH, PER, true); else PIC_LAUNCH_K9(PUSH, PER, false); } while (0)
+    if (p->pusher == PIC_PUSHER_BORIS) { if (per1) PIC_LAUNCH_K9_J(PIC_PUSHER_BORIS, true); else PIC_LAUNCH_K9_J(PIC_PUSHER_BORIS, false); }
+    else { if (per1) PIC_LAUNCH_K9_J(PIC_PUSHER_BORIS_REL, true); else PIC_LAUNCH_K9_J(PIC_PUSHER_BORIS_REL, false); }
+#undef PIC_LAUNCH_K9_J
 #undef PIC_LAUNCH_K9
     PIC_LAUNCH_RET();
 }
@@ -892,14 +1014,14 @@ int pic_fused_push_deposit(const PicParams* p, int species, int deposition, cons
     PIC_DISPATCH_T_SF(p, launch_fused, p, species, deposition, soa, E, B, extE, extB, J, leave, flags, (cudaStream_t)stream);
 }
 
-int pic_fused_tile3d(const PicParams* p, int species, const PicSoA* soa, const int32_t* blk_off, int nblk, const void* const E[3],
-                     const void* const B[3], void* const J[3], const PicLeave* leave, int32_t* flags, void* stream) {
+int pic_fused_tile3d(const PicParams* p, int species, const PicSoA* soa, const int32_t* blk_off, int nblk, int options,
+                     const void* const E[3], const void* const B[3], void* const J[3], const PicLeave* leave, int32_t* flags, void* stream) {
     PIC_CHECK_ARG(p && soa && blk_off && E && B && J && flags && species >= 0 && species < p->n_species && nblk > 0);
     PIC_CHECK_ARG(p->mesh[0] == 1 && p->mesh[1] == 1 && p->mesh[2] == 1);
     bool distributed = false;
     for (int c = 0; c < 3; ++c) distributed |= (p->gmesh[c] != p->mesh[c]);
     if (distributed) PIC_CHECK_ARG(leave && leave->buf);
-    PIC_DISPATCH_T(p, launch_tile3d, p, species, soa, blk_off, nblk, E, B, J, leave, flags, (cudaStream_t)stream);
+    PIC_DISPATCH_T(p, launch_tile3d, p, species, soa, blk_off, nblk, options, E, B, J, leave, flags, (cudaStream_t)stream);
 }
 
 int pic_packets_reset(const PicParams* p, const PicLeave* leave, void* stream) {

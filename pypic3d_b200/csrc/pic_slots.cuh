@@ -668,8 +668,11 @@ struct TileSrc {
 template <typename T, int SF, int PUSHER, bool HAS_EXT, bool TILE = false, bool PERIODIC1 = false>
 PIC_HD int fast3d_advance(const PicParams& p, int species, const FastConst<T>& k, int64_t i, const SoAView<T>& s, const Field6<T>& F,
                           const Field6<T>& X, const LeaveBuf& leave, bool distributed, int32_t* flags, T pos_old[3], T xn[3], T vout[3],
-                          int& key, T* vals, const T* pre = nullptr, const TileSrc<T>* ts = nullptr) {
+                          int& key, T* vals, const T* pre = nullptr, const TileSrc<T>* ts = nullptr, int* srel = nullptr) {
     static_assert(!TILE || (SF == 1 && !HAS_EXT), "the tile gather is built for CIC without external fields");
+    // srel (TILE only, may be null): element offset of the particle's first deposit node inside an 8x8x8 shared-memory J tile
+    // with the E/B tile's origin, or -1 when the particle's stencil is not covered by the tile
+    int srel_ = -1;
     constexpr int NN = SF + 1;
     constexpr int K0 = (SF == 1) ? 1 : 0;
     // `pre`: x,y,z,vx,vy,vz of particle i already loaded by the caller (software prefetch of the next iteration)
@@ -695,6 +698,7 @@ PIC_HD int fast3d_advance(const PicParams& p, int species, const FastConst<T>& k
             rv[a] = av[a] - ts->o[a];
             in_tile = in_tile && ((unsigned)rc[a] <= (unsigned)(TILE_N - 2)) && ((unsigned)rv[a] <= (unsigned)(TILE_N - 2));
         }
+        if (in_tile) srel_ = (rc[0] * TILE_N + rc[1]) * TILE_N + rc[2];
         if (!in_tile) {      // drifted out of the tile's one-cell margin (rare): same arithmetic from global memory
             gather_rows<T, SF, HAS_EXT>(k, F, X, ac, av, wc, wv, EB);
             atomic_add_i32(flags + 2, 1);    // diagnostic: flags[2] counts the particles that took this path
@@ -864,6 +868,7 @@ PIC_HD int fast3d_advance(const PicParams& p, int species, const FastConst<T>& k
     int kind = 2;
     if (same) {
         kind = 1;
+        if (srel) *srel = srel_;
         key = (ac[0] - (SF == 1 ? 0 : 1)) * k.sx + (ac[1] - (SF == 1 ? 0 : 1)) * k.sy + (ac[2] - (SF == 1 ? 0 : 1));
         const T third = (T)(1.0 / 3.0), sixth = (T)(1.0 / 6.0);
         T P[2][NN], Q[2][NN], cum[3][NN - 1];

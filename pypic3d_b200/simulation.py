@@ -99,6 +99,12 @@ class Simulation:
         self.k1_variant = self._pick_k1_variant(sp)
         self._import(particles, capacity_factor)
         self.sort_every = self._sort_intervals(particles)
+        # K1 v9 option bit 0 (shared-memory J tiles + TMA reduce) per species: PIC_K9_JTILE = "0" off, "1" on for every species,
+        # "fast" only for the species on the base sort cadence (whose sort goes stale between re-sorts)
+        import os
+        mode = os.environ.get("PIC_K9_JTILE", "0")
+        fastest = min(self.sort_every) if self.sort_every else 0
+        self.k1_options = [1 if (mode == "1" or (mode == "fast" and self.sort_every[s] == fastest)) else 0 for s in range(self.S)]
         self.leave_fraction = float(leave_fraction)
         if self.distributed:
             self._alloc_packets()
@@ -264,7 +270,7 @@ class Simulation:
             rc = _lib.PIC_EUNSUPPORTED
             if self.k1_variant == "tile":
                 rc = L.pic_fused_tile3d(ctypes.byref(p), s, ctypes.byref(soa), ops._p(sp_.blk_off), self.ncells // 64,
-                                        ops._v(self.E), ops._v(self.B), ops._v(self.J), leave, ops._p(self.flags), st)
+                                        self.k1_options[s], ops._v(self.E), ops._v(self.B), ops._v(self.J), leave, ops._p(self.flags), st)
                 if rc == _lib.PIC_EUNSUPPORTED:     # e.g. no TMA driver entry point: the global-gather K1 computes the same step
                     self.k1_variant = "global"
                 else:

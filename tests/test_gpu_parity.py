@@ -380,12 +380,14 @@ TILE_CASES = [
 @pytest.mark.parametrize("c", TILE_CASES)
 @pytest.mark.parametrize("dtype", (F64, F32))
 @pytest.mark.parametrize("sort_interval", (1, 5, 0))
-def test_resident_tile_kernel_matches_oracle(c, dtype, sort_interval):
+@pytest.mark.parametrize("jtile", ("0", "1"))
+def test_resident_tile_kernel_matches_oracle(c, dtype, sort_interval, jtile, monkeypatch):
     """K1 v9 (pic_fused_tile3d): E/B gathered from shared-memory supercell tiles.  Fast particles (up to 0.16 cells per step)
     and sort_interval 5 / never let particles drift into the tile margin and beyond it, so the tile gather, its global-memory
     fallback and the deferred cell-crossers are all exercised; 12 steps (dt inside the Yee CFL limit), slot-exact against the
     oracle."""
     from pypic3d_b200.simulation import Simulation
+    monkeypatch.setenv("PIC_K9_JTILE", jtile)       # "1": same-cell currents through shared-memory J tiles + TMA reduce (f32 only)
     N = c["N"]
     sp, dp, tp, sc, E, B = make_case(N, N, 1, current_deposition="esirkepov", relativistic=c["rel"],
                                      particle_boundary_conditions=c["pbc"], capacity=3.0, vmax=4.0, C=10.0, dt=0.015, n=200)
@@ -410,17 +412,21 @@ def test_resident_tile_kernel_matches_oracle(c, dtype, sort_interval):
 
 
 @pytest.mark.parametrize("dtype,tol", [(F64, 1e-11), (F32, 2e-4)])
-def test_tile_and_global_k1_variants_agree(dtype, tol, monkeypatch):
-    """Same 32^3 x 16 ppc thermal plasma, 12 steps with a sort every 5: the supercell-tile K1 and the global-gather K1 differ only
-    by the order of the floating-point atomics."""
+@pytest.mark.parametrize("n,ppc", [(32, 8), (16, 24)])
+@pytest.mark.parametrize("jtile", ("0", "1"))
+def test_tile_and_global_k1_variants_agree(dtype, tol, n, ppc, jtile, monkeypatch):
+    """Same thermal plasma, 12 steps with a sort every 5: the supercell-tile K1 and the global-gather K1 differ only by the
+    order of the floating-point atomics.  32^3 x 16 ppc is the bench's density (512 particles per supercell and species, inside
+    the 640-slot particle stage); 16^3 x 48 ppc puts 1536 particles into every supercell, so most chunks lie beyond the staged
+    slice and are read from global memory."""
     from pypic3d_b200.simulation import Simulation
-    n = 32
     sp, dp = fx.kernel_parameters(Nx=n, Ny=n, Nz=n, x_wind=float(n), y_wind=float(n), z_wind=float(n), shape_factor=1, dt=0.3,
                                   current_deposition="esirkepov", particle_tile_capacity_factor=1.0)
-    tp, sc = fx.thermal_plasma(sp, dp, ppc_per_species=8, vth=(0.15, 0.02), seed=5)
+    tp, sc = fx.thermal_plasma(sp, dp, ppc_per_species=ppc, vth=(0.15, 0.02), seed=5)
     fields = make_fields(sp, dp, scale=0.02)
     ps, pd = gu.to_pkg_params(sp, dp)
     out = {}
+    monkeypatch.setenv("PIC_K9_JTILE", jtile)
     for variant in ("tile", "global"):
         monkeypatch.setenv("PIC_K1_VARIANT", variant)
         sim = Simulation(gu.particles_to_gpu(tp, dtype), gu.species_to_pkg(sc), gu.fields_to_gpu(fields, dtype), ps, pd, sort_interval=5)
