@@ -530,7 +530,9 @@ __global__ void __launch_bounds__(NW * 32, (sizeof(T) == 8 ? 1 : PIC_K9_CTAS)) k
     int* chunk_ctr = requested + 1;                          // [NSTAGE + 1] next undealt chunk of the supercell in each ring slot (+ tail pass)
     int* jdone = chunk_ctr + NSTAGE + 1;                     // [2] warps that have left the supercell whose currents sit in J tile 0 / 1
     uint64_t* jfree = reinterpret_cast<uint64_t*>(smem_raw + 96);   // [2] J tile flushed and zeroed again
-    T* stages = reinterpret_cast<T*>(smem_raw + 128);        // [NSTAGE][6][8][9][8] + [6][PCAP]
+    int* desc = reinterpret_cast<int*>(smem_raw + 128);      // [NSTAGE][8] what the requester knows about the supercell in each slot:
+                                                             // first slot, end slot, end of the staged slice, tile origin x, y, z
+    T* stages = reinterpret_cast<T*>(smem_raw + 256);        // [NSTAGE][6][8][9][8] + [6][PCAP]
     T* q_old = stages + NSTAGE * STAGE_ELEMS;                // [NW][3][QW]
     T* q_new = q_old + NW * 3 * QW;
     constexpr int JT_ELEMS = 3 * TILE_N * TILE_N * TILE_N;
@@ -591,7 +593,10 @@ __global__ void __launch_bounds__(NW * 32, (sizeof(T) == 8 ? 1 : PIC_K9_CTAS)) k
         if (end > n_live) end = n_live;
         const int n = slice_len(beg, end);
         T* st = stages + sr * STAGE_ELEMS;
-        chunk_ctr[sr] = 0;           // (published to the other warps by the release of the expect_tx arrive)
+        chunk_ctr[sr] = 0;           // (published to the other warps, like the descriptor, by the release of the expect_tx arrive)
+        int* d = desc + sr * 8;
+        d[0] = beg; d[1] = end; d[2] = (beg & ~(AL - 1)) + n;
+        d[4] = bx * TILE_B; d[5] = by * TILE_B; d[6] = bz * TILE_B;
         mbar_arrive_expect_tx(full + sr, TILE_BYTES + 6 * n * (int)sizeof(T));
 #pragma unroll
         for (int c = 0; c < 6; ++c)
@@ -602,9 +607,6 @@ __global__ void __launch_bounds__(NW * 32, (sizeof(T) == 8 ? 1 : PIC_K9_CTAS)) k
             for (int c = 0; c < 6; ++c) tma_load_bytes(st + TILE_ALL + c * PCAP, s.c[c] + beg_al, n * (int)sizeof(T), full + sr);
         }
     };
-    int cx = b0 / (nbz * nby), cy = (b0 / nbz) % nby, cz = b0 % nbz;    // supercell being processed
-    int off_cur = 0, off_next = 0;                                       // blk_off[b], [b+1]
-    if (b0 < b1) { off_cur = blk_off[b0]; off_next = blk_off[b0 + 1]; }
     int slot = 0, par = 0;       // ring slot of the supercell being processed and the parity of its use count
     int jsel = 0, juse = 0;      // J tile of the supercell being processed (alternates) and how often that tile has been used
     int rot = 0;                 // 32-particle chunks are dealt to the warps round-robin, continuing across supercells, so every
@@ -617,18 +619,17 @@ __global__ void __launch_bounds__(NW * 32, (sizeof(T) == 8 ? 1 : PIC_K9_CTAS)) k
         const T* st = stages + slot * STAGE_ELEMS;
         TileSrc<T> ts;
         ts.t = st;
-        int p_beg, p_end, n_staged = 0;
+        int p_beg, p_end, i_staged_end = 0;
         if (!tail_pass) {
-            const int off_nn = (b + 2 <= nblk) ? blk_off[b + 2] : off_next;    // read one supercell ahead of its use
-            ts.o[0] = cx * TILE_B; ts.o[1] = cy * TILE_B; ts.o[2] = cz * TILE_B;
-            if (++cz == nbz) { cz = 0; if (++cy == nby) { cy = 0; ++cx; } }      // now the coordinates of supercell b + 1
             if (lane == 0) try_request(b + 1);
-            p_beg = off_cur;
-            p_end = (off_next < n_live) ? off_next : n_live;
-            n_staged = slice_len(p_beg, p_end);
-            off_cur = off_next; off_next = off_nn;
             while (!mbar_try_wait(full + slot, par, 1000)) {
                 if (lane == 0) try_request(b + 1);       // the stage we wait for may not even have been requested yet
+            }
+            {   // everything else about this supercell was worked out once, by the thread that requested its stage
+                const int4 d0 = *reinterpret_cast<const int4*>(desc + slot * 8);
+                const int4 d1 = *reinterpret_cast<const int4*>(desc + slot * 8 + 4);
+                p_beg = d0.x; p_end = d0.y; i_staged_end = d0.z;
+                ts.o[0] = d1.x; ts.o[1] = d1.y; ts.o[2] = d1.z;
             }
             if (JT && juse > 0) {                        // this J tile last held supercell b - 2: wait for its flush
                 while (!mbar_try_wait(jfree + jsel, (juse - 1) & 1, 1000)) {}
@@ -644,7 +645,6 @@ __global__ void __launch_bounds__(NW * 32, (sizeof(T) == 8 ? 1 : PIC_K9_CTAS)) k
         }
         const int nchunk = p_end > p_beg ? (p_end - p_beg + 31) >> 5 : 0;
         const T* pst = st + TILE_ALL - (p_beg & ~(AL - 1));      // staged particle i of array c sits at pst[c * PCAP + i]
-        const int i_staged_end = (p_beg & ~(AL - 1)) + n_staged;
 #if PIC_K9_DEAL == 1
         // a warp that finishes early takes the next undealt chunk, or moves on to the next supercell: the warps stay within
         // one chunk of each other, so ring slots are released promptly
@@ -890,7 +890,7 @@ static int launch_tile3d(const PicParams* p, int species, const PicSoA* soa, con
     for (int c = 0; c < 3; ++c) distributed |= (p->gmesh[c] != p->mesh[c]);
     constexpr int NW = PIC_K9_NW, QW = K9_QW;
     const bool jt = (options & 1) && sizeof(T) == 4;          // shared-memory J tiles: f32 only (TMA reduce type)
-    const size_t smem = 128 + (size_t)(3 * (6 * TILE_ELEMS + 6 * K9_PCAP) + 2 * NW * 3 * QW + (jt ? 2 * 3 * TILE_N * TILE_N * TILE_N : 0)) * sizeof(T);
+    const size_t smem = 256 + (size_t)(3 * (6 * TILE_ELEMS + 6 * K9_PCAP) + 2 * NW * 3 * QW + (jt ? 2 * 3 * TILE_N * TILE_N * TILE_N : 0)) * sizeof(T);
     if (smem > 227 * 1024) return PIC_EUNSUPPORTED;
     int grid = num_sms() * (sizeof(T) == 8 ? 1 : PIC_K9_CTAS);
     int stage_particles = 1;     // TMA bulk copies need 16-byte aligned sources

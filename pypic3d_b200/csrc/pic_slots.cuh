@@ -418,6 +418,9 @@ PIC_HD void make_fast_const(const PicParams& p, int species, const Geom<T>& gm, 
 #ifndef PIC_FASTMATH
 #define PIC_FASTMATH 0   /* measured slower on B200 (profiles/r01_k1_versions.md): the kernel is latency-, not issue-bound */
 #endif
+#ifndef PIC_GATHER_F32X2
+#define PIC_GATHER_F32X2 1   /* tile gather (K1 v9): packed f32x2 arithmetic for the z / y interpolation of the two x planes */
+#endif
 #ifndef PIC_GATHER_V
 #define PIC_GATHER_V 2   /* 2: 64-bit row offsets from the constant bank (4.88 ms); 0: pointer + int row (5.15 ms); 1: u32 offsets (slower) */
 #endif
@@ -711,6 +714,21 @@ PIC_HD int fast3d_advance(const PicParams& p, int species, const FastConst<T>& k
             const T* wy = gy ? wv[1] : wc[1];
             const T* wz = gz ? wv[2] : wc[2];
             const T* f = ts->t + c * TILE_ELEMS + ((gx ? rv[0] : rc[0]) * TILE_SX + (gy ? rv[1] : rc[1]) * TILE_N + (gz ? rv[2] : rc[2]));
+#if defined(__CUDA_ARCH__) && PIC_GATHER_F32X2
+            if constexpr (sizeof(T) == 4) {
+                // Blackwell packed FP32: the two x planes of the stencil travel through the z and y interpolation side by side in
+                // one FMUL2 / FFMA2 each (8 floating-point instructions per component instead of 14; same roundings as below)
+                const float2 z0y0 = make_float2(f[0], f[TILE_SX]), z1y0 = make_float2(f[1], f[TILE_SX + 1]);
+                const float2 z0y1 = make_float2(f[TILE_N], f[TILE_SX + TILE_N]), z1y1 = make_float2(f[TILE_N + 1], f[TILE_SX + TILE_N + 1]);
+                const float2 wz1 = make_float2(wz[1], wz[1]), wz2 = make_float2(wz[2], wz[2]);
+                const float2 wy1 = make_float2(wy[1], wy[1]), wy2 = make_float2(wy[2], wy[2]);
+                const float2 ay0 = __ffma2_rn(z1y0, wz2, __fmul2_rn(z0y0, wz1));
+                const float2 ay1 = __ffma2_rn(z1y1, wz2, __fmul2_rn(z0y1, wz1));
+                const float2 ax = __ffma2_rn(ay1, wy2, __fmul2_rn(ay0, wy1));
+                EB[c] = ax.x * wx[1] + ax.y * wx[2];
+                continue;
+            }
+#endif
             T acc = (T)0;
 #pragma unroll
             for (int a_ = 0; a_ < 2; ++a_) {
