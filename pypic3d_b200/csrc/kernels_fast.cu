@@ -411,6 +411,33 @@ struct TileMaps {
     CUtensorMap j[3];      // Jx Jy Jz with an 8 x 8 x 8 box (TMA reduce target of the shared-memory J tiles)
 };
 
+// One level of the segmented scan: vals[n] += vals[n] of the lane d below, for the lanes that take.  float: the twelve adds are
+// six packed FADD2 (Blackwell f32x2); the shuffles move the two halves of each register pair separately.
+#ifndef PIC_SCAN_F32X2
+#define PIC_SCAN_F32X2 1
+#endif
+template <typename T, int NV>
+__device__ __forceinline__ void scan_level_add(T* vals, int d, bool take) {
+#if PIC_SCAN_F32X2
+    if constexpr (sizeof(T) == 4 && NV % 2 == 0) {
+#pragma unroll
+        for (int n = 0; n < NV; n += 2) {
+            const float2 o = make_float2(__shfl_up_sync(0xffffffffu, vals[n], d), __shfl_up_sync(0xffffffffu, vals[n + 1], d));
+            if (take) {
+                const float2 r = __fadd2_rn(make_float2(vals[n], vals[n + 1]), o);
+                vals[n] = r.x; vals[n + 1] = r.y;
+            }
+        }
+        return;
+    }
+#endif
+#pragma unroll
+    for (int n = 0; n < NV; ++n) {
+        const T o = __shfl_up_sync(0xffffffffu, vals[n], d);
+        if (take) vals[n] += o;      // predicated add (one instruction instead of select + add)
+    }
+}
+
 // Segmented inclusive scan (depth STEPS) of the same-cell current values over lanes with equal key; the last lane of every run
 // issues the REDs.  (flag = "a segment head lies in (lane-d, lane]")
 template <typename T, int SF, int STEPS>
@@ -425,11 +452,7 @@ __device__ __forceinline__ void same_cell_scan_red(T* vals, int key, int lane, c
     for (int d = 1; d < G; d <<= 1) {
         const int fo = __shfl_up_sync(0xffffffffu, flag, d);
         const bool take = (gl >= d) && (flag == 0);
-#pragma unroll
-        for (int n = 0; n < NV; ++n) {
-            const T o = __shfl_up_sync(0xffffffffu, vals[n], d);
-            if (take) vals[n] += o;      // predicated add (one instruction instead of select + add)
-        }
+        scan_level_add<T, NV>(vals, d, take);
         if (take) flag |= fo;
     }
     const int head_next = __shfl_down_sync(0xffffffffu, head ? 1 : 0, 1);
@@ -464,11 +487,7 @@ __device__ __forceinline__ void same_cell_scan_red_tile(T* vals, int key, int sr
     for (int d = 1; d < G; d <<= 1) {
         const int fo = __shfl_up_sync(0xffffffffu, flag, d);
         const bool take = (gl >= d) && (flag == 0);
-#pragma unroll
-        for (int n = 0; n < NV; ++n) {
-            const T o = __shfl_up_sync(0xffffffffu, vals[n], d);
-            if (take) vals[n] += o;
-        }
+        scan_level_add<T, NV>(vals, d, take);
         if (take) flag |= fo;
     }
     const int head_next = __shfl_down_sync(0xffffffffu, head ? 1 : 0, 1);
