@@ -418,8 +418,7 @@ struct TileMaps {
 #endif
 template <typename T, int NV>
 __device__ __forceinline__ void scan_level_add(T* vals, int d, bool take) {
-#if PIC_SCAN_F32X2
-    if constexpr (sizeof(T) == 4 && NV % 2 == 0) {
+    if constexpr (PIC_SCAN_F32X2 && sizeof(T) == 4 && NV % 2 == 0) {
 #pragma unroll
         for (int n = 0; n < NV; n += 2) {
             const float2 o = make_float2(__shfl_up_sync(0xffffffffu, vals[n], d), __shfl_up_sync(0xffffffffu, vals[n + 1], d));
@@ -428,13 +427,12 @@ __device__ __forceinline__ void scan_level_add(T* vals, int d, bool take) {
                 vals[n] = r.x; vals[n + 1] = r.y;
             }
         }
-        return;
-    }
-#endif
+    } else {
 #pragma unroll
-    for (int n = 0; n < NV; ++n) {
-        const T o = __shfl_up_sync(0xffffffffu, vals[n], d);
-        if (take) vals[n] += o;      // predicated add (one instruction instead of select + add)
+        for (int n = 0; n < NV; ++n) {
+            const T o = __shfl_up_sync(0xffffffffu, vals[n], d);
+            if (take) vals[n] += o;      // predicated add (one instruction instead of select + add)
+        }
     }
 }
 
