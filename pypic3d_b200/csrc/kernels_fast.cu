@@ -42,21 +42,42 @@ __global__ void __launch_bounds__(256) k_export(int species, SoAView<T> s, T* __
 }
 
 // ---------------------------------------------------------------- counting sort by local cell
+// Both sort kernels aggregate their atomics per warp: the stream is nearly sorted, so the 32 consecutive particles a warp holds
+// fall into a handful of cells; `__match_any_sync` groups the lanes by cell and one lane per group issues a single atomic for the
+// whole group (4-8x fewer atomics; the scatter's were returning atomics on 8-way contended addresses).
 template <typename T>
 __global__ void __launch_bounds__(256) k_sort_hist(const __grid_constant__ PicParams p, SoAView<T> s, int32_t* __restrict__ count) {
     const int64_t n = s.count();
-    for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x)
-        atomicAdd(&count[local_cell<T>(p, s.c[0][j], s.c[1][j], s.c[2][j])], 1);
+    const int lane = threadIdx.x & 31;
+    for (int64_t j0 = blockIdx.x * (int64_t)blockDim.x + (threadIdx.x - lane); j0 < n; j0 += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t j = j0 + lane;
+        const bool valid = j < n;
+        const unsigned mask = __ballot_sync(0xffffffffu, valid);
+        if (!valid) continue;
+        const int cell = local_cell<T>(p, s.c[0][j], s.c[1][j], s.c[2][j]);
+        const unsigned group = __match_any_sync(mask, cell);
+        if (lane == __ffs(group) - 1) atomicAdd(&count[cell], __popc(group));
+    }
 }
 
 template <typename T>
 __global__ void __launch_bounds__(256) k_sort_scatter(const __grid_constant__ PicParams p, SoAView<T> s, SoAView<T> d,
                                                       const int32_t* __restrict__ offset, int32_t* __restrict__ cursor) {
     const int64_t n = s.count();
-    for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x) {
+    const int lane = threadIdx.x & 31;
+    for (int64_t j0 = blockIdx.x * (int64_t)blockDim.x + (threadIdx.x - lane); j0 < n; j0 += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t j = j0 + lane;
+        const bool valid = j < n;
+        const unsigned mask = __ballot_sync(0xffffffffu, valid);
+        if (!valid) continue;
         const T px = s.c[0][j], py = s.c[1][j], pz = s.c[2][j];
         const int cell = local_cell<T>(p, px, py, pz);
-        const int64_t dst = (int64_t)offset[cell] + atomicAdd(&cursor[cell], 1);
+        const unsigned group = __match_any_sync(mask, cell);
+        const int leader = __ffs(group) - 1;
+        int base = 0;
+        if (lane == leader) base = atomicAdd(&cursor[cell], __popc(group));
+        base = __shfl_sync(group, base, leader);
+        const int64_t dst = (int64_t)offset[cell] + base + __popc(group & ((1u << lane) - 1u));
         if (dst >= d.cap) continue;
         d.c[0][dst] = px; d.c[1][dst] = py; d.c[2][dst] = pz;
         d.c[3][dst] = s.c[3][j]; d.c[4][dst] = s.c[4][j]; d.c[5][dst] = s.c[5][j];
@@ -470,6 +491,57 @@ __device__ __forceinline__ void same_cell_scan_red(T* vals, int key, int lane, c
     }
 }
 
+// Alternative to the segmented scan: reduce over ALL lanes of the warp that deposit to the same cell, contiguous or not.
+// `__match_any_sync` yields each lane's group; the groups are linked lists over the lanes and are summed by pointer doubling
+// (log2 of the longest group many rounds of 12 index shuffles); the lowest lane of every group issues the REDs.  A stale sort
+// fragments the same-cell runs (cell changers sit between them), which costs the scan one RED set per fragment but this
+// reduction nothing: REDs per warp = distinct cells per warp.
+#ifndef PIC_K9_REDUCE
+#define PIC_K9_REDUCE 0      /* 0 = segmented scan over contiguous runs, 1 = match-any groups + pointer doubling */
+#endif
+template <typename T, int SF>
+__device__ __forceinline__ void same_cell_group_red(T* vals, int key, int lane, const TileSink<T>& sink, int sx, int sy) {
+    constexpr int NV = SameCell<SF>::NV, NN = SameCell<SF>::NN;
+    const unsigned group = __match_any_sync(0xffffffffu, key);
+    const unsigned above = group & (0xfffffffeu << lane);
+    int next = above ? __ffs(above) - 1 : 32;
+    while (__any_sync(0xffffffffu, next < 32)) {
+        const bool has = next < 32;
+        const int src = has ? next : lane;
+        if constexpr (sizeof(T) == 4 && NV % 2 == 0) {
+#pragma unroll
+            for (int n = 0; n < NV; n += 2) {
+                const float2 o = make_float2(__shfl_sync(0xffffffffu, vals[n], src), __shfl_sync(0xffffffffu, vals[n + 1], src));
+                if (has) {
+                    const float2 r = __fadd2_rn(make_float2(vals[n], vals[n + 1]), o);
+                    vals[n] = r.x; vals[n + 1] = r.y;
+                }
+            }
+        } else {
+#pragma unroll
+            for (int n = 0; n < NV; ++n) {
+                const T o = __shfl_sync(0xffffffffu, vals[n], src);
+                if (has) vals[n] += o;
+            }
+        }
+        const int nn = __shfl_sync(0xffffffffu, next, src);
+        next = has ? nn : 32;
+    }
+    if (key >= 0 && lane == __ffs(group) - 1) {
+        int n = 0;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            T* Jc = sink.J[c] + key;
+#pragma unroll
+            for (int f = 0; f < NN - 1; ++f)
+#pragma unroll
+                for (int m1 = 0; m1 < NN; ++m1)
+#pragma unroll
+                    for (int m2 = 0; m2 < NN; ++m2) atomicAdd(Jc + SameCell<SF>::offset(c, f, m1, m2, sx, sy), vals[n++]);
+        }
+    }
+}
+
 // Same reduction, but the run tails add into the supercell's shared-memory J tile (`jt`: [3][8][8][8], origin = the E/B tile's)
 // when their stencil is covered by it (srel >= 0), and into global memory otherwise.
 template <typename T, int STEPS>
@@ -704,6 +776,7 @@ __global__ void __launch_bounds__(NW * 32, (sizeof(T) == 8 ? 1 : PIC_K9_CTAS)) k
                 for (int n = 0; n < NV; ++n) vals[n] = (T)0;
             }
             if (JT) same_cell_scan_red_tile<T, STEPS>(vals, key, tail_pass ? -1 : srel, lane, sink, k.sx, k.sy, jtiles + jsel * JT_ELEMS);
+            else if (PIC_K9_REDUCE == 1) same_cell_group_red<T, SF>(vals, key, lane, sink, k.sx, k.sy);
             else same_cell_scan_red<T, SF, STEPS>(vals, key, lane, sink, k.sx, k.sy);
             // ---- flush the warp queue once half a warp of them is waiting
             if (qn >= QW - 32) {
