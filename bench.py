@@ -349,7 +349,7 @@ def main():
                 "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
                 "config": workload_config(args, n_gpus), "particles": total_particles, "overflow": overflow,
                 "roofline": roof, "roofline_step": roof_step, "cpu_baseline": cpu_base, "e2e": e2e, "gpu_launches": launches,
-                "k1_variant": sim.k1_variant, "k1_options": list(sim.k1_options), "k1_global_fallback_particles": int(sim.flags[2].item()),
+                "k1_variant": sim.k1_variant, "k1_options_now": [sim._k1_options(i) for i in range(sim.S)], "k1_global_fallback_particles": int(sim.flags[2].item()),
                 "clocks": sampler.summary() if sampler else None}
         if check is not None:
             line["check"] = check

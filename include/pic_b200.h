@@ -213,7 +213,10 @@ int pic_fused_push_deposit(const PicParams* p, int species, int deposition, cons
  * particles that took the global-memory gather.  Returns PIC_EUNSUPPORTED for any other configuration or when the driver has
  * no cuTensorMapEncodeTiled (call pic_fused_push_deposit instead).  Replaces, like pic_fused_push_deposit, evolve.py:33-79.
  * options bit 0 (float32 only): accumulate the same-cell currents in per-supercell shared-memory J tiles (shared-memory
- * atomics) and flush each tile with one TMA reduce per component instead of global REDs -- for species whose sort is stale. */
+ * atomics) and flush each tile with one TMA reduce per component instead of global REDs (measured slower; kept as evidence).
+ * options bit 1: reduce the same-cell currents over ALL lanes of a warp that share a cell (__match_any_sync groups summed by
+ * pointer doubling) instead of the segmented scan over contiguous runs -- REDs no longer grow when cell changers fragment the
+ * runs of a stale-sorted species, at the price of ~30 more instructions per 32 particles. */
 int pic_fused_tile3d(const PicParams* p, int species, const PicSoA* soa, const int32_t* blk_off, int nblk, int options,
                      const void* const E[3], const void* const B[3], void* const J[3], const PicLeave* leave, int32_t* flags,
                      void* stream);

@@ -42,42 +42,22 @@ __global__ void __launch_bounds__(256) k_export(int species, SoAView<T> s, T* __
 }
 
 // ---------------------------------------------------------------- counting sort by local cell
-// Both sort kernels aggregate their atomics per warp: the stream is nearly sorted, so the 32 consecutive particles a warp holds
-// fall into a handful of cells; `__match_any_sync` groups the lanes by cell and one lane per group issues a single atomic for the
-// whole group (4-8x fewer atomics; the scatter's were returning atomics on 8-way contended addresses).
+// (Warp-aggregating these atomics with __match_any_sync was measured: the sort got 0.9 ms slower, the plain version stays.)
 template <typename T>
 __global__ void __launch_bounds__(256) k_sort_hist(const __grid_constant__ PicParams p, SoAView<T> s, int32_t* __restrict__ count) {
     const int64_t n = s.count();
-    const int lane = threadIdx.x & 31;
-    for (int64_t j0 = blockIdx.x * (int64_t)blockDim.x + (threadIdx.x - lane); j0 < n; j0 += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t j = j0 + lane;
-        const bool valid = j < n;
-        const unsigned mask = __ballot_sync(0xffffffffu, valid);
-        if (!valid) continue;
-        const int cell = local_cell<T>(p, s.c[0][j], s.c[1][j], s.c[2][j]);
-        const unsigned group = __match_any_sync(mask, cell);
-        if (lane == __ffs(group) - 1) atomicAdd(&count[cell], __popc(group));
-    }
+    for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x)
+        atomicAdd(&count[local_cell<T>(p, s.c[0][j], s.c[1][j], s.c[2][j])], 1);
 }
 
 template <typename T>
 __global__ void __launch_bounds__(256) k_sort_scatter(const __grid_constant__ PicParams p, SoAView<T> s, SoAView<T> d,
                                                       const int32_t* __restrict__ offset, int32_t* __restrict__ cursor) {
     const int64_t n = s.count();
-    const int lane = threadIdx.x & 31;
-    for (int64_t j0 = blockIdx.x * (int64_t)blockDim.x + (threadIdx.x - lane); j0 < n; j0 += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t j = j0 + lane;
-        const bool valid = j < n;
-        const unsigned mask = __ballot_sync(0xffffffffu, valid);
-        if (!valid) continue;
+    for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x) {
         const T px = s.c[0][j], py = s.c[1][j], pz = s.c[2][j];
         const int cell = local_cell<T>(p, px, py, pz);
-        const unsigned group = __match_any_sync(mask, cell);
-        const int leader = __ffs(group) - 1;
-        int base = 0;
-        if (lane == leader) base = atomicAdd(&cursor[cell], __popc(group));
-        base = __shfl_sync(group, base, leader);
-        const int64_t dst = (int64_t)offset[cell] + base + __popc(group & ((1u << lane) - 1u));
+        const int64_t dst = (int64_t)offset[cell] + atomicAdd(&cursor[cell], 1);
         if (dst >= d.cap) continue;
         d.c[0][dst] = px; d.c[1][dst] = py; d.c[2][dst] = pz;
         d.c[3][dst] = s.c[3][j]; d.c[4][dst] = s.c[4][j]; d.c[5][dst] = s.c[5][j];
@@ -496,9 +476,6 @@ __device__ __forceinline__ void same_cell_scan_red(T* vals, int key, int lane, c
 // (log2 of the longest group many rounds of 12 index shuffles); the lowest lane of every group issues the REDs.  A stale sort
 // fragments the same-cell runs (cell changers sit between them), which costs the scan one RED set per fragment but this
 // reduction nothing: REDs per warp = distinct cells per warp.
-#ifndef PIC_K9_REDUCE
-#define PIC_K9_REDUCE 0      /* 0 = segmented scan over contiguous runs, 1 = match-any groups + pointer doubling */
-#endif
 template <typename T, int SF>
 __device__ __forceinline__ void same_cell_group_red(T* vals, int key, int lane, const TileSink<T>& sink, int sx, int sy) {
     constexpr int NV = SameCell<SF>::NV, NN = SameCell<SF>::NN;
@@ -597,12 +574,13 @@ constexpr int K9_QW = 48;        // per-warp queue of anchor-changing particles,
 // with shared-memory atomics and flushed to global memory by ONE TMA reduce per component when the last warp leaves the
 // supercell -- instead of 12 global REDs per run of same-cell particles.  It pays for species whose sort is stale (cell
 // changers fragment the runs: 5.3 RED sectors per particle for electrons 8 steps after a sort, 3.5 right after it).
-template <typename T, int PUSHER, int STEPS, int NW, bool PER1, bool JT>
+template <typename T, int PUSHER, int STEPS, int NW, bool PER1, int MODE>
 __global__ void __launch_bounds__(NW * 32, (sizeof(T) == 8 ? 1 : PIC_K9_CTAS)) k_tile3d(const __grid_constant__ PicParams p, int species, const __grid_constant__ Geom<T> gm,
                                                    const __grid_constant__ FastConst<T> k, const __grid_constant__ SoAView<T> s, const __grid_constant__ Field6<T> F, Field3W<T> J,
                                                    LeaveBuf leave, int distributed, int32_t* flags, const __grid_constant__ TileMaps tm,
                                                    const int32_t* __restrict__ blk_off, int nblk, int nby, int nbz, int stage_particles) {
     constexpr int SF = 1;
+    constexpr bool JT = (MODE == 1);      // same-cell reduction: 0 segmented scan + RED, 1 shared-memory J tile, 2 match-any groups + RED
     constexpr int NV = SameCell<SF>::NV;
     constexpr int QW = K9_QW;
     constexpr int NSTAGE = 3;                                // ring: the next supercell is in flight while the current one is
@@ -776,7 +754,7 @@ __global__ void __launch_bounds__(NW * 32, (sizeof(T) == 8 ? 1 : PIC_K9_CTAS)) k
                 for (int n = 0; n < NV; ++n) vals[n] = (T)0;
             }
             if (JT) same_cell_scan_red_tile<T, STEPS>(vals, key, tail_pass ? -1 : srel, lane, sink, k.sx, k.sy, jtiles + jsel * JT_ELEMS);
-            else if (PIC_K9_REDUCE == 1) same_cell_group_red<T, SF>(vals, key, lane, sink, k.sx, k.sy);
+            else if (MODE == 2) same_cell_group_red<T, SF>(vals, key, lane, sink, k.sx, k.sy);
             else same_cell_scan_red<T, SF, STEPS>(vals, key, lane, sink, k.sx, k.sy);
             // ---- flush the warp queue once half a warp of them is waiting
             if (qn >= QW - 32) {
@@ -980,6 +958,7 @@ static int launch_tile3d(const PicParams* p, int species, const PicSoA* soa, con
     for (int c = 0; c < 3; ++c) distributed |= (p->gmesh[c] != p->mesh[c]);
     constexpr int NW = PIC_K9_NW, QW = K9_QW;
     const bool jt = (options & 1) && sizeof(T) == 4;          // shared-memory J tiles: f32 only (TMA reduce type)
+    const bool grp = !jt && (options & 2);                    // match-any group reduction instead of the segmented scan
     const size_t smem = 256 + (size_t)(3 * (6 * TILE_ELEMS + 6 * K9_PCAP) + 2 * NW * 3 * QW + (jt ? 2 * 3 * TILE_N * TILE_N * TILE_N : 0)) * sizeof(T);
     if (smem > 227 * 1024) return PIC_EUNSUPPORTED;
     int grid = num_sms() * (sizeof(T) == 8 ? 1 : PIC_K9_CTAS);
@@ -1030,7 +1009,7 @@ static int launch_tile3d(const PicParams* p, int species, const PicSoA* soa, con
         }                                                                                                                \
         k_tile3d<T, PUSH, 3, NW, PER, JTV><<<grid, NW * 32, smem, st>>>(*p, species, gm, k, sv, F, Jw, lb, distributed, flags, tm, blk_off, nblk, nby, nbz, stage_particles); \
     } while (0)
-#define PIC_LAUNCH_K9_J(PUSH, PER) do { if (jt) PIC_LAUNCH_K9(PUSH, PER, true); else PIC_LAUNCH_K9(PUSH, PER, false); } while (0)
+#define PIC_LAUNCH_K9_J(PUSH, PER) do { if (jt) PIC_LAUNCH_K9(PUSH, PER, 1); else if (grp) PIC_LAUNCH_K9(PUSH, PER, 2); else PIC_LAUNCH_K9(PUSH, PER, 0); } while (0)
     if (p->pusher == PIC_PUSHER_BORIS) { if (per1) PIC_LAUNCH_K9_J(PIC_PUSHER_BORIS, true); else PIC_LAUNCH_K9_J(PIC_PUSHER_BORIS, false); }
     else { if (per1) PIC_LAUNCH_K9_J(PIC_PUSHER_BORIS_REL, true); else PIC_LAUNCH_K9_J(PIC_PUSHER_BORIS_REL, false); }
 #undef PIC_LAUNCH_K9_J

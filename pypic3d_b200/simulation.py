@@ -99,12 +99,14 @@ class Simulation:
         self.k1_variant = self._pick_k1_variant(sp)
         self._import(particles, capacity_factor)
         self.sort_every = self._sort_intervals(particles)
-        # K1 v9 option bit 0 (shared-memory J tiles + TMA reduce) per species: PIC_K9_JTILE = "0" off, "1" on for every species,
-        # "fast" only for the species on the base sort cadence (whose sort goes stale between re-sorts)
+        # K1 v9 options (include/pic_b200.h): bit 0 = shared-memory J tiles + TMA reduce (PIC_K9_JTILE = "1"; measured slower, off);
+        # bit 1 = match-any group reduction instead of the segmented scan.  PIC_K9_GROUPRED = "auto" (default): per launch, for a
+        # species that has drifted more than 4 % of a cell (rms) since its last sort -- its same-cell runs are fragmented by then
+        # and the scan would pay one RED set per fragment; "1" always, "0" never.
         import os
-        mode = os.environ.get("PIC_K9_JTILE", "0")
-        fastest = min(self.sort_every) if self.sort_every else 0
-        self.k1_options = [1 if (mode == "1" or (mode == "fast" and self.sort_every[s] == fastest)) else 0 for s in range(self.S)]
+        self._jtile_mode = os.environ.get("PIC_K9_JTILE", "0")
+        self._groupred_mode = os.environ.get("PIC_K9_GROUPRED", "auto")
+        self._sorted_at = [0] * self.S
         self.leave_fraction = float(leave_fraction)
         if self.distributed:
             self._alloc_packets()
@@ -124,6 +126,17 @@ class Simulation:
         if os.environ.get("PIC_K1_VARIANT", "tile") != "tile":
             ok = False
         return "tile" if ok else "global"
+
+    def _k1_options(self, s):
+        opt = 1 if self._jtile_mode == "1" else 0
+        if self._groupred_mode == "1":
+            opt |= 2
+        elif self._groupred_mode == "auto":
+            dmin = min(float(self.p.dx), float(self.p.dy), float(self.p.dz))
+            drift = self._vrms[s] * float(self.p.dt) * (self.step_count - self._sorted_at[s]) / dmin
+            if drift > 0.04:
+                opt |= 2
+        return opt
 
     def _soa(self, sp_, which=None):
         k = sp_.cur if which is None else which
@@ -206,11 +219,14 @@ class Simulation:
         Sorting never changes results (only memory order), so this is purely a cost knob.  Multi-GPU runs keep the base
         interval for every species because the sort is also what compacts migrated slots."""
         base = max(1, self.sort_interval)
+        self._vrms = [0.0] * self.S
+        if particles.x.shape[4] > 0:
+            a = particles.active.reshape(self.S, -1)
+            v2 = (particles.u.to(torch.float64) ** 2).sum(-1).reshape(self.S, -1)
+            self._vrms = torch.sqrt((v2 * a).sum(1) / a.sum(1).clamp(min=1)).tolist()
         if self.sort_interval <= 0 or self.distributed or particles.x.shape[4] == 0:
             return [base] * self.S
-        a = particles.active.reshape(self.S, -1)
-        v2 = (particles.u.to(torch.float64) ** 2).sum(-1).reshape(self.S, -1)
-        vrms = torch.sqrt((v2 * a).sum(1) / a.sum(1).clamp(min=1)).tolist()
+        vrms = self._vrms
         vmax = max(vrms) if max(vrms) > 0 else 1.0
         return [int(min(20 * base, max(base, round(base * vmax / v)))) if v > 0 else 20 * base for v in vrms]
 
@@ -241,6 +257,8 @@ class Simulation:
             check(L.pic_sort_scatter(ctypes.byref(self.p), ctypes.byref(src), ctypes.byref(dst), ops._p(self._cell_offset),
                                      ops._p(self._cell_count), st), "pic_sort_scatter")
             sp_.cur = 1 - sp_.cur           # (the scatter also set n_dev = number of live particles, on the device)
+            if hasattr(self, "_sorted_at"):
+                self._sorted_at[s] = self.step_count
             if self.k1_variant == "tile":   # first slot of every 4x4x4-cell supercell of the blocked sort order (K1 v9)
                 sp_.blk_off.copy_(self._cell_offset[::64])
 
@@ -270,7 +288,7 @@ class Simulation:
             rc = _lib.PIC_EUNSUPPORTED
             if self.k1_variant == "tile":
                 rc = L.pic_fused_tile3d(ctypes.byref(p), s, ctypes.byref(soa), ops._p(sp_.blk_off), self.ncells // 64,
-                                        self.k1_options[s], ops._v(self.E), ops._v(self.B), ops._v(self.J), leave, ops._p(self.flags), st)
+                                        self._k1_options(s), ops._v(self.E), ops._v(self.B), ops._v(self.J), leave, ops._p(self.flags), st)
                 if rc == _lib.PIC_EUNSUPPORTED:     # e.g. no TMA driver entry point: the global-gather K1 computes the same step
                     self.k1_variant = "global"
                 else:

@@ -380,14 +380,16 @@ TILE_CASES = [
 @pytest.mark.parametrize("c", TILE_CASES)
 @pytest.mark.parametrize("dtype", (F64, F32))
 @pytest.mark.parametrize("sort_interval", (1, 5, 0))
-@pytest.mark.parametrize("jtile", ("0", "1"))
+@pytest.mark.parametrize("jtile", ("0", "1", "group"))
 def test_resident_tile_kernel_matches_oracle(c, dtype, sort_interval, jtile, monkeypatch):
     """K1 v9 (pic_fused_tile3d): E/B gathered from shared-memory supercell tiles.  Fast particles (up to 0.16 cells per step)
     and sort_interval 5 / never let particles drift into the tile margin and beyond it, so the tile gather, its global-memory
     fallback and the deferred cell-crossers are all exercised; 12 steps (dt inside the Yee CFL limit), slot-exact against the
     oracle."""
     from pypic3d_b200.simulation import Simulation
-    monkeypatch.setenv("PIC_K9_JTILE", jtile)       # "1": same-cell currents through shared-memory J tiles + TMA reduce (f32 only)
+    # "1": same-cell currents through shared-memory J tiles + TMA reduce (f32 only); "group": match-any group reduction; "0": scan
+    monkeypatch.setenv("PIC_K9_JTILE", "1" if jtile == "1" else "0")
+    monkeypatch.setenv("PIC_K9_GROUPRED", "1" if jtile == "group" else "0")
     N = c["N"]
     sp, dp, tp, sc, E, B = make_case(N, N, 1, current_deposition="esirkepov", relativistic=c["rel"],
                                      particle_boundary_conditions=c["pbc"], capacity=3.0, vmax=4.0, C=10.0, dt=0.015, n=200)
@@ -413,7 +415,7 @@ def test_resident_tile_kernel_matches_oracle(c, dtype, sort_interval, jtile, mon
 
 @pytest.mark.parametrize("dtype,tol", [(F64, 1e-11), (F32, 2e-4)])
 @pytest.mark.parametrize("n,ppc", [(32, 8), (16, 24)])
-@pytest.mark.parametrize("jtile", ("0", "1"))
+@pytest.mark.parametrize("jtile", ("0", "1", "group", "auto"))
 def test_tile_and_global_k1_variants_agree(dtype, tol, n, ppc, jtile, monkeypatch):
     """Same thermal plasma, 12 steps with a sort every 5: the supercell-tile K1 and the global-gather K1 differ only by the
     order of the floating-point atomics.  32^3 x 16 ppc is the bench's density (512 particles per supercell and species, inside
@@ -426,7 +428,8 @@ def test_tile_and_global_k1_variants_agree(dtype, tol, n, ppc, jtile, monkeypatc
     fields = make_fields(sp, dp, scale=0.02)
     ps, pd = gu.to_pkg_params(sp, dp)
     out = {}
-    monkeypatch.setenv("PIC_K9_JTILE", jtile)
+    monkeypatch.setenv("PIC_K9_JTILE", "1" if jtile == "1" else "0")
+    monkeypatch.setenv("PIC_K9_GROUPRED", {"group": "1", "auto": "auto"}.get(jtile, "0"))
     for variant in ("tile", "global"):
         monkeypatch.setenv("PIC_K1_VARIANT", variant)
         sim = Simulation(gu.particles_to_gpu(tp, dtype), gu.species_to_pkg(sc), gu.fields_to_gpu(fields, dtype), ps, pd, sort_interval=5)
