@@ -676,8 +676,10 @@ __global__ void __launch_bounds__(NW * 32, (sizeof(T) == 8 ? 1 : PIC_K9_CTAS)) k
     };
     int slot = 0, par = 0;       // ring slot of the supercell being processed and the parity of its use count
     int jsel = 0, juse = 0;      // J tile of the supercell being processed (alternates) and how often that tile has been used
-    int rot = 0;                 // 32-particle chunks are dealt to the warps round-robin, continuing across supercells, so every
-                                 // warp gets the same number of chunks (+-1) whatever the supercell populations are
+#if PIC_K9_DEAL == 0
+    int rot = 0;                 // static dealing: chunks go to the warps round-robin, continuing across supercells, so every warp
+                                 // gets the same number of chunks (+-1) whatever the supercell populations are
+#endif
     // iteration b == b1 is the tail pass: this CTA's share of the slots appended since the last sort (particles received from
     // neighbour ranks, ~1e-4 of the stream per step).  They are not binned; an impossible tile origin sends them through
     // the global-memory gather of the same body.
@@ -768,7 +770,9 @@ __global__ void __launch_bounds__(NW * 32, (sizeof(T) == 8 ? 1 : PIC_K9_CTAS)) k
                 __syncwarp();
             }
         }
+#if PIC_K9_DEAL == 0
         rot = (rot + nchunk) % NW;
+#endif
         if (!tail_pass) {
             __syncwarp();
             if (JT) {
