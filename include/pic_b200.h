@@ -203,7 +203,7 @@ int pic_fused_push_deposit(const PicParams* p, int species, int deposition, cons
 /* K1 v9, the supercell tile variant of pic_fused_push_deposit for the headline configuration (Esirkepov, CIC, all three axes
  * active, g == 2, every tile width a multiple of 4, Boris or relativistic Boris, no external fields): same result, different
  * data path.  The blocked sort order keeps the particles of one 4x4x4-cell supercell contiguous; per supercell one thread issues
- * TMA copies of the 8x9x8-node E/B neighbourhood of all six components and of the supercell's slice of the six particle
+ * TMA copies of the 8x8x8-node E/B neighbourhood (padded to 8x10x8 in shared memory) of all six components and of the supercell's slice of the six particle
  * arrays into a three-stage shared-memory ring (mbarrier complete_tx), and the CTA's warps gather, push and deposit from
  * shared memory.  blk_off: int32[nblk+1] device array, blk_off[b] = first slot of supercell b in the cell-sorted SoA =
  * cell_offset[64*b] of the last pic_sort_scan (nblk = tile[0]*tile[1]*tile[2]/64); slots >= blk_off[nblk] (appended since

@@ -383,7 +383,7 @@ __device__ __forceinline__ bool mbar_test(uint64_t* bar, int parity) {
         " selp.u32 %0, 1, 0, p;\n}\n" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
     return ok != 0;
 }
-// TMA: one [x 8][y 9][z 8] box of a field component -> shared memory, completion signalled on `bar` (complete_tx)
+// TMA: one [x 8][y TILE_NY][z 8] box of a field component -> shared memory, completion signalled on `bar` (complete_tx)
 __device__ __forceinline__ void tma_load_box(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int z, int y, int x) {
     asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];\n"
                  ::"r"(smem_u32(smem_dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(z), "r"(y), "r"(x)
@@ -408,7 +408,7 @@ __device__ __forceinline__ void red_shared_add(double* p, double v) {
     asm volatile("red.shared.add.f64 [%0], %1;\n" ::"r"(smem_u32(p)), "d"(v) : "memory");
 }
 struct TileMaps {
-    CUtensorMap m[6];      // Ex Ey Ez Bx By Bz, each the ghosted (Lx, Ly, Lz) tile with an 8 x 9 x 8 box
+    CUtensorMap m[6];      // Ex Ey Ez Bx By Bz, each the ghosted (Lx, Ly, Lz) tile with an 8 x TILE_NY x 8 box
     CUtensorMap j[3];      // Jx Jy Jz with an 8 x 8 x 8 box (TMA reduce target of the shared-memory J tiles)
 };
 
@@ -642,7 +642,7 @@ __global__ void __launch_bounds__(NW * 32, (sizeof(T) == 8 ? 1 : PIC_K9_CTAS)) k
         return n > 0 ? n : 0;
     };
     // The ring is fed by single threads: six TMA box copies (g == 2: the tile's first node is the supercell's first cell; the
-    // 9th y row of the last supercell row lies outside the array and is zero-filled, it is never read) and six bulk copies of
+    // spare y rows beyond the 8th are padding -- zero-filled where they leave the array, never read) and six bulk copies of
     // the particle slice per supercell.  Requests are made in order; `requested` is the last supercell asked for.  Any warp's
     // lane 0 may make the next one (compare-and-swap) as soon as the ring slot it needs has been released by every warp --
     // it never blocks for that: if the slot is still in use the attempt is dropped and repeated by the next warp that enters
@@ -972,7 +972,7 @@ static int launch_tile3d(const PicParams* p, int species, const PicSoA* soa, con
     if (grid > nblk) grid = nblk;
     const SoAView<T> sv = view_of<T>(soa);
     const LeaveBuf lb = leave_of(leave);
-    // TMA descriptors of the six ghosted field tiles: dims (z, y, x) = (Lz, Ly, Lx), box 8 x 9 x 8
+    // TMA descriptors of the six ghosted field tiles: dims (z, y, x) = (Lz, Ly, Lx), box 8 x TILE_NY x 8
     static PFN_tensorMapEncodeTiled encode = nullptr;
     if (!encode) {
         void* fn = nullptr;

@@ -650,9 +650,14 @@ PIC_HD void gather_rows(const FastConst<T>& k, const Field6<T>& F, const Field6<
 // or at most one cell outside it: centre anchors o+1 .. o+6 and vertex anchors o .. o+6, each reading nodes (a, a+1).
 constexpr int TILE_B = 4;
 constexpr int TILE_N = 8;
-constexpr int TILE_NY = TILE_N + 1;                      // one spare y row per x plane: with a plane stride of 72 words the centre and
-                                                         // vertex anchors of one cell (one plane apart) fall into different banks
-constexpr int TILE_SX = TILE_NY * TILE_N;                // x-plane stride (the tile is the dense TMA box [x 8][y 9][z 8])
+#ifndef PIC_TILE_YPAD
+#define PIC_TILE_YPAD 2
+#endif
+constexpr int TILE_NY = TILE_N + PIC_TILE_YPAD;          // spare y rows per x plane (never read): with 10 rows the plane stride is 80
+                                                         // words, so bank = 16 x + 8 y + z and neither the centre / vertex anchors of
+                                                         // one cell nor a warp that straddles a y step collide (72 words: 8 (x + y) + z
+                                                         // made (x - 1, y + 1) and (x, y) collide -- 30 % shared-memory replays)
+constexpr int TILE_SX = TILE_NY * TILE_N;                // x-plane stride (the tile is the dense TMA box [x 8][y TILE_NY][z 8])
 constexpr int TILE_ELEMS = TILE_N * TILE_SX;             // per component
 template <typename T>
 struct TileSrc {
