@@ -651,12 +651,11 @@ PIC_HD void gather_rows(const FastConst<T>& k, const Field6<T>& F, const Field6<
 constexpr int TILE_B = 4;
 constexpr int TILE_N = 8;
 #ifndef PIC_TILE_YPAD
-#define PIC_TILE_YPAD 2
+#define PIC_TILE_YPAD 1   /* spare y rows per x plane.  1: plane stride 72 words, so the centre / vertex anchors of one cell (one plane
+                             apart) fall into different banks.  2 (stride 80, also conflict-free for a warp that straddles a y step)
+                             was measured: 4.209 vs 4.213 ms per launch -- no difference, so the smaller tile stays. */
 #endif
-constexpr int TILE_NY = TILE_N + PIC_TILE_YPAD;          // spare y rows per x plane (never read): with 10 rows the plane stride is 80
-                                                         // words, so bank = 16 x + 8 y + z and neither the centre / vertex anchors of
-                                                         // one cell nor a warp that straddles a y step collide (72 words: 8 (x + y) + z
-                                                         // made (x - 1, y + 1) and (x, y) collide -- 30 % shared-memory replays)
+constexpr int TILE_NY = TILE_N + PIC_TILE_YPAD;
 constexpr int TILE_SX = TILE_NY * TILE_N;                // x-plane stride (the tile is the dense TMA box [x 8][y TILE_NY][z 8])
 constexpr int TILE_ELEMS = TILE_N * TILE_SX;             // per component
 template <typename T>
