@@ -131,3 +131,52 @@ def test_electrostatic_config_matches_oracle(tmp_path):
     assert scale > 0
     for a, b in zip(gf[0], of[0]):       # (a one-iteration difference at the stopping threshold moves E by ~1e-3 of its scale)
         assert np.abs(gu.npy(a) - np.asarray(b)).max() <= 1e-2 * scale
+
+
+WEIBEL = {   # /root/reference/demos/weibel/weibel.toml as packaged (1-D, 201 cells, TSC, j_from_rhov + bilinear filter by default)
+    "simulation_parameters": {"name": "Demo of a 1D Weibel instability with 3,000 electrons", "Nt": 6000, "bc": "periodic",
+                              "solver": "electrodynamic_yee", "Nx": 201, "Ny": 1, "Nz": 1, "x_wind": 3e-1, "y_wind": 1, "z_wind": 1,
+                              "verbose": False, "cfl": 0.99, "shape_factor": 2, "relativistic": True},
+    "plotting": {"plot_errors": False, "phaseSpace": False, "plotfields": False, "plotting_interval": 30},
+    "particle1": {"name": "electron1", "N_per_cell": 40, "charge": -1.602e-19, "mass": 9.1093837e-31, "number_density": 1.0e15,
+                  "Tx": 296494.82871735515, "Tz": 29649482.87173552, "Ty": 0},
+    "particle2": {"name": "ion1", "N_per_cell": 40, "charge": 1.602e-19, "mass": 1.67e-27, "Tx": 296494.82871735515,
+                  "Tz": 29649482.87173552, "Ty": 0},
+}
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dep", ["j_from_rhov", "esirkepov"])
+def test_weibel_config_matches_oracle(tmp_path, dep):
+    """demos/weibel/weibel.toml as packaged (SURVEY section 8d input 2), and its Esirkepov variant: 30 steps from the identical
+    initial state through `run_PyPIC3D` (resident path) against the oracle; the anisotropy-driven B_y growth is compared too."""
+    from tests import gpu_util as gu
+    gu.require_cuda()
+    from pypic3d_b200.initialization import initialize_simulation
+    from pypic3d_b200.__main__ import run_PyPIC3D
+    from oracle import evolve as oevolve
+    from oracle.params import StaticParameters as OS, DynamicParameters as OD, GridParameters as OG, TiledParticles as OT, SpeciesConfig as OC
+    cfg = {k: dict(v) for k, v in WEIBEL.items()}
+    cfg["simulation_parameters"].update(output_dir=str(tmp_path), Nt=30, current_calculation=dep,
+                                        filter_j="bilinear" if dep == "j_from_rhov" else "none")
+    np.random.seed(0)
+    loop, particles, fields, sp, dp, plotting, plasma, species = initialize_simulation(cfg, verbose=False)
+    assert tuple(sp.tile_shape) == (201, 1, 1) and int(sp.shape_factor) == 2 and int(particles.active.sum()) == 2 * 40 * 201
+    osp = OS(**sp._asdict()); odp = OD(**{**dp._asdict(), "grids": OG(**dp.grids._asdict())})
+    otp = OT(gu.npy(particles.x), gu.npy(particles.u), gu.npy(particles.active))
+    osc = OC(*[np.asarray(v) for v in species])
+    n = lambda F: tuple(gu.npy(c) for c in F)
+    of = (n(fields[0]), n(fields[1]), n(fields[2]), gu.npy(fields[3]), gu.npy(fields[4]), (n(fields[5][0]), n(fields[5][1])), None, False)
+    for _ in range(30):
+        otp, of = oevolve.time_loop_electrodynamic(otp, osc, of, osp, odp)
+    np.random.seed(0)
+    sp2, dp2, plotting2, plasma2, gp, gf, species2 = run_PyPIC3D(cfg, verbose=False)
+    assert np.array_equal(gu.npy(gp.active), otp.active)
+    gu.assert_close(gp.x, otp.x, 1e-10, "x")
+    assert np.abs(gu.npy(gp.u) - otp.u).max() <= 1e-9 * np.abs(otp.u).max()
+    for k in range(3):
+        scale = max(max(np.abs(np.asarray(c)).max() for c in of[k]), 1e-300)
+        for a, b in zip(gf[k], of[k]):
+            assert np.abs(gu.npy(a) - np.asarray(b)).max() <= 1e-8 * scale, "EBJ"[k]
+    by_gpu = float((gu.npy(gf[1][1]) ** 2).sum()); by_ref = float((np.asarray(of[1][1]) ** 2).sum())
+    assert by_ref > 0 and abs(by_gpu - by_ref) <= 1e-7 * by_ref
