@@ -12,6 +12,7 @@ parameters) for ONE tile per GPU, keeps the state resident in HBM in the kernels
 Host orchestration is Python; every array operation on the step is a hand-written kernel behind the C ABI.
 """
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -103,7 +104,6 @@ class Simulation:
         # bit 1 = match-any group reduction instead of the segmented scan.  PIC_K9_GROUPRED = "auto" (default): per launch, for a
         # species that has drifted more than 4 % of a cell (rms) since its last sort -- its same-cell runs are fragmented by then
         # and the scan would pay one RED set per fragment; "1" always, "0" never.
-        import os
         self._jtile_mode = os.environ.get("PIC_K9_JTILE", "0")
         self._groupred_mode = os.environ.get("PIC_K9_GROUPRED", "auto")
         self._sorted_at = [0] * self.S
@@ -117,7 +117,6 @@ class Simulation:
         """"tile": K1 v9 (pic_fused_tile3d, supercell E/B tiles in shared memory) when the configuration is the one it was
         built for; "global": pic_fused_push_deposit (every other configuration).  PIC_K1_VARIANT=global forces the latter
         (A/B measurements); both give the same result."""
-        import os
         p = self.p
         ok = (self.deposition == 0 and int(p.shape_factor) == 1 and int(p.g) == 2
               and int(p.pusher) in (0, 1)   # PIC_PUSHER_BORIS, PIC_PUSHER_BORIS_REL
