@@ -180,3 +180,88 @@ def test_weibel_config_matches_oracle(tmp_path, dep):
             assert np.abs(gu.npy(a) - np.asarray(b)).max() <= 1e-8 * scale, "EBJ"[k]
     by_gpu = float((gu.npy(gf[1][1]) ** 2).sum()); by_ref = float((np.asarray(of[1][1]) ** 2).sum())
     assert by_ref > 0 and abs(by_gpu - by_ref) <= 1e-7 * by_ref
+
+
+@pytest.mark.gpu
+def test_harris_sheet_config_matches_oracle(tmp_path):
+    """demos/reconnection_2d/harris_current.toml scaled down (48 x 1 x 48 instead of 500 x 1 x 500; SURVEY section 8d input 3):
+    x periodic / z conducting fields, `[field1]` / `[field2]` .npy magnetic field (types 3 and 5), four species of which two
+    come from .npy position / velocity files (the demo's initial_conditions.py recipe, seeded, with the sheet profile
+    sampled properly), TSC, j_from_rhov + bilinear,
+    cfl 0.1.  The per-species `z_bc = "reflecting"` keys are metadata only in the reference (particle BCs stay periodic).
+    6 steps from the identical initial state against the oracle."""
+    from tests import gpu_util as gu
+    gu.require_cuda()
+    from pypic3d_b200.initialization import initialize_simulation
+    from pypic3d_b200.__main__ import run_PyPIC3D
+    from oracle import evolve as oevolve
+    from oracle.params import StaticParameters as OS, DynamicParameters as OD, GridParameters as OG, TiledParticles as OT, SpeciesConfig as OC
+    # ---- the demo's initial_conditions.py on a smaller grid, seeded
+    eps, me, c, q = 8.854e-12, 9.10938356e-31, 2.99792458e8, 1.602e-19
+    vth = 0.05 * c
+    n_peak, n_bg = 4000, 1200
+    n0 = 1e22
+    nb = 0.3 * n0
+    di = c / (q * np.sqrt(n0 / me / eps))
+    wind = 15 * di
+    nx = nz = 48
+    lam, B0 = 0.5 * di, 0.2
+    x = np.linspace(-wind / 2, wind / 2, nx); z = np.linspace(-wind / 2, wind / 2, nz)
+    X, Z = np.meshgrid(x, z, indexing="ij")
+    Bx = B0 * np.tanh(Z / lam) + 100 * B0 * np.cos(2 * np.pi * X / wind) * np.sin(np.pi * Z / wind)
+    Bz = -100 * B0 * np.sin(2 * np.pi * X / wind) * np.cos(np.pi * Z / wind)
+    rng = np.random.default_rng(7)
+    files = {"Bx": Bx[:, None, :], "Bz": Bz[:, None, :]}
+    for sp_name in ("electron", "ion"):
+        files[f"{sp_name}_x"] = rng.uniform(-wind / 2, wind / 2, n_peak)
+        files[f"{sp_name}_y"] = np.zeros(n_peak)
+        # sech^2 sheet by inverse CDF (the demo's own line stores the PROFILE VALUE 1/cosh^2 as the coordinate, which puts every
+        # particle up to a metre outside the 0.8 mm box; the sheet it means to load is this one)
+        files[f"{sp_name}_z"] = np.clip(lam * np.arctanh(rng.uniform(-0.999, 0.999, n_peak)), -0.45 * wind, 0.45 * wind)
+        for a in "xyz":
+            files[f"{sp_name}_v{a}"] = rng.normal(0, vth, n_peak)
+    zbar = files["electron_z"] / lam
+    files["electron_vy"] = files["electron_vy"] + (-c * B0 / (4 * np.pi * q * lam)) / np.cosh(zbar) ** 2 / (n0 * np.cosh(zbar) ** 2 + nb)
+    for k, v in files.items():
+        np.save(tmp_path / f"{k}.npy", v)
+    path = lambda k: str(tmp_path / f"{k}.npy")
+    weight = n0 / n_peak * wind * wind
+    species = lambda name, n, charge, pre=None: dict(
+        {"name": name, "N_particles": n, "charge": charge, "mass": 9.1093837e-31, "vth": 14989622.9, "weight": weight,
+         "x_bc": "periodic", "z_bc": "reflecting", "y_bc": "periodic"},
+        **({} if pre is None else {f"initial_{a}": path(f"{pre}_{a}") for a in ("x", "y", "z", "vx", "vy", "vz")}))
+    cfg = {
+        "simulation_parameters": {"name": "harris", "Nt": 6, "x_bc": "periodic", "z_bc": "conducting", "solver": "electrodynamic_yee",
+                                  "Nx": nx, "Ny": 1, "Nz": nz, "x_wind": wind, "y_wind": 1, "z_wind": wind, "verbose": False,
+                                  "cfl": 0.1, "shape_factor": 2, "relativistic": True, "output_dir": str(tmp_path),
+                                  "particle_tile_capacity_factor": 1.5},
+        "plotting": {"plotting_interval": 50},
+        "field1": {"name": "Bx field", "type": 3, "path": path("Bx")},
+        "field2": {"name": "Bz field", "type": 5, "path": path("Bz")},
+        "particle1": species("peak electrons", n_peak, -1.602e-19, "electron"),
+        "particle2": species("peak ions", n_peak, 1.602e-19, "ion"),
+        "particle3": species("background electrons", n_bg, -1.602e-19),
+        "particle4": species("background ions", n_bg, 1.602e-19),
+    }
+    np.random.seed(0)
+    loop, particles, fields, sp, dp, plotting, plasma, spc = initialize_simulation(cfg, verbose=False)
+    assert tuple(sp.boundary_conditions) == (0, 0, 1) and tuple(sp.particle_boundary_conditions) == (0, 0, 0)
+    assert int(particles.active.sum()) == 2 * (n_peak + n_bg)
+    g = int(sp.guard_cells)
+    assert np.allclose(gu.npy(fields[1][0])[0, 0, 0, g:-g, g, g:-g], Bx)          # [field1] landed in Bx's interior
+    osp = OS(**sp._asdict()); odp = OD(**{**dp._asdict(), "grids": OG(**dp.grids._asdict())})
+    otp = OT(gu.npy(particles.x), gu.npy(particles.u), gu.npy(particles.active))
+    osc = OC(*[np.asarray(v) for v in spc])
+    n = lambda F: tuple(gu.npy(c) for c in F)
+    of = (n(fields[0]), n(fields[1]), n(fields[2]), gu.npy(fields[3]), gu.npy(fields[4]), (n(fields[5][0]), n(fields[5][1])), None, False)
+    for _ in range(6):
+        otp, of = oevolve.time_loop_electrodynamic(otp, osc, of, osp, odp)
+    np.random.seed(0)
+    sp2, dp2, plotting2, plasma2, gp, gf, spc2 = run_PyPIC3D(cfg, verbose=False)
+    assert np.array_equal(gu.npy(gp.active), otp.active)
+    gu.assert_close(gp.x, otp.x, 1e-10, "x")
+    assert np.abs(gu.npy(gp.u) - otp.u).max() <= 1e-9 * np.abs(otp.u).max()
+    for k in range(3):
+        scale = max(max(np.abs(np.asarray(c)).max() for c in of[k]), 1e-300)
+        for a, b in zip(gf[k], of[k]):
+            assert np.abs(gu.npy(a) - np.asarray(b)).max() <= 1e-8 * scale, "EBJ"[k]
