@@ -300,3 +300,152 @@ def test_update_B_is_a_half_step():
     By = diagnostics.assemble_tiled_scalar_field(B[1], sp.tile_shape, 2)[1:-1, 1, 1]
     dEz = (np.roll(np.sin(xc), -1) - np.sin(xc)) / dp.dx
     assert np.allclose(By, +0.5 * dp.dt * dEz, atol=1e-14)   # By -= (dt/2) * (dEx/dz - dEz/dx)
+
+
+# ---- tests/code_tests/ghost_cells_test.py:41-165 (tile_shape (2,2,2), g = 1; literal inputs and expectations) -----
+def test_gc_periodic_refresh_between_two_tiles():
+    """ghost_cells_test.py:41-57"""
+    sp = _SP((0, 0, 0), (2, 2, 2))
+    f = np.zeros((2, 1, 1, 4, 4, 4))
+    f[0, 0, 0, 1:3, 1:3, 1:3] = 1.0
+    f[1, 0, 0, 1:3, 1:3, 1:3] = 2.0
+    r = halo.update_tiled_ghost_cells(f, sp, 1)
+    assert np.all(r[0, 0, 0, -1, 1:3, 1:3] == 2.0) and np.all(r[1, 0, 0, 0, 1:3, 1:3] == 1.0)
+
+
+def test_gc_periodic_fold_adds_to_owner_tile():
+    """ghost_cells_test.py:75-97"""
+    sp = _SP((0, 0, 0), (2, 2, 2))
+    f = np.zeros((2, 1, 1, 4, 4, 4))
+    f[0, 0, 0, -1, 2, 2] = 3.0
+    f[1, 0, 0, 0, 2, 2] = 5.0
+    r = halo.fold_tiled_ghost_cells(f, sp, 1)
+    assert r[1, 0, 0, 1, 2, 2] == pytest.approx(3.0) and r[0, 0, 0, -2, 2, 2] == pytest.approx(5.0)
+    assert r[0, 0, 0, -1, 2, 2] == 0.0 and r[1, 0, 0, 0, 2, 2] == 0.0
+
+
+def test_gc_zero_boundary_zeros_global_tangential_faces():
+    """ghost_cells_test.py:99-128"""
+    sp = _SP((1, 1, 1), (2, 2, 2))
+    Ex, Ey, Ez = (np.ones((1, 1, 1, 4, 4, 4)) for _ in range(3))
+    Ey = halo.apply_tiled_zero_boundary(Ey, sp, axis=0, num_guard_cells=1)
+    Ez = halo.apply_tiled_zero_boundary(Ez, sp, axis=0, num_guard_cells=1)
+    Ex = halo.apply_tiled_zero_boundary(Ex, sp, axis=1, num_guard_cells=1)
+    Ez = halo.apply_tiled_zero_boundary(Ez, sp, axis=1, num_guard_cells=1)
+    Ex = halo.apply_tiled_zero_boundary(Ex, sp, axis=2, num_guard_cells=1)
+    Ey = halo.apply_tiled_zero_boundary(Ey, sp, axis=2, num_guard_cells=1)
+    assert np.all(Ey[0, 0, 0, 1, :, :] == 0.0) and np.all(Ez[0, 0, 0, 1, :, :] == 0.0)
+    assert np.all(Ex[0, 0, 0, :, 1, :] == 0.0) and np.all(Ez[0, 0, 0, :, 1, :] == 0.0)
+    assert np.all(Ex[0, 0, 0, :, :, 1] == 0.0) and np.all(Ey[0, 0, 0, :, :, 1] == 0.0)
+
+
+def test_gc_zero_and_constant_boundary_keep_a_periodic_field():
+    """ghost_cells_test.py:130-139 and :157-165"""
+    sp = _SP((0, 0, 0), (2, 2, 2))
+    field = np.arange(64, dtype=float).reshape((1, 1, 1, 4, 4, 4))
+    refreshed = halo.update_tiled_ghost_cells(field, sp, 1)
+    assert np.allclose(halo.apply_tiled_zero_boundary(refreshed, sp, axis=0, num_guard_cells=1), refreshed)
+    assert np.allclose(halo.apply_tiled_constant_boundary(field, sp, axis=0, num_guard_cells=1), refreshed)
+
+
+def test_gc_constant_boundary_copies_adjacent_interior_to_global_ghosts():
+    """ghost_cells_test.py:141-155"""
+    sp = _SP((1, 0, 0), (2, 2, 2))
+    field = np.arange(64, dtype=float).reshape((1, 1, 1, 4, 4, 4))
+    r = halo.apply_tiled_constant_boundary(field, sp, axis=0, num_guard_cells=1)
+    assert np.allclose(r[0, 0, 0, 0, :, :], r[0, 0, 0, 1, :, :]) and np.allclose(r[0, 0, 0, -1, :, :], r[0, 0, 0, -2, :, :])
+    assert np.allclose(r[0, 0, 0, 1:-1, 1:-1, 1:-1], field[0, 0, 0, 1:-1, 1:-1, 1:-1])
+
+
+# ---- tests/code_tests/direct_deposition_test.py:535-620 (fold KATs with hand-set ghost deposits) -----
+def test_dd_fold_periodic_adds_current_deposits_to_neighbors():
+    """direct_deposition_test.py:535-548 (Nx=4, tile (2,1,1), g = 1)"""
+    sp = _SP((0, 0, 0), (2, 1, 1))
+    t = np.zeros((2, 1, 1, 4, 3, 3))
+    t[0, 0, 0, -1, 1, 1] = 2.0
+    t[1, 0, 0, 0, 1, 1] = 3.0
+    f = halo.fold_tiled_ghost_cells(t, sp, 1)
+    assert f[1, 0, 0, 1, 1, 1] == 2.0 and f[0, 0, 0, -2, 1, 1] == 3.0
+    assert np.allclose(f[:, :, :, 0, :, :], 0.0) and np.allclose(f[:, :, :, -1, :, :], 0.0)
+
+
+def test_dd_fold_two_guard_layers_adds_deposits_to_neighbors():
+    """direct_deposition_test.py:550-570 (Nx=8, Ny=Nz=4, tile (4,4,4), g = 2)"""
+    sp = _SP((0, 0, 0), (4, 4, 4))
+    t = np.zeros((2, 1, 1, 8, 8, 8))
+    t[1, 0, 0, 0, 2, 2] = 2.0
+    t[1, 0, 0, 1, 2, 2] = 3.0
+    t[0, 0, 0, -2, 2, 2] = 5.0
+    t[0, 0, 0, -1, 2, 2] = 7.0
+    f = halo.fold_tiled_ghost_cells(t, sp, 2)
+    assert f[0, 0, 0, 4, 2, 2] == 2.0 and f[0, 0, 0, 5, 2, 2] == 3.0 and f[1, 0, 0, 2, 2, 2] == 5.0 and f[1, 0, 0, 3, 2, 2] == 7.0
+    assert np.allclose(f[:, :, :, :2, :, :], 0.0) and np.allclose(f[:, :, :, -2:, :, :], 0.0)
+
+
+def test_dd_fold_two_guard_reduced_axis_folds_to_single_active_cell():
+    """direct_deposition_test.py:572-590 (Nx=8, Ny=Nz=1, tile (4,1,1), g = 2)"""
+    sp = _SP((0, 0, 0), (4, 1, 1))
+    t = np.zeros((2, 1, 1, 8, 5, 5))
+    t[0, 0, 0, 2, 0, 2] = 1.0
+    t[0, 0, 0, 2, 1, 2] = 2.0
+    t[0, 0, 0, 2, 3, 2] = 3.0
+    t[0, 0, 0, 2, 4, 2] = 4.0
+    f = halo.fold_tiled_ghost_cells(t, sp, 2)
+    assert f[0, 0, 0, 2, 2, 2] == 10.0
+    assert np.allclose(f[:, :, :, :, :2, :], 0.0) and np.allclose(f[:, :, :, :, -2:, :], 0.0)
+
+
+def test_dd_fold_conducting_reflects_exterior_deposits():
+    """direct_deposition_test.py:592-616 (x conducting, tile (2,1,1), g = 1)"""
+    sp = _SP((1, 0, 0), (2, 1, 1))
+    t = np.zeros((2, 1, 1, 4, 3, 3))
+    t[0, 0, 0, 0, 1, 1] = 4.0
+    t[-1, 0, 0, -1, 1, 1] = 7.0
+    t[0, 0, 0, -1, 1, 1] = 2.0
+    t[1, 0, 0, 0, 1, 1] = 3.0
+    f = halo.fold_tiled_ghost_cells(t, sp, 1)
+    assert f[0, 0, 0, 1, 1, 1] == -4.0 and f[-1, 0, 0, -2, 1, 1] == -7.0 and f[1, 0, 0, 1, 1, 1] == 2.0 and f[0, 0, 0, -2, 1, 1] == 3.0
+    assert np.allclose(f[:, :, :, 0, :, :], 0.0) and np.allclose(f[:, :, :, -1, :, :], 0.0)
+
+
+def test_dd_fold_matches_global_fold_for_mixed_boundaries():
+    """direct_deposition_test.py:618-663: tiled fold + refresh == the test's own global one-ghost fold + refresh
+    (`_fold_ghost_cells:105-127`, `_update_ghost_cells:82-102`), x periodic / y conducting / z periodic, tiles (2,2,1) of 4x4x2."""
+    def update_global(f, bcs):                                                                     # :82-102
+        f = f.copy()
+        for a, bc in enumerate(bcs):
+            lo = [slice(None)] * 3; hi = [slice(None)] * 3; lo[a] = 0; hi[a] = -1
+            il = [slice(None)] * 3; ih = [slice(None)] * 3; il[a] = 1; ih[a] = -2
+            if bc == 0:
+                f[tuple(lo)], f[tuple(hi)] = f[tuple(ih)].copy(), f[tuple(il)].copy()
+            else:
+                f[tuple(lo)] = 0.0; f[tuple(hi)] = 0.0
+        return f
+
+    def fold_global(f, bcs):                                                                       # :105-127
+        f = f.copy()
+        for a, bc in enumerate(bcs):
+            lo = [slice(None)] * 3; hi = [slice(None)] * 3; lo[a] = 0; hi[a] = -1
+            il = [slice(None)] * 3; ih = [slice(None)] * 3; il[a] = 1; ih[a] = -2
+            sgn = 1.0 if bc == 0 else -1.0
+            if bc == 0:
+                f[tuple(il)] += f[tuple(hi)]; f[tuple(ih)] += f[tuple(lo)]
+            else:
+                f[tuple(il)] += sgn * f[tuple(lo)]; f[tuple(ih)] += sgn * f[tuple(hi)]
+            f[tuple(lo)] = 0.0; f[tuple(hi)] = 0.0
+        return f
+
+    bcs, tile = (0, 1, 0), (2, 2, 1)
+    sp = _SP(bcs, tile)
+    field = np.zeros((6, 6, 4))
+    tiles = np.zeros((2, 2, 2, 4, 4, 3))
+    field[0, 2, 1] = 1.5;   tiles[0, 0, 0, 0, 2, 1] = 1.5
+    field[-1, 3, 2] = -0.5; tiles[-1, 1, 1, -1, 1, 1] = -0.5
+    field[2, 0, 1] = 3.0;   tiles[0, 0, 0, 2, 0, 1] = 3.0
+    field[3, -1, 2] = -4.0; tiles[1, -1, 1, 1, -1, 1] = -4.0
+    field[2, 2, 0] = 2.0;   tiles[0, 0, 0, 2, 2, 0] = 2.0
+    field[3, 3, -1] = 5.0;  tiles[1, 1, -1, 1, 1, -1] = 5.0
+    folded = halo.update_tiled_ghost_cells(halo.fold_tiled_ghost_cells(tiles, sp, 1), sp, 1)
+    got = diagnostics.assemble_tiled_scalar_field(folded, tile, 1)
+    want = update_global(fold_global(field, bcs), bcs)
+    assert np.allclose(got, want, rtol=1e-15, atol=1e-15)
