@@ -32,6 +32,40 @@ def test_defaults_and_toml_merge():
     assert plotting["plotting_interval"] == 3
 
 
+def test_default_parameters_reference_pins():
+    """tests/code_tests/initialization_test.py:27-44, literal expectations."""
+    plotting, sim, dynamic = default_parameters()
+    assert "Nx" in dynamic and "particle_pusher" in sim and sim["particle_pusher"] == "boris"
+    assert sim["solver"] == "electrodynamic_yee" and "electrostatic" not in sim and "fast_backend" not in sim
+    assert sim["particle_x_bc"] == sim["particle_y_bc"] == sim["particle_z_bc"] == "periodic" and sim["guard_cells"] == 2
+    for k in ("plot_vtk_particles", "plot_vtk_scalars", "plot_vtk_vectors"):
+        assert k not in plotting
+    assert "eps" in dynamic and "plotfields" in plotting
+
+
+@pytest.mark.parametrize("solver", ("old_solver", "spectral"))
+def test_initialize_simulation_rejects_unknown_solver(tmp_path, solver):
+    """initialization_test.py:276-301: ValueError("Unsupported solver ...") before anything is allocated (no GPU needed)."""
+    from pypic3d_b200.initialization import initialize_simulation
+    cfg = {"simulation_parameters": {"name": "unknown solver test", "output_dir": str(tmp_path), "solver": solver, "Nx": 4, "Ny": 1,
+                                     "Nz": 1, "x_wind": 1.0, "y_wind": 1.0, "z_wind": 1.0, "Nt": 1, "dt": 1.0e-10},
+           "plotting": {"plotting": False}}
+    with pytest.raises(ValueError, match="Unsupported solver"):
+        initialize_simulation(cfg, verbose=False)
+
+
+def test_initialize_simulation_rejects_bad_options_on_the_host(tmp_path):
+    """initialization.py:97-124 validation (current_calculation / filter / tile divisibility), all raised on the host."""
+    from pypic3d_b200.initialization import initialize_simulation
+    base = {"name": "v", "output_dir": str(tmp_path), "Nx": 4, "Ny": 1, "Nz": 1, "x_wind": 1.0, "y_wind": 1.0, "z_wind": 1.0, "Nt": 1, "dt": 1e-10}
+    for extra, msg in ((dict(current_calculation="villasenor"), "current_calculation"),
+                       (dict(current_calculation="esirkepov", filter_j="bilinear"), "Esirkepov current filtering"),
+                       (dict(filter_j="boxcar"), "filter_j"),
+                       (dict(particle_tile_nx=3), "divide the physical grid")):
+        with pytest.raises(ValueError, match=msg):
+            initialize_simulation({"simulation_parameters": dict(base, **extra), "plotting": {"plotting": False}}, verbose=False)
+
+
 def test_particle_loading_weight_carry_over_and_packing():
     sp, dp = fx.kernel_parameters(Nx=100, Ny=1, Nz=1, x_wind=1.0, y_wind=1.0, z_wind=1.0, tile_shape=(50, 1, 1), kb=1.380649e-23)
     np.random.seed(0)
@@ -265,3 +299,38 @@ def test_harris_sheet_config_matches_oracle(tmp_path):
         scale = max(max(np.abs(np.asarray(c)).max() for c in of[k]), 1e-300)
         for a, b in zip(gf[k], of[k]):
             assert np.abs(gu.npy(a) - np.asarray(b)).max() <= 1e-8 * scale, "EBJ"[k]
+
+
+@pytest.mark.gpu
+def test_initialize_simulation_reference_pins(tmp_path):
+    """initialization_test.py:138-274 with the reference's literal configurations: the Courant dt is computed when no dt is
+    given (:138-183); the GLOBAL particle boundary conditions are encoded as (1, 2, 0) while the per-species x_bc stays
+    metadata (:185-231); an electrostatic configuration gets the electrostatic loop, 6-D field tiles and collocated grids
+    (:233-274)."""
+    from tests import gpu_util as gu
+    gu.require_cuda()
+    from pypic3d_b200.initialization import initialize_simulation
+    from pypic3d_b200.evolve import time_loop_electrostatic
+    from pypic3d_b200.particles.particle_class import TiledParticles
+    zeros4, x4, zeros1 = str(tmp_path / "zeros4.npy"), str(tmp_path / "x4.npy"), str(tmp_path / "zeros1.npy")
+    np.save(x4, np.array([-0.375, -0.125, 0.125, 0.375])); np.save(zeros4, np.zeros(4)); np.save(zeros1, np.zeros(1))
+    sp_block = lambda n, z, x=None: {"name": "electrons", "N_particles": n, "charge": -1.0, "mass": 1.0, "temperature": 1.0,
+                                     "initial_x": x or z, "initial_y": z, "initial_z": z, "initial_vx": z, "initial_vy": z, "initial_vz": z}
+    cfg = {"simulation_parameters": {"name": "courant dt tiled runtime test", "output_dir": str(tmp_path), "Nx": 4, "Ny": 1, "Nz": 1,
+                                     "x_wind": 1.0, "y_wind": 1.0, "z_wind": 1.0, "Nt": 1, "particle_tile_nx": 4, "particle_tile_ny": 1,
+                                     "particle_tile_nz": 1, "filter_j": "none"},
+           "plotting": {"plotting": False}, "particle1": sp_block(4, zeros4, x4)}
+    assert float(initialize_simulation(cfg, verbose=False)[4].dt) > 0.0
+    cfg = {"simulation_parameters": {"name": "global particle bc test", "output_dir": str(tmp_path), "solver": "electrodynamic_yee",
+                                     "Nx": 1, "Ny": 1, "Nz": 1, "x_wind": 1.0, "y_wind": 1.0, "z_wind": 1.0, "Nt": 1, "dt": 1.0e-10,
+                                     "particle_x_bc": "reflecting", "particle_y_bc": "absorbing", "particle_z_bc": "periodic"},
+           "plotting": {"plotting": False}, "particle1": dict(sp_block(1, zeros1), x_bc="absorbing")}
+    _, particles, _, sp, *_ = initialize_simulation(cfg, verbose=False)
+    assert tuple(sp.particle_boundary_conditions) == (1, 2, 0) and isinstance(particles, TiledParticles)
+    cfg = {"simulation_parameters": {"name": "electrostatic collocated grid test", "output_dir": str(tmp_path), "solver": "electrostatic",
+                                     "Nx": 4, "Ny": 2, "Nz": 1, "x_wind": 1.0, "y_wind": 1.0, "z_wind": 1.0, "Nt": 1, "dt": 1.0e-10},
+           "plotting": {"plotting": False}, "particle1": sp_block(1, zeros1)}
+    loop, particles, fields, sp, dp, *_ = initialize_simulation(cfg, verbose=False)
+    assert loop is time_loop_electrostatic and isinstance(particles, TiledParticles) and fields[0][0].ndim == 6
+    for v, c in zip(dp.grids.vertex, dp.grids.center):
+        assert np.allclose(np.asarray(v), np.asarray(c))
