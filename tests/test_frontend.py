@@ -334,3 +334,63 @@ def test_initialize_simulation_reference_pins(tmp_path):
     assert loop is time_loop_electrostatic and isinstance(particles, TiledParticles) and fields[0][0].ndim == 6
     for v, c in zip(dp.grids.vertex, dp.grids.center):
         assert np.allclose(np.asarray(v), np.asarray(c))
+
+
+# ---- tests/code_tests/particle_initialization_test.py:188-424 (literal loader KATs; host-side NumPy, no GPU) -----
+def _loader_params(N, wind, tile):
+    return fx.kernel_parameters(Nx=N[0], Ny=N[1], Nz=N[2], x_wind=wind[0], y_wind=wind[1], z_wind=wind[2], dx=1.0, dy=1.0, dz=1.0, dt=0.1,
+                                tile_shape=tile, kb=1.0, eps=1.0, shape_factor=1)
+
+
+def _npy(tmp_path, name, values):
+    path = str(tmp_path / name)
+    np.save(path, np.asarray(values, dtype=float))
+    return path
+
+
+def test_loader_uses_tile_axes_before_species(tmp_path):
+    """particle_initialization_test.py:188-261"""
+    sp, dp = _loader_params((4, 2, 1), (4.0, 2.0, 1.0), (2, 1, 1))
+    cfg = {"particle1": {"name": "electrons", "N_particles": 3, "charge": -1.0, "mass": 2.0, "weight": 4.0, "temperature": 1.0,
+                         "initial_x": _npy(tmp_path, "x.npy", [-1.5, 0.5, 1.5]), "initial_y": _npy(tmp_path, "y.npy", [-0.5, 0.5, 0.5]),
+                         "initial_z": _npy(tmp_path, "z.npy", [0.0, 0.0, 0.0]), "initial_vx": _npy(tmp_path, "vx.npy", [0.1, 0.2, 0.3]),
+                         "initial_vy": _npy(tmp_path, "vy.npy", [0.0, 0.0, 0.0]), "initial_vz": _npy(tmp_path, "vz.npy", [1.0, 2.0, 3.0])}}
+    tp, sc, names, meta = load_particles_from_toml(cfg, sp, dp, verbose=False)
+    assert names == ("electrons",) and meta[0]["name"] == "electrons"
+    assert tp.x.shape == (2, 2, 1, 1, 2, 3) and tp.u.shape == (2, 2, 1, 1, 2, 3)
+    assert tp.active[0, 0, 0, 0, 0] and tp.active[1, 1, 0, 0, 0] and tp.active[1, 1, 0, 0, 1] and int(tp.active.sum()) == 3
+    assert np.allclose(tp.x[0, 0, 0, 0, 0], [-1.5, -0.5, 0.0]) and np.allclose(tp.x[1, 1, 0, 0, 0], [0.5, 0.5, 0.0])
+    assert np.allclose(tp.x[1, 1, 0, 0, 1], [1.5, 0.5, 0.0]) and np.allclose(tp.u[1, 1, 0, 0, 1], [0.3, 0.0, 3.0])
+    assert np.allclose(sc.charge, [-1.0]) and np.allclose(sc.mass, [2.0]) and np.allclose(sc.weight, [4.0])
+
+
+def test_loader_preserves_interleaved_tile_order(tmp_path):
+    """particle_initialization_test.py:263-350"""
+    sp, dp = _loader_params((4, 1, 1), (4.0, 1.0, 1.0), (2, 1, 1))
+    y = _npy(tmp_path, "y.npy", [0.0] * 4); z = _npy(tmp_path, "z.npy", [0.0] * 4)
+    vy = _npy(tmp_path, "vy.npy", [0.0] * 4); vz = _npy(tmp_path, "vz.npy", [1.0, 2.0, 3.0, 4.0])
+    blk = lambda name, q, m, w, x, vx: {"name": name, "N_particles": 4, "charge": q, "mass": m, "weight": w, "temperature": 1.0,
+                                        "initial_x": x, "initial_y": y, "initial_z": z, "initial_vx": vx, "initial_vy": vy, "initial_vz": vz}
+    cfg = {"particle1": blk("electrons", -1.0, 2.0, 4.0, _npy(tmp_path, "ex.npy", [-1.5, 0.5, -0.5, 1.5]), _npy(tmp_path, "evx.npy", [10.0, 20.0, 30.0, 40.0])),
+           "particle2": blk("ions", 1.0, 3.0, 5.0, _npy(tmp_path, "ix.npy", [1.5, -1.5, 0.5, -0.5]), _npy(tmp_path, "ivx.npy", [100.0, 200.0, 300.0, 400.0]))}
+    tp, sc, names, meta = load_particles_from_toml(cfg, sp, dp, verbose=False)
+    assert names == ("electrons", "ions") and tuple(m["name"] for m in meta) == ("electrons", "ions")
+    assert tp.x.shape == (2, 1, 1, 2, 2, 3) and int(tp.active.sum()) == 8
+    assert np.allclose(tp.x[0, 0, 0, 0, :, 0], [-1.5, -0.5]) and np.allclose(tp.u[0, 0, 0, 0, :, 0], [10.0, 30.0])
+    assert np.allclose(tp.x[1, 0, 0, 0, :, 0], [0.5, 1.5]) and np.allclose(tp.u[1, 0, 0, 0, :, 0], [20.0, 40.0])
+    assert np.allclose(tp.x[0, 0, 0, 1, :, 0], [-1.5, -0.5]) and np.allclose(tp.u[0, 0, 0, 1, :, 0], [200.0, 400.0])
+    assert np.allclose(tp.x[1, 0, 0, 1, :, 0], [1.5, 0.5]) and np.allclose(tp.u[1, 0, 0, 1, :, 0], [100.0, 300.0])
+    assert np.allclose(sc.charge, [-1.0, 1.0]) and np.allclose(sc.mass, [2.0, 3.0]) and np.allclose(sc.weight, [4.0, 5.0])
+
+
+def test_loader_maps_update_flags(tmp_path):
+    """particle_initialization_test.py:357-420"""
+    sp, dp = _loader_params((1, 1, 1), (1.0, 1.0, 1.0), (1, 1, 1))
+    zero = _npy(tmp_path, "zero.npy", [0.0])
+    cfg = {"particle1": {"name": "partly fixed", "N_particles": 1, "charge": 1.0, "mass": 1.0, "temperature": 1.0, "initial_x": zero,
+                         "initial_y": zero, "initial_z": zero, "initial_vx": 0.0, "initial_vy": 0.0, "initial_vz": 0.0, "update_pos": True,
+                         "update_x": True, "update_y": False, "update_z": True, "update_v": True, "update_vx": False, "update_vy": True,
+                         "update_vz": False}}
+    tp, sc, names, meta = load_particles_from_toml(cfg, sp, dp, verbose=False)
+    assert bool(sc.update_x[0, 0]) and not bool(sc.update_x[0, 1]) and bool(sc.update_x[0, 2])
+    assert not bool(sc.update_u[0, 0]) and bool(sc.update_u[0, 1]) and not bool(sc.update_u[0, 2])
