@@ -449,3 +449,39 @@ def test_dd_fold_matches_global_fold_for_mixed_boundaries():
     got = diagnostics.assemble_tiled_scalar_field(folded, tile, 1)
     want = update_global(fold_global(field, bcs), bcs)
     assert np.allclose(got, want, rtol=1e-15, atol=1e-15)
+
+
+# ---- tests/code_tests/evolve_test.py:75-293 (one-particle end-to-end steps with literal expectations) -----
+def _one_particle_step(N, x, u, ext_Ex=0.0, pbc=(0, 0, 0)):
+    sp, dp = fx.kernel_parameters(Nx=N[0], Ny=N[1], Nz=N[2], x_wind=1.0, y_wind=1.0, z_wind=1.0, dt=0.1, shape_factor=1,
+                                  current_deposition="direct", current_filter="none", relativistic=False, particle_boundary_conditions=pbc,
+                                  C=1.0, eps=1.0, mu=1.0, alpha=1.0, guard_cells=2)
+    tp = TiledParticles(x=np.asarray(x, dtype=float).reshape((1, 1, 1, 1, 1, 3)), u=np.asarray(u, dtype=float).reshape((1, 1, 1, 1, 1, 3)),
+                        active=np.ones((1, 1, 1, 1, 1), dtype=bool))
+    sc = SpeciesConfig(charge=np.array([1.0]), mass=np.array([1.0]), weight=np.array([1.0]), update_x=np.ones((1, 3), dtype=bool),
+                       update_u=np.ones((1, 3), dtype=bool))
+    z = fx.empty_tiled_vector
+    ext_E = list(z(sp, dp)); ext_E[0] = np.full_like(ext_E[0], ext_Ex)
+    fields = (z(sp, dp), z(sp, dp), z(sp, dp), fx.empty_tiled_scalar(sp, dp), fx.empty_tiled_scalar(sp, dp), (tuple(ext_E), z(sp, dp)), None, False)
+    return evolve.time_loop_electrodynamic(tp, sc, fields, sp, dp), fields
+
+
+def test_evolve_external_E_pushes_particle_without_evolving_it():
+    """evolve_test.py:75-157"""
+    (tp, f), f0 = _one_particle_step((3, 3, 3), [0.0, 0.0, 0.0], [0.0, 0.0, 0.0], ext_Ex=1.0)
+    assert f[6] is None and not bool(f[7])
+    assert tp.u[0, 0, 0, 0, 0, 0] > 0.0 and tp.u[0, 0, 0, 0, 0, 1] == 0.0 and tp.u[0, 0, 0, 0, 0, 2] == 0.0
+    assert np.allclose(f[5][0][0], f0[5][0][0])
+
+
+def test_evolve_step_moves_the_particle():
+    """evolve_test.py:159-215"""
+    (tp, f), _ = _one_particle_step((3, 1, 1), [0.0, 0.0, 0.0], [0.05, 0.0, 0.0])
+    assert not bool(f[-1]) and np.all(tp.active) and tp.x[0, 0, 0, 0, 0, 0] > 0.0
+
+
+def test_evolve_absorbing_particle_mask():
+    """evolve_test.py:217-289: x = 0.49, u = 0.2, dt = 0.1 crosses the absorbing wall at 0.5 -> inactive"""
+    (tp, f), _ = _one_particle_step((3, 1, 1), [0.49, 0.0, 0.0], [0.2, 0.0, 0.0], pbc=(2, 0, 0))
+    assert tp.x[:, :, :, 0, :, 0].reshape(-1).shape[0] == 1
+    assert np.array_equal(tp.active[:, :, :, 0, :].reshape(-1), np.array([False]))
