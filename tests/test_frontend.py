@@ -394,3 +394,45 @@ def test_loader_maps_update_flags(tmp_path):
     tp, sc, names, meta = load_particles_from_toml(cfg, sp, dp, verbose=False)
     assert bool(sc.update_x[0, 0]) and not bool(sc.update_x[0, 1]) and bool(sc.update_x[0, 2])
     assert not bool(sc.update_u[0, 0]) and bool(sc.update_u[0, 1]) and not bool(sc.update_u[0, 2])
+
+
+# ---- tests/code_tests/utils_test.py:187-284 (external-field loading; host-side NumPy, no GPU) -----
+def _ext_setup(tmp_path, name, value_shape, value):
+    sp, dp = fx.kernel_parameters(Nx=2, Ny=2, Nz=2, x_wind=1.0, y_wind=1.0, z_wind=1.0, guard_cells=2)
+    shape = (1, 1, 1, 6, 6, 6)
+    fields = [np.zeros(shape) for _ in range(9)]
+    ext = (tuple(np.zeros(shape) for _ in range(3)), tuple(np.zeros(shape) for _ in range(3)))
+    path = str(tmp_path / name)
+    np.save(path, np.ones(value_shape) * value)
+    return sp, dp, fields, ext, path, (0, 0, 0, slice(2, -2), slice(2, -2), slice(2, -2))
+
+
+def test_add_external_fields_adds_components():
+    """utils_test.py:187-200 (oracle restatement of utils.py:205-216)"""
+    from oracle.evolve import add_external_fields
+    E = tuple(np.ones((2, 2, 2)) * v for v in (1, 2, 3)); B = tuple(np.ones((2, 2, 2)) * v for v in (4, 5, 6))
+    xE = tuple(np.ones((2, 2, 2)) * v for v in (10, 20, 30)); xB = tuple(np.ones((2, 2, 2)) * v for v in (40, 50, 60))
+    tE, tB = add_external_fields(E, B, (xE, xB))
+    for got, want in zip(tE + tB, (11.0, 22.0, 33.0, 44.0, 55.0, 66.0)):
+        assert np.allclose(got, want)
+
+
+def test_load_external_fields_reference_pins(tmp_path):
+    """utils_test.py:202-284: default / evolve=true -> evolved fields; evolve=false -> external-only; external currents and
+    wrong shapes are rejected."""
+    from pypic3d_b200.initialization import load_external_fields_from_toml
+    sp, dp, fields, ext, path, I = _ext_setup(tmp_path, "ex.npy", (2, 2, 2), 1.0)
+    fields, ext = load_external_fields_from_toml(fields, ext, {"field1": {"name": "Ex", "type": 0, "path": path}}, sp, dp)
+    assert np.allclose(fields[0][I], 1.0) and np.allclose(ext[0][0], 0.0)
+    sp, dp, fields, ext, path, I = _ext_setup(tmp_path, "by.npy", (2, 2, 2), 3.0)
+    fields, ext = load_external_fields_from_toml(fields, ext, {"field1": {"name": "By", "type": 4, "path": path, "evolve": True}}, sp, dp)
+    assert np.allclose(fields[4][I], 3.0) and np.allclose(ext[1][1], 0.0)
+    sp, dp, fields, ext, path, I = _ext_setup(tmp_path, "bz.npy", (2, 2, 2), 5.0)
+    fields, ext = load_external_fields_from_toml(fields, ext, {"field1": {"name": "external Bz", "type": 5, "path": path, "evolve": False}}, sp, dp)
+    assert np.allclose(fields[5][I], 0.0) and np.allclose(ext[1][2][I], 5.0)
+    sp, dp, fields, ext, path, I = _ext_setup(tmp_path, "jx.npy", (2, 2, 2), 1.0)
+    with pytest.raises(ValueError, match="External-only fields must be electric or magnetic"):
+        load_external_fields_from_toml(fields, ext, {"field1": {"name": "external Jx", "type": 6, "path": path, "evolve": False}}, sp, dp)
+    sp, dp, fields, ext, path, I = _ext_setup(tmp_path, "wrong.npy", (3, 2, 2), 1.0)
+    with pytest.raises(ValueError, match="Shape mismatch"):
+        load_external_fields_from_toml(fields, ext, {"field1": {"name": "wrong Ex", "type": 0, "path": path, "evolve": False}}, sp, dp)
