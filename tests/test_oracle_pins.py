@@ -485,3 +485,17 @@ def test_evolve_absorbing_particle_mask():
     (tp, f), _ = _one_particle_step((3, 1, 1), [0.49, 0.0, 0.0], [0.2, 0.0, 0.0], pbc=(2, 0, 0))
     assert tp.x[:, :, :, 0, :, 0].reshape(-1).shape[0] == 1
     assert np.array_equal(tp.active[:, :, :, 0, :].reshape(-1), np.array([False]))
+
+
+def test_build_yee_grid_reference_pins():
+    """utils_test.py:144-170: "center" is the collocated grid (one ghost node each side), "vertex" the half-cell staggered one;
+    the same for the package's host-side builder."""
+    from types import SimpleNamespace
+    from pypic3d_b200.utilities.grids import build_yee_grid as pkg_build
+    ps = SimpleNamespace(Nx=8, Ny=6, Nz=4, x_wind=4.0, y_wind=3.0, z_wind=2.0, dx=0.5, dy=0.5, dz=0.5)
+    for build in (grids.build_yee_grid, pkg_build):
+        center, vertex = build(ps)
+        assert len(center) == 3 and len(vertex) == 3
+        assert [len(c) for c in center] == [10, 8, 6] and [len(v) for v in vertex] == [10, 8, 6]
+        assert np.allclose(center[0][1:-1], -ps.x_wind / 2 + ps.dx * np.arange(ps.Nx))
+        assert np.allclose(vertex[0][1:-1], center[0][1:-1] + 0.5 * ps.dx)
