@@ -499,3 +499,22 @@ def test_build_yee_grid_reference_pins():
         assert [len(c) for c in center] == [10, 8, 6] and [len(v) for v in vertex] == [10, 8, 6]
         assert np.allclose(center[0][1:-1], -ps.x_wind / 2 + ps.dx * np.arange(ps.Nx))
         assert np.allclose(vertex[0][1:-1], center[0][1:-1] + 0.5 * ps.dx)
+
+
+@pytest.mark.parametrize("layout", ["one tile", (8, 1, 1), (16, 1, 1)])
+def test_update_B_second_order_convergence(layout):
+    """physics_tests/yee_convergence_test.py:56-101 with its literal set-up (E_z = sin x on [.., 2 pi), dt = 1e-3, g = 2, Nx = 32 / 64 /
+    128, one-tile and multi-tile layouts, observed order > 1.8) -- against (dt/2) cos x, the half step the code takes
+    (first_order_yee.py:116), not the stale dt cos x of the test."""
+    errors = []
+    for n in (32, 64, 128):
+        tile = (n, 1, 1) if layout == "one tile" else layout
+        sp, dp = fx.kernel_parameters(Nx=n, Ny=1, Nz=1, x_wind=2 * np.pi, y_wind=1.0, z_wind=1.0, dt=1.0e-3, tile_shape=tile, guard_cells=2)
+        center, vertex = grids.build_tiled_yee_grids(sp, dp)
+        A = slice(2, -2)
+        E = [np.array(c, copy=True) for c in fx.empty_tiled_vector(sp, dp)]
+        E[2][:, :, :, A, A, A] = np.sin(center[0][:, A])[:, None, None, :, None, None]
+        B = yee.update_B(tuple(E), fx.empty_tiled_vector(sp, dp), sp, dp)
+        exact = 0.5 * dp.dt * np.cos(vertex[0][:, A])[:, None, None, :, None, None]
+        errors.append(float(np.sqrt(np.mean((B[1][:, :, :, A, A, A] - exact) ** 2))))
+    assert np.log2(errors[0] / errors[1]) > 1.8 and np.log2(errors[1] / errors[2]) > 1.8
