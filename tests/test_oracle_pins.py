@@ -518,3 +518,30 @@ def test_update_B_second_order_convergence(layout):
         exact = 0.5 * dp.dt * np.cos(vertex[0][:, A])[:, None, None, :, None, None]
         errors.append(float(np.sqrt(np.mean((B[1][:, :, :, A, A, A] - exact) ** 2))))
     assert np.log2(errors[0] / errors[1]) > 1.8 and np.log2(errors[1] / errors[2]) > 1.8
+
+
+# ---- tests/physics_tests/boris_test.py:133-247 (single-particle pusher KATs, C = 10) -----
+def test_boris_single_particle_gyroradius():
+    """boris_test.py:133-183: v = (1,0,0), B = (0,1,0), q = m = 1, dt = 0.1, 5000 steps; mean |(x, z)| ~ 1.28 +- 0.5."""
+    from oracle import pusher as opush
+    v, x = (1.0, 0.0, 0.0), np.zeros(3)
+    r = []
+    for _ in range(5000):
+        v = opush.boris(v, (0.0, 0.0, 0.0), (0.0, 1.0, 0.0), 1.0, 1.0, 0.1, None)
+        x = x + np.asarray(v) * 0.1
+        r.append(np.hypot(x[0], x[2]))
+    assert abs(np.mean(r) - 1.28) <= 0.5
+
+
+def test_higuera_cary_single_particle_kats():
+    """boris_test.py:185-247"""
+    from oracle import pusher as opush
+    C = 10.0
+    assert np.allclose(opush.higuera_cary((0.2, -0.1, 0.05), (0.0, 0.0, 0.0), (0.0, 0.0, 0.0), 1.0, 1.0, 0.1, C), [0.2, -0.1, 0.05])
+    v = opush.higuera_cary((0.2, 0.0, 0.0), (0.0, 0.0, 0.0), (0.0, 0.0, 1.0), 1.0, 1.0, 0.1, C)
+    assert np.isclose(np.sqrt(sum(c * c for c in v)), 0.2, rtol=1e-12, atol=1e-12)
+    v = opush.higuera_cary((0.0, 0.0, 0.0), (1.0, 0.0, 0.0), (0.0, 0.0, 0.0), 1.0, 1.0, 0.1, C)
+    assert v[0] > 0.0 and np.allclose(v[1:], 0.0)
+    z2 = np.zeros(2)
+    v = opush.higuera_cary((z2, z2, z2), (np.ones(2), z2, z2), (z2, z2, z2), np.array([1.0, 2.0]), np.array([1.0, 1.0]), 0.1, C)
+    assert v[0].shape == (2,) and v[0][1] > v[0][0] and np.allclose(v[1], 0.0) and np.allclose(v[2], 0.0)
