@@ -545,3 +545,29 @@ def test_higuera_cary_single_particle_kats():
     z2 = np.zeros(2)
     v = opush.higuera_cary((z2, z2, z2), (np.ones(2), z2, z2), (z2, z2, z2), np.array([1.0, 2.0]), np.array([1.0, 1.0]), 0.1, C)
     assert v[0].shape == (2,) and v[0][1] > v[0][0] and np.allclose(v[1], 0.0) and np.allclose(v[2], 0.0)
+
+
+@pytest.mark.parametrize("shape_factor", (1, 2))
+@pytest.mark.parametrize("case", ("wave", "polynomial", "oscillatory"))
+def test_interpolation_order_reference_pins(shape_factor, case):
+    """boris_test.py:249-451: interpolate_field_to_particles on the three analytic fields, offset test points, the reference's
+    regression (utils.py:73-105: slope of log(err) + 3 log(dx) against log(dx), must exceed 1.9) -- on nx = 30, 50, 70, 90 of the
+    reference's 30..220 to keep the NumPy gather cheap."""
+    from oracle import pusher as opush
+    spec = {"wave": (2 * np.pi, 3.0, lambda X, Y, Z: np.sin(X) * np.cos(Y) * np.sin(Z)),
+            "polynomial": (1.0, 2.0, lambda X, Y, Z: X ** 3 * Y + Y ** 3 * Z + Z ** 3 * X),
+            "oscillatory": (np.pi, 4.0, lambda X, Y, Z: np.cos(2 * X) * np.sin(3 * Y) * np.cos(4 * Z))}[case]
+    wind, frac, f = spec
+    dxs, errs = [], []
+    for nx in (30, 50, 70, 90):
+        g = np.linspace(0, wind, nx)
+        dx = wind / (nx - 1)
+        X, Y, Z = np.meshgrid(g, g, g, indexing="ij")
+        t = np.linspace(dx / frac, wind - dx / frac, nx)
+        Xt, Yt, Zt = (a.ravel() for a in np.meshgrid(t, t, t, indexing="ij"))
+        got = opush.interpolate_field_to_particles(f(X, Y, Z), Xt, Yt, Zt, (g, g, g), shape_factor)
+        errs.append(float(np.mean(np.abs(got - f(Xt, Yt, Zt)))))
+        dxs.append(dx)
+    slope = abs(np.polyfit(np.log(dxs), np.log(errs) + 3 * np.log(dxs), 1)[0])
+    assert slope > 1.9
+    assert abs(np.polyfit(np.log(dxs), np.log(errs), 1)[0]) > 1.8      # and the interpolation itself is second order
