@@ -571,3 +571,85 @@ def test_interpolation_order_reference_pins(shape_factor, case):
     slope = abs(np.polyfit(np.log(dxs), np.log(errs) + 3 * np.log(dxs), 1)[0])
     assert slope > 1.9
     assert abs(np.polyfit(np.log(dxs), np.log(errs), 1)[0]) > 1.8      # and the interpolation itself is second order
+
+
+# ---- tests/physics_tests/pusher_schmitz_test.py:69-211 (q = m = C = 1; the reference's literal thresholds) -----
+def _gamma(v):
+    return 1.0 / np.sqrt(1.0 - sum(c * c for c in v))
+
+
+def _v_from_u(u):
+    g = np.sqrt(1.0 + sum(c * c for c in u))
+    return tuple(c / g for c in u)
+
+
+def _advance(fn, v, E, B, dt, steps):
+    for _ in range(steps):
+        v = tuple(float(c) for c in fn(v, E, B, 1.0, 1.0, dt, 1.0))
+    return v
+
+
+def test_schmitz_constant_B_preserves_energy():
+    """pusher_schmitz_test.py:69-84"""
+    from oracle import pusher as opush
+    for gamma0 in (1.001, 10.0):
+        v0 = _v_from_u((np.sqrt(gamma0 ** 2 - 1.0), 0.0, 0.0))
+        for fn in (opush.relativistic_boris, opush.higuera_cary):
+            v = _advance(fn, v0, (0.0, 0.0, 0.0), (0.0, 0.0, 1.0), 0.2 * np.pi * gamma0, 10)
+            assert abs(_gamma(v) - gamma0) <= 2.0e-12
+
+
+def test_schmitz_force_free_crossed_fields():
+    """pusher_schmitz_test.py:86-123: Higuera-Cary keeps the force-free trajectory exact, relativistic Boris does not."""
+    from oracle import pusher as opush
+    gamma0 = 10.0
+    v0 = np.sqrt(gamma0 ** 2 - 1.0) / gamma0
+    E, B, dt = (0.0, v0, 0.0), (0.0, 0.0, 1.0), 0.2 * np.pi * gamma0
+    worst = {}
+    for name, fn in (("hc", opush.higuera_cary), ("boris", opush.relativistic_boris)):
+        v, angle, err = (v0, 0.0, 0.0), 0.0, 0.0
+        for _ in range(20):
+            v = _advance(fn, v, E, B, dt, 1)
+            angle = max(angle, abs(np.arctan2(v[1], v[0])))
+            err = max(err, abs((_gamma(v) - gamma0) / (gamma0 - 1.0)))
+        worst[name] = (angle, err)
+    assert worst["hc"][0] < 1.0e-13 and worst["hc"][1] < 1.0e-12
+    assert 1.0e-3 < worst["boris"][0] < 2.0e-1 and worst["boris"][1] > 1.0e-2
+
+
+def test_schmitz_lorentz_boosted_gyration():
+    """pusher_schmitz_test.py:125-183"""
+    from oracle import pusher as opush
+    gp, gf = 10.0, 5.0
+    bf = np.sqrt(1.0 - 1.0 / gf ** 2)
+    vp = np.sqrt(1.0 - 1.0 / gp ** 2)
+    omega = 1.0 / gp
+    radius = vp / omega
+    dt, steps = 1.0e-3 * 2.0 * np.pi * gp * gf, 20
+    lab_time = steps * dt
+    tm = lab_time / gf
+    for _ in range(8):
+        res = gf * (tm + bf * radius * (1.0 - np.cos(omega * tm))) - lab_time
+        tm -= res / (gf * (1.0 + bf * vp * np.sin(omega * tm)))
+    vx_m, vy_m = vp * np.sin(omega * tm), vp * np.cos(omega * tm)
+    den = 1.0 + bf * vx_m
+    exact = ((vx_m + bf) / den, vy_m / (gf * den), 0.0)
+    E, B, v0 = (0.0, bf * gf, 0.0), (0.0, 0.0, gf), (bf, vp / gf, 0.0)
+    err = lambda v: np.sqrt(sum((v[i] - exact[i]) ** 2 for i in range(3)))
+    assert err(_advance(opush.higuera_cary, v0, E, B, dt, steps)) < 1.0e-6
+    assert err(_advance(opush.relativistic_boris, v0, E, B, dt, steps)) < 1.0e-3
+
+
+def test_schmitz_oscillating_parallel_E_returns_to_initial_energy():
+    """pusher_schmitz_test.py:185-211"""
+    from oracle import pusher as opush
+    gamma_perp = 1.1
+    v0 = _v_from_u((np.sqrt(gamma_perp ** 2 - 1.0), 0.0, 0.0))
+    omega0 = 0.5 * (1.0 / gamma_perp)
+    E0 = 10.0 * omega0
+    dt = (2.0 * np.pi / omega0) / 100
+    for fn in (opush.relativistic_boris, opush.higuera_cary):
+        v = v0
+        for step in range(500):
+            v = _advance(fn, v, (0.0, 0.0, E0 * np.cos(omega0 * (step + 0.5) * dt)), (0.0, 0.0, 1.0), dt, 1)
+        assert abs(v[2]) <= 1.0e-10 and abs(_gamma(v) - gamma_perp) <= 1.0e-10
