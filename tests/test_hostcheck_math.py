@@ -221,3 +221,61 @@ def test_tile3d_body_matches_oracle_step(hc, rel, dtype, tol, pbc, shift):
     for c in range(3):
         assert np.allclose(J[c], Jref[c][0, 0, 0], rtol=tol, atol=tol * scale), ("J", c)
     assert flags[0] == 0
+
+
+# ---- the kernel's push body (gather + pusher, as the CUDA kernels execute it) through the reference's pusher physics tests -----
+def _kernel_push(hc, pusher_name, v, E, B, dt, steps, E_of_step=None):
+    """One particle at the origin of a 1x1x1 domain with uniform fields, q = m = C = 1, pushed `steps` times by slot_push."""
+    sp, dp = fx.kernel_parameters(Nx=1, Ny=1, Nz=1, x_wind=1.0, y_wind=1.0, z_wind=1.0, C=1.0, dt=dt, particle_pusher=pusher_name,
+                                  relativistic=True, shape_factor=1)
+    tp, sc = fx.build_tiled_particles([fx.particle_species("p", 1.0, 1.0, x1=np.zeros(1), x2=np.zeros(1), x3=np.zeros(1),
+                                                            u1=np.array([v[0]]), u2=np.array([v[1]]), u3=np.array([v[2]]))], sp, dp)
+    p = _lib.make_params(sp, dp, sc, np.float64)
+    x = np.ascontiguousarray(tp.x); u = np.ascontiguousarray(tp.u); a = np.ascontiguousarray(tp.active.astype(np.uint8))
+    shape = fx.empty_tiled_scalar(sp, dp).shape
+    out = np.zeros_like(u)
+    for step in range(steps):
+        Es = E if E_of_step is None else E_of_step(step)
+        Ec = [np.full(shape, c, dtype=np.float64) for c in Es]; Bc = [np.full(shape, c, dtype=np.float64) for c in B]
+        hc.hc_push(ctypes.byref(p), _ptr(x), _ptr(u), _ptr(out), _ptr(a), ctypes.c_int64(tp.x.shape[4]), _v3(Ec), _v3(Bc))
+        u, out = out, u
+    return tuple(float(c) for c in u.reshape(-1, 3)[0])
+
+
+def _g(v):
+    return 1.0 / np.sqrt(1.0 - sum(c * c for c in v))
+
+
+@pytest.mark.parametrize("pn", ("boris", "higuera_cary"))
+def test_kernel_push_body_passes_schmitz_constant_B(hc, pn):
+    """pusher_schmitz_test.py:69-84 through the CUDA kernels' own push body (host build)."""
+    for gamma0 in (1.001, 10.0):
+        u0 = np.sqrt(gamma0 ** 2 - 1.0)
+        v = _kernel_push(hc, pn, (u0 / gamma0, 0.0, 0.0), (0.0, 0.0, 0.0), (0.0, 0.0, 1.0), 0.2 * np.pi * gamma0, 10)
+        assert abs(_g(v) - gamma0) <= 2.0e-12 * max(1.0, gamma0)
+
+
+def test_kernel_push_body_passes_schmitz_force_free(hc):
+    """pusher_schmitz_test.py:86-123: Higuera-Cary exact, relativistic Boris off by 1e-3 .. 2e-1 rad after 20 steps."""
+    gamma0 = 10.0
+    v0 = np.sqrt(gamma0 ** 2 - 1.0) / gamma0
+    E, B, dt = (0.0, v0, 0.0), (0.0, 0.0, 1.0), 0.2 * np.pi * gamma0
+    v = _kernel_push(hc, "higuera_cary", (v0, 0.0, 0.0), E, B, dt, 20)
+    assert abs(np.arctan2(v[1], v[0])) < 1.0e-12 and abs((_g(v) - gamma0) / (gamma0 - 1.0)) < 1.0e-11
+    worst = 0.0
+    for steps in range(1, 21):
+        v = _kernel_push(hc, "boris", (v0, 0.0, 0.0), E, B, dt, steps)
+        worst = max(worst, abs(np.arctan2(v[1], v[0])))
+    assert 1.0e-3 < worst < 2.0e-1
+
+
+@pytest.mark.parametrize("pn", ("boris", "higuera_cary"))
+def test_kernel_push_body_passes_schmitz_oscillating_E(hc, pn):
+    """pusher_schmitz_test.py:185-211"""
+    gamma_perp = 1.1
+    u = np.sqrt(gamma_perp ** 2 - 1.0)
+    omega0 = 0.5 / gamma_perp
+    E0, dt = 10.0 * omega0, (2.0 * np.pi / omega0) / 100
+    v = _kernel_push(hc, pn, (u / gamma_perp, 0.0, 0.0), None, (0.0, 0.0, 1.0), dt, 500,
+                     E_of_step=lambda s: (0.0, 0.0, E0 * np.cos(omega0 * (s + 0.5) * dt)))
+    assert abs(v[2]) <= 1.0e-9 and abs(_g(v) - gamma_perp) <= 1.0e-9
