@@ -436,3 +436,46 @@ def test_load_external_fields_reference_pins(tmp_path):
     sp, dp, fields, ext, path, I = _ext_setup(tmp_path, "wrong.npy", (3, 2, 2), 1.0)
     with pytest.raises(ValueError, match="Shape mismatch"):
         load_external_fields_from_toml(fields, ext, {"field1": {"name": "wrong Ex", "type": 0, "path": path, "evolve": False}}, sp, dp)
+
+
+@pytest.mark.gpu
+def test_two_stream_growth_rate_and_energy_history(tmp_path):
+    """The observable the north star names: demos/two_stream/two_stream.toml as packaged, 120 steps (the whole linear phase: the
+    field energy grows ~20x and starts to saturate).  The electric-field energy history written by `run_PyPIC3D` (reference file
+    format) equals the oracle's from the identical initial state, the fitted growth rates agree, and both sit in the band the
+    warm-beam (vth / v0 = 0.3), 1500-particle-per-beam run can reach of the cold-beam rate w_p / (2 sqrt 2) (0.40 - 0.46 over seeds)."""
+    from tests import gpu_util as gu
+    gu.require_cuda()
+    from pypic3d_b200.initialization import initialize_simulation
+    from pypic3d_b200.__main__ import run_PyPIC3D
+    from oracle import evolve as oevolve, diagnostics as odiag
+    from oracle.params import StaticParameters as OS, DynamicParameters as OD, GridParameters as OG, TiledParticles as OT, SpeciesConfig as OC
+    cfg = {k: dict(v) for k, v in TWO_STREAM.items()}
+    cfg["simulation_parameters"].update(output_dir=str(tmp_path), Nt=121, particle_tile_capacity_factor=1.5)
+    np.random.seed(0)
+    loop, particles, fields, sp, dp, plotting, plasma, species = initialize_simulation(cfg, verbose=False)
+    osp = OS(**sp._asdict()); odp = OD(**{**dp._asdict(), "grids": OG(**dp.grids._asdict())})
+    otp = OT(gu.npy(particles.x), gu.npy(particles.u), gu.npy(particles.active))
+    osc = OC(*[np.asarray(v) for v in species])
+    n = lambda F: tuple(gu.npy(c) for c in F)
+    of = (n(fields[0]), n(fields[1]), n(fields[2]), gu.npy(fields[3]), gu.npy(fields[4]), (n(fields[5][0]), n(fields[5][1])), None, False)
+    t_ref, e_ref = [], []
+    for step in range(121):
+        if step % 8 == 0:
+            e, b, k = odiag.compute_energy(otp, of[0], of[1], osp, odp, osc)
+            t_ref.append(step * float(dp.dt)); e_ref.append(float(e))
+        otp, of = oevolve.time_loop_electrodynamic(otp, osc, of, osp, odp)
+    np.random.seed(0)
+    run_PyPIC3D(cfg, verbose=False)
+    rows = [r.split(",") for r in open(os.path.join(str(tmp_path), "data", "electric_field_energy.txt")).read().strip().splitlines()]
+    t_gpu = np.array([float(r[0]) for r in rows]); e_gpu = np.array([float(r[1]) for r in rows])
+    t_ref, e_ref = np.array(t_ref), np.array(e_ref)
+    assert t_gpu.shape == t_ref.shape == (16,) and np.allclose(t_gpu, t_ref, rtol=1e-12, atol=0)
+    assert e_gpu[0] == 0.0 and np.allclose(e_gpu[1:], e_ref[1:], rtol=1e-6)
+    assert e_ref[-1] > 10 * e_ref[1]                                   # the instability did grow
+    sel = slice(2, 13)                                                 # steps 16 .. 96
+    rate = lambda t, e: np.polyfit(t[sel], np.log(e[sel]), 1)[0] / 2
+    g_gpu, g_ref = rate(t_gpu, e_gpu), rate(t_ref, e_ref)
+    wp_total = np.sqrt(2 * 1.0e15 * 1.602e-19 ** 2 / (float(dp.eps) * 9.1093837e-31))
+    assert abs(g_gpu - g_ref) <= 1e-5 * abs(g_ref)
+    assert 0.25 <= g_ref / (wp_total / (2 * np.sqrt(2))) <= 0.7
