@@ -186,3 +186,40 @@ def test_force_free_ExB_drift():
     E = (-(v[1] * B[2]), np.zeros(1), np.zeros(1))
     out = pusher.boris(v, E, B, 1.0, 1.0, 0.01, 1.0)
     assert np.allclose([o[0] for o in out], [0.0, 0.1, 0.0], atol=1e-6)
+
+
+# ---- rho properties (tests/code_tests/rho_test.py:255-345) ---------------------------------------------
+def _rho_case(sf=2, **kw):
+    from tests.cases import make_case
+    sp, dp, tp, sc, E, B = make_case((8, 6, 4), (4, 3, 2), sf, **kw)
+    return sp, dp, tp, sc
+
+
+def test_rho_uses_current_positions_not_velocities():
+    """rho_test.py:329-369: the same positions with zeroed velocities deposit the same rho."""
+    sp, dp, tp, sc = _rho_case()
+    z = fx.empty_tiled_scalar(sp, dp)
+    a = dep.compute_rho(tp, sc, z, sp, dp)
+    b = dep.compute_rho(tp._replace(u=np.zeros_like(tp.u)), sc, z, sp, dp)
+    assert np.allclose(a, b, rtol=1e-12, atol=1e-12)
+
+
+def test_rho_ghost_folding_uses_the_particle_boundary_conditions():
+    """rho_test.py:301-327: periodic vs absorbing particle BC on x change the folded rho (the field BCs are identical)."""
+    sp0, dp0, tp, sc = _rho_case(sf=1, particle_boundary_conditions=(0, 0, 0))
+    sp1, dp1, _, _ = _rho_case(sf=1, particle_boundary_conditions=(2, 0, 0))
+    a = dep.compute_rho(tp, sc, fx.empty_tiled_scalar(sp0, dp0), sp0, dp0)
+    b = dep.compute_rho(tp, sc, fx.empty_tiled_scalar(sp1, dp1), sp1, dp1)
+    assert float(np.abs(np.asarray(a) - np.asarray(b)).max()) > 1e-12
+
+
+def test_rho_digital_filter_depends_on_alpha():
+    """rho_test.py:255-299: current_filter = "digital": rho(alpha = 0.55) == digital_filter(rho(alpha = 1), 0.55) + ghost refresh."""
+    from oracle import filters as ofil, halo as ohalo
+    sp, dp, tp, sc = _rho_case(current_filter="digital", alpha=1.0)
+    z = fx.empty_tiled_scalar(sp, dp)
+    r10 = np.asarray(dep.compute_rho(tp, sc, z, sp, dp))
+    r055 = np.asarray(dep.compute_rho(tp, sc, z, sp, dp._replace(alpha=0.55)))
+    g = int(sp.guard_cells)
+    want = ohalo.update_tiled_ghost_cells(ofil.digital_filter(r10, 0.55, num_guard_cells=g), sp, g, bc_type=1)
+    assert np.allclose(r055, want, rtol=1e-13, atol=1e-13) and np.abs(r055 - r10).max() > 1e-6
