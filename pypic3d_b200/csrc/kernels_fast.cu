@@ -344,6 +344,13 @@ __global__ void __launch_bounds__(256, (SF == 1 ? PIC_K1_CTAS : 2)) k_fused3d(co
 #ifndef PIC_K9_PREFETCH
 #define PIC_K9_PREFETCH 0   /* L2 prefetch of the particles NW chunks ahead: measured 5.08 vs 5.00 ms without */
 #endif
+#ifndef PIC_K9_JT_SYNC
+/* J-tile (MODE 1) hand-over between warps: 0 = __threadfence_block() + atomicAdd -- the build every J-tile number of round 1 was
+   measured with; its fence.sc makes ptxas turn ALL 126 global REDG of that kernel into returning ATOMG (cuobjdump, see
+   tests/test_sass_evidence.py).  1 = one atom.acq_rel.cta on the arrival counter: same ordering guarantee for the tile, the global
+   adds stay REDG.  Compiles, not yet run on a GPU -- to be A/B'd before it becomes the default. */
+#define PIC_K9_JT_SYNC 0
+#endif
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 // mbarrier (shared::cta) + TMA helpers for the tile pipeline
@@ -780,13 +787,22 @@ __global__ void __launch_bounds__(NW * 32, (sizeof(T) == 8 ? 1 : PIC_K9_CTAS)) k
                 asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");      // our shared-memory adds -> visible to the TMA
                 int last = 0;
                 if (lane == 0) {
+#if PIC_K9_JT_SYNC == 0
                     __threadfence_block();
                     last = (atomicAdd(jdone + jsel, 1) == NW - 1) ? 1 : 0;
+#else
+                    unsigned old_;
+                    asm volatile("atom.acq_rel.cta.shared::cta.add.u32 %0, [%1], 1;\n"
+                                 : "=r"(old_) : "r"(smem_u32(jdone + jsel)) : "memory");
+                    last = (old_ == (unsigned)(NW - 1)) ? 1 : 0;
+#endif
                 }
                 last = __shfl_sync(0xffffffffu, last, 0);
                 if (last) {
                     T* jt = jtiles + jsel * JT_ELEMS;
+#if PIC_K9_JT_SYNC == 0
                     __threadfence_block();
+#endif
                     if (lane == 0) {
                         asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
 #pragma unroll
@@ -800,8 +816,10 @@ __global__ void __launch_bounds__(NW * 32, (sizeof(T) == 8 ? 1 : PIC_K9_CTAS)) k
                     __syncwarp();
                     if (lane == 0) {
                         jdone[jsel] = 0;
+#if PIC_K9_JT_SYNC == 0
                         __threadfence_block();
-                        mbar_arrive(jfree + jsel);
+#endif
+                        mbar_arrive(jfree + jsel);               // release: orders the zeroing above before the tile's reuse
                     }
                 }
                 if (jsel == 1) ++juse;
