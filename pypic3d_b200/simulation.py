@@ -70,6 +70,7 @@ class Simulation:
             raise ValueError("guard_cells must be >= 1")
         self.sort_interval = int(sort_interval)
         self.step_count = 0
+        self._J_ghosts_stale = False
         if halo is None:
             self.halo = LocalHalo(self.p)
         else:
@@ -230,13 +231,15 @@ class Simulation:
         return [int(min(20 * base, max(base, round(base * vmax / v)))) if v > 0 else 20 * base for v in vrms]
 
     def load_state(self, particles, fields3=None):
-        self._J_ghosts_stale = False
-        """Replace the resident state from reference-layout pytrees (same shapes as at construction); re-sorts."""
+        """Replace the resident state from reference-layout pytrees (same shapes as at construction); re-sorts.
+        The sort cadence and the drift estimate behind the K1 reduction choice keep the rms velocities seen at construction
+        (cost knobs only: neither changes results)."""
         self._import(particles, 1.0)
         if fields3 is not None:
             for dst, src in zip((self.E, self.B, self.J), fields3):
                 for d, s_ in zip(dst, src):
                     d.copy_(ops._chk(s_, "field", self.dtype))
+            self._J_ghosts_stale = False          # the caller's J comes with its ghosts; a kept J may still owe its refresh
         self.sort()
 
     def sort(self, which=None):
@@ -374,7 +377,7 @@ class Simulation:
             live = self._counter[:self.S].cpu().tolist()
             if any(int(n) > cap for n in live):          # fixed-capacity contract of the reference layout (:169-230)
                 self.flags[0:1] |= 2
-        if getattr(self, "_J_ghosts_stale", False):
+        if self._J_ghosts_stale:
             self.halo.refresh_(self.J, tuple(self.p.particle_bc))
             self._J_ghosts_stale = False
         rho, phi, ext = self._passthrough
