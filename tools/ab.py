@@ -1,0 +1,83 @@
+"""A/B harness for kernel variants selected by compile-time macros (the PIC_K9_* / PIC_* switches in csrc/).
+
+    # here (no GPU): build the variants next to the product library, git-ignored but shipped to the GPU box
+    python tools/ab.py build base jtsync:-DPIC_K9_JT_SYNC=1 nw16:-DPIC_K9_CTAS=1,-DPIC_K9_NW=16
+
+    # on the GPU box (one gpurun call): time each variant with the product bench, same box, back to back
+    gpurun --timeout 900 -- 'python tools/ab.py run base jtsync nw16 -- --steps 20 --warmup 5'
+
+`build` writes build_ab/<name>/libpic_b200.so (the product library is untouched); `run` executes
+`bench.py --no-e2e --no-cpu-baseline` once per variant with PIC_B200_LIB pointing at it (extra environment as name@K=V,
+e.g. jt@PIC_K9_JTILE=1), stores gpurun_out/ab_<name>.json and prints one comparison line per variant.  A variant is only
+adopted after `pytest -m gpu` has passed with PIC_B200_LIB set to it."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def split(spec):
+    name, _, rest = spec.partition(":")
+    name, *env = name.split("@")
+    return name, [f for f in rest.split(",") if f], dict(e.split("=", 1) for e in env)
+
+
+def lib_of(name):
+    return os.path.join(ROOT, "build_ab", name, "libpic_b200.so")
+
+
+def build(specs):
+    from pypic3d_b200 import _lib
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    for spec in specs:
+        name, flags, _ = split(spec)
+        os.makedirs(os.path.dirname(lib_of(name)), exist_ok=True)
+        cmd = ([nvcc] + _lib.NVCC_FLAGS + ["-Xptxas", "-v"] + flags + ["-o", lib_of(name)]
+               + [os.path.join(ROOT, "pypic3d_b200", "csrc", f) for f in _lib.SOURCES])
+        out = subprocess.run(cmd, check=True, capture_output=True, text=True).stderr
+        spilled, entry = [], ""
+        for l in out.splitlines():                                   # ptxas -v: "Compiling entry function '<name>'" ... "N bytes spill stores"
+            if "Compiling entry function" in l:
+                entry = l.split("'")[1]
+            elif "spill stores" in l and "0 bytes spill stores, 0 bytes spill loads" not in l:
+                spilled.append(entry)
+        tile = [e for e in spilled if "k_tile3d" in e]
+        print(f"{name}: built {lib_of(name)} ({' '.join(flags) or 'default flags'}); spilling kernels: k_tile3d {len(tile)}, "
+              f"others {len(spilled) - len(tile)} (the general-configuration kernels spill in the default build too)")
+
+
+def run(specs, bench_args):
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    for spec in specs:
+        name, _, env = split(spec)
+        e = dict(os.environ, PIC_B200_LIB=lib_of(name), **env)
+        cmd = [sys.executable, os.path.join(ROOT, "bench.py"), "--no-e2e", "--no-cpu-baseline"] + bench_args
+        r = subprocess.run(cmd, env=e, capture_output=True, text=True, timeout=600)
+        line = next((l for l in reversed(r.stdout.splitlines()) if l.startswith("{")), None)
+        if line is None:
+            print(f"{name}: FAILED rc={r.returncode} {r.stderr[-400:]}")
+            continue
+        with open(os.path.join(ROOT, "gpurun_out", f"ab_{name}.json"), "w") as f:
+            f.write(line + "\n")
+        d = json.loads(line)
+        rf = d["roofline"]
+        print(f"{name:12s} step {d['ms_per_step']:.3f} ms  K1 {rf['avg_launch_ms']:.3f} ms {rf.get('avg_launch_ms_by_species')}  "
+              f"frac {rf['frac']:.3f}  sm {d['clocks']['sm_mhz']} MHz {d['clocks']['reasons']}")
+
+
+def main(argv):
+    if len(argv) < 2 or argv[0] not in ("build", "run"):
+        sys.exit(__doc__)
+    rest = argv[1:]
+    extra = []
+    if "--" in rest:
+        i = rest.index("--")
+        rest, extra = rest[:i], rest[i + 1:]
+    (build if argv[0] == "build" else lambda s: run(s, extra))(rest)
+
+
+if __name__ == "__main__":
+    main(sys.argv[1:])
