@@ -6,7 +6,7 @@ BASELINE.json configs[3] at N=1 (256^3 cells x 16 ppc, Esirkepov + Yee, periodic
 per GPU, weak scaling, NCCL halo exchange + particle migration).
 
     python bench.py --gpus 1 --steps 20 --warmup 5            # ours (CUDA, C ABI)
-    python bench.py --impl reference --steps 3 --warmup 1      # CPU arm: NumPy restatement of the reference (oracle)
+    python bench.py --impl reference --steps 3 --warmup 1      # CPU arm: NumPy restatement of the reference (oracle), one tile per core
     torchrun ... bench.py --gpus N ...                         # N>1: one rank per GPU
 
 Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for every key.
@@ -116,16 +116,56 @@ def cpu_reference(steps, warmup, shape_factor, n=16, ppc=16, seed=1234):
     for _ in range(steps):
         tp, fields = oevolve.time_loop_electrodynamic(tp, sc, fields, sp, dp)
     el = time.perf_counter() - t0
-    return {"value": npart * steps / el, "unit": "particle-steps/s", "cores": 1, "kind": "port",
+    return {"value": npart * steps / el, "unit": "particle-steps/s", "cores": 1, "kind": "port", "particles": npart,
             "sample": f"{n}^3 cells x {ppc} ppc ({npart} particles), {steps} steps, NumPy float64 restatement of the reference "
                       f"(jax is not installable here); NumPy scatter-add is single-threaded"}, el / max(steps, 1)
+
+
+def host_cores():
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
+def cpu_reference_all_cores(steps, warmup, shape_factor, n=16, ppc=16, workers=0):
+    """The CPU arm on every host core.  NumPy runs the restatement on one thread, so the cores are used the way the reference uses
+    devices: one tile per worker (its `field_mesh`, ghost_cells.py:181-316) -- `workers` oracle processes, each stepping its own
+    n^3 tile of the same plasma (seed 1234 + worker).  The tiles do not exchange halos, so this is an upper bound for a
+    `workers`-tile CPU run.  value = all particles x steps / the slowest worker's time."""
+    workers = int(workers) if workers else min(host_cores(), 128)
+    if workers <= 1:
+        return cpu_reference(steps, warmup, shape_factor, n=n, ppc=ppc)
+    env = dict(os.environ, OMP_NUM_THREADS="1", OPENBLAS_NUM_THREADS="1", MKL_NUM_THREADS="1", CUDA_VISIBLE_DEVICES="")
+    cmd = [sys.executable, os.path.abspath(__file__), "--cpu-worker", "--steps", str(steps), "--warmup", str(warmup),
+           "--shape-factor", str(shape_factor), "--cpu-n", str(n), "--ppc", str(ppc)]
+    procs = [subprocess.Popen(cmd + ["--seed", str(1234 + w)], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+             for w in range(workers)]
+    results = []
+    for pr in procs:
+        out, err = pr.communicate(timeout=1200)
+        line = next((l for l in reversed(out.splitlines()) if l.startswith("{")), None)
+        if pr.returncode != 0 or line is None:
+            raise RuntimeError(f"cpu worker failed (rc={pr.returncode}): {err[-500:]}")
+        results.append(json.loads(line))
+    npart = sum(r["particles"] for r in results)
+    slowest = max(r["seconds"] for r in results)
+    return {"value": npart * steps / slowest, "unit": "particle-steps/s", "cores": workers, "kind": "port",
+            "sample": f"{workers} tiles of {n}^3 cells x {ppc} ppc ({npart} particles in all), {steps} steps, one process per host core, "
+                      f"each the NumPy float64 restatement of the reference on its own tile without halo exchange (jax is not "
+                      f"installable here; NumPy itself runs the step on one thread); slowest worker {slowest:.2f} s"}, slowest / max(steps, 1)
+
+
+def run_cpu_worker(args):
+    base, sec = cpu_reference(args.steps, args.warmup, args.shape_factor, n=args.cpu_n, ppc=args.ppc, seed=args.seed)
+    _emit({"particles": base["particles"], "seconds": sec * args.steps})
 
 
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    base, ms = cpu_reference(args.steps, args.warmup, args.shape_factor, n=args.cpu_n)
+    base, ms = cpu_reference_all_cores(args.steps, args.warmup, args.shape_factor, n=args.cpu_n, ppc=args.ppc, workers=args.cpu_workers)
     line = {"impl": "reference", "metric": "particle-steps/sec (push+deposit+Yee)", "value": base["value"], "unit": "particle-steps/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -214,10 +254,15 @@ def main():
     ap.add_argument("--sort-interval", type=int, default=10)
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--cpu-n", type=int, default=16)
+    ap.add_argument("--cpu-workers", type=int, default=0, help="CPU arm: oracle processes (0 = one per host core, at most 128)")
+    ap.add_argument("--cpu-worker", action="store_true", help=argparse.SUPPRESS)
+    ap.add_argument("--seed", type=int, default=1234, help=argparse.SUPPRESS)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--check", action="store_true", help="also verify charge conservation at full size after the timed run")
     args = ap.parse_args()
+    if args.cpu_worker:
+        return run_cpu_worker(args)
     if args.impl == "reference":
         return run_reference_arm(args)
 
@@ -337,7 +382,7 @@ def main():
 
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu_base, _ = cpu_reference(3, 1, args.shape_factor, n=args.cpu_n, ppc=args.ppc)
+        cpu_base, _ = cpu_reference_all_cores(3, 1, args.shape_factor, n=args.cpu_n, ppc=args.ppc, workers=args.cpu_workers)
 
     check = None
     if args.check:
