@@ -344,6 +344,14 @@ __global__ void __launch_bounds__(256, (SF == 1 ? PIC_K1_CTAS : 2)) k_fused3d(co
 #ifndef PIC_K9_PREFETCH
 #define PIC_K9_PREFETCH 0   /* L2 prefetch of the particles NW chunks ahead: measured 5.08 vs 5.00 ms without */
 #endif
+#ifndef PIC_K9_PPT
+/* particles per thread and chunk-loop iteration: 1 = the measured kernel.  2 = lane l advances the ADJACENT particles 2l and 2l+1
+   of a 64-particle chunk: dealing, descriptor reads, queue bookkeeping and -- because neighbours in the sorted stream mostly share
+   their cell -- the warp reduction are paid once per pair (B's values are added to A's when the cells match, sent out directly
+   when they do not).  Needs ~100 registers: build with -DPIC_K9_PPT=2 -DPIC_K9_NW=10.  Compiles; not yet run on a GPU
+   (profiles/r01_k1_instruction_budget.md, candidate 1). */
+#define PIC_K9_PPT 1
+#endif
 #ifndef PIC_K9_JT_SYNC
 /* J-tile (MODE 1) hand-over between warps: 0 = __threadfence_block() + atomicAdd -- the build every J-tile number of round 1 was
    measured with; its fence.sc makes ptxas turn ALL 126 global REDG of that kernel into returning ATOMG (cuobjdump, see
@@ -719,7 +727,12 @@ __global__ void __launch_bounds__(NW * 32, (sizeof(T) == 8 ? 1 : PIC_K9_CTAS)) k
             p_beg = tail0 + (int)blockIdx.x * per;
             p_end = (p_beg + per < n_live) ? p_beg + per : n_live;
         }
+#if PIC_K9_PPT == 2
+        const int p_even = p_beg & ~1;                           // pairs start on even slots (the staged slice does too)
+        const int nchunk = p_end > p_beg ? (p_end - p_even + 63) >> 6 : 0;
+#else
         const int nchunk = p_end > p_beg ? (p_end - p_beg + 31) >> 5 : 0;
+#endif
         const T* pst = st + TILE_ALL - (p_beg & ~(AL - 1));      // staged particle i of array c sits at pst[c * PCAP + i]
 #if PIC_K9_DEAL == 1
         // a warp that finishes early takes the next undealt chunk, or moves on to the next supercell: the warps stay within
@@ -733,6 +746,80 @@ __global__ void __launch_bounds__(NW * 32, (sizeof(T) == 8 ? 1 : PIC_K9_CTAS)) k
 #else
         for (int ch = (warp - rot + NW * 64) % NW; ch < nchunk; ch += NW) {
 #endif
+#if PIC_K9_PPT == 2
+            // ---- two adjacent particles per lane: A = slot i0 (even), B = i0 + 1
+            auto flush_queue = [&]() {
+                if (qn >= QW - 32) {
+                    for (int e = lane; e < qn; e += 32) {
+                        const T o3[3] = {qo[e], qo[QW + e], qo[2 * QW + e]};
+                        const T n3[3] = {qn_[e], qn_[QW + e], qn_[2 * QW + e]};
+                        const T v3[3] = {(T)0, (T)0, (T)0};
+                        union_deposit<T, SF>(p, species, gm, k, o3, n3, v3, sink);
+                    }
+                    qn = 0;
+                    __syncwarp();
+                }
+            };
+            auto advance_one = [&](int i, bool valid, T* vals, int& key, int dead_key) {
+                T po[3], xn[3], v[3], cur[6];
+                int kind = 0;
+                key = 0;
+                if (valid) {
+                    if (i < i_staged_end) {
+#pragma unroll
+                        for (int c = 0; c < 6; ++c) cur[c] = pst[c * PCAP + i];
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < 6; ++c) cur[c] = s.c[c][i];
+                    }
+                    kind = fast3d_advance<T, SF, PUSHER, false, true, PER1>(p, species, k, i, s, F, X, leave, distributed != 0, flags, po, xn, v, key, vals, cur, &ts, nullptr);
+                }
+                const unsigned defer = __ballot_sync(0xffffffffu, kind == 2);
+                if (defer) {
+                    if (kind == 2) {
+                        const int slot_q = qn + __popc(defer & ((1u << lane) - 1u));
+#pragma unroll
+                        for (int a = 0; a < 3; ++a) { qo[a * QW + slot_q] = po[a]; qn_[a * QW + slot_q] = xn[a]; }
+                    }
+                    qn += __popc(defer);
+                    __syncwarp();
+                }
+                if (kind != 1) {
+                    key = dead_key;
+#pragma unroll
+                    for (int n = 0; n < NV; ++n) vals[n] = (T)0;
+                }
+                return kind;
+            };
+            const int i0 = p_even + ch * 64 + 2 * lane;
+            T vals[NV], valsB[NV];
+            int key, keyB;
+            const int kindA = advance_one(i0, i0 >= p_beg && i0 < p_end, vals, key, -1 - lane);
+            flush_queue();                                   // <= 47 queued before B may add another 32
+            const int kindB = advance_one(i0 + 1, i0 + 1 < p_end, valsB, keyB, -33 - lane);
+            {
+                const bool b_live = (kindB == 1);
+                const bool join = b_live && (kindA != 1 || key == keyB);     // A's slot is empty, or A and B share the cell
+                if (b_live && !join) {                       // neighbours in different cells (a run boundary): B goes out by itself
+                    int n = 0;
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        T* Jc = sink.J[c] + keyB;
+#pragma unroll
+                        for (int m1 = 0; m1 < SameCell<SF>::NN; ++m1)
+#pragma unroll
+                            for (int m2 = 0; m2 < SameCell<SF>::NN; ++m2) atomicAdd(Jc + SameCell<SF>::offset(c, 0, m1, m2, k.sx, k.sy), valsB[n++]);
+                    }
+                }
+#pragma unroll
+                for (int n = 0; n < NV; ++n) vals[n] += join ? valsB[n] : (T)0;     // (A's values are zero when its slot is empty)
+                if (join) key = keyB;
+            }
+            if (JT) same_cell_scan_red_tile<T, STEPS>(vals, key, -1, lane, sink, k.sx, k.sy, jtiles + jsel * JT_ELEMS);
+            else if (MODE == 2) same_cell_group_red<T, SF>(vals, key, lane, sink, k.sx, k.sy);
+            else same_cell_scan_red<T, SF, STEPS>(vals, key, lane, sink, k.sx, k.sy);
+            flush_queue();
+#else
             const int i = p_beg + ch * 32 + lane;
             T vals[NV], po[3], xn[3], v[3], cur[6];
             int key = 0, kind = 0, srel = -1;
@@ -776,6 +863,7 @@ __global__ void __launch_bounds__(NW * 32, (sizeof(T) == 8 ? 1 : PIC_K9_CTAS)) k
                 qn = 0;
                 __syncwarp();
             }
+#endif
         }
 #if PIC_K9_DEAL == 0
         rot = (rot + nchunk) % NW;
