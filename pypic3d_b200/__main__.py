@@ -9,17 +9,12 @@ import numpy as np
 import toml
 import torch
 
+from .diagnostics.plotting import write_data
 from .evolve import time_loop_electrodynamic
 from .initialization import initialize_simulation
 from .parameters import static_parameters_for_output, dynamic_parameters_for_output
 from .simulation import Simulation
 from .utils import add_external_fields, compute_energy, compute_total_momentum
-
-
-def write_data(filename, t, data):
-    """diagnostics/plotting.py:258-278: one `"t, value"` row per sample."""
-    with open(filename, "a") as f:
-        f.write(f"{float(t)}, {float(data)}\n")
 
 
 def _raise_if_overflowed(flag):

@@ -55,6 +55,20 @@ def neighbor(coords, mesh, axis, step, periodic):
     return rank_of(c, mesh)
 
 
+def gather_tiles(tile, gmesh, group=None):
+    """Diagnostics boundary of a multi-GPU run: every rank contributes its (1,1,1,Lx,Ly,Lz) field tile and receives the tile-major
+    array (ntx,nty,ntz,Lx,Ly,Lz) of the whole job -- what `diagnostics.assemble_tiled_scalar_field` and the reference's
+    `jax.device_get` of a sharded field (output_adapters.py:48) start from.  Ranks are laid out like `rank_of`."""
+    gmesh = tuple(int(v) for v in gmesh)
+    n = gmesh[0] * gmesh[1] * gmesh[2]
+    t = tile.reshape((1,) + tuple(tile.shape[3:])).contiguous()
+    if n == 1:
+        return tile.reshape((1, 1, 1) + tuple(tile.shape[3:])).clone()
+    out = [torch.empty_like(t) for _ in range(n)]
+    dist.all_gather(out, t, group=group)
+    return torch.cat(out, 0).reshape(gmesh + tuple(tile.shape[3:]))
+
+
 DIRS = [(1 - sx, 1 - sy, 1 - sz) for sx in range(3) for sy in range(3) for sz in range(3)]   # dir code -> offset (ox,oy,oz)
 
 

@@ -37,6 +37,13 @@ def test_sub_entry_points_keep_the_reference_argument_names():
     assert names(update_B) == ["E_tiles", "B_tiles", "static_parameters", "dynamic_parameters", "pml_state", "do_filter"]
     assert names(update_tiled_particle_positions)[:3] == ["tiled_particles", "species_config", "dt"]
     assert names(refresh_tiled_particle_tiles) == ["tiled_particles", "static_parameters", "dynamic_parameters"]
+    # diagnostics boundary: diagnostics/output_adapters.py:40,78,154; diagnostics/plotting.py:258
+    from pypic3d_b200.diagnostics.output_adapters import assemble_tiled_scalar_field, assemble_tiled_vector_field, particles_for_output
+    from pypic3d_b200.diagnostics.plotting import write_data
+    for f in (assemble_tiled_scalar_field, assemble_tiled_vector_field):
+        assert names(f) == ["field_tiles", "static_parameters", "tile_shape", "num_guard_cells"]
+    assert names(particles_for_output) == ["particles", "species_config", "species_names", "static_parameters", "dynamic_parameters"]
+    assert names(write_data) == ["filename", "time", "data"]
 
 
 def test_static_and_dynamic_parameters_split_kernel_contract():

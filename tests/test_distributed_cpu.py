@@ -15,7 +15,7 @@ import torch.multiprocessing as mp
 
 from oracle import halo as ohalo
 from pypic3d_b200 import _lib
-from pypic3d_b200.distributed import DistributedHalo, coords_of, rank_of, neighbor, DIRS
+from pypic3d_b200.distributed import DistributedHalo, coords_of, rank_of, neighbor, gather_tiles, DIRS
 
 
 class NumpyHaloKernels:
@@ -146,6 +146,9 @@ def _worker(rank, world, port, mesh, tile, g, bcs, q):
                 want = float(1000 * s_ + 100 * src + d) if src is not None else 0.0
                 ok = ok and bool((blk == want).all())
         out["packets_ok"] = ok
+        # diagnostics boundary: every rank gets the tile-major array of the whole job
+        whole = gather_tiles(mine(full)[0], mesh)
+        out["gather"] = float(np.abs(whole.numpy() - full[0]).max()) if tuple(whole.shape) == full[0].shape else 1e9
         q.put((rank, out))
     finally:
         dist.destroy_process_group()
@@ -168,6 +171,7 @@ def test_two_rank_halo_and_packets(mesh, tile, g, bcs):
         assert out["refresh"] < 1e-13, (rank, out)
         assert out["fold"] < 1e-13, (rank, out)
         assert out["packets_ok"], (rank, out)
+        assert out["gather"] == 0.0, (rank, out)
 
 
 def test_topology_helpers():
