@@ -12,9 +12,8 @@ import torch
 from .diagnostics.plotting import write_data
 from .evolve import time_loop_electrodynamic
 from .initialization import initialize_simulation
-from .parameters import static_parameters_for_output, dynamic_parameters_for_output
 from .simulation import Simulation
-from .utils import add_external_fields, compute_energy, compute_total_momentum
+from .utils import add_external_fields, compute_energy, compute_total_momentum, dump_parameters_to_toml
 
 
 def _raise_if_overflowed(flag):
@@ -79,10 +78,7 @@ def main(argv=None):
     print(f"Final Electric Field Energy: {float(e)}\nFinal Magnetic Field Energy: {float(b)}\nFinal Kinetic Energy: {float(k)}")
     print(f"Total Final Energy: {float(e) + float(b) + float(k)}\n")
     stats = {"total_time": duration, "total_iterations": sp.Nt, "time_per_iteration": duration / max(sp.Nt, 1)}
-    with open(os.path.join(sp.output_dir, "data", "output.toml"), "w") as f:       # utils.py:655-700 dump_parameters_to_toml
-        toml.dump({"simulation_stats": stats, "static_parameters": static_parameters_for_output(sp),
-                   "dynamic_parameters": dynamic_parameters_for_output(dp),
-                   "plotting": {k: v for k, v in plotting.items() if not isinstance(v, tuple)}}, f)
+    dump_parameters_to_toml(stats, sp, dp, plasma, plotting, particles)                # __main__.py:226-233
     print(f"\nSimulation Complete\nTotal Simulation Time: {duration} s\nTime Per Iteration: {duration / max(sp.Nt, 1)} s")
 
 

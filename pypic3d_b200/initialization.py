@@ -162,6 +162,7 @@ def initialize_simulation(toml_file, device=None, dtype=torch.float64, verbose=T
 
     particles_np, species_np, names, meta = load_particles_from_toml(config, sp, dp, verbose=verbose)
     plotting["particle_species_names"] = names
+    plotting["particle_species_metadata"] = meta                                             # :359-360
     w, g = [int(v) for v in sp.tile_shape], int(sp.guard_cells)
     shape = tuple(sp.field_mesh) + (w[0] + 2 * g, w[1] + 2 * g, w[2] + 2 * g)
     fields_np = [np.zeros(shape) for _ in range(9)]

@@ -1,8 +1,15 @@
 """Drop-ins for the step-adjacent helpers of PyPIC3D/utils.py: add_external_fields:205, compute_energy:108,
-compute_total_momentum:190, courant_condition:761."""
+compute_total_momentum:190, courant_condition:761, dump_parameters_to_toml:655; `load_external_fields_from_toml` (:540) and
+`update_parameters_from_toml` (:621) are implemented in `initialization.py` and re-exported here under the reference's path."""
+import os
+from datetime import datetime
+
+import numpy as np
+import toml
 import torch
 
 from . import ops
+from .parameters import static_parameters_for_output, dynamic_parameters_for_output
 
 
 def add_external_fields(E, B, external_fields):
@@ -48,3 +55,50 @@ def compute_total_momentum(particles, species_config=None, static_parameters=Non
 def courant_condition(courant_number, dx, dy, dz, dynamic_parameters):
     inv = sum(1 / d for d, n in zip((dx, dy, dz), (dynamic_parameters.Nx, dynamic_parameters.Ny, dynamic_parameters.Nz)) if n > 1)
     return courant_number / (dynamic_parameters.C * inv)
+
+
+def _toml_ready(value):
+    """Plain TOML-encodable data: tuples -> lists, arrays / tensors / NumPy scalars -> Python values, None entries dropped (TOML has
+    no null; the `toml` encoder would otherwise write a tuple of dicts as the list of their keys)."""
+    if isinstance(value, dict):
+        return {str(k): _toml_ready(v) for k, v in value.items() if v is not None}
+    if isinstance(value, (list, tuple)):
+        return [_toml_ready(v) for v in value if v is not None]
+    if hasattr(value, "tolist"):
+        return _toml_ready(value.tolist())
+    return value
+
+
+def dump_parameters_to_toml(simulation_stats, static_parameters, dynamic_parameters, plasma_parameters, plotting_parameters, particles):
+    """`<output_dir>/data/output.toml` with the reference's sections (utils.py:655-737): simulation_stats, static/dynamic parameters
+    (without mesh / grids), plasma_parameters, plotting (without the per-species bookkeeping keys), one `[[particles]]` summary per
+    species (its metadata + storage / active_particles / tile_shape), version and package_versions."""
+    from . import __version__
+    drop = ("particle_species_names", "particle_species_metadata")
+    config = {"simulation_stats": simulation_stats,
+              "static_parameters": static_parameters_for_output(static_parameters),
+              "dynamic_parameters": dynamic_parameters_for_output(dynamic_parameters),
+              "plasma_parameters": plasma_parameters,
+              "plotting": {k: v for k, v in plotting_parameters.items() if k not in drop},
+              "particles": []}
+    names = plotting_parameters.get("particle_species_names")
+    metadata = plotting_parameters.get("particle_species_metadata")
+    tile_shape = [int(w) for w in static_parameters.tile_shape]
+    active = torch.as_tensor(particles.active)
+    for s in range(int(active.shape[3])):
+        entry = {"name": f"species_{s}" if names is None else names[s]} if metadata is None else dict(metadata[s])
+        entry["storage"] = "tiled"
+        entry["active_particles"] = int(active[:, :, :, s, :].sum())
+        entry["tile_shape"] = tile_shape
+        config["particles"].append(entry)
+    config["version"] = {"PyPIC3D_version": f"pypic3d_b200 {__version__}", "date": datetime.now().strftime("%Y-%m-%d")}
+    config["package_versions"] = {"torch": torch.__version__, "numpy": np.__version__, "toml": toml.__version__}
+    with open(os.path.join(static_parameters.output_dir, "data/output.toml"), "w") as f:
+        toml.dump(_toml_ready(config), f)
+
+
+def __getattr__(name):      # reference module path for the two TOML helpers that live in initialization.py (import cycle otherwise)
+    if name in ("load_external_fields_from_toml", "update_parameters_from_toml"):
+        from . import initialization
+        return getattr(initialization, name)
+    raise AttributeError(name)

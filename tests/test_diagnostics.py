@@ -134,3 +134,68 @@ def test_write_data_row_format(tmp_path):
     write_data(f, 0, torch.tensor(4.0, dtype=torch.float64))
     write_data(f, 0.25, 1.125)
     assert open(f).read() == "0.0, 4.0\n0.25, 1.125\n"
+
+
+def test_dump_parameters_to_toml_writes_tiled_species_summaries(tmp_path):
+    """utils_test.py:348-421 with its literal inputs."""
+    import toml
+    from pypic3d_b200.parameters import build_static_parameters, build_dynamic_parameters
+    from pypic3d_b200.utils import dump_parameters_to_toml
+    active = torch.tensor([[[[[True, False, True], [False, True, False]]]]])
+    zeros3 = torch.zeros(tuple(active.shape) + (3,), dtype=torch.float64)
+    particles = TiledParticles(x=zeros3, u=zeros3, active=active)
+    os.makedirs(os.path.join(tmp_path, "data"))
+    sp = build_static_parameters({"name": "dump test", "output_dir": str(tmp_path), "shape_factor": 1, "guard_cells": 2, "tile_shape": (2, 1, 1),
+                                  "boundary_conditions": {"x": 0, "y": 0, "z": 0}, "particle_boundary_conditions": {"x": 0, "y": 0, "z": 0},
+                                  "field_mesh": object()})
+    z = np.zeros
+    dp = build_dynamic_parameters({"dt": 0.1, "dx": 1.0, "dy": 1.0, "dz": 1.0, "Nx": 2, "Ny": 1, "Nz": 1, "x_wind": 2.0, "y_wind": 1.0, "z_wind": 1.0,
+                                   "grids": {"vertex": (z(4), z(3), z(3)), "center": (z(4), z(3), z(3)),
+                                             "tiled_vertex_grid": (z((1, 1, 1, 6)),) * 3, "tiled_center_grid": (z((1, 1, 1, 6)),) * 3}}, {})
+    plotting = {"particle_species_names": ("electrons", "ions"),
+                "particle_species_metadata": ({"name": "electrons", "charge": -1.0}, {"name": "ions", "charge": 1.0}),
+                "plotting_interval": 10}
+    dump_parameters_to_toml({"total_time": 1.0}, sp, dp, {}, plotting, particles)
+    cfg = toml.load(os.path.join(tmp_path, "data/output.toml"))
+    for key in ("particle_species_names", "particle_species_metadata"):
+        assert key not in cfg["static_parameters"] and key not in cfg.get("plotting", {})
+    assert cfg["plotting"]["plotting_interval"] == 10 and cfg["simulation_stats"]["total_time"] == 1.0
+    assert "field_mesh" not in cfg["static_parameters"] and "grids" not in cfg["dynamic_parameters"]
+    e, i = cfg["particles"]
+    assert (e["name"], e["charge"], e["storage"], e["active_particles"], e["tile_shape"]) == ("electrons", -1.0, "tiled", 2, [2, 1, 1])
+    assert (i["name"], i["charge"], i["storage"], i["active_particles"]) == ("ions", 1.0, "tiled", 1)
+    assert "date" in cfg["version"] and "torch" in cfg["package_versions"]
+    # without metadata: default species names
+    dump_parameters_to_toml({"total_time": 1.0}, sp, dp, {}, {}, particles)
+    cfg = toml.load(os.path.join(tmp_path, "data/output.toml"))
+    assert [p_["name"] for p_ in cfg["particles"]] == ["species_0", "species_1"]
+
+
+def test_utils_exposes_the_reference_paths_of_the_toml_helpers():
+    from pypic3d_b200 import utils, initialization
+    assert utils.load_external_fields_from_toml is initialization.load_external_fields_from_toml
+    assert utils.update_parameters_from_toml is initialization.update_parameters_from_toml
+    with pytest.raises(AttributeError):
+        utils.no_such_helper
+
+
+def test_dump_parameters_to_toml_encodes_the_front_ends_metadata(tmp_path):
+    """What `python -m pypic3d_b200` hands over: tuples of per-species dicts with tuple / NumPy / None leaves must survive the TOML
+    round trip (the encoder alone would write a tuple of dicts as the list of their keys)."""
+    import toml
+    from pypic3d_b200.utils import dump_parameters_to_toml
+    sp, dp = fx.kernel_parameters(Nx=4, Ny=2, Nz=1, x_wind=4.0, y_wind=2.0, z_wind=1.0, tile_shape=(2, 1, 1))
+    sp = sp._replace(output_dir=str(tmp_path))
+    os.makedirs(os.path.join(tmp_path, "data"))
+    tp, sc = _tiled(sp, dp)
+    meta = ({"name": "ions", "N_particles": 4, "N_per_cell": None, "charge": np.float64(2.0), "temperature": np.float32(1.5),
+             "update_x": (True, np.bool_(False), True), "x_bc": "periodic"},
+            {"name": "electrons", "N_particles": 3, "N_per_cell": 1.5, "charge": -1.0, "update_x": (True, True, True)})
+    plotting = {"plotting_interval": np.int64(5), "particle_species_names": ("ions", "electrons"), "particle_species_metadata": meta}
+    dump_parameters_to_toml({"total_time": 2.0, "total_iterations": 7}, sp, dp, {"species": meta}, plotting, tp)
+    cfg = toml.load(os.path.join(tmp_path, "data/output.toml"))
+    assert cfg["plasma_parameters"]["species"][0]["update_x"] == [True, False, True]
+    assert "N_per_cell" not in cfg["plasma_parameters"]["species"][0] and cfg["plasma_parameters"]["species"][1]["N_per_cell"] == 1.5
+    assert cfg["particles"][0]["active_particles"] == 3 and cfg["particles"][1]["active_particles"] == 2
+    assert cfg["particles"][0]["temperature"] == 1.5 and cfg["plotting"]["plotting_interval"] == 5
+    assert cfg["static_parameters"]["tile_shape"] == [2, 1, 1] and cfg["dynamic_parameters"]["Nx"] == 4
