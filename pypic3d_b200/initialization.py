@@ -182,7 +182,12 @@ def initialize_simulation(toml_file, device=None, dtype=torch.float64, verbose=T
     ext_B = update_tiled_vector_ghost_cells(tuple(t(a) for a in ext[1]), sp, g)
     rho, phi = t(np.zeros(shape)), t(np.zeros(shape))
     fields = (E, B, J, rho, phi, (ext_E, ext_B), None, torch.tensor(False, device=device))
-    plasma_parameters = {"species": meta}
+    from .utils import build_plasma_parameters_dict, particle_sanity_check, print_stats
+    plasma_parameters = build_plasma_parameters_dict(sp, dp, meta[0]) if meta else {}       # :381-384 (first species)
+    plasma_parameters["species"] = meta
+    particle_sanity_check(particles)                                                          # :386
+    if verbose:
+        print_stats(sp, dp)                                                                   # :379
     if verbose:
         print(f"Initializing Simulation: {sp.name}\nUsing tiled Yee storage with tile shape: {sp.tile_shape}; dt = {dt}; Nt = {sp.Nt}")
     loop = time_loop_electrostatic if electrostatic else time_loop_electrodynamic             # :466-470

@@ -57,6 +57,69 @@ def courant_condition(courant_number, dx, dy, dz, dynamic_parameters):
     return courant_number / (dynamic_parameters.C * inv)
 
 
+def make_dir(path):
+    if not os.path.exists(path):                                                       # utils.py:218-226
+        os.makedirs(path)
+
+
+def vth_to_T(vth, m, kb):
+    return m * vth ** 2 / kb                                                           # utils.py:229-241
+
+
+def T_to_vth(T, m, kb):
+    return float(np.sqrt(kb * T / m))                                                  # utils.py:243-255
+
+
+def particle_sanity_check(particles):
+    """Shape contract of the tiled storage (utils.py:299-312)."""
+    assert tuple(particles.x.shape) == tuple(particles.u.shape)
+    assert particles.x.shape[-1] == 3
+    assert tuple(particles.active.shape) == tuple(particles.x.shape[:-1])
+
+
+def print_stats(static_parameters, dynamic_parameters):
+    sp, dp = static_parameters, dynamic_parameters                                     # utils.py:315-339
+    print(f"\ntime window: {sp.Nt * dp.dt} s with {sp.Nt} time steps of {dp.dt} s")
+    print(f"x window: {dp.x_wind} m with dx: {dp.dx} m")
+    print(f"y window: {dp.y_wind} m with dy: {dp.dy} m")
+    print(f"z window: {dp.z_wind} m with dz: {dp.dz} m\n")
+
+
+def build_plasma_parameters_dict(static_parameters, dynamic_parameters, electrons):
+    """Plasma frequency, Debye length and thermal velocity of the FIRST species' metadata (utils.py:384-423; the reference passes
+    `particle_metadata[0]` whatever that species is)."""
+    dp = dynamic_parameters
+    me, Te, q, weight = (np.float64(electrons[k]) for k in ("mass", "temperature", "charge", "weight"))
+    N = electrons["N_particles"]
+    with np.errstate(all="ignore"):           # a neutral or weightless first species gives inf / nan like the reference, not an exception
+        density = weight * N / np.float64(dp.x_wind * dp.y_wind * dp.z_wind)
+        debye = float(np.sqrt(dp.eps * dp.kb * Te / (density * q ** 2)))
+        wp = float(np.sqrt(density) * abs(q) / np.sqrt(dp.eps * me))
+        vth = float(np.sqrt(3 * dp.kb * Te / me))
+    Te = float(Te)
+    return {"Theoretical Plasma Frequency": wp,
+            "Debye Length": debye,
+            "Thermal Velocity": vth,
+            "Number of Electrons": N,
+            "Temperature of Electrons": Te,
+            "dx per debye length": debye / dp.dx, "dy per debye length": debye / dp.dy, "dz per debye length": debye / dp.dz}
+
+
+def check_stability(plasma_parameters, dt):
+    """The reference's start-up report and its two warnings (utils.py:341-381)."""
+    wp, debye = plasma_parameters["Theoretical Plasma Frequency"], plasma_parameters["Debye Length"]
+    per = plasma_parameters["dx per debye length"]
+    if wp * dt > 2.0:
+        print("# of Electrons is Low and may introduce numerical stability")
+    if per < 1:
+        print("Debye Length is less than the spatial resolution, this may introduce numerical instability")
+    print(f"Theoretical Plasma Frequency: {wp} Hz")
+    print(f"Debye Length: {debye} m")
+    print(f"Thermal Velocity: {plasma_parameters['Thermal Velocity']}")
+    print(f"Dx Per Debye Length: {per}")
+    print(f"Number of Electrons: {plasma_parameters['Number of Electrons']}\n")
+
+
 def _toml_ready(value):
     """Plain TOML-encodable data: tuples -> lists, arrays / tensors / NumPy scalars -> Python values, None entries dropped (TOML has
     no null; the `toml` encoder would otherwise write a tuple of dicts as the list of their keys)."""

@@ -199,3 +199,26 @@ def test_dump_parameters_to_toml_encodes_the_front_ends_metadata(tmp_path):
     assert cfg["particles"][0]["active_particles"] == 3 and cfg["particles"][1]["active_particles"] == 2
     assert cfg["particles"][0]["temperature"] == 1.5 and cfg["plotting"]["plotting_interval"] == 5
     assert cfg["static_parameters"]["tile_shape"] == [2, 1, 1] and cfg["dynamic_parameters"]["Nx"] == 4
+
+
+def test_plasma_parameter_helpers(capsys):
+    """utils.py:229-255, 299-423 and utils_test.py:172-185."""
+    from pypic3d_b200 import utils
+    assert utils.vth_to_T(2.0, 3.0, 4.0) == 3.0 and np.isclose(utils.T_to_vth(3.0, 3.0, 4.0), 2.0)
+    sp, dp = fx.kernel_parameters(Nx=4, Ny=2, Nz=1, x_wind=4.0, y_wind=2.0, z_wind=1.0, dx=1.0, dy=1.0, dz=1.0, eps=2.0, kb=0.5)
+    e = {"mass": 2.0, "temperature": 8.0, "N_particles": 16, "charge": -1.0, "weight": 0.5}
+    pl = utils.build_plasma_parameters_dict(sp, dp, e)
+    n = 0.5 * 16 / 8.0
+    assert np.isclose(pl["Theoretical Plasma Frequency"], np.sqrt(n) / np.sqrt(2.0 * 2.0))
+    assert np.isclose(pl["Debye Length"], np.sqrt(2.0 * 0.5 * 8.0 / n)) and np.isclose(pl["Thermal Velocity"], np.sqrt(3 * 0.5 * 8.0 / 2.0))
+    assert pl["Number of Electrons"] == 16 and np.isclose(pl["dx per debye length"], pl["Debye Length"] / 1.0)
+    utils.check_stability({"Theoretical Plasma Frequency": 1.0, "Debye Length": 1.0, "Thermal Velocity": 1.0, "Number of Electrons": 100,
+                           "dx per debye length": 0.5}, 3.0)
+    out = capsys.readouterr().out
+    assert "# of Electrons is Low" in out and "Debye Length is less than the spatial resolution" in out and "Number of Electrons: 100" in out
+    tp, sc = _tiled(sp._replace(tile_shape=(2, 1, 1)), dp)
+    utils.particle_sanity_check(tp)
+    with pytest.raises(AssertionError):
+        utils.particle_sanity_check(tp._replace(active=tp.active[..., :1]))
+    utils.print_stats(sp, dp)
+    assert "x window: 4.0 m with dx: 1.0 m" in capsys.readouterr().out
