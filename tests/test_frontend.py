@@ -479,3 +479,33 @@ def test_two_stream_growth_rate_and_energy_history(tmp_path):
     wp_total = np.sqrt(2 * 1.0e15 * 1.602e-19 ** 2 / (float(dp.eps) * 9.1093837e-31))
     assert abs(g_gpu - g_ref) <= 1e-5 * abs(g_ref)
     assert 0.25 <= g_ref / (wp_total / (2 * np.sqrt(2))) <= 0.7
+
+
+def test_front_end_host_logic_without_a_gpu(tmp_path, monkeypatch, capsys):
+    """Everything `initialize_simulation` does on the host for the packaged two-stream configuration -- parameters, particle loading,
+    species metadata, plasma parameters, the start-up report -- and the `output.toml` the driver writes from it.  The only device
+    operation on that path (the initial guard-cell refresh of zero fields) is replaced by the identity, so this runs on CPU tensors."""
+    import toml
+    import torch
+    import pypic3d_b200.initialization as ini
+    from pypic3d_b200.utils import dump_parameters_to_toml
+    monkeypatch.setattr(ini, "update_tiled_vector_ghost_cells", lambda v, sp, g: v)
+    cfg = {k: dict(v) for k, v in TWO_STREAM.items()}
+    cfg["simulation_parameters"].update(output_dir=str(tmp_path))
+    np.random.seed(0)
+    loop, particles, fields, sp, dp, plotting, plasma, species = ini.initialize_simulation(cfg, device=torch.device("cpu"), verbose=True)
+    out = capsys.readouterr().out
+    assert "time window:" in out and "x window: 1.0 m with dx: 0.01 m" in out
+    assert loop is ini.time_loop_electrodynamic and tuple(particles.x.shape[:4]) == (1, 1, 1, 3)
+    assert plotting["particle_species_names"] == ("electron1", "electron2", "ion1") and len(plotting["particle_species_metadata"]) == 3
+    e1 = plotting["particle_species_metadata"][0]
+    n = e1["weight"] * e1["N_particles"] / 1.0                      # first species: the reference's "electrons" (initialization.py:381-384)
+    assert np.isclose(plasma["Theoretical Plasma Frequency"], np.sqrt(n) * abs(e1["charge"]) / np.sqrt(dp.eps * e1["mass"]))
+    assert np.isclose(plasma["dx per debye length"], plasma["Debye Length"] / dp.dx) and plasma["Number of Electrons"] == 1500
+    os.makedirs(os.path.join(tmp_path, "data"), exist_ok=True)
+    dump_parameters_to_toml({"total_time": 1.0, "total_iterations": sp.Nt}, sp, dp, plasma, plotting, particles)
+    c = toml.load(os.path.join(tmp_path, "data/output.toml"))
+    assert [p_["name"] for p_ in c["particles"]] == ["electron1", "electron2", "ion1"]
+    assert [p_["active_particles"] for p_ in c["particles"]] == [1500, 1500, 3000] and c["particles"][0]["storage"] == "tiled"
+    assert c["static_parameters"]["current_deposition"] == "direct" and c["dynamic_parameters"]["Nx"] == 100     # j_from_rhov (initialization.py:97-102)
+    assert np.isclose(c["plasma_parameters"]["Debye Length"], plasma["Debye Length"])
