@@ -653,3 +653,33 @@ def test_schmitz_oscillating_parallel_E_returns_to_initial_energy():
         for step in range(500):
             v = _advance(fn, v, (0.0, 0.0, E0 * np.cos(omega0 * (step + 0.5) * dt)), (0.0, 0.0, 1.0), dt, 1)
         assert abs(v[2]) <= 1.0e-10 and abs(_gamma(v) - gamma_perp) <= 1.0e-10
+
+
+# ---------------------------------------------------------------- tiling fixture (tests/kernel_fixtures.py:529-594)
+def test_fixture_tiled_particles_preserve_inactive_slots_and_metadata():
+    """particle_initialization_test.py:27-94, literal inputs: the tile-major packing every parity test builds its particles with."""
+    sp, dp = fx.kernel_parameters(Nx=4, Ny=2, Nz=1, x_wind=4.0, y_wind=2.0, z_wind=1.0, dx=1.0, dy=1.0, dz=1.0, dt=0.1, tile_shape=(2, 1, 1))
+    ions = fx.particle_species("ions", 2.0, 3.0, weight=4.0, x1=[-1.5, 0.5, 1.5], x2=[-0.5, 0.5, 0.5], x3=[0.0, 0.0, 0.0],
+                               u1=[0.1, 0.2, 0.3], u2=[0.0, 0.0, 0.0], u3=[1.0, 2.0, 3.0], update_x=(True, False, True),
+                               update_u=(False, True, True), active_mask=[True, False, True])
+    tp, sc = fx.build_tiled_particles([ions], sp, dp)
+    assert tp.x.shape == (2, 2, 1, 1, 2, 3) and int(tp.active.sum()) == 2
+    assert not hasattr(tp, "charge") and not hasattr(tp, "mass") and not hasattr(tp, "weight")
+    assert np.allclose(tp.x[0, 0, 0, 0, 0], [-1.5, -0.5, 0.0]) and np.allclose(tp.x[1, 1, 0, 0, 0], [0.5, 0.5, 0.0])
+    assert np.allclose(tp.x[1, 1, 0, 0, 1], [1.5, 0.5, 0.0]) and np.allclose(tp.u[1, 1, 0, 0, 1], [0.3, 0.0, 3.0])
+    assert sc.charge.shape == sc.mass.shape == sc.weight.shape == (1,) and sc.update_x.shape == sc.update_u.shape == (1, 3)
+    assert np.allclose(sc.charge, [2.0]) and np.allclose(sc.mass, [3.0]) and np.allclose(sc.weight, [4.0])
+    assert list(sc.update_x[0]) == [True, False, True] and list(sc.update_u[0]) == [False, True, True]
+
+
+def test_fixture_species_metadata_is_not_slot_shaped_and_capacity_headroom():
+    """particle_initialization_test.py:94-186."""
+    sp, dp = fx.kernel_parameters(Nx=4, Ny=1, Nz=1, x_wind=4.0, y_wind=1.0, z_wind=1.0, dx=1.0, dy=1.0, dz=1.0, dt=0.1, tile_shape=(1, 1, 1))
+    sps = [fx.particle_species("electrons", -1.0, 2.0, weight=0.5, x1=[-1.5, -0.5]), fx.particle_species("ions", 2.0, 5.0, weight=0.25, x1=[0.5, 1.5])]
+    tp, sc = fx.build_tiled_particles(sps, sp, dp)
+    assert tp.x.shape[:4] == (4, 1, 1, 2)
+    assert sc.charge.shape == sc.mass.shape == sc.weight.shape == (2,) and sc.update_x.shape == sc.update_u.shape == (2, 3)
+    sp, dp = fx.kernel_parameters(Nx=4, Ny=1, Nz=1, x_wind=4.0, y_wind=1.0, z_wind=1.0, dx=1.0, dy=1.0, dz=1.0, dt=0.1, tile_shape=(2, 1, 1),
+                                  particle_tile_capacity_factor=3.0)
+    tp, sc = fx.build_tiled_particles([fx.particle_species("ions", 1.0, 1.0, x1=[-1.5, -0.5, 1.5])], sp, dp)
+    assert tp.active.shape[-1] == 6 and int(tp.active.sum()) == 3 and sc.charge.shape == (1,)
