@@ -6,7 +6,11 @@
     # on the GPU box (one gpurun call): time each variant with the product bench, same box, back to back
     gpurun --timeout 900 -- 'python tools/ab.py run base jtsync nw16 -- --steps 20 --warmup 5'
 
-`build` writes build_ab/<name>/libpic_b200.so (the product library is untouched); `run` executes
+    # parity of a variant before believing its time (GPU box): the tile-kernel parity tests with PIC_B200_LIB pointing at it
+    gpurun --timeout 900 -- 'python tools/ab.py test jtsync@PIC_K9_JTILE=1 nw16'
+
+`build` writes build_ab/<name>/libpic_b200.so (the product library is untouched); `test` runs
+`pytest -m gpu tests/test_gpu_parity.py tests/test_golden.py -k "tile or variant or golden or supercell"` per variant; `run` executes
 `bench.py --no-e2e --no-cpu-baseline` once per variant with PIC_B200_LIB pointing at it (extra environment as name@K=V,
 e.g. jt@PIC_K9_JTILE=1), stores gpurun_out/ab_<name>.json and prints one comparison line per variant.  A variant is only
 adopted after `pytest -m gpu` has passed with PIC_B200_LIB set to it."""
@@ -68,15 +72,28 @@ def run(specs, bench_args):
               f"frac {rf['frac']:.3f}  sm {d['clocks']['sm_mhz']} MHz {d['clocks']['reasons']}")
 
 
+def test(specs, pytest_args):
+    for spec in specs:
+        name, _, env = split(spec)
+        e = dict(os.environ, PIC_B200_LIB=lib_of(name), **env)
+        cmd = [sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu", "tests/test_gpu_parity.py", "tests/test_golden.py",
+               "-k", "tile or variant or golden or supercell"] + pytest_args
+        r = subprocess.run(cmd, env=e, capture_output=True, text=True, timeout=1500, cwd=ROOT)
+        tail = (r.stdout.strip().splitlines() or ["(no output)"])[-1]
+        print(f"{name:12s} pytest rc={r.returncode}  {tail}")
+        if r.returncode != 0:
+            print(r.stdout[-1500:])
+
+
 def main(argv):
-    if len(argv) < 2 or argv[0] not in ("build", "run"):
+    if len(argv) < 2 or argv[0] not in ("build", "run", "test"):
         sys.exit(__doc__)
     rest = argv[1:]
     extra = []
     if "--" in rest:
         i = rest.index("--")
         rest, extra = rest[:i], rest[i + 1:]
-    (build if argv[0] == "build" else lambda s: run(s, extra))(rest)
+    {"build": build, "run": lambda s_: run(s_, extra), "test": lambda s_: test(s_, extra)}[argv[0]](rest)
 
 
 if __name__ == "__main__":
