@@ -122,10 +122,23 @@ def cpu_reference(steps, warmup, shape_factor, n=16, ppc=16, seed=1234):
 
 
 def host_cores():
+    """CPUs this process may actually use: the affinity mask, capped by a cgroup CPU quota when the container has one."""
     try:
-        return max(1, len(os.sched_getaffinity(0)))
+        n = len(os.sched_getaffinity(0))
     except AttributeError:
-        return max(1, os.cpu_count() or 1)
+        n = os.cpu_count() or 1
+    for path, parse in (("/sys/fs/cgroup/cpu.max", lambda t: t.split()),                                  # cgroup v2: "<quota|max> <period>"
+                        ("/sys/fs/cgroup/cpu/cpu.cfs_quota_us", lambda t: (t.strip(), None))):            # cgroup v1
+        try:
+            quota, period = parse(open(path).read())
+            if period is None:
+                period = open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read().strip()
+            if quota not in ("max", "-1") and int(quota) > 0 and int(period) > 0:
+                n = min(n, max(1, int(quota) // int(period)))
+            break
+        except (OSError, ValueError):
+            continue
+    return max(1, n)
 
 
 def cpu_reference_all_cores(steps, warmup, shape_factor, n=16, ppc=16, workers=0):
