@@ -2,15 +2,12 @@
 CUDA path: initialise from TOML, step Nt times, write the same `data/*.txt` energy/momentum histories and `data/output.toml`.
 A single-tile configuration runs on the resident fused path (`Simulation`); a multi-tile one on the drop-in composition."""
 import argparse
-import os
 import time
 
-import numpy as np
 import toml
 import torch
 
 from .diagnostics.plotting import write_data
-from .evolve import time_loop_electrodynamic
 from .initialization import initialize_simulation
 from .simulation import Simulation
 from .utils import add_external_fields, compute_energy, compute_total_momentum, dump_parameters_to_toml

@@ -12,7 +12,7 @@ from .boundary_conditions.grid_and_stencil import BC_CONDUCTING, BC_PERIODIC
 from .boundary_conditions.ghost_cells import update_tiled_vector_ghost_cells
 from .evolve import time_loop_electrodynamic, time_loop_electrostatic
 from .parameters import build_dynamic_parameters, build_static_parameters, make_field_mesh
-from .particles.particle_class import SpeciesConfig, TiledParticles
+from .particles.particle_class import TiledParticles
 from .particles.particle_initialization import load_particles_from_toml
 from .utilities.grids import build_collocated_grid, build_tiled_yee_grids, build_yee_grid
 from .utils import courant_condition

@@ -5,8 +5,6 @@ device mesh here: on one GPU every tile of the mesh is resident, across GPUs `py
 rank (the reference's one-tile-per-device contract, ghost_cells.py:98-116)."""
 from typing import NamedTuple
 
-import numpy as np
-
 
 class GridParameters(NamedTuple):
     vertex: tuple
