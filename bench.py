@@ -392,7 +392,8 @@ def main():
     roof = None
     if k1_avg_ms:
         achieved = k1_bytes_pp * per_launch_particles / (k1_avg_ms * 1e-3) / 1e9
-        kname = "k_tile3d (K1 v9: supercell E/B tiles in shared memory" if sim.k1_variant == "tile" else "k_fused3d (K1 v8: global gather"
+        kname = {"pair": "k_pair3d (K1 v10: supercell E/B tiles in shared memory, two particles per thread in packed f32x2",
+                 "tile": "k_tile3d (K1 v9: supercell E/B tiles in shared memory"}.get(sim.k1_variant, "k_fused3d (K1 v8: global gather")
         roof = {"bound": "hbm", "kernel": kname + "; gather+push+deposit+move+BC, one species per launch)", "achieved": achieved,
                 "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": "profiles/r01_k1_traffic.json (ncu dram__bytes_read+write, bytes per launch)" if traffic else None,
                 "algorithmic_bytes_per_launch": k1_bytes_pp * per_launch_particles, "peak_source": peak_src,

@@ -221,6 +221,28 @@ int pic_fused_tile3d(const PicParams* p, int species, const PicSoA* soa, const i
                      const void* const E[3], const void* const B[3], void* const J[3], const PicLeave* leave, int32_t* flags,
                      void* stream);
 
+/* K1 v10, the pair variant of pic_fused_tile3d (same configurations, same result, same arguments): the per-thread body advances
+ * two particles at once in packed f32x2 arithmetic (float; one at a time in double), a dedicated producer warp feeds the TMA
+ * ring, and particles that change cell are finished by full warps.  Requires the supercell slices of `blk_off` to start on
+ * 16-byte boundaries, i.e. the SoA to come from the blocked, padded sort below (flags[0] |= 8 otherwise).
+ * options bit 1 as for pic_fused_tile3d.
+ * Replaces, like pic_fused_push_deposit, PyPIC3D/evolve.py:33-79 (particle_push -> Esirkepov_current ->
+ * update_tiled_particle_positions -> refresh_tiled_particle_tiles) for one local tile. */
+int pic_fused_pair3d(const PicParams* p, int species, const PicSoA* soa, const int32_t* blk_off, int nblk, int options,
+                     const void* const E[3], const void* const B[3], void* const J[3], const PicLeave* leave, int32_t* flags,
+                     void* stream);
+
+/* Blocked, padded counting sort (tile widths multiples of 4): cells in 4x4x4-supercell-major order, every supercell's slice
+ * padded with dead slots (x = NaN) to a multiple of 4 slots.  Sequence: pic_sort_histogram -> pic_sort_blocked_offsets ->
+ * pic_sort_scatter (with the cell_offset computed here) -> pic_sort_blocked_finish.
+ * blk_off: int32[nblk + 1] out, first slot of every supercell (blk_off[nblk] = padded length of the stream); blk_work:
+ * int32[nblk + 1] scratch; scan_scratch as for pic_sort_scan; flags[0] |= 2 when the padded stream exceeds `cap`.
+ * (No reference counterpart: the reference keeps fixed-capacity slots with an `active` mask, particles/particle_class.py:17-31.) */
+int pic_sort_blocked_offsets(const PicParams* p, const int32_t* cell_count, int32_t* cell_offset, int32_t* blk_work,
+                             int32_t* blk_off, int32_t* scan_scratch, int64_t cap, int32_t* flags, void* stream);
+int pic_sort_blocked_finish(const PicParams* p, const int32_t* cell_offset, const int32_t* cell_count, const int32_t* blk_off,
+                            const PicSoA* dst, void* stream);
+
 /* Zero the 27 packet headers of `leave` (before K1 of a step). */
 int pic_packets_reset(const PicParams* p, const PicLeave* leave, void* stream);
 /* Append every received packet of `recv` (same layout as PicLeave) to the SoA tail, advancing soa->n_dev on the device. */

@@ -5,20 +5,24 @@ operators raise.  PyTorch is used only for device memory and streams; every comp
 hand-written sm_100a kernel behind the C ABI.
 """
 import ctypes
+import hashlib
 import os
 import subprocess
+import time
 
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
 LIB_PATH = os.environ.get("PIC_B200_LIB", os.path.join(_HERE, "libpic_b200.so"))   # override: A/B builds for profiling
-SOURCES = ["kernels_particles_ref.cu", "kernels_fields.cu", "kernels_fast.cu", "kernels_poisson.cu", "microbench.cu"]
-HEADERS = ["pic_common.cuh", "pic_math.cuh", "pic_slots.cuh"]
+SOURCES = ["kernels_particles_ref.cu", "kernels_fields.cu", "kernels_fast.cu", "kernels_pair.cu", "kernels_poisson.cu", "microbench.cu"]
+HEADERS = ["pic_common.cuh", "pic_math.cuh", "pic_slots.cuh", "pic_pair.cuh", "pic_tma.cuh"]
 MAX_SPECIES = 16
 
-NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-Xcompiler", "-fPIC", "-shared"]
+VERSION_SOURCE = "kernels_fields.cu"      # the unit that defines pic_version(): compiled with -DPIC_SOURCE_HASH=...
+COMPILE_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC"]
+LINK_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-Xcompiler", "-fPIC"]
+NVCC_FLAGS = COMPILE_FLAGS + ["-shared"]   # (one-shot form: nvcc NVCC_FLAGS -o lib.so *.cu)
 
 
 class PicParams(ctypes.Structure):
@@ -49,33 +53,104 @@ class PicLeave(ctypes.Structure):
     _fields_ = [("buf", ctypes.c_void_p), ("row_off", ctypes.c_int32 * 27), ("cap", ctypes.c_int32 * 27)]
 
 
+def source_hash():
+    """sha256 over every CUDA source, header and the compile flags: identifies the build the loaded library must come from."""
+    h = hashlib.sha256()
+    for f in SOURCES + HEADERS:
+        with open(os.path.join(_HERE, "csrc", f), "rb") as fh:
+            h.update(f.encode()); h.update(fh.read())
+    with open(os.path.join(_ROOT, "include", "pic_b200.h"), "rb") as fh:
+        h.update(fh.read())
+    h.update(" ".join(NVCC_FLAGS).encode())
+    return h.hexdigest()[:16]
+
+
+def built_hash(path=None):
+    """Source hash recorded next to a built library (written by build(); checked against pic_version() when it is loaded)."""
+    try:
+        with open((path or LIB_PATH) + ".hash") as fh:
+            return fh.read().strip()
+    except OSError:
+        return None
+
+
 def needs_build():
     if "PIC_B200_LIB" in os.environ:
         return False
-    if not os.path.exists(LIB_PATH):
-        return True
-    t = os.path.getmtime(LIB_PATH)
-    deps = [os.path.join(_HERE, "csrc", f) for f in SOURCES + HEADERS] + [os.path.join(_ROOT, "include", "pic_b200.h")]
-    return any(os.path.getmtime(d) > t for d in deps)
+    return not os.path.exists(LIB_PATH) or built_hash() != source_hash()
 
 
-def build(force=False, verbose=False):
-    """Compile every CUDA translation unit for sm_100a into pypic3d_b200/libpic_b200.so (in-tree)."""
-    if not force and not needs_build():
+def _tu_hash(src, extra_flags=()):
+    h = hashlib.sha256()
+    for f in [src] + HEADERS:
+        with open(os.path.join(_HERE, "csrc", f), "rb") as fh:
+            h.update(f.encode()); h.update(fh.read())
+    with open(os.path.join(_ROOT, "include", "pic_b200.h"), "rb") as fh:
+        h.update(fh.read())
+    h.update(" ".join(list(NVCC_FLAGS) + list(extra_flags)).encode())
+    return h.hexdigest()[:16]
+
+
+def build(force=False, verbose=False, extra_flags=(), out=None, ptxas_verbose=False):
+    """Compile every CUDA translation unit for sm_100a into pypic3d_b200/libpic_b200.so (in-tree).
+
+    One nvcc process per translation unit, in parallel; objects are cached under csrc/_obj keyed by the hash of the unit, the
+    shared headers and the flags, so editing one kernel file recompiles one unit.  The hash of ALL sources is compiled into
+    pic_version() and written beside the library; lib() refuses a library whose hash differs from the sources it sits next to.
+    Returns the library path (and, with ptxas_verbose, the ptxas -v log as second value)."""
+    out = out or LIB_PATH
+    if not force and out == LIB_PATH and not needs_build() and not extra_flags:
         return LIB_PATH
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     if not os.path.exists(nvcc):
         nvcc = "nvcc"
-    cmd = [nvcc] + NVCC_FLAGS + ["-o", LIB_PATH] + [os.path.join(_HERE, "csrc", f) for f in SOURCES]
+    objdir = os.path.join(_HERE, "csrc", "_obj")
+    os.makedirs(objdir, exist_ok=True)
+    shash = source_hash() + ("+" + hashlib.sha256(" ".join(extra_flags).encode()).hexdigest()[:6] if extra_flags else "")
+    jobs, objs, logs = [], [], {}
+    for src in SOURCES:
+        flags = list(extra_flags)
+        if src == VERSION_SOURCE:
+            flags = flags + [f'-DPIC_SOURCE_HASH="{shash}"']
+        obj = os.path.join(objdir, f"{os.path.splitext(src)[0]}.{_tu_hash(src, flags)}.o")
+        objs.append(obj)
+        if force or ptxas_verbose or not os.path.exists(obj):
+            cmd = [nvcc] + COMPILE_FLAGS + (["-Xptxas", "-v"] if ptxas_verbose else []) + flags + ["-c", os.path.join(_HERE, "csrc", src), "-o", obj]
+            jobs.append((src, cmd))
     if verbose:
-        print(" ".join(cmd))
-    subprocess.run(cmd, check=True)
-    return LIB_PATH
+        for _, cmd in jobs:
+            print(" ".join(cmd))
+
+    def run(job):
+        src, cmd = job
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"nvcc failed on {src}:\n{r.stderr[-4000:]}")
+        return src, r.stderr
+    if jobs:
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 4)) as ex:
+            for src, log in ex.map(run, jobs):
+                logs[src] = log
+    r = subprocess.run([nvcc] + LINK_FLAGS + ["-o", out] + objs, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"link failed:\n{r.stderr[-4000:]}")
+    with open(out + ".hash", "w") as fh:
+        fh.write(shash + "\n")
+    # drop cached objects of older source versions (keep the ones just linked and anything built in the last day by an A/B)
+    keep = set(objs)
+    for f in os.listdir(objdir):
+        fp = os.path.join(objdir, f)
+        if fp not in keep and f.endswith(".o") and time.time() - os.path.getmtime(fp) > 86400:
+            os.remove(fp)
+    if ptxas_verbose:
+        return out, "\n".join(logs.get(s, "") for s in SOURCES)
+    return out
 
 
 _LIB = None
 LAUNCHES = 0   # kernels launched through the C ABI since last reset (bench.py "gpu_launches")
-KERNELS_PER_CALL = {"pic_poisson_cg": 0, "pic_phi_boundaries": 3, "pic_halo_fold_axis": 2, "pic_sort_scan": 3, "pic_retile": 2, "pic_microbench": 0, "pic_params_size": 0,
+KERNELS_PER_CALL = {"pic_poisson_cg": 0, "pic_phi_boundaries": 3, "pic_halo_fold_axis": 2, "pic_sort_scan": 3, "pic_sort_blocked_offsets": 5, "pic_sort_blocked_finish": 2, "pic_retile": 2, "pic_microbench": 0, "pic_params_size": 0,
                     "pic_version": 0}
 
 
@@ -132,6 +207,9 @@ SIGNATURES = {
     "pic_sort_scatter": [_PP, _SOA, _SOA, _VP, _VP, _VP],
     "pic_fused_push_deposit": [_PP, _INT, _INT, _SOA, _V3, _V3, _V3, _V3, _V3, _LEAVE, _VP, _VP],
     "pic_fused_tile3d": [_PP, _INT, _SOA, _VP, _INT, _INT, _V3, _V3, _V3, _LEAVE, _VP, _VP],
+    "pic_fused_pair3d": [_PP, _INT, _SOA, _VP, _INT, _INT, _V3, _V3, _V3, _LEAVE, _VP, _VP],
+    "pic_sort_blocked_offsets": [_PP, _VP, _VP, _VP, _VP, _VP, _I64, _VP, _VP],
+    "pic_sort_blocked_finish": [_PP, _VP, _VP, _VP, _SOA, _VP],
     "pic_packets_reset": [_PP, _LEAVE, _VP],
     "pic_soa_append_packets": [_PP, _SOA, _LEAVE, _VP, _VP],
     "pic_microbench": [_INT, _INT, ctypes.POINTER(ctypes.c_float)],
@@ -159,6 +237,10 @@ def lib():
         setattr(ns, name, _Counted(fn, KERNELS_PER_CALL.get(name, 1)))
     if L.pic_params_size() != ctypes.sizeof(PicParams):
         raise RuntimeError("pypic3d_b200: PicParams layout mismatch between Python and libpic_b200.so")
+    version = ns.pic_version().decode()
+    if "PIC_B200_LIB" not in os.environ and source_hash() not in version:
+        raise RuntimeError(f"pypic3d_b200: {LIB_PATH} ({version}) was not built from the sources beside it "
+                           f"(source hash {source_hash()}); run pypic3d_b200._lib.build(force=True)")
     ns._cdll = L
     _LIB = ns
     return ns

@@ -7,6 +7,7 @@
 #include <cuda.h>
 
 #include "pic_common.cuh"
+#include "pic_tma.cuh"
 
 namespace pic {
 
@@ -359,73 +360,6 @@ __global__ void __launch_bounds__(256, (SF == 1 ? PIC_K1_CTAS : 2)) k_fused3d(co
    adds stay REDG.  Compiles, not yet run on a GPU -- to be A/B'd before it becomes the default. */
 #define PIC_K9_JT_SYNC 0
 #endif
-
-__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-// mbarrier (shared::cta) + TMA helpers for the tile pipeline
-__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("{\n .reg .b64 st;\n mbarrier.arrive.shared::cta.b64 st, [%0];\n}\n" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, int bytes) {
-    asm volatile("{\n .reg .b64 st;\n mbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n}\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, int parity) {
-    asm volatile(
-        "{\n .reg .pred p;\n"
-        "MBAR_WAIT:\n"
-        " mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        " @p bra MBAR_DONE;\n"
-        " bra MBAR_WAIT;\n"
-        "MBAR_DONE:\n}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-// one bounded wait: true once the phase with `parity` has completed; otherwise the hardware may suspend the thread for up to
-// `hint_ns` before returning false (no issue slots burnt while waiting)
-__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, int parity, int hint_ns) {
-    unsigned ok;
-    asm volatile(
-        "{\n .reg .pred p;\n"
-        " mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
-        " selp.u32 %0, 1, 0, p;\n}\n" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity), "r"(hint_ns) : "memory");
-    return ok != 0;
-}
-__device__ __forceinline__ bool mbar_test(uint64_t* bar, int parity) {
-    unsigned ok;
-    asm volatile(
-        "{\n .reg .pred p;\n"
-        " mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-        " selp.u32 %0, 1, 0, p;\n}\n" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-    return ok != 0;
-}
-// TMA: one [x 8][y TILE_NY][z 8] box of a field component -> shared memory, completion signalled on `bar` (complete_tx)
-__device__ __forceinline__ void tma_load_box(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int z, int y, int x) {
-    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];\n"
-                 ::"r"(smem_u32(smem_dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(z), "r"(y), "r"(x)
-                 : "memory");
-}
-// TMA bulk copy of `bytes` contiguous bytes (16-byte aligned, multiple of 16) global -> shared, completion on `bar`
-__device__ __forceinline__ void tma_load_bytes(void* smem_dst, const void* gmem_src, int bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
-                 ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-// TMA reduce: global J box (8 x 8 x 8 nodes at z, y, x) += the shared-memory tile (element-wise add performed in L2)
-__device__ __forceinline__ void tma_reduce_add_box(const CUtensorMap* map, const void* smem_src, int z, int y, int x) {
-    asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.bulk_group [%0, {%2, %3, %4}], [%1];\n"
-                 ::"l"((uint64_t)map), "r"(smem_u32(smem_src)), "r"(z), "r"(y), "r"(x)
-                 : "memory");
-}
-__device__ __forceinline__ void red_shared_add(float* p, float v) {
-    asm volatile("red.shared.add.f32 [%0], %1;\n" ::"r"(smem_u32(p)), "f"(v) : "memory");
-}
-__device__ __forceinline__ void red_shared_add(double* p, double v) {
-    asm volatile("red.shared.add.f64 [%0], %1;\n" ::"r"(smem_u32(p)), "d"(v) : "memory");
-}
-struct TileMaps {
-    CUtensorMap m[6];      // Ex Ey Ez Bx By Bz, each the ghosted (Lx, Ly, Lz) tile with an 8 x TILE_NY x 8 box
-    CUtensorMap j[3];      // Jx Jy Jz with an 8 x 8 x 8 box (TMA reduce target of the shared-memory J tiles)
-};
 
 // One level of the segmented scan: vals[n] += vals[n] of the lane d below, for the lanes that take.  float: the twelve adds are
 // six packed FADD2 (Blackwell f32x2); the shuffles move the two halves of each register pair separately.
@@ -1039,10 +973,6 @@ static int launch_fused(const PicParams* p, int species, int deposition, const P
     PIC_LAUNCH_RET();
 }
 
-typedef CUresult (*PFN_tensorMapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                             const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                             CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
 // K1 v9 launcher: returns PIC_EUNSUPPORTED when the configuration is outside what the tile kernel was built for (the caller then
 // uses pic_fused_push_deposit).
 template <typename T>
@@ -1079,34 +1009,8 @@ static int launch_tile3d(const PicParams* p, int species, const PicSoA* soa, con
     const SoAView<T> sv = view_of<T>(soa);
     const LeaveBuf lb = leave_of(leave);
     // TMA descriptors of the six ghosted field tiles: dims (z, y, x) = (Lz, Ly, Lx), box 8 x TILE_NY x 8
-    static PFN_tensorMapEncodeTiled encode = nullptr;
-    if (!encode) {
-        void* fn = nullptr;
-        cudaDriverEntryPointQueryResult qres;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn)
-            return PIC_EUNSUPPORTED;
-        encode = (PFN_tensorMapEncodeTiled)fn;
-    }
     TileMaps tm;
-    {
-        const cuuint64_t dims[3] = {(cuuint64_t)gm.L[2], (cuuint64_t)gm.L[1], (cuuint64_t)gm.L[0]};
-        const cuuint64_t strides[2] = {(cuuint64_t)gm.L[2] * sizeof(T), (cuuint64_t)gm.L[2] * gm.L[1] * sizeof(T)};
-        const cuuint32_t box[3] = {(cuuint32_t)TILE_N, (cuuint32_t)TILE_NY, (cuuint32_t)TILE_N};
-        const cuuint32_t estr[3] = {1, 1, 1};
-        for (int c = 0; c < 6; ++c) {
-            const CUresult r = encode(&tm.m[c], sizeof(T) == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3,
-                                      const_cast<T*>(F.f[c]), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                                      CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-            if (r != CUDA_SUCCESS) return PIC_EUNSUPPORTED;
-        }
-        const cuuint32_t jbox[3] = {(cuuint32_t)TILE_N, (cuuint32_t)TILE_N, (cuuint32_t)TILE_N};
-        for (int c = 0; c < 3; ++c) {
-            const CUresult r = encode(&tm.j[c], sizeof(T) == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3,
-                                      Jw.f[c], dims, strides, jbox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                                      CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-            if (r != CUDA_SUCCESS) return PIC_EUNSUPPORTED;
-        }
-    }
+    if (!make_tile_maps<T>(gm.L, F.f, Jw.f, tm)) return PIC_EUNSUPPORTED;
     bool per1 = !distributed;
     for (int a = 0; a < 3; ++a) per1 = per1 && (p->particle_bc[a] == PIC_BC_PERIODIC);
 #define PIC_LAUNCH_K9(PUSH, PER, JTV)                                                                                    \

@@ -444,7 +444,12 @@ static bool halo_args_ok(const PicParams* p, int axis, int ncomp, void* const* f
 
 extern "C" {
 
-const char* pic_version(void) { return "pic_b200 0.1 (sm_100a)"; }
+#ifndef PIC_SOURCE_HASH
+#define PIC_SOURCE_HASH "unhashed"
+#endif
+// the hash of every CUDA source + header + flag this library was built from (pypic3d_b200/_lib.py source_hash()): the loader
+// refuses a library that does not match the sources it sits next to
+const char* pic_version(void) { return "pic_b200 0.2 (sm_100a) src " PIC_SOURCE_HASH; }
 int pic_params_size(void) { return (int)sizeof(PicParams); }
 
 int pic_update_E(const PicParams* p, void* const E[3], const void* const B[3], const void* const J[3], void* stream) {

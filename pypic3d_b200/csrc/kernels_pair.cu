@@ -1,0 +1,565 @@
+// kernels_pair.cu -- K1 v10: the supercell tile kernel with the pair body (pic_pair.cuh), and the blocked, padded cell sort that
+// feeds it.
+//
+//   k_pair3d      gather E,B -> push -> Esirkepov deposit -> move -> particle BC for one species, one pass over particle memory.
+//                 Same walk as K1 v9 (kernels_fast.cu k_tile3d): a CTA takes a contiguous range of 4x4x4-cell supercells of the
+//                 blocked sort order; per supercell the 8x9x8-node E/B box of all six components (six cp.async.bulk.tensor.3d) and
+//                 the supercell's slice of x,y,z,vx,vy,vz (six cp.async.bulk) land in a shared-memory ring.  New in v10:
+//                   * the per-thread body advances W particles at once (float: W = 2, packed f32x2 arithmetic) -- pic_pair.cuh;
+//                   * one dedicated producer warp feeds the ring; the consumer warps never touch the request logic;
+//                   * supercell slices start on 16-byte boundaries (padded sort below), so a thread's pair is one 8-byte
+//                     shared-memory load per array and one 8-byte global store per array, and no pair straddles two supercells;
+//                   * chunks of 32 W particles are dealt round-robin, continuing across supercells (no dealing atomics);
+//                   * particles that change cell are queued per warp (index, old and new position) and finished by full warps:
+//                     union-stencil deposit + wrap / reflect / absorb / ownership + store (crosser_finish);
+//                   * particles whose stencil the tile does not cover (they drifted more than a cell out of their supercell since
+//                     the last sort) and slots appended since the sort take the scalar global-memory body of K1 v8, so the result
+//                     never depends on how fresh the sort is.
+//   k_sortb_*     counting sort by cell in the 4^3-blocked order with every supercell's slice padded to a multiple of 4 slots
+//                 (NaN = dead slot, the convention of the resident layout), producing blk_off for K1 directly.
+#include <stdlib.h>
+#include <cuda.h>
+
+#include "pic_common.cuh"
+#include "pic_tma.cuh"
+#include "pic_pair.cuh"
+
+namespace pic {
+
+#ifndef PIC_K10_NWC
+#define PIC_K10_NWC 7          /* float: consumer warps per CTA (+ 1 producer warp) */
+#endif
+#ifndef PIC_K10_CTAS
+#define PIC_K10_CTAS 2         /* float: CTAs per SM -> 128 registers per thread at 2 x 8 warps */
+#endif
+#ifndef PIC_K10_NWC64
+#define PIC_K10_NWC64 15       /* double: one CTA per SM (the ring is twice as large) */
+#endif
+#ifndef PIC_K10_NSTAGE
+#define PIC_K10_NSTAGE 3
+#endif
+#ifndef PIC_K10_W
+#define PIC_K10_W 2            /* particles per thread in float (1 = scalar control) */
+#endif
+constexpr int K10_PCAP = 640;   // staged particle slots per supercell and array (mean 512 at 8 ppc per species)
+// per-warp queue of cell-crossers: flushed in full warps, so at most 31 wait while up to 32 W join in one iteration
+template <int W> struct K10Queue { static constexpr int QW = 32 * (W + 1); };
+
+template <typename T, int W>
+__device__ __forceinline__ Vec<T, W> ld_vec(const T* ptr) {
+    Vec<T, W> r;
+    if constexpr (W == 2 && sizeof(T) == 4) {
+        const float2 f = *reinterpret_cast<const float2*>(ptr);
+        r.v[0] = f.x; r.v[1] = f.y;
+    } else if constexpr (W == 2 && sizeof(T) == 8) {
+        const double2 f = *reinterpret_cast<const double2*>(ptr);
+        r.v[0] = f.x; r.v[1] = f.y;
+    } else {
+#pragma unroll
+        for (int j = 0; j < W; ++j) r.v[j] = ptr[j];
+    }
+    return r;
+}
+template <typename T, int W>
+__device__ __forceinline__ void st_vec(T* ptr, const Vec<T, W>& a) {
+    if constexpr (W == 2 && sizeof(T) == 4) *reinterpret_cast<float2*>(ptr) = make_float2(a.v[0], a.v[1]);
+    else if constexpr (W == 2 && sizeof(T) == 8) *reinterpret_cast<double2*>(ptr) = make_double2(a.v[0], a.v[1]);
+    else {
+#pragma unroll
+        for (int j = 0; j < W; ++j) ptr[j] = a.v[j];
+    }
+}
+
+// the 12 same-cell currents of one cell -> global J (fire-and-forget REDs)
+template <typename T>
+__device__ __forceinline__ void red_cell(const TileSink<T>& sink, int base, int sx, int sy, const T* v) {
+    int n = 0;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        T* Jc = sink.J[c] + base;
+#pragma unroll
+        for (int m1 = 0; m1 < 2; ++m1)
+#pragma unroll
+            for (int m2 = 0; m2 < 2; ++m2) atomicAdd(Jc + SameCell<1>::offset(c, 0, m1, m2, sx, sy), v[n++]);
+    }
+}
+
+// one level of the segmented scan (float: packed adds)
+template <typename T>
+__device__ __forceinline__ void pair_scan_level(T* v, int d, bool take) {
+    if constexpr (sizeof(T) == 4) {
+#pragma unroll
+        for (int n = 0; n < 12; n += 2) {
+            const float2 o = make_float2(__shfl_up_sync(0xffffffffu, v[n], d), __shfl_up_sync(0xffffffffu, v[n + 1], d));
+            if (take) {
+                const float2 r = __fadd2_rn(make_float2(v[n], v[n + 1]), o);
+                v[n] = r.x; v[n + 1] = r.y;
+            }
+        }
+    } else {
+#pragma unroll
+        for (int n = 0; n < 12; ++n) {
+            const T o = __shfl_up_sync(0xffffffffu, v[n], d);
+            if (take) v[n] += o;
+        }
+    }
+}
+
+// Segmented inclusive scan (runs of up to 1 << STEPS lanes with equal key); run tails issue the REDs.  key < 0: nothing to add.
+template <typename T, int STEPS>
+__device__ __forceinline__ void pair_scan_red(T* v, int key, int lane, const TileSink<T>& sink, int key0, int sx, int sy) {
+    constexpr int G = 1 << STEPS;
+    const int gl = lane & (G - 1);
+    const int key_prev = __shfl_up_sync(0xffffffffu, key, 1);
+    const bool head = (gl == 0) || (key != key_prev);
+    int flag = head ? 1 : 0;
+#pragma unroll
+    for (int d = 1; d < G; d <<= 1) {
+        const int fo = __shfl_up_sync(0xffffffffu, flag, d);
+        const bool take = (gl >= d) && (flag == 0);
+        pair_scan_level<T>(v, d, take);
+        if (take) flag |= fo;
+    }
+    const int head_next = __shfl_down_sync(0xffffffffu, head ? 1 : 0, 1);
+    const bool tail = (gl == G - 1) || (head_next != 0);
+    if (tail && key >= 0) red_cell<T>(sink, key0 + (key >> 6) * sx + ((key >> 3) & 7) * sy + (key & 7), sx, sy, v);
+}
+
+// All lanes of the warp with the same key are summed, contiguous or not (match-any groups, pointer doubling); the lowest lane of
+// every group issues the REDs.  For a species whose sort is stale (cell changers fragment the runs).
+template <typename T>
+__device__ __forceinline__ void pair_group_red(T* v, int key, int lane, const TileSink<T>& sink, int key0, int sx, int sy) {
+    const unsigned group = __match_any_sync(0xffffffffu, key);
+    const unsigned above = group & (0xfffffffeu << lane);
+    int next = above ? __ffs(above) - 1 : 32;
+    while (__any_sync(0xffffffffu, next < 32)) {
+        const bool has = next < 32;
+        const int src = has ? next : lane;
+        if constexpr (sizeof(T) == 4) {
+#pragma unroll
+            for (int n = 0; n < 12; n += 2) {
+                const float2 o = make_float2(__shfl_sync(0xffffffffu, v[n], src), __shfl_sync(0xffffffffu, v[n + 1], src));
+                if (has) {
+                    const float2 r = __fadd2_rn(make_float2(v[n], v[n + 1]), o);
+                    v[n] = r.x; v[n + 1] = r.y;
+                }
+            }
+        } else {
+#pragma unroll
+            for (int n = 0; n < 12; ++n) {
+                const T o = __shfl_sync(0xffffffffu, v[n], src);
+                if (has) v[n] += o;
+            }
+        }
+        const int nn = __shfl_sync(0xffffffffu, next, src);
+        next = has ? nn : 32;
+    }
+    if (key >= 0 && lane == __ffs(group) - 1) red_cell<T>(sink, key0 + (key >> 6) * sx + ((key >> 3) & 7) * sy + (key & 7), sx, sy, v);
+}
+
+constexpr int K10_STAGE_ELEMS = 6 * TILE_ELEMS + 6 * K10_PCAP;
+constexpr int K10_HDR = 512;    // barriers + descriptors in front of the ring
+
+template <typename T, int W, int NWC>
+struct PairSmem {
+    static constexpr size_t bytes = (size_t)K10_HDR + (size_t)PIC_K10_NSTAGE * K10_STAGE_ELEMS * sizeof(T)
+                                    + (size_t)NWC * K10Queue<W>::QW * (sizeof(int) + 6 * sizeof(T));
+};
+
+// MODE: 0 = segmented scan + RED, 2 = match-any groups + RED (same numbering as K1 v9)
+template <typename T, int W, int PUSHER, int NWC, int CTAS, bool PER1, int MODE>
+__global__ void __launch_bounds__((NWC + 1) * 32, CTAS)
+k_pair3d(const __grid_constant__ PicParams p, int species, const __grid_constant__ Geom<T> gm, const __grid_constant__ FastConst<T> k,
+         const __grid_constant__ PairConst<T> pc, const __grid_constant__ SoAView<T> s, const __grid_constant__ Field6<T> F, Field3W<T> J,
+         const __grid_constant__ LeaveBuf leave, int distributed, int32_t* flags, const __grid_constant__ TileMaps tm,
+         const int32_t* __restrict__ blk_off, int nblk, int nbx, int nby, int nbz) {
+    constexpr int NSTAGE = PIC_K10_NSTAGE;
+    constexpr int PCAP = K10_PCAP, QW = K10Queue<W>::QW;
+    constexpr int TILE_ALL = 6 * TILE_ELEMS;
+    constexpr int STAGE_ELEMS = K10_STAGE_ELEMS;
+    constexpr int AL = 16 / (int)sizeof(T);
+    constexpr int CH = 32 * W;                               // particles per chunk (one warp iteration)
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);  // [NSTAGE] tile + particles have landed (TMA complete_tx)
+    uint64_t* empty = full + NSTAGE;                         // [NSTAGE] every consumer warp is done with the stage
+    int* desc = reinterpret_cast<int*>(smem_raw + 64);       // [NSTAGE][8]: slice begin, end, staged end, edge flag, J key of the tile origin
+    T* dx0 = reinterpret_cast<T*>(smem_raw + 256);           // [NSTAGE][4]: position of the tile's first centre-line node
+    T* stages = reinterpret_cast<T*>(smem_raw + K10_HDR);    // [NSTAGE]([6][8][9][8] + [6][PCAP])
+    unsigned char* qraw = smem_raw + K10_HDR + (size_t)NSTAGE * STAGE_ELEMS * sizeof(T);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int per_cta = (nblk + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int b0 = (int)blockIdx.x * per_cta;
+    int b1 = (b0 + per_cta < nblk) ? b0 + per_cta : nblk;
+    if (b1 < b0) b1 = b0;
+    if (tid == 0) {
+        for (int i = 0; i < NSTAGE; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, NWC); }
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    __syncthreads();
+    const int n_live = (int)s.count();
+    const int cap_al = (int)(s.cap < 0x7fffffff ? s.cap : 0x7fffffff) & ~(AL - 1);
+
+    // ------------------------------------------------------------------ producer warp: one thread feeds the ring
+    if (warp == NWC) {
+        if (lane == 0) {
+            for (int b = b0; b < b1; ++b) {
+                const int j = b - b0, sr = j % NSTAGE;
+                if (j >= NSTAGE) mbar_wait(empty + sr, ((j / NSTAGE) - 1) & 1);        // previous occupant: supercell b - NSTAGE
+                const int bz = b % nbz, by = (b / nbz) % nby, bx = b / (nbz * nby);
+                const int beg = blk_off[b];
+                int end = blk_off[b + 1];
+                if (end > n_live) end = n_live;
+                int n = 0;
+                if (end > beg && !(beg & (AL - 1))) {
+                    n = (end - beg + AL - 1) & ~(AL - 1);
+                    if (n > PCAP) n = PCAP;
+                    if (beg + n > cap_al) n = cap_al - beg;
+                    if (n < 0) n = 0;
+                }
+                if (beg & (AL - 1)) atomicOr(flags, 8);          // contract: slices come from the padded sort (pic_sort_blocked)
+                int* d = desc + sr * 8;
+                const int ox = bx * TILE_B + gm.g - 2, oy = by * TILE_B + gm.g - 2, oz = bz * TILE_B + gm.g - 2;
+                d[0] = beg; d[1] = (beg & (AL - 1)) ? beg : end; d[2] = beg + n;
+                d[3] = (bx == 0 || bx == nbx - 1 || by == 0 || by == nby - 1 || bz == 0 || bz == nbz - 1) ? 1 : 0;
+                d[4] = ox * k.sx + oy * k.sy + oz;
+                T* x0 = dx0 + sr * 4;
+                x0[0] = pic_fma((T)ox, k.sc[0], k.oc[0]); x0[1] = pic_fma((T)oy, k.sc[1], k.oc[1]); x0[2] = pic_fma((T)oz, k.sc[2], k.oc[2]);
+                T* st = stages + sr * STAGE_ELEMS;
+                mbar_arrive_expect_tx(full + sr, TILE_ALL * (int)sizeof(T) + 6 * n * (int)sizeof(T));
+#pragma unroll
+                for (int c = 0; c < 6; ++c) tma_load_box(st + c * TILE_ELEMS, &tm.m[c], full + sr, oz, oy, ox);
+                if (n > 0) {
+#pragma unroll
+                    for (int c = 0; c < 6; ++c) tma_load_bytes(st + TILE_ALL + c * PCAP, s.c[c] + beg, n * (int)sizeof(T), full + sr);
+                }
+            }
+        }
+        return;
+    }
+
+    // ------------------------------------------------------------------ consumer warps
+    TileSink<T> sink;
+    for (int c = 0; c < 3; ++c) { sink.J[c] = J.f[c]; sink.L[c] = gm.L[c]; }
+    sink.off = 0;
+    Field6<T> X;
+    for (int c = 0; c < 6; ++c) X.f[c] = nullptr;
+    int* qi = reinterpret_cast<int*>(qraw) + warp * QW;                                                 // [NWC][QW] particle index
+    T* qo = reinterpret_cast<T*>(qraw + (size_t)NWC * QW * sizeof(int)) + (size_t)warp * 6 * QW;        // [NWC]([3][QW] old + [3][QW] new position)
+    T* qx = qo + 3 * QW;
+    int qn = 0;                                              // warp-uniform queue fill
+    auto flush = [&](int keep_below) {
+        while (qn > keep_below) {
+            const int n_now = qn < 32 ? qn : 32;
+            const int e = qn - n_now + lane;
+            if (lane < n_now) {
+                const T o3[3] = {qo[e], qo[QW + e], qo[2 * QW + e]};
+                const T n3[3] = {qx[e], qx[QW + e], qx[2 * QW + e]};
+                crosser_finish<T, PER1>(p, species, gm, k, qi[e], s, o3, n3, sink, leave, distributed != 0, flags);
+            }
+            qn -= n_now;
+        }
+        __syncwarp();
+    };
+    int slot = 0, par = 0, rot = 0;
+    for (int b = b0; b < b1; ++b) {
+        while (!mbar_try_wait(full + slot, par, 1000)) {}
+        const int4 d0 = *reinterpret_cast<const int4*>(desc + slot * 8);
+        const int key0 = desc[slot * 8 + 4];
+        const int p_beg = d0.x, p_end = d0.y, staged_end = d0.z;
+        const bool edge = d0.w != 0;
+        const T x0[3] = {dx0[slot * 4], dx0[slot * 4 + 1], dx0[slot * 4 + 2]};
+        const T* tile = stages + slot * STAGE_ELEMS;
+        const T* pst = tile + TILE_ALL;
+        const int nchunk = p_end > p_beg ? (p_end - p_beg + CH - 1) / CH : 0;
+        for (int ch = (warp + NWC - rot) % NWC; ch < nchunk; ch += NWC) {
+            const int i0 = p_beg + ch * CH + W * lane;
+            Vec<T, W> pos[3], vel[3];
+            bool live[W];
+            if (p_beg + (ch + 1) * CH <= staged_end) {                     // the whole chunk sits in the staged slice
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    pos[c] = ld_vec<T, W>(pst + c * PCAP + (i0 - p_beg));
+                    vel[c] = ld_vec<T, W>(pst + (3 + c) * PCAP + (i0 - p_beg));
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < W; ++j) {
+                    const bool in = i0 + j < p_end;
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        pos[c].v[j] = in ? s.c[c][i0 + j] : pic_nan<T>();
+                        vel[c].v[j] = in ? s.c[3 + c][i0 + j] : (T)0;
+                    }
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < W; ++j) live[j] = (i0 + j < p_end) && !pic_isnan(pos[0].v[j]);
+            Vec<T, W> pos_out[3], vel_out[3], xraw[3], vals[12];
+            int kind[W], cid[W];
+            pair_advance<T, W, PUSHER, PER1>(k, pc, tile, x0, edge, pos, vel, live, pos_out, vel_out, xraw, kind, cid, vals);
+            // ---- not covered by the tile: the scalar global-memory body does the whole step for that particle
+            {
+                unsigned slow = 0;
+#pragma unroll
+                for (int j = 0; j < W; ++j) slow |= (kind[j] == PAIR_SLOW) ? (1u << j) : 0u;
+                while (slow) {
+                    const int j = __ffs(slow) - 1;
+                    slow &= slow - 1;
+                    fused_particle_fast3d<T, 1, PUSHER, false>(p, species, gm, k, (int64_t)(i0 + j), s, F, X, sink, leave, distributed != 0, flags);
+                    atomic_add_i32(flags + 2, 1);
+                }
+            }
+            // ---- store (cell crossers get their final position from crosser_finish later)
+            {
+                bool stv[W];
+#pragma unroll
+                for (int j = 0; j < W; ++j) stv[j] = (kind[j] == PAIR_SAME) || (kind[j] == PAIR_CROSS);
+                bool all = true;
+#pragma unroll
+                for (int j = 0; j < W; ++j) all = all && stv[j];
+                if (all) {
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) { st_vec<T, W>(s.c[c] + i0, pos_out[c]); st_vec<T, W>(s.c[3 + c] + i0, vel_out[c]); }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < W; ++j)
+                        if (stv[j]) {
+#pragma unroll
+                            for (int c = 0; c < 3; ++c) { s.c[c][i0 + j] = pos_out[c].v[j]; s.c[3 + c][i0 + j] = vel_out[c].v[j]; }
+                        }
+                }
+            }
+            // ---- queue the cell crossers
+            {
+                unsigned m[W];
+                unsigned any = 0;
+#pragma unroll
+                for (int j = 0; j < W; ++j) { m[j] = __ballot_sync(0xffffffffu, kind[j] == PAIR_CROSS); any |= m[j]; }
+                if (any) {
+                    int base = qn;
+#pragma unroll
+                    for (int j = 0; j < W; ++j) {
+                        if (kind[j] == PAIR_CROSS) {
+                            const int e = base + __popc(m[j] & ((1u << lane) - 1u));
+                            qi[e] = i0 + j;
+#pragma unroll
+                            for (int a = 0; a < 3; ++a) { qo[a * QW + e] = pos[a].v[j]; qx[a * QW + e] = xraw[a].v[j]; }
+                        }
+                        base += __popc(m[j]);
+                    }
+                    qn = base;
+                    __syncwarp();
+                }
+            }
+            // ---- same-cell currents: join the thread's particles, reduce over the lanes of one cell, RED at the run tails
+            {
+                T lv[12];
+                int key;
+                if constexpr (W == 2) {
+                    const bool dA = kind[0] == PAIR_SAME, dB = kind[1] == PAIR_SAME;
+                    const bool solo = dA && dB && (cid[0] != cid[1]);      // the pair straddles a cell boundary: B goes out by itself
+#pragma unroll
+                    for (int n = 0; n < 12; ++n) lv[n] = solo ? vals[n].v[0] : vals[n].v[0] + vals[n].v[1];
+                    key = dA ? cid[0] : (dB ? cid[1] : -1 - lane);
+                    if (solo) {
+                        T bv[12];
+#pragma unroll
+                        for (int n = 0; n < 12; ++n) bv[n] = vals[n].v[1];
+                        red_cell<T>(sink, key0 + (cid[1] >> 6) * k.sx + ((cid[1] >> 3) & 7) * k.sy + (cid[1] & 7), k.sx, k.sy, bv);
+                    }
+                } else {
+#pragma unroll
+                    for (int n = 0; n < 12; ++n) lv[n] = vals[n].v[0];
+                    key = (kind[0] == PAIR_SAME) ? cid[0] : -1 - lane;
+                }
+                if (MODE == 2) pair_group_red<T>(lv, key, lane, sink, key0, k.sx, k.sy);
+                else pair_scan_red<T, 3>(lv, key, lane, sink, key0, k.sx, k.sy);
+            }
+            if (qn >= 32) flush(31);
+        }
+        rot = (rot + nchunk) % NWC;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty + slot);            // this warp no longer reads the stage in `slot`
+        if (++slot == NSTAGE) { slot = 0; par ^= 1; }
+    }
+    // ---- tail pass: slots appended since the last sort (particles received from neighbour ranks): scalar global-memory body
+    {
+        const int tail0 = blk_off[nblk];
+        for (int i = tail0 + ((int)blockIdx.x * NWC + warp) * 32 + lane; i < n_live; i += (int)gridDim.x * NWC * 32)
+            fused_particle_fast3d<T, 1, PUSHER, false>(p, species, gm, k, (int64_t)i, s, F, X, sink, leave, distributed != 0, flags);
+    }
+    flush(0);
+}
+
+// ---------------------------------------------------------------- blocked, padded counting sort
+// Cells are ordered supercell-major (local_cell, PIC_SORT_BLOCK = 4); every supercell's slice starts on a multiple of 4 slots.
+// k_sortb_blocks: padded particle count per supercell.  (exclusive scan: pic_sort_scan)  k_sortb_cells: first slot of every cell;
+// k_sortb_pad: the padding slots are dead (x = NaN).  The scatter is kernels_fast.cu k_sort_scatter.
+__global__ void __launch_bounds__(256) k_sortb_blocks(int nblk, const int32_t* __restrict__ cell_count, int32_t* __restrict__ blk_padded) {
+    // one warp per supercell: 64 cell counts -> padded sum; entry nblk is 0 (scan total lands there)
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (w > nblk) return;
+    int v = 0;
+    if (w < nblk) v = cell_count[w * 64 + lane] + cell_count[w * 64 + 32 + lane];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) blk_padded[w] = (w < nblk) ? ((v + 3) & ~3) : 0;
+}
+
+__global__ void __launch_bounds__(256) k_sortb_cells(int nblk, const int32_t* __restrict__ cell_count, const int32_t* __restrict__ blk_off,
+                                                     int32_t* __restrict__ cell_offset, int64_t cap, int32_t* flags) {
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (w >= nblk) {
+        if (w == nblk && lane == 0) {
+            cell_offset[nblk * 64] = blk_off[nblk];          // the trash bin (dead particles) starts after the last padded slice
+            if ((int64_t)blk_off[nblk] > cap) atomicOr(flags, 2);
+        }
+        return;
+    }
+    const int c0 = cell_count[w * 64 + 2 * lane], c1 = cell_count[w * 64 + 2 * lane + 1];
+    int inc = c0 + c1;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int n = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += n;
+    }
+    const int excl = blk_off[w] + inc - (c0 + c1);
+    cell_offset[w * 64 + 2 * lane] = excl;
+    cell_offset[w * 64 + 2 * lane + 1] = excl + c0;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_sortb_pad(int nblk, const int32_t* __restrict__ cell_offset, const int32_t* __restrict__ cell_count,
+                                                   const int32_t* __restrict__ blk_off, SoAView<T> d) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nblk) return;
+    const int last = b * 64 + 63;
+    const int used_end = cell_offset[last] + cell_count[last];
+    const int end = blk_off[b + 1];
+    for (int i = used_end; i < end && i < d.cap; ++i) {
+        d.c[0][i] = pic_nan<T>();
+        for (int c = 1; c < 6; ++c) d.c[c][i] = (T)0;
+        if (d.id) d.id[i] = -1;
+    }
+}
+
+__global__ void k_set_count_pair(int32_t* n_dev, const int32_t* src, int64_t cap) {
+    const int v = *src;
+    *n_dev = (int64_t)v < cap ? v : (int32_t)cap;
+}
+
+// ---------------------------------------------------------------- launchers
+template <typename T>
+static int launch_pair3d(const PicParams* p, int species, const PicSoA* soa, const int32_t* blk_off, int nblk, int options, const void* const E[3],
+                         const void* const B[3], void* const J[3], const PicLeave* leave, int32_t* flags, cudaStream_t st) {
+    static_assert(PIC_SORT_BLOCK == TILE_B, "the tile kernel walks the supercells of the blocked sort order");
+    if (p->shape_factor != 1 || p->g != 2 || (p->pusher != PIC_PUSHER_BORIS && p->pusher != PIC_PUSHER_BORIS_REL)) return PIC_EUNSUPPORTED;
+    for (int a = 0; a < 3; ++a) {
+        if (p->tile[a] % TILE_B != 0 || p->gmesh[a] * p->tile[a] <= 1) return PIC_EUNSUPPORTED;
+    }
+    const int nbx = p->tile[0] / TILE_B, nby = p->tile[1] / TILE_B, nbz = p->tile[2] / TILE_B;
+    if (nblk != nbx * nby * nbz) return PIC_EINVAL;
+    for (int c = 0; c < 3; ++c)
+        if (((uintptr_t)E[c] | (uintptr_t)B[c]) & 15) return PIC_EUNSUPPORTED;     // TMA global addresses are 16-byte aligned
+    for (int c = 0; c < 6; ++c)
+        if ((uintptr_t)soa->comp[c] & 15) return PIC_EUNSUPPORTED;
+    if (soa->n == 0 && !soa->n_dev) return 0;
+    Field6<T> F;
+    Field3W<T> Jw;
+    for (int c = 0; c < 3; ++c) { F.f[c] = (const T*)E[c]; F.f[3 + c] = (const T*)B[c]; Jw.f[c] = (T*)J[c]; }
+    Geom<T> gm;
+    make_geom<T>(*p, 0, 0, 0, gm);
+    FastConst<T> k;
+    make_fast_const<T>(*p, species, gm, k);
+    PairConst<T> pc;
+    make_pair_const<T>(k, pc);
+    // the pair body takes the vertex line to be the centre line shifted up by half a cell (utilities/grids.py): verify
+    for (int a = 0; a < 3; ++a)
+        if (fabs((double)(gm.ov[a] - gm.oc[a]) - 0.5 * (double)gm.d[a]) > 1e-4 * (double)gm.d[a]) return PIC_EUNSUPPORTED;
+    int distributed = 0;
+    for (int c = 0; c < 3; ++c) distributed |= (p->gmesh[c] != p->mesh[c]);
+    const bool grp = (options & 2) != 0;
+    TileMaps tm;
+    if (!make_tile_maps<T>(gm.L, F.f, Jw.f, tm)) return PIC_EUNSUPPORTED;
+    bool per1 = !distributed;
+    for (int a = 0; a < 3; ++a) per1 = per1 && (p->particle_bc[a] == PIC_BC_PERIODIC);
+    constexpr bool F32 = sizeof(T) == 4;
+    constexpr int W = F32 ? PIC_K10_W : 1;
+    constexpr int NWC = F32 ? PIC_K10_NWC : PIC_K10_NWC64;
+    constexpr int CTAS = F32 ? PIC_K10_CTAS : 1;
+    constexpr size_t smem = PairSmem<T, W, NWC>::bytes;
+    static_assert(smem <= 227 * 1024, "ring + queues exceed the shared memory of one CTA");
+    int grid = num_sms() * CTAS;
+    if (grid > nblk) grid = nblk;
+    const SoAView<T> sv = view_of<T>(soa);
+    const LeaveBuf lb = leave_of(leave);
+#define PIC_LAUNCH_K10(PUSH, PER, MD)                                                                                    \
+    do {                                                                                                                 \
+        static bool attr_set = false;                                                                                    \
+        if (!attr_set) {                                                                                                 \
+            cudaError_t e = cudaFuncSetAttribute(k_pair3d<T, W, PUSH, NWC, CTAS, PER, MD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+            if (e != cudaSuccess) return (int)e;                                                                         \
+            attr_set = true;                                                                                             \
+        }                                                                                                                \
+        k_pair3d<T, W, PUSH, NWC, CTAS, PER, MD><<<grid, (NWC + 1) * 32, smem, st>>>(*p, species, gm, k, pc, sv, F, Jw, lb, distributed, flags, tm, blk_off, nblk, nbx, nby, nbz); \
+    } while (0)
+#define PIC_LAUNCH_K10_M(PUSH, PER) do { if (grp) PIC_LAUNCH_K10(PUSH, PER, 2); else PIC_LAUNCH_K10(PUSH, PER, 0); } while (0)
+    if (p->pusher == PIC_PUSHER_BORIS) { if (per1) PIC_LAUNCH_K10_M(PIC_PUSHER_BORIS, true); else PIC_LAUNCH_K10_M(PIC_PUSHER_BORIS, false); }
+    else { if (per1) PIC_LAUNCH_K10_M(PIC_PUSHER_BORIS_REL, true); else PIC_LAUNCH_K10_M(PIC_PUSHER_BORIS_REL, false); }
+#undef PIC_LAUNCH_K10_M
+#undef PIC_LAUNCH_K10
+    PIC_LAUNCH_RET();
+}
+
+template <typename T>
+static int launch_sortb_pad(const PicParams* p, int nblk, const int32_t* cell_offset, const int32_t* cell_count, const int32_t* blk_off,
+                            const PicSoA* dst, cudaStream_t st) {
+    k_sortb_pad<T><<<(nblk + 255) / 256, 256, 0, st>>>(nblk, cell_offset, cell_count, blk_off, view_of<T>(dst));
+    PIC_LAUNCH_RET();
+}
+
+}  // namespace pic
+
+using namespace pic;
+
+extern "C" {
+
+int pic_fused_pair3d(const PicParams* p, int species, const PicSoA* soa, const int32_t* blk_off, int nblk, int options,
+                     const void* const E[3], const void* const B[3], void* const J[3], const PicLeave* leave, int32_t* flags, void* stream) {
+    PIC_CHECK_ARG(p && soa && blk_off && E && B && J && flags && species >= 0 && species < p->n_species && nblk > 0);
+    PIC_CHECK_ARG(p->mesh[0] == 1 && p->mesh[1] == 1 && p->mesh[2] == 1);
+    bool distributed = false;
+    for (int c = 0; c < 3; ++c) distributed |= (p->gmesh[c] != p->mesh[c]);
+    if (distributed) PIC_CHECK_ARG(leave && leave->buf);
+    PIC_DISPATCH_T(p, launch_pair3d, p, species, soa, blk_off, nblk, options, E, B, J, leave, flags, (cudaStream_t)stream);
+}
+
+// Offsets of the blocked, padded sort from the per-cell histogram (pic_sort_histogram): blk_off[nblk + 1] (first slot of every
+// supercell, multiples of 4) and cell_offset[ncells + 1] (first slot of every cell; the last entry is the trash bin = total padded
+// length).  blk_work: nblk + 1 ints; scan_scratch as for pic_sort_scan.  flags |= 2 when the padded stream exceeds `cap`.
+int pic_sort_blocked_offsets(const PicParams* p, const int32_t* cell_count, int32_t* cell_offset, int32_t* blk_work, int32_t* blk_off,
+                             int32_t* scan_scratch, int64_t cap, int32_t* flags, void* stream) {
+    PIC_CHECK_ARG(p && cell_count && cell_offset && blk_work && blk_off && scan_scratch && flags);
+    for (int a = 0; a < 3; ++a) PIC_CHECK_ARG(p->tile[a] % TILE_B == 0);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int nblk = (p->tile[0] / TILE_B) * (p->tile[1] / TILE_B) * (p->tile[2] / TILE_B);
+    const int warps = nblk + 1;
+    k_sortb_blocks<<<(warps * 32 + 255) / 256, 256, 0, st>>>(nblk, cell_count, blk_work);
+    const int rc = pic_sort_scan(nblk + 1, blk_work, blk_off, scan_scratch, stream);
+    if (rc) return rc;
+    k_sortb_cells<<<(warps * 32 + 255) / 256, 256, 0, st>>>(nblk, cell_count, blk_off, cell_offset, cap, flags);
+    PIC_LAUNCH_RET();
+}
+
+// After pic_sort_scatter with the offsets above: mark the padding slots of every supercell dead and set the live slot count
+// (= total padded length) on the device.
+int pic_sort_blocked_finish(const PicParams* p, const int32_t* cell_offset, const int32_t* cell_count, const int32_t* blk_off,
+                            const PicSoA* dst, void* stream) {
+    PIC_CHECK_ARG(p && cell_offset && cell_count && blk_off && dst);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int nblk = (p->tile[0] / TILE_B) * (p->tile[1] / TILE_B) * (p->tile[2] / TILE_B);
+    if (dst->n_dev) k_set_count_pair<<<1, 1, 0, st>>>(dst->n_dev, blk_off + nblk, dst->cap);
+    PIC_DISPATCH_T(p, launch_sortb_pad, p, nblk, cell_offset, cell_count, blk_off, dst, st);
+}
+
+}  // extern "C"

@@ -95,6 +95,7 @@ class Simulation:
         self._cell_count = torch.zeros(self.ncells + 1, dtype=torch.int32, device=self.device)
         self._cell_offset = torch.zeros(self.ncells + 1, dtype=torch.int32, device=self.device)
         self._scan_scratch = torch.zeros((self.ncells + 1 + 2047) // 2048 + 1, dtype=torch.int32, device=self.device)
+        self._blk_work = torch.zeros(self.ncells // 64 + 2, dtype=torch.int32, device=self.device)
         self._counter = torch.zeros(max(self.S, 1) + 27, dtype=torch.int32, device=self.device)
         self.cap_ref = int(x.shape[4])
         self.track_ids = bool(track_ids)
@@ -115,17 +116,19 @@ class Simulation:
 
     # ------------------------------------------------------------------------------------------ layout
     def _pick_k1_variant(self, sp):
-        """"tile": K1 v9 (pic_fused_tile3d, supercell E/B tiles in shared memory) when the configuration is the one it was
-        built for; "global": pic_fused_push_deposit (every other configuration).  PIC_K1_VARIANT=global forces the latter
-        (A/B measurements); both give the same result."""
+        """"pair": K1 v10 (pic_fused_pair3d: supercell E/B tiles in shared memory, two particles per thread in packed f32x2
+        arithmetic, fed by the blocked + padded sort) when the configuration is the one the tile kernels were built for;
+        "tile": K1 v9 (pic_fused_tile3d), same configurations, kept as the A/B control (PIC_K1_VARIANT=tile);
+        "global": pic_fused_push_deposit (every other configuration, or PIC_K1_VARIANT=global).  All give the same result."""
         p = self.p
         ok = (self.deposition == 0 and int(p.shape_factor) == 1 and int(p.g) == 2
               and int(p.pusher) in (0, 1)   # PIC_PUSHER_BORIS, PIC_PUSHER_BORIS_REL
               and all(int(p.tile[a]) % 4 == 0 and int(p.gmesh[a]) * int(p.tile[a]) > 1 for a in range(3))
               and self.ext_E is None)
-        if os.environ.get("PIC_K1_VARIANT", "tile") != "tile":
-            ok = False
-        return "tile" if ok else "global"
+        want = os.environ.get("PIC_K1_VARIANT", "pair")
+        if not ok or want not in ("pair", "tile"):
+            return "global"
+        return want
 
     def _k1_options(self, s):
         opt = 1 if self._jtile_mode == "1" else 0
@@ -195,7 +198,9 @@ class Simulation:
             if first:
                 sp_ = _Species()
                 # a multiple of 64 slots keeps every row of the (6, cap) SoA 16-byte aligned (TMA bulk copies in K1 v9)
-                sp_.cap = (max(16, int(np.ceil(counts[s] * float(capacity_factor))) + 16) + 63) // 64 * 64
+                # (+ 4 slots per supercell: the blocked sort of K1 v10 pads every supercell's slice to a multiple of 4 slots)
+                pad = 4 * (self.ncells // 64) if self.k1_variant == "pair" else 0
+                sp_.cap = (max(16, int(np.ceil(counts[s] * float(capacity_factor))) + 16 + pad) + 63) // 64 * 64
                 sp_.buf = [torch.empty((6, sp_.cap), dtype=self.dtype, device=self.device) for _ in range(2)]
                 sp_.ids = [torch.empty(sp_.cap, dtype=torch.int32, device=self.device) for _ in range(2)] if self.track_ids else None
                 sp_.n_dev = torch.zeros(1, dtype=torch.int32, device=self.device)
@@ -254,11 +259,19 @@ class Simulation:
             src, dst = self._soa(sp_), self._soa(sp_, 1 - sp_.cur)
             self._cell_count.zero_()
             check(L.pic_sort_histogram(ctypes.byref(self.p), ctypes.byref(src), ops._p(self._cell_count), st), "pic_sort_histogram")
-            check(L.pic_sort_scan(n, ops._p(self._cell_count), ops._p(self._cell_offset), ops._p(self._scan_scratch), st), "pic_sort_scan")
+            if self.k1_variant == "pair":   # blocked + padded: every supercell's slice starts on a multiple of 4 slots (K1 v10)
+                check(L.pic_sort_blocked_offsets(ctypes.byref(self.p), ops._p(self._cell_count), ops._p(self._cell_offset),
+                                                 ops._p(self._blk_work), ops._p(sp_.blk_off), ops._p(self._scan_scratch), sp_.cap,
+                                                 ops._p(self.flags), st), "pic_sort_blocked_offsets")
+            else:
+                check(L.pic_sort_scan(n, ops._p(self._cell_count), ops._p(self._cell_offset), ops._p(self._scan_scratch), st), "pic_sort_scan")
             self._cell_count.zero_()
             check(L.pic_sort_scatter(ctypes.byref(self.p), ctypes.byref(src), ctypes.byref(dst), ops._p(self._cell_offset),
                                      ops._p(self._cell_count), st), "pic_sort_scatter")
-            sp_.cur = 1 - sp_.cur           # (the scatter also set n_dev = number of live particles, on the device)
+            if self.k1_variant == "pair":   # (the cursor array now holds the per-cell counts again) padding slots -> dead
+                check(L.pic_sort_blocked_finish(ctypes.byref(self.p), ops._p(self._cell_offset), ops._p(self._cell_count),
+                                                ops._p(sp_.blk_off), ctypes.byref(dst), st), "pic_sort_blocked_finish")
+            sp_.cur = 1 - sp_.cur           # (the scatter also set n_dev = number of slots in use, on the device)
             if hasattr(self, "_sorted_at"):
                 self._sorted_at[s] = self.step_count
             if self.k1_variant == "tile":   # first slot of every 4x4x4-cell supercell of the blocked sort order (K1 v9)
@@ -288,14 +301,15 @@ class Simulation:
                 e0.record()
             leave = ctypes.byref(sp_.leave) if sp_.leave is not None else None
             rc = _lib.PIC_EUNSUPPORTED
-            if self.k1_variant == "tile":
-                rc = L.pic_fused_tile3d(ctypes.byref(p), s, ctypes.byref(soa), ops._p(sp_.blk_off), self.ncells // 64,
-                                        self._k1_options(s), ops._v(self.E), ops._v(self.B), ops._v(self.J), leave, ops._p(self.flags), st)
+            if self.k1_variant in ("pair", "tile"):
+                fn = L.pic_fused_pair3d if self.k1_variant == "pair" else L.pic_fused_tile3d
+                rc = fn(ctypes.byref(p), s, ctypes.byref(soa), ops._p(sp_.blk_off), self.ncells // 64,
+                        self._k1_options(s), ops._v(self.E), ops._v(self.B), ops._v(self.J), leave, ops._p(self.flags), st)
                 if rc == _lib.PIC_EUNSUPPORTED:     # e.g. no TMA driver entry point: the global-gather K1 computes the same step
-                    self.k1_variant = "global"
+                    self.k1_variant = "global"      # (it reads the padded stream as it is: padding slots are dead slots)
                 else:
-                    check(rc, "pic_fused_tile3d")
-            if self.k1_variant != "tile":
+                    check(rc, "pic_fused_" + self.k1_variant + "3d")
+            if self.k1_variant not in ("pair", "tile"):
                 check(L.pic_fused_push_deposit(ctypes.byref(p), s, self.deposition, ctypes.byref(soa), ops._v(self.E), ops._v(self.B),
                                                extE, extB, ops._v(self.J), leave, ops._p(self.flags), st), "pic_fused_push_deposit")
             if self.k1_events is not None:
@@ -343,12 +357,19 @@ class Simulation:
     # ------------------------------------------------------------------------------------------ results
     def overflow(self):
         """Host sync: the reference's overflow flag (invalid > 1 tile jump or a capacity overflow), OR-ed over steps."""
-        return self.overflow_previous or bool((self.flags[0] != 0).item())
+        f = int(self.flags[0].item())
+        if f & 8:
+            raise PicError("pic_fused_pair3d was handed supercell slices that do not come from the blocked, padded sort")
+        return self.overflow_previous or f != 0
 
     def n_particles(self):
-        """Slots in use (host sync).  Exact particle count on a single GPU; between sorts of a multi-GPU run it still
-        includes the holes left by migrated particles."""
-        return sum(min(int(s.n_dev.item()), s.cap) for s in self.species)
+        """Live particles on this GPU (host sync): the slots in use minus the dead ones (x = NaN: holes left by migrated or
+        absorbed particles, and the padding slots of the blocked sort)."""
+        total = 0
+        for sp_ in self.species:
+            n = min(int(sp_.n_dev.item()), sp_.cap)
+            total += n - int(torch.isnan(sp_.buf[sp_.cur][0][:n]).sum().item())
+        return total
 
     def export_state(self, cap_ref=None, out=None):
         """Reference pytrees: (TiledParticles, fields 8-tuple).  Slots are restored by id on a single GPU.

@@ -100,8 +100,10 @@ def test_distributed_resident_matches_oracle(mesh, sf, pbc):
 
 @pytest.mark.parametrize("mesh", [(2, 1, 1), (1, 1, 2)])
 @pytest.mark.parametrize("pbc", [(0, 0, 0), (2, 0, 1)])
-def test_distributed_tile_kernel_matches_oracle(mesh, pbc):
-    """K1 v9 (supercell tiles) on a split domain: leaver packets, the appended-slot tail pass and the non-periodic move."""
+@pytest.mark.parametrize("variant", ("pair", "tile"))
+def test_distributed_tile_kernel_matches_oracle(mesh, pbc, variant, monkeypatch):
+    """K1 v10 / v9 (supercell tiles) on a split domain: leaver packets, the appended-slot tail pass and the non-periodic move."""
+    monkeypatch.setenv("PIC_K1_VARIANT", variant)
     world = mesh[0] * mesh[1] * mesh[2]
     if not torch.cuda.is_available():
         pytest.fail("-m gpu tests need a CUDA device")
@@ -110,7 +112,7 @@ def test_distributed_tile_kernel_matches_oracle(mesh, pbc):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, mesh, 1, pbc, 5, q, (8, 8, 4), "tile")) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, mesh, 1, pbc, 5, q, (8, 8, 4), variant)) for r in range(world)]
     for pr in procs:
         pr.start()
     res = [q.get(timeout=90) for _ in range(world)]

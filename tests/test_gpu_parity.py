@@ -380,14 +380,15 @@ TILE_CASES = [
 @pytest.mark.parametrize("c", TILE_CASES)
 @pytest.mark.parametrize("dtype", (F64, F32))
 @pytest.mark.parametrize("sort_interval", (1, 5, 0))
-@pytest.mark.parametrize("jtile", ("0", "1", "group"))
-def test_resident_tile_kernel_matches_oracle(c, dtype, sort_interval, jtile, monkeypatch):
-    """K1 v9 (pic_fused_tile3d): E/B gathered from shared-memory supercell tiles.  Fast particles (up to 0.16 cells per step)
-    and sort_interval 5 / never let particles drift into the tile margin and beyond it, so the tile gather, its global-memory
-    fallback and the deferred cell-crossers are all exercised; 12 steps (dt inside the Yee CFL limit), slot-exact against the
-    oracle."""
+@pytest.mark.parametrize("variant,jtile", [("pair", "0"), ("pair", "group"), ("tile", "0"), ("tile", "1"), ("tile", "group")])
+def test_resident_tile_kernel_matches_oracle(c, dtype, sort_interval, variant, jtile, monkeypatch):
+    """K1 v10 (pic_fused_pair3d) and K1 v9 (pic_fused_tile3d): E/B gathered from shared-memory supercell tiles.  Fast particles
+    (up to 0.16 cells per step) and sort_interval 5 / never let particles drift into the tile margin and beyond it, so the tile
+    gather, its global-memory fallback and the deferred cell-crossers are all exercised; 12 steps (dt inside the Yee CFL limit),
+    slot-exact against the oracle."""
     from pypic3d_b200.simulation import Simulation
-    # "1": same-cell currents through shared-memory J tiles + TMA reduce (f32 only); "group": match-any group reduction; "0": scan
+    monkeypatch.setenv("PIC_K1_VARIANT", variant)
+    # "1": same-cell currents through shared-memory J tiles + TMA reduce (v9, f32 only); "group": match-any group reduction; "0": scan
     monkeypatch.setenv("PIC_K9_JTILE", "1" if jtile == "1" else "0")
     monkeypatch.setenv("PIC_K9_GROUPRED", "1" if jtile == "group" else "0")
     N = c["N"]
@@ -396,7 +397,7 @@ def test_resident_tile_kernel_matches_oracle(c, dtype, sort_interval, jtile, mon
     fields = make_fields(sp, dp)
     ps, pd = gu.to_pkg_params(sp, dp)
     sim = Simulation(gu.particles_to_gpu(tp, dtype), gu.species_to_pkg(sc), gu.fields_to_gpu(fields, dtype), ps, pd, sort_interval=sort_interval)
-    assert sim.k1_variant == "tile"
+    assert sim.k1_variant == variant
     for _ in range(12):
         tp, fields = oevolve.time_loop_electrodynamic(tp, sc, fields, sp, dp)
     assert np.isfinite(tp.x[tp.active]).all()
@@ -415,8 +416,8 @@ def test_resident_tile_kernel_matches_oracle(c, dtype, sort_interval, jtile, mon
 
 @pytest.mark.parametrize("dtype,tol", [(F64, 1e-11), (F32, 2e-4)])
 @pytest.mark.parametrize("n,ppc", [(32, 8), (16, 24)])
-@pytest.mark.parametrize("jtile", ("0", "1", "group", "auto"))
-def test_tile_and_global_k1_variants_agree(dtype, tol, n, ppc, jtile, monkeypatch):
+@pytest.mark.parametrize("tiled,jtile", [("pair", "0"), ("pair", "group"), ("pair", "auto"), ("tile", "0"), ("tile", "1"), ("tile", "group"), ("tile", "auto")])
+def test_tile_and_global_k1_variants_agree(dtype, tol, n, ppc, tiled, jtile, monkeypatch):
     """Same thermal plasma, 12 steps with a sort every 5: the supercell-tile K1 and the global-gather K1 differ only by the
     order of the floating-point atomics.  32^3 x 16 ppc is the bench's density (512 particles per supercell and species, inside
     the 640-slot particle stage); 16^3 x 48 ppc puts 1536 particles into every supercell, so most chunks lie beyond the staged
@@ -430,14 +431,14 @@ def test_tile_and_global_k1_variants_agree(dtype, tol, n, ppc, jtile, monkeypatc
     out = {}
     monkeypatch.setenv("PIC_K9_JTILE", "1" if jtile == "1" else "0")
     monkeypatch.setenv("PIC_K9_GROUPRED", {"group": "1", "auto": "auto"}.get(jtile, "0"))
-    for variant in ("tile", "global"):
+    for variant in (tiled, "global"):
         monkeypatch.setenv("PIC_K1_VARIANT", variant)
         sim = Simulation(gu.particles_to_gpu(tp, dtype), gu.species_to_pkg(sc), gu.fields_to_gpu(fields, dtype), ps, pd, sort_interval=5)
         assert sim.k1_variant == variant
         sim.step(12)
         out[variant] = sim.export_state()
         assert not sim.overflow()
-    (pa, fa), (pb, fb) = out["tile"], out["global"]
+    (pa, fa), (pb, fb) = out[tiled], out["global"]
     assert torch.equal(pa.active, pb.active)
     gu.assert_close(pa.x, gu.npy(pb.x), tol, "x"); gu.assert_close(pa.u, gu.npy(pb.u), tol, "u")
     for k in range(3):

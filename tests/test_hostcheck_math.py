@@ -223,6 +223,53 @@ def test_tile3d_body_matches_oracle_step(hc, rel, dtype, tol, pbc, shift):
     assert flags[0] == 0
 
 
+@pytest.mark.parametrize("rel", (True, False))
+@pytest.mark.parametrize("dtype,tol", [(np.float64, 1e-12), (np.float32, 3e-5)])
+@pytest.mark.parametrize("pbc", [(0, 0, 0), (1, 0, 2)])
+@pytest.mark.parametrize("shift", (0, 1, -1))
+@pytest.mark.parametrize("W", (1, 2))
+@pytest.mark.parametrize("vmax", (0.4, 3.0))
+def test_pair3d_body_matches_oracle_step(hc, rel, dtype, tol, pbc, shift, W, vmax):
+    """K1 v10 body (pic_pair.cuh pair_advance + crosser_finish + the scalar fallback, finished as kernels_pair.cu does) == oracle
+    push -> Esirkepov -> move -> retile on one tile.  W = 2 hands the body two particles at a time that need not share a cell or
+    even a supercell; shift != 0 gives every group the tile of a neighbouring supercell, so particles land in the margin or
+    outside it (scalar global-memory body); vmax = 3 makes a third of the particles change cell; the (1, 0, 2) case puts
+    reflecting and absorbing walls on the rim supercells (the `edge` path)."""
+    from tests.cases import make_case
+    N = (8, 8, 4)
+    sp, dp, tp, sc, E, B = make_case(N, N, 1, current_deposition="esirkepov", relativistic=rel, particle_boundary_conditions=pbc,
+                                     vmax=vmax, C=10.0, n=120)
+    assert int(sp.guard_cells) == 2
+    pushed = pusher.particle_push(tp, sc, E, B, sp, dp)
+    z = fx.empty_tiled_vector(sp, dp)
+    Jref = dep.Esirkepov_current(pushed, sc, z, sp, dp, fold=False)
+    moved, _ = opart.refresh_tiled_particle_tiles(opart.update_tiled_particle_positions(pushed, sc, dp.dt), sp, dp)
+    p = _lib.make_params(sp, dp, sc, dtype)
+    Ec = [np.ascontiguousarray(c[0, 0, 0], dtype=dtype) for c in E]; Bc = [np.ascontiguousarray(c[0, 0, 0], dtype=dtype) for c in B]
+    J = [np.zeros_like(Ec[0]) for _ in range(3)]
+    flags = np.zeros(4, dtype=np.int32)
+    for s in range(2):
+        act = tp.active[0, 0, 0, s]
+        comp = [np.ascontiguousarray(tp.x[0, 0, 0, s][act][:, c], dtype=dtype) for c in range(3)] + \
+               [np.ascontiguousarray(tp.u[0, 0, 0, s][act][:, c], dtype=dtype) for c in range(3)]
+        cp = (ctypes.c_void_p * 6)(*[a.ctypes.data for a in comp])
+        hc.hc_pair3d(ctypes.byref(p), s, cp, ctypes.c_int64(int(act.sum())), _v3(Ec), _v3(Bc), _v3(J), ctypes.c_int(W), ctypes.c_int(shift), _ptr(flags))
+        alive = moved.active[0, 0, 0, s][act]
+        xr = moved.x[0, 0, 0, s][act]; ur = moved.u[0, 0, 0, s][act]
+        assert np.array_equal(~np.isnan(comp[0]), alive)
+        for c in range(3):
+            assert np.allclose(comp[c][alive], xr[alive][:, c], rtol=tol, atol=tol * 4), ("x", s, c)
+            assert np.allclose(comp[3 + c][alive], ur[alive][:, c], rtol=tol, atol=tol * 10), ("u", s, c)
+    scale = max(np.abs(r).max() for r in Jref)
+    for c in range(3):
+        assert np.allclose(J[c], Jref[c][0, 0, 0], rtol=tol, atol=tol * scale), ("J", c)
+    assert flags[0] == 0
+    if shift == 0 and W == 1:
+        assert flags[2] == 0        # every particle is covered by the tile of its own supercell
+    if shift != 0:
+        assert flags[2] > 0         # some particles are not: they took the scalar global-memory body
+
+
 # ---- the kernel's push body (gather + pusher, as the CUDA kernels execute it) through the reference's pusher physics tests -----
 def _kernel_push(hc, pusher_name, v, E, B, dt, steps, E_of_step=None):
     """One particle at the origin of a 1x1x1 domain with uniform fields, q = m = C = 1, pushed `steps` times by slot_push."""

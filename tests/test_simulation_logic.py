@@ -19,7 +19,10 @@ def _bare(**kw):
 
 def test_k1_variant_selection(monkeypatch):
     monkeypatch.delenv("PIC_K1_VARIANT", raising=False)
-    assert _bare()._pick_k1_variant(None) == "tile"
+    assert _bare()._pick_k1_variant(None) == "pair"            # K1 v10 is the default for the headline configuration
+    monkeypatch.setenv("PIC_K1_VARIANT", "tile")
+    assert _bare()._pick_k1_variant(None) == "tile"            # K1 v9, the A/B control
+    monkeypatch.delenv("PIC_K1_VARIANT", raising=False)
     for bad in (dict(deposition=1), dict(ext_E=[object()]),
                 dict(p=SimpleNamespace(shape_factor=2, g=2, pusher=1, tile=(8, 8, 4), gmesh=(1, 1, 1))),
                 dict(p=SimpleNamespace(shape_factor=1, g=1, pusher=1, tile=(8, 8, 4), gmesh=(1, 1, 1))),

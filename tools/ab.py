@@ -35,22 +35,22 @@ def lib_of(name):
 
 def build(specs):
     from pypic3d_b200 import _lib
-    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     for spec in specs:
         name, flags, _ = split(spec)
         os.makedirs(os.path.dirname(lib_of(name)), exist_ok=True)
-        cmd = ([nvcc] + _lib.NVCC_FLAGS + ["-Xptxas", "-v"] + flags + ["-o", lib_of(name)]
-               + [os.path.join(ROOT, "pypic3d_b200", "csrc", f) for f in _lib.SOURCES])
-        out = subprocess.run(cmd, check=True, capture_output=True, text=True).stderr
-        spilled, entry = [], ""
+        _, out = _lib.build(force=True, extra_flags=tuple(flags), out=lib_of(name), ptxas_verbose=True)
+        spilled, entry, regs = [], "", {}
         for l in out.splitlines():                                   # ptxas -v: "Compiling entry function '<name>'" ... "N bytes spill stores"
             if "Compiling entry function" in l:
                 entry = l.split("'")[1]
             elif "spill stores" in l and "0 bytes spill stores, 0 bytes spill loads" not in l:
                 spilled.append(entry)
-        tile = [e for e in spilled if "k_tile3d" in e]
-        print(f"{name}: built {lib_of(name)} ({' '.join(flags) or 'default flags'}); spilling kernels: k_tile3d {len(tile)}, "
-              f"others {len(spilled) - len(tile)} (the general-configuration kernels spill in the default build too)")
+            elif "Used " in l and "registers" in l:
+                regs[entry] = int(l.split("Used ")[1].split(" ")[0])
+        hot = [e for e in spilled if "k_tile3d" in e or "k_pair3d" in e]
+        hot_regs = sorted({v for e, v in regs.items() if "k_pair3d" in e})
+        print(f"{name}: built {lib_of(name)} ({' '.join(flags) or 'default flags'}); spilling hot kernels: {len(hot)}, "
+              f"others {len(spilled) - len(hot)} (the general-configuration kernels spill in the default build too); k_pair3d registers {hot_regs}")
 
 
 def run(specs, bench_args):
