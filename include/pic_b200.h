@@ -113,6 +113,16 @@ int pic_update_E(const PicParams* p, void* const E[3], const void* const B[3], c
 /* solvers/first_order_yee.py:116-142 : B[A] -= (dt/2) curl E on every tile interior (half step). */
 int pic_update_B(const PicParams* p, void* const B[3], const void* const E[3], void* stream);
 
+/* The whole field half of the step -- update_B (half, E_old) -> update_E -> update_B (half, E_new), evolve.py:88-96 with
+ * solvers/first_order_yee.py:12-162 -- for ONE ghosted tile in one pass: 15 reals per cell instead of 30 plus three refreshes.
+ * Reads E, B (guard cells valid two deep) and J (interior folded; on an axis split across ranks also its first upper guard plane
+ * refreshed), writes E_out, B_out != E, B: interior, the guard cells of single-rank periodic axes (wrapped copies), zeros stay in
+ * the exterior guards of non-periodic walls; the guard cells of axes split across ranks are left to the halo exchange.
+ * Conducting walls zero the tangential E on the first / last interior plane.  Bit-identical to the three sweeps + refreshes.
+ * PIC_EUNSUPPORTED for g < 2 or alpha != 1 (the digital filter needs the separate sweeps). */
+int pic_yee_fused(const PicParams* p, const void* const E[3], const void* const B[3], const void* const J[3], void* const E_out[3],
+                  void* const B_out[3], void* stream);
+
 /* utilities/filters.py:73/98 : out[A] = sum_27 k*in[A+off]; ghosts copied.  in != out. */
 int pic_filter(const PicParams* p, int kind, double alpha, const void* in, void* out, void* stream);
 
@@ -146,6 +156,13 @@ int pic_phi_boundaries(const PicParams* p, void* field, void* stream);
 int pic_constant_wall(const PicParams* p, int axis, void* field, void* stream);
 /* solvers/electrostatic_yee.py:212-246: E_c = -(phi[+1] - phi[-1]) / (2 d_c) on the tile interior (ghosts untouched). */
 int pic_gradient_neg(const PicParams* p, const void* phi, void* const E[3], void* stream);
+
+/* Conservation diagnostics (SURVEY.md section 8b pic_gauss_residual; not in the reference, which only tests the continuity
+ * invariant: tests/code_tests/esirkepov_test.py:700-744).  out[A] = div_backward(F)[A] + ca*a[A] + cb*b[A] on every tile interior
+ * (ghosts of `out` untouched; a / b may be NULL).  Gauss residual: F = E, a = rho, ca = -1/eps.  Discrete continuity:
+ * F = J, a = rho_new, ca = 1/dt, b = rho_old, cb = -1/dt. */
+int pic_div_residual(const PicParams* p, const void* const F[3], const void* a, double ca, const void* b, double cb, void* out,
+                     void* stream);
 
 /* utils.py:160-187 compute_energy pieces: out[0] += sum over interiors of f^2 (double accumulate). */
 int pic_sum_squares_interior(const PicParams* p, const void* field, double* out, void* stream);

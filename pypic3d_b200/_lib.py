@@ -80,14 +80,29 @@ def needs_build():
     return not os.path.exists(LIB_PATH) or built_hash() != source_hash()
 
 
+def _includes(fname, seen=None):
+    """Project headers a translation unit pulls in (recursive scan of #include "..." inside csrc/)."""
+    seen = set() if seen is None else seen
+    path = os.path.join(_HERE, "csrc", fname)
+    with open(path) as fh:
+        for line in fh:
+            line = line.strip()
+            if line.startswith("#include \""):
+                inc = os.path.basename(line.split("\"")[1])
+                if inc not in seen and os.path.exists(os.path.join(_HERE, "csrc", inc)):
+                    seen.add(inc)
+                    _includes(inc, seen)
+    return seen
+
+
 def _tu_hash(src, extra_flags=()):
     h = hashlib.sha256()
-    for f in [src] + HEADERS:
+    for f in [src] + sorted(_includes(src)):
         with open(os.path.join(_HERE, "csrc", f), "rb") as fh:
             h.update(f.encode()); h.update(fh.read())
     with open(os.path.join(_ROOT, "include", "pic_b200.h"), "rb") as fh:
         h.update(fh.read())
-    h.update(" ".join(list(NVCC_FLAGS) + list(extra_flags)).encode())
+    h.update(" ".join(list(COMPILE_FLAGS) + list(extra_flags)).encode())
     return h.hexdigest()[:16]
 
 
@@ -188,6 +203,7 @@ SIGNATURES = {
     "pic_retile": [_PP, _VP, _VP, _VP, _VP, _VP, _VP, _I64, _VP, _VP, _VP],
     "pic_update_E": [_PP, _V3, _V3, _V3, _VP],
     "pic_update_B": [_PP, _V3, _V3, _VP],
+    "pic_yee_fused": [_PP, _V3, _V3, _V3, _V3, _V3, _VP],
     "pic_filter": [_PP, _INT, _DBL, _VP, _VP, _VP],
     "pic_halo_refresh_axis": [_PP, _INT, _INT, _INT, _V3, _VP],
     "pic_halo_fold_axis": [_PP, _INT, _INT, _INT, _V3, _VP],
@@ -198,6 +214,7 @@ SIGNATURES = {
     "pic_gradient_neg": [_PP, _VP, _V3, _VP],
     "pic_pack_planes": [_PP, _INT, _INT, _INT, _INT, _V3, _VP, _VP],
     "pic_unpack_planes": [_PP, _INT, _INT, _INT, _INT, _V3, _VP, _INT, _VP],
+    "pic_div_residual": [_PP, _V3, _VP, _DBL, _VP, _DBL, _VP, _VP],
     "pic_sum_squares_interior": [_PP, _VP, _VP, _VP],
     "pic_particle_energy": [_PP, _VP, _VP, _I64, _VP, _VP],
     "pic_soa_import": [_PP, _INT, _VP, _VP, _VP, _I64, _SOA, _VP, _VP],

@@ -148,6 +148,7 @@ __global__ void __launch_bounds__(256) k_fused(const __grid_constant__ PicParams
     TileSink<T> sink;
     for (int c = 0; c < 3; ++c) { sink.J[c] = J.f[c]; sink.L[c] = gm.L[c]; }
     sink.off = 0;
+    sink.flags = flags;
     bool distributed = false;
     for (int c = 0; c < 3; ++c) distributed |= (p.gmesh[c] != p.mesh[c]);
     const int64_t n = s.count();
@@ -189,6 +190,7 @@ __global__ void __launch_bounds__(256, (SF == 1 ? PIC_K1_CTAS : 2)) k_fused3d(co
     TileSink<T> sink;
     for (int c = 0; c < 3; ++c) { sink.J[c] = J.f[c]; sink.L[c] = gm.L[c]; }
     sink.off = 0;
+    sink.flags = flags;
     Field6<T> X;
     for (int c = 0; c < 6; ++c) X.f[c] = nullptr;
     const int lane = threadIdx.x & 31;
@@ -556,6 +558,7 @@ __global__ void __launch_bounds__(NW * 32, (sizeof(T) == 8 ? 1 : PIC_K9_CTAS)) k
     TileSink<T> sink;
     for (int c = 0; c < 3; ++c) { sink.J[c] = J.f[c]; sink.L[c] = gm.L[c]; }
     sink.off = 0;
+    sink.flags = flags;
     Field6<T> X;
     for (int c = 0; c < 6; ++c) X.f[c] = nullptr;
     const int tid = threadIdx.x;

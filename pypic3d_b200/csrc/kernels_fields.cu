@@ -431,6 +431,214 @@ static int launch_sumsq(const PicParams* p, const void* f, double* out, cudaStre
     PIC_LAUNCH_RET();
 }
 
+
+// ---------------------------------------------------------------- fused Yee step (first_order_yee.py:12-162, evolve.py:88-96)
+// B(half, E_old) -> E(full, B', J) -> B(half, E_new) for one tile in ONE pass over the fields: 15 reals per cell (read E, B, J,
+// write E, B) instead of 30 for the three sweeps plus their guard-cell refreshes.  A CTA stages the E box [-1, +2] and the B box
+// [-1, +1] around its TX x TY x TZ cells in shared memory, recomputes the intermediate B' on [-1, +1] and E_new on [0, +1] (the
+// one-cell redundancy the stencils need), and writes E_new, B_new of its own cells to the OUTPUT arrays (never in place: other CTAs
+// still read the old values).  Same expressions as k_update_B / k_update_E, so the results are bit-identical to the three sweeps.
+// How an axis side is closed (per side, YeeSides):
+//   WRAP  single-rank periodic axis: indices outside the interior are wrapped; the epilogue also writes the guard copies;
+//   HALO  the guard cells hold the neighbour rank's values (refreshed E, B two deep, J one deep): intermediates are recomputed;
+//   WALL  non-periodic global boundary: the refresh the reference performs leaves zeros in the exterior guards, so the
+//         intermediates there are zero; conducting walls zero the tangential E on the first / last interior plane.
+constexpr int YEE_WRAP = 0, YEE_HALO = 1, YEE_WALL = 2;
+struct YeeSides {
+    int lo[3], hi[3];        // YEE_* per axis side
+    int cond_lo[3], cond_hi[3];   // conducting wall on this rank's low / high side of the axis
+};
+constexpr int YTX = 4, YTY = 8, YTZ = 32;
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_yee_fused(Dims d, YeeSides sd, const T* __restrict__ Ex, const T* __restrict__ Ey,
+                                                   const T* __restrict__ Ez, const T* __restrict__ Bx, const T* __restrict__ By,
+                                                   const T* __restrict__ Bz, const T* __restrict__ Jx, const T* __restrict__ Jy,
+                                                   const T* __restrict__ Jz, T* __restrict__ Ex2, T* __restrict__ Ey2, T* __restrict__ Ez2,
+                                                   T* __restrict__ Bx2, T* __restrict__ By2, T* __restrict__ Bz2, T dt, T hdt, T dx, T dy,
+                                                   T dz, T C2, T eps, int nbx, int nby, int nbz) {
+    constexpr int EX = YTX + 3, EY = YTY + 3, EZ = YTZ + 3;      // E box: cells [-1, T + 2)
+    constexpr int BX = YTX + 2, BY = YTY + 2, BZ = YTZ + 2;      // B box: cells [-1, T + 1)
+    extern __shared__ __align__(16) unsigned char yee_smem[];
+    T* sE = reinterpret_cast<T*>(yee_smem);                      // [3][EX][EY][EZ]
+    T* sB = sE + 3 * EX * EY * EZ;                               // [3][BX][BY][BZ]
+    int b = blockIdx.x;
+    const int bz = b % nbz; b /= nbz;
+    const int by = b % nby; b /= nby;
+    const int bx = b;
+    const int o[3] = {d.g + bx * YTX, d.g + by * YTY, d.g + bz * YTZ};       // array index of the tile's first cell
+    const int g = d.g;
+    const size_t sx = (size_t)d.L[1] * d.L[2], sy = d.L[2];
+    const int tid = threadIdx.x;
+    // array index -> source index (WRAP) and "is an exterior guard cell of a wall" (WALL)
+    auto src = [&](int a, int i) {       // (modulo wrap: a reduced axis, W = 1, maps every guard index to its single interior plane)
+        if ((i < g && sd.lo[a] == YEE_WRAP) || (i >= d.L[a] - g && sd.hi[a] == YEE_WRAP)) {
+            int r = (i - g) % d.W[a];
+            if (r < 0) r += d.W[a];
+            return g + r;
+        }
+        return i;
+    };
+    auto wall = [&](int a, int i) { return (i < g && sd.lo[a] == YEE_WALL) || (i >= d.L[a] - g && sd.hi[a] == YEE_WALL); };
+    auto clampi = [&](int a, int i) { return i < 0 ? 0 : (i > d.L[a] - 1 ? d.L[a] - 1 : i); };
+    // ---- phase 0: stage E_old on [-1, +2] and B_old on [-1, +1]
+    for (int l = tid; l < EX * EY * EZ; l += 256) {
+        const int lz = l % EZ, ly = (l / EZ) % EY, lx = l / (EZ * EY);
+        const size_t gi = (size_t)src(0, clampi(0, o[0] - 1 + lx)) * sx + (size_t)src(1, clampi(1, o[1] - 1 + ly)) * sy + src(2, clampi(2, o[2] - 1 + lz));
+        sE[l] = Ex[gi]; sE[EX * EY * EZ + l] = Ey[gi]; sE[2 * EX * EY * EZ + l] = Ez[gi];
+    }
+    for (int l = tid; l < BX * BY * BZ; l += 256) {
+        const int lz = l % BZ, ly = (l / BZ) % BY, lx = l / (BZ * BY);
+        const size_t gi = (size_t)src(0, clampi(0, o[0] - 1 + lx)) * sx + (size_t)src(1, clampi(1, o[1] - 1 + ly)) * sy + src(2, clampi(2, o[2] - 1 + lz));
+        sB[l] = Bx[gi]; sB[BX * BY * BZ + l] = By[gi]; sB[2 * BX * BY * BZ + l] = Bz[gi];
+    }
+    __syncthreads();
+    constexpr int ESX = EY * EZ, ESY = EZ, BSX = BY * BZ, BSY = BZ;
+    T* sEx = sE; T* sEy = sE + EX * EY * EZ; T* sEz = sE + 2 * EX * EY * EZ;
+    T* sBx = sB; T* sBy = sB + BX * BY * BZ; T* sBz = sB + 2 * BX * BY * BZ;
+    // ---- phase 1: B' = B - (dt/2) curl_forward(E_old) on [-1, +1]  (k_update_B; exterior wall guards: zero)
+    for (int l = tid; l < BX * BY * BZ; l += 256) {
+        const int lz = l % BZ, ly = (l / BZ) % BY, lx = l / (BZ * BY);
+        const int ai[3] = {o[0] - 1 + lx, o[1] - 1 + ly, o[2] - 1 + lz};
+        const int e = lx * ESX + ly * ESY + lz;                  // same cell in the E box (both boxes start at -1)
+        const T ex = sEx[e], ey = sEy[e], ez = sEz[e];
+        const T dEz_dy = (sEz[e + ESY] - ez) / dy;
+        const T dEy_dz = (sEy[e + 1] - ey) / dz;
+        const T dEx_dz = (sEx[e + 1] - ex) / dz;
+        const T dEx_dy = (sEx[e + ESY] - ex) / dy;
+        const T dEz_dx = (sEz[e + ESX] - ez) / dx;
+        const T dEy_dx = (sEy[e + ESX] - ey) / dx;
+        const bool w = wall(0, ai[0]) || wall(1, ai[1]) || wall(2, ai[2]);
+        const bool inner = ai[0] >= g && ai[0] < d.L[0] - g && ai[1] >= g && ai[1] < d.L[1] - g && ai[2] >= g && ai[2] < d.L[2] - g;
+        // a guard cell of a HALO / WRAP side is recomputed like the interior cell it mirrors; wall guards hold zeros
+        (void)inner;
+        sBx[l] = w ? (T)0 : sBx[l] - hdt * (dEz_dy - dEy_dz);
+        sBy[l] = w ? (T)0 : sBy[l] - hdt * (dEx_dz - dEz_dx);
+        sBz[l] = w ? (T)0 : sBz[l] - hdt * (dEy_dx - dEx_dy);
+    }
+    __syncthreads();
+    // ---- phase 2: E_new = E + dt (C^2 curl_backward(B') - J / eps) on [0, +1]  (k_update_E; walls as above)
+    constexpr int PX = YTX + 1, PY = YTY + 1, PZ = YTZ + 1;
+    for (int l = tid; l < PX * PY * PZ; l += 256) {
+        const int lz = l % PZ, ly = (l / PZ) % PY, lx = l / (PZ * PY);
+        const int ai[3] = {o[0] + lx, o[1] + ly, o[2] + lz};
+        const int e = (lx + 1) * ESX + (ly + 1) * ESY + (lz + 1);
+        const int bb = (lx + 1) * BSX + (ly + 1) * BSY + (lz + 1);
+        const T bx_ = sBx[bb], by_ = sBy[bb], bz_ = sBz[bb];
+        const T dBz_dy = (bz_ - sBz[bb - BSY]) / dy;
+        const T dBy_dz = (by_ - sBy[bb - 1]) / dz;
+        const T dBx_dz = (bx_ - sBx[bb - 1]) / dz;
+        const T dBx_dy = (bx_ - sBx[bb - BSY]) / dy;
+        const T dBz_dx = (bz_ - sBz[bb - BSX]) / dx;
+        const T dBy_dx = (by_ - sBy[bb - BSX]) / dx;
+        const bool w = wall(0, ai[0]) || wall(1, ai[1]) || wall(2, ai[2]);
+        const size_t gi = (size_t)src(0, clampi(0, ai[0])) * sx + (size_t)src(1, clampi(1, ai[1])) * sy + src(2, clampi(2, ai[2]));
+        T ex = sEx[e] + (C2 * (dBz_dy - dBy_dz) - Jx[gi] / eps) * dt;
+        T ey = sEy[e] + (C2 * (dBx_dz - dBz_dx) - Jy[gi] / eps) * dt;
+        T ez = sEz[e] + (C2 * (dBy_dx - dBx_dy) - Jz[gi] / eps) * dt;
+        // conducting walls: tangential E vanishes on the first / last interior plane (first_order_yee.py:80-89)
+        const bool cx = (sd.cond_lo[0] && ai[0] == g) || (sd.cond_hi[0] && ai[0] == d.L[0] - g - 1);
+        const bool cy = (sd.cond_lo[1] && ai[1] == g) || (sd.cond_hi[1] && ai[1] == d.L[1] - g - 1);
+        const bool cz = (sd.cond_lo[2] && ai[2] == g) || (sd.cond_hi[2] && ai[2] == d.L[2] - g - 1);
+        if (cy || cz || w) ex = (T)0;
+        if (cx || cz || w) ey = (T)0;
+        if (cx || cy || w) ez = (T)0;
+        sEx[e] = ex; sEy[e] = ey; sEz[e] = ez;
+    }
+    __syncthreads();
+    // ---- phase 3: B_new = B' - (dt/2) curl_forward(E_new) on the tile's own cells; store E_new, B_new (+ wrapped guard copies)
+    for (int l = tid; l < YTX * YTY * YTZ; l += 256) {
+        const int lz = l % YTZ, ly = (l / YTZ) % YTY, lx = l / (YTZ * YTY);
+        const int ai[3] = {o[0] + lx, o[1] + ly, o[2] + lz};
+        if (ai[0] >= d.L[0] - g || ai[1] >= d.L[1] - g || ai[2] >= d.L[2] - g) continue;       // partial tile at the upper end
+        const int e = (lx + 1) * ESX + (ly + 1) * ESY + (lz + 1);
+        const int bb = (lx + 1) * BSX + (ly + 1) * BSY + (lz + 1);
+        const T ex = sEx[e], ey = sEy[e], ez = sEz[e];
+        const T dEz_dy = (sEz[e + ESY] - ez) / dy;
+        const T dEy_dz = (sEy[e + 1] - ey) / dz;
+        const T dEx_dz = (sEx[e + 1] - ex) / dz;
+        const T dEx_dy = (sEx[e + ESY] - ex) / dy;
+        const T dEz_dx = (sEz[e + ESX] - ez) / dx;
+        const T dEy_dx = (sEy[e + ESX] - ey) / dx;
+        const T bxn = sBx[bb] - hdt * (dEz_dy - dEy_dz);
+        const T byn = sBy[bb] - hdt * (dEx_dz - dEz_dx);
+        const T bzn = sBz[bb] - hdt * (dEy_dx - dEx_dy);
+        // guard copies along WRAP axes: a cell also lives at every index i + k W that falls into the guard layers
+        int off[3][6], noff[3];
+        for (int a = 0; a < 3; ++a) {
+            noff[a] = 1; off[a][0] = 0;
+            if (sd.lo[a] != YEE_WRAP) continue;                  // (WRAP closes both sides of an axis)
+            for (int kk = 1; kk * d.W[a] <= ai[a] && noff[a] < 6; ++kk) off[a][noff[a]++] = -kk * d.W[a];
+            for (int kk = 1; ai[a] + kk * d.W[a] < d.L[a] && noff[a] < 6; ++kk) off[a][noff[a]++] = kk * d.W[a];
+        }
+        for (int i0 = 0; i0 < noff[0]; ++i0)
+            for (int i1 = 0; i1 < noff[1]; ++i1)
+                for (int i2 = 0; i2 < noff[2]; ++i2) {
+                    const size_t gi = (size_t)(ai[0] + off[0][i0]) * sx + (size_t)(ai[1] + off[1][i1]) * sy + (ai[2] + off[2][i2]);
+                    Ex2[gi] = ex; Ey2[gi] = ey; Ez2[gi] = ez;
+                    Bx2[gi] = bxn; By2[gi] = byn; Bz2[gi] = bzn;
+                }
+    }
+}
+
+template <typename T>
+static int launch_yee_fused(const PicParams* p, const void* const E[3], const void* const B[3], const void* const J[3], void* const E2[3],
+                            void* const B2[3], cudaStream_t st) {
+    const Dims d = dims_of(p);
+    YeeSides sd;
+    for (int a = 0; a < 3; ++a) {
+        const bool split = p->gmesh[a] != p->mesh[a];
+        const bool periodic = p->field_bc[a] == PIC_BC_PERIODIC;
+        const bool at_lo = p->moff[a] == 0, at_hi = p->moff[a] + p->mesh[a] == p->gmesh[a];
+        sd.lo[a] = periodic ? (split ? YEE_HALO : YEE_WRAP) : (at_lo ? YEE_WALL : YEE_HALO);
+        sd.hi[a] = periodic ? (split ? YEE_HALO : YEE_WRAP) : (at_hi ? YEE_WALL : YEE_HALO);
+        sd.cond_lo[a] = (p->field_bc[a] == PIC_BC_CONDUCTING && at_lo) ? 1 : 0;
+        sd.cond_hi[a] = (p->field_bc[a] == PIC_BC_CONDUCTING && at_hi) ? 1 : 0;
+        if (d.W[a] > 1 && d.W[a] < d.g) return PIC_EUNSUPPORTED;     // (only reduced axes may be narrower than the guard depth)
+    }
+    const int nbx = (d.W[0] + YTX - 1) / YTX, nby = (d.W[1] + YTY - 1) / YTY, nbz = (d.W[2] + YTZ - 1) / YTZ;
+    const size_t smem = (size_t)(3 * (YTX + 3) * (YTY + 3) * (YTZ + 3) + 3 * (YTX + 2) * (YTY + 2) * (YTZ + 2)) * sizeof(T);
+    static size_t attr = 0;
+    if (attr < smem) {
+        cudaError_t e = cudaFuncSetAttribute(k_yee_fused<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        attr = smem;
+    }
+    k_yee_fused<T><<<nbx * nby * nbz, 256, smem, st>>>(d, sd, (const T*)E[0], (const T*)E[1], (const T*)E[2], (const T*)B[0], (const T*)B[1],
+                                                       (const T*)B[2], (const T*)J[0], (const T*)J[1], (const T*)J[2], (T*)E2[0], (T*)E2[1],
+                                                       (T*)E2[2], (T*)B2[0], (T*)B2[1], (T*)B2[2], (T)p->dt, (T)(p->dt / 2), (T)p->dx,
+                                                       (T)p->dy, (T)p->dz, (T)(p->C * p->C), (T)p->eps, nbx, nby, nbz);
+    PIC_LAUNCH_RET();
+}
+
+// ---------------------------------------------------------------- divergence residuals (conservation diagnostics)
+// out[A] = div_backward(F)[A] + ca * a[A] + cb * b[A] on every tile interior: with F = E, a = rho, ca = -1/eps this is the Gauss
+// residual div E - rho/eps; with F = J, a = rho_new, b = rho_old, ca = -cb = 1/dt the discrete continuity residual
+// (rho_new - rho_old)/dt + div J that Esirkepov's deposition keeps at round-off (the reference checks it in
+// tests/code_tests/esirkepov_test.py:700-744).  Backward differences: E/J components sit half a cell above the nodes of rho.
+template <typename T>
+__global__ void __launch_bounds__(256) k_div_residual(Dims d, int nby, int nbz, const T* __restrict__ Fx, const T* __restrict__ Fy,
+                                                      const T* __restrict__ Fz, const T* __restrict__ a, T ca, const T* __restrict__ b,
+                                                      T cb, T* __restrict__ out, T dx, T dy, T dz) {
+    int64_t tile; int ix, iy, iz;
+    if (!cell_of_block(d, nby, nbz, tile, ix, iy, iz)) return;
+    const size_t sx = (size_t)d.L[1] * d.L[2], sy = d.L[2];
+    const size_t i = tile * d.tile_elems + ix * sx + iy * sy + iz;
+    T r = (Fx[i] - Fx[i - sx]) / dx + (Fy[i] - Fy[i - sy]) / dy + (Fz[i] - Fz[i - 1]) / dz;
+    if (a) r += ca * a[i];
+    if (b) r += cb * b[i];
+    out[i] = r;
+}
+template <typename T>
+static int launch_div_residual(const PicParams* p, const void* const F[3], const void* a, double ca, const void* b, double cb, void* out,
+                               cudaStream_t st) {
+    const Dims d = dims_of(p);
+    const CellGrid cg = cell_grid(d);
+    k_div_residual<T><<<cg.grid, cg.block, 0, st>>>(d, cg.nby, cg.nbz, (const T*)F[0], (const T*)F[1], (const T*)F[2], (const T*)a, (T)ca,
+                                                    (const T*)b, (T)cb, (T*)out, (T)p->dx, (T)p->dy, (T)p->dz);
+    PIC_LAUNCH_RET();
+}
+
 }  // namespace pic
 
 using namespace pic;
@@ -494,6 +702,21 @@ int pic_unpack_planes(const PicParams* p, int axis, int start, int nplanes, int 
     PIC_CHECK_ARG(halo_args_ok(p, axis, ncomp, fields) && buf && start >= 0 && nplanes >= 0 &&
                   start + nplanes <= p->tile[axis] + 2 * p->g && mode >= 0 && mode <= 2);
     PIC_DISPATCH_T(p, launch_planes, p, 1, axis, start, nplanes, ncomp, fields, (void*)buf, mode, (cudaStream_t)stream);
+}
+
+int pic_yee_fused(const PicParams* p, const void* const E[3], const void* const B[3], const void* const J[3], void* const E_out[3],
+                  void* const B_out[3], void* stream) {
+    PIC_CHECK_ARG(p && E && B && J && E_out && B_out);
+    PIC_CHECK_ARG(p->mesh[0] == 1 && p->mesh[1] == 1 && p->mesh[2] == 1);
+    if (p->g < 2 || p->alpha != 1.0) return PIC_EUNSUPPORTED;   // the E box reaches two guard cells; the digital filter needs the sweeps
+    for (int c = 0; c < 3; ++c) PIC_CHECK_ARG(E[c] != E_out[c] && B[c] != B_out[c]);
+    PIC_DISPATCH_T(p, launch_yee_fused, p, E, B, J, E_out, B_out, (cudaStream_t)stream);
+}
+
+int pic_div_residual(const PicParams* p, const void* const F[3], const void* a, double ca, const void* b, double cb, void* out,
+                     void* stream) {
+    PIC_CHECK_ARG(p && F && out && p->g >= 1);
+    PIC_DISPATCH_T(p, launch_div_residual, p, F, a, ca, b, cb, out, (cudaStream_t)stream);
 }
 
 int pic_sum_squares_interior(const PicParams* p, const void* field, double* out, void* stream) {

@@ -38,10 +38,14 @@ namespace pic {
 #ifndef PIC_K10_NSTAGE
 #define PIC_K10_NSTAGE 3
 #endif
+#ifndef PIC_K10_DEAL
+#define PIC_K10_DEAL 0         /* chunks of a supercell reach the warps 0: round-robin continuing across supercells, 1: through a shared-memory counter */
+#endif
 #ifndef PIC_K10_W
 #define PIC_K10_W 2            /* particles per thread in float (1 = scalar control) */
 #endif
-constexpr int K10_PCAP = 640;   // staged particle slots per supercell and array (mean 512 at 8 ppc per species)
+// staged particle slots per supercell and array (mean 512 at 8 ppc per species); double with the wider tile: 576, to fit 227 KB
+template <typename T> struct K10Cap { static constexpr int PCAP = (sizeof(T) == 8 && PIC_TILE_YPAD > 1) ? 576 : 640; };
 // per-warp queue of cell-crossers: flushed in full warps, so at most 31 wait while up to 32 W join in one iteration
 template <int W> struct K10Queue { static constexpr int QW = 32 * (W + 1); };
 
@@ -157,12 +161,12 @@ __device__ __forceinline__ void pair_group_red(T* v, int key, int lane, const Ti
     if (key >= 0 && lane == __ffs(group) - 1) red_cell<T>(sink, key0 + (key >> 6) * sx + ((key >> 3) & 7) * sy + (key & 7), sx, sy, v);
 }
 
-constexpr int K10_STAGE_ELEMS = 6 * TILE_ELEMS + 6 * K10_PCAP;
+template <typename T> struct K10Stage { static constexpr int ELEMS = 6 * TILE_ELEMS + 6 * K10Cap<T>::PCAP; };
 constexpr int K10_HDR = 512;    // barriers + descriptors in front of the ring
 
 template <typename T, int W, int NWC>
 struct PairSmem {
-    static constexpr size_t bytes = (size_t)K10_HDR + (size_t)PIC_K10_NSTAGE * K10_STAGE_ELEMS * sizeof(T)
+    static constexpr size_t bytes = (size_t)K10_HDR + (size_t)PIC_K10_NSTAGE * K10Stage<T>::ELEMS * sizeof(T)
                                     + (size_t)NWC * K10Queue<W>::QW * (sizeof(int) + 6 * sizeof(T));
 };
 
@@ -174,9 +178,9 @@ k_pair3d(const __grid_constant__ PicParams p, int species, const __grid_constant
          const __grid_constant__ LeaveBuf leave, int distributed, int32_t* flags, const __grid_constant__ TileMaps tm,
          const int32_t* __restrict__ blk_off, int nblk, int nbx, int nby, int nbz) {
     constexpr int NSTAGE = PIC_K10_NSTAGE;
-    constexpr int PCAP = K10_PCAP, QW = K10Queue<W>::QW;
+    constexpr int PCAP = K10Cap<T>::PCAP, QW = K10Queue<W>::QW;
     constexpr int TILE_ALL = 6 * TILE_ELEMS;
-    constexpr int STAGE_ELEMS = K10_STAGE_ELEMS;
+    constexpr int STAGE_ELEMS = K10Stage<T>::ELEMS;
     constexpr int AL = 16 / (int)sizeof(T);
     constexpr int CH = 32 * W;                               // particles per chunk (one warp iteration)
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -201,13 +205,22 @@ k_pair3d(const __grid_constant__ PicParams p, int species, const __grid_constant
 
     // ------------------------------------------------------------------ producer warp: one thread feeds the ring
     if (warp == NWC) {
-        if (lane == 0) {
+        if (lane == 0 && b1 > b0) {
+            // slice bounds are read two supercells ahead of their use, so the producer never sits on a DRAM round trip between a
+            // stage being released and its refill being issued
+            int beg = blk_off[b0];
+            int end_next = blk_off[b0 + 1];
+            int end_next2 = (b0 + 2 <= nblk) ? blk_off[b0 + 2] : end_next;
             for (int b = b0; b < b1; ++b) {
                 const int j = b - b0, sr = j % NSTAGE;
-                if (j >= NSTAGE) mbar_wait(empty + sr, ((j / NSTAGE) - 1) & 1);        // previous occupant: supercell b - NSTAGE
+                int end = end_next;
+                const int beg_following = end;
+                end_next = end_next2;
+                if (b + 3 <= nblk) end_next2 = blk_off[b + 3];
+                if (j >= NSTAGE) {                               // previous occupant: supercell b - NSTAGE (suspended wait, no spinning)
+                    while (!mbar_try_wait(empty + sr, ((j / NSTAGE) - 1) & 1, 20000)) {}
+                }
                 const int bz = b % nbz, by = (b / nbz) % nby, bx = b / (nbz * nby);
-                const int beg = blk_off[b];
-                int end = blk_off[b + 1];
                 if (end > n_live) end = n_live;
                 int n = 0;
                 if (end > beg && !(beg & (AL - 1))) {
@@ -216,12 +229,13 @@ k_pair3d(const __grid_constant__ PicParams p, int species, const __grid_constant
                     if (beg + n > cap_al) n = cap_al - beg;
                     if (n < 0) n = 0;
                 }
-                if (beg & (AL - 1)) atomicOr(flags, 8);          // contract: slices come from the padded sort (pic_sort_blocked)
+                if (beg & (AL - 1)) atomicOr(flags, 8);          // contract: slices come from the padded sort (pic_sort_blocked_*)
                 int* d = desc + sr * 8;
                 const int ox = bx * TILE_B + gm.g - 2, oy = by * TILE_B + gm.g - 2, oz = bz * TILE_B + gm.g - 2;
                 d[0] = beg; d[1] = (beg & (AL - 1)) ? beg : end; d[2] = beg + n;
                 d[3] = (bx == 0 || bx == nbx - 1 || by == 0 || by == nby - 1 || bz == 0 || bz == nbz - 1) ? 1 : 0;
                 d[4] = ox * k.sx + oy * k.sy + oz;
+                d[5] = 0;                                        // (PIC_K10_DEAL == 1) next undealt chunk of this supercell
                 T* x0 = dx0 + sr * 4;
                 x0[0] = pic_fma((T)ox, k.sc[0], k.oc[0]); x0[1] = pic_fma((T)oy, k.sc[1], k.oc[1]); x0[2] = pic_fma((T)oz, k.sc[2], k.oc[2]);
                 T* st = stages + sr * STAGE_ELEMS;
@@ -232,6 +246,7 @@ k_pair3d(const __grid_constant__ PicParams p, int species, const __grid_constant
 #pragma unroll
                     for (int c = 0; c < 6; ++c) tma_load_bytes(st + TILE_ALL + c * PCAP, s.c[c] + beg, n * (int)sizeof(T), full + sr);
                 }
+                beg = beg_following;
             }
         }
         return;
@@ -241,6 +256,7 @@ k_pair3d(const __grid_constant__ PicParams p, int species, const __grid_constant
     TileSink<T> sink;
     for (int c = 0; c < 3; ++c) { sink.J[c] = J.f[c]; sink.L[c] = gm.L[c]; }
     sink.off = 0;
+    sink.flags = flags;
     Field6<T> X;
     for (int c = 0; c < 6; ++c) X.f[c] = nullptr;
     int* qi = reinterpret_cast<int*>(qraw) + warp * QW;                                                 // [NWC][QW] particle index
@@ -271,11 +287,21 @@ k_pair3d(const __grid_constant__ PicParams p, int species, const __grid_constant
         const T* tile = stages + slot * STAGE_ELEMS;
         const T* pst = tile + TILE_ALL;
         const int nchunk = p_end > p_beg ? (p_end - p_beg + CH - 1) / CH : 0;
+#if PIC_K10_DEAL == 1
+        for (;;) {
+            int ch = 0;
+            if (lane == 0) ch = atomicAdd(desc + slot * 8 + 5, 1);
+            ch = __shfl_sync(0xffffffffu, ch, 0);
+            if (ch >= nchunk) break;
+#else
         for (int ch = (warp + NWC - rot) % NWC; ch < nchunk; ch += NWC) {
+#endif
             const int i0 = p_beg + ch * CH + W * lane;
             Vec<T, W> pos[3], vel[3];
             bool live[W];
-            if (p_beg + (ch + 1) * CH <= staged_end) {                     // the whole chunk sits in the staged slice
+            // the chunk's live slots all sit in the staged slice (the lanes past p_end read stage memory that is never used)
+            const int ch_end = (p_beg + (ch + 1) * CH < p_end) ? p_beg + (ch + 1) * CH : p_end;
+            if (ch_end <= staged_end && (ch + 1) * CH <= PCAP) {
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
                     pos[c] = ld_vec<T, W>(pst + c * PCAP + (i0 - p_beg));
@@ -358,8 +384,9 @@ k_pair3d(const __grid_constant__ PicParams p, int species, const __grid_constant
                 if constexpr (W == 2) {
                     const bool dA = kind[0] == PAIR_SAME, dB = kind[1] == PAIR_SAME;
                     const bool solo = dA && dB && (cid[0] != cid[1]);      // the pair straddles a cell boundary: B goes out by itself
+                    const T mB = solo ? (T)0 : (T)1;                       // (B's values are exact zeros unless it deposits: one FMA per value)
 #pragma unroll
-                    for (int n = 0; n < 12; ++n) lv[n] = solo ? vals[n].v[0] : vals[n].v[0] + vals[n].v[1];
+                    for (int n = 0; n < 12; ++n) lv[n] = pic_fma(vals[n].v[1], mB, vals[n].v[0]);
                     key = dA ? cid[0] : (dB ? cid[1] : -1 - lane);
                     if (solo) {
                         T bv[12];

@@ -225,6 +225,7 @@ struct TileSink {
     T* J[3];
     size_t off;
     int L[3];
+    int32_t* flags = nullptr;   // when set: flags[0] |= 4 if a particle moved more than one cell in a step (its current is NOT deposited)
     PIC_HD void add(int c, int ix, int iy, int iz, T val) const {
         if ((unsigned)ix >= (unsigned)L[0] || (unsigned)iy >= (unsigned)L[1] || (unsigned)iz >= (unsigned)L[2]) return;
         T* ptr = J[c] + off + ((size_t)ix * L[1] + iy) * L[2] + iz;
@@ -232,6 +233,14 @@ struct TileSink {
         atomicAdd(ptr, val);
 #else
         *ptr += val;
+#endif
+    }
+    PIC_HD void report_cfl() const {
+        if (!flags) return;
+#if defined(__CUDA_ARCH__)
+        atomicOr(flags, 4);
+#else
+        *flags |= 4;
 #endif
     }
     PIC_HD void add_unchecked(T* ptr, T val) const {
@@ -268,7 +277,10 @@ PIC_HD void esirkepov_deposit(const Geom<T>& gm, const T xo[3], const T xn[3], c
             continue;
         }
         const int s = an - ao;  // shift_old_stencil, Esirkepov.py:17-25
-        if (s > 1 || s < -1) return;  // > 1 cell per step violates the Courant limit; the reference result is undefined
+        if (s > 1 || s < -1) {        // > 1 cell per step violates the Courant limit; the reference result is undefined
+            sink.report_cfl();
+            return;
+        }
         n[a] = NS;
         const int b = ((SF == 1) ? 2 : 1) - (s > 0 ? s : 0);  // first visited slot of the 5-slot frame
         base_idx[a] = an - 2 + b;

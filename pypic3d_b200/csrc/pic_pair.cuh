@@ -146,7 +146,9 @@ template <> struct Magic<float> { static constexpr float value = 12582912.0f; };
 template <> struct Magic<double> { static constexpr double value = 6755399441055744.0; };         // 1.5 * 2^52
 PIC_HD int magic_int(float t) {
 #if defined(__CUDA_ARCH__)
-    return __float_as_int(t) - 0x4B400000;
+    int v = __float_as_int(t) - 0x4B400000;
+    asm("" : "+r"(v));      // keep the small integer a value of its own: folded into the address arithmetic, the 0x4B400000 no
+    return v;               // longer fits the load instructions' immediate offsets and costs one add PER LOAD
 #else
     int32_t b;
     memcpy(&b, &t, 4);
@@ -236,14 +238,16 @@ constexpr int PAIR_SLOW = 3;      // NOT advanced: its stencil is not covered by
 // Per-launch constants of the pair body that FastConst does not already carry.
 template <typename T>
 struct PairConst {
-    T dt_inv_d[3];     // dt / d_a
+    T dt_inv_d[3];     // dt / d_a   (0 on an axis this species does not move along: SpeciesConfig.update_x)
+    T dt_move[3];      // dt         (0 on such an axis)
     T ndJ[3];          // -dJ_a = (q w / (d_b d_c)) / dt: current per unit of (r0 - r1) ... sign folded, see pair_advance
     T half[3];         // wind_a / 2
 };
 template <typename T>
 PIC_HD void make_pair_const(const FastConst<T>& k, PairConst<T>& pc) {
     for (int a = 0; a < 3; ++a) {
-        pc.dt_inv_d[a] = k.dt * k.inv_d[a];
+        pc.dt_inv_d[a] = k.upd_x[a] ? k.dt * k.inv_d[a] : (T)0;
+        pc.dt_move[a] = k.upd_x[a] ? k.dt : (T)0;
         pc.ndJ[a] = -k.dJ[a];
         pc.half[a] = (T)0.5 * k.wind[a];
     }
@@ -371,14 +375,12 @@ PIC_HD void pair_advance(const FastConst<T>& k, const PairConst<T>& pc, const T*
     for (int a = 0; a < 3; ++a) {
         if (!k.upd_u[a]) vn[a] = vel[a];                           // frozen velocity component of this species (uniform branch)
         vel_out[a] = vn[a];
-        V qn = vfma(vn[a], vsplat<T, W>(pc.dt_inv_d[a]), q[a]);
-        if (!k.upd_x[a]) qn = q[a];                                // frozen axis: the particle does not move along it
+        const V qn = vfma(vn[a], vsplat<T, W>(pc.dt_inv_d[a]), q[a]);      // (frozen axis: dt_inv_d = dt_move = 0)
         const V tn = vmagic_floor(qn);
         r1[a] = vsub(qn, vadds(tn, -Magic<T>::value));
 #pragma unroll
         for (int j = 0; j < W; ++j) same[j] = same[j] && (magic_int(tn.v[j]) == ic[a][j]);
-        xraw[a] = vfma(vn[a], vsplat<T, W>(k.dt), pos[a]);
-        if (!k.upd_x[a]) xraw[a] = pos[a];
+        xraw[a] = vfma(vn[a], vsplat<T, W>(pc.dt_move[a]), pos[a]);
         const V th = vadds(xraw[a], pc.half[a]);
         pos_out[a] = vadds(th, -pc.half[a]);                       // what mod(x + h, wind) - h leaves an interior particle with
         if (edge) {

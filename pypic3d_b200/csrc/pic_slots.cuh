@@ -468,8 +468,7 @@ PIC_HD T wrap_periodic_fast(T x, T wind) {
     // one rarely-taken branch: interior particles only pay (x + h) - h, exactly what the reference's mod() leaves them with
     if (t >= wind || t < (T)0) {
         if (t >= (T)2 * wind || t < -wind) return wrap_periodic(x, wind);
-        t = (t >= wind) ? t - wind : t + wind;
-        if (t >= wind) t -= wind;
+        t = (t >= wind) ? t - wind : t + wind;     // (a tiny negative t rounds t + wind to wind: mod() leaves +h there too)
         const T w = t - h;
         return (w == -h && x >= h) ? h : w;
     }

@@ -120,13 +120,19 @@ class DistributedHalo:
         return [int(v) for v in t.tolist()]
 
     # ------------------------------------------------------------------ guard cells
-    def refresh_(self, fields, bcs):
+    def refresh_split_(self, fields, bcs):
+        """Refresh only along the axes that are split across ranks (the caller has filled the other axes' guard cells itself,
+        e.g. pic_yee_fused); same x -> y -> z order and full transverse extent, so edges and corners still propagate."""
+        self.refresh_(fields, bcs, only_split=True)
+
+    def refresh_(self, fields, bcs, only_split=False):
         """In-place refresh x -> y -> z (ghost_cells.py:181-215)."""
         g, p = self.g, self.p
         for axis in range(3):
             bc = int(bcs[axis])
             if not self._is_split(axis):
-                self.k.refresh_axis(p, axis, bc, fields)
+                if not only_split:
+                    self.k.refresh_axis(p, axis, bc, fields)
                 continue
             n = self._plane_elems(axis, len(fields))
             L = self.L[axis]

@@ -142,7 +142,10 @@ def initialize_simulation(toml_file, device=None, dtype=torch.float64, verbose=T
     if dynamic_config["dt"] is None:                                                          # :267-272
         dynamic_config["dt"] = courant_condition(static_config["cfl"], dx, dy, dz, SimpleNamespace(**dynamic_config))
     dt = dynamic_config["dt"]
-    static_config["Nt"] = int(static_config["Nt"]) if static_config["Nt"] is not None else int(dynamic_config["t_wind"] / dt)
+    nt_given = static_config["Nt"] is not None
+    static_config["Nt"] = int(static_config["Nt"]) if nt_given else int(dynamic_config["t_wind"] / dt)
+    if nt_given:                                   # initialization.py:279-283: an explicit Nt defines the time window
+        dynamic_config["t_wind"] = dt * static_config["Nt"]
     static_config["electrostatic"] = electrostatic                                            # :237-238
     static_config["current_deposition"] = "esirkepov" if static_config["current_calculation"] == "esirkepov" else "direct"
     static_config["current_filter"] = static_config["filter_j"]

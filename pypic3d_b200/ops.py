@@ -160,6 +160,15 @@ def zero_wall_(p, f, axis):
     check(_lib.lib().pic_zero_wall(ctypes.byref(p), int(axis), _p(f), _stream()), "pic_zero_wall")
 
 
+def div_residual(p, F, a=None, ca=0.0, b=None, cb=0.0, out=None):
+    """out[interior] = div_backward(F) + ca*a + cb*b (pic_div_residual); ghosts of `out` are zero."""
+    if out is None:
+        out = torch.zeros_like(F[0])
+    check(_lib.lib().pic_div_residual(ctypes.byref(p), _v(F), _p(a) if a is not None else None, float(ca),
+                                      _p(b) if b is not None else None, float(cb), _p(out), _stream()), "pic_div_residual")
+    return out
+
+
 def sum_squares_interior(p, f, out):
     check(_lib.lib().pic_sum_squares_interior(ctypes.byref(p), _p(f), _p(out), _stream()), "pic_sum_squares_interior")
 

@@ -39,6 +39,9 @@ class LocalHalo:
     def fold_(self, fields, bcs):
         ops.halo_fold_(self.p, fields, bcs)
 
+    def refresh_split_(self, fields, bcs):
+        return None                 # no axis is split across ranks
+
     def migrate(self, sim):
         return None
 
@@ -75,6 +78,10 @@ class Simulation:
             self.halo = LocalHalo(self.p)
         else:
             self.halo = halo(self.p) if callable(halo) and not hasattr(halo, "refresh_") else halo
+        # the field half of the step in one kernel (pic_yee_fused) unless the digital filter is on; PIC_YEE=sweeps keeps the three
+        # sweeps + refreshes (A/B control, same result bit for bit)
+        self._yee_fused = (os.environ.get("PIC_YEE", "fused") == "fused") and float(self.p.alpha) == 1.0 and int(self.p.g) >= 2
+        self._E2 = self._B2 = None
         self.k1_events = None   # set to [] to record (start, end) CUDA events around every K1 launch (bench.py roofline)
         self.distributed = any(self.p.gmesh[a] != self.p.mesh[a] for a in range(3))
         E, B, J, rho, phi, ext, pml_state, overflow = fields
@@ -112,6 +119,7 @@ class Simulation:
         self.leave_fraction = float(leave_fraction)
         if self.distributed:
             self._alloc_packets()
+        self._refresh_imported_fields()
         self.sort()
 
     # ------------------------------------------------------------------------------------------ layout
@@ -245,7 +253,15 @@ class Simulation:
                 for d, s_ in zip(dst, src):
                     d.copy_(ops._chk(s_, "field", self.dtype))
             self._J_ghosts_stale = False          # the caller's J comes with its ghosts; a kept J may still owe its refresh
+            self._refresh_imported_fields()
         self.sort()
+
+    def _refresh_imported_fields(self):
+        """The reference refreshes E's guard cells at the top of update_B and B's at the top of update_E (first_order_yee.py:115, 41);
+        the resident step relies on guard cells that are valid from the previous step, so imported fields are refreshed once here."""
+        fbc = tuple(self.p.field_bc)
+        self.halo.refresh_(self.E, fbc)
+        self.halo.refresh_(self.B, fbc)
 
     def sort(self, which=None):
         """K2: counting sort of the given species (default: all) by local cell; also compacts dead (absorbed / migrated)
@@ -325,6 +341,9 @@ class Simulation:
         # (Esirkepov.py:359 / J_from_rhov.py:228,246) is deferred until somebody looks at J (export_state): one guard-cell
         # exchange less per step; the exported J is identical.
         self._J_ghosts_stale = True
+        if self._yee_fused and self._step_fields_fused(fbc, pbc):
+            self._after_fields()
+            return
         # B half step from E_old (evolve.py:88); E halos are valid from the previous step
         ops.update_B_(p, self.B, self.E)
         self.halo.refresh_(self.B, fbc)
@@ -348,6 +367,32 @@ class Simulation:
             self.halo.refresh_(self.B, fbc)
             self.B = [ops.filter27(p, "digital", self.alpha, c) for c in self.B]
         self.halo.refresh_(self.B, fbc)
+        self._after_fields()
+
+    def _step_fields_fused(self, fbc, pbc):
+        """B(half) -> E -> B(half) in one pass over the fields (pic_yee_fused) into the spare E/B arrays, then swap.  Guard cells of
+        single-rank periodic axes are written by the kernel; axes split across ranks exchange E and B together afterwards, and
+        need J's guard planes refreshed beforehand (the refresh the reference performs after the fold, Esirkepov.py:359)."""
+        p = self.p
+        if self._E2 is None:
+            self._E2 = [torch.zeros_like(c) for c in self.E]
+            self._B2 = [torch.zeros_like(c) for c in self.B]
+        if self.distributed:
+            self.halo.refresh_(self.J, pbc)
+            self._J_ghosts_stale = False
+        rc = _lib.lib().pic_yee_fused(ctypes.byref(p), ops._v(self.E), ops._v(self.B), ops._v(self.J), ops._v(self._E2), ops._v(self._B2),
+                                      ops._stream())
+        if rc == _lib.PIC_EUNSUPPORTED:
+            self._yee_fused = False
+            return False
+        check(rc, "pic_yee_fused")
+        self.E, self._E2 = self._E2, self.E
+        self.B, self._B2 = self._B2, self.B
+        if self.distributed:
+            self.halo.refresh_split_(self.E + self.B, fbc)
+        return True
+
+    def _after_fields(self):
         self.step_count += 1
         if self.sort_interval > 0:
             due = [s for s in range(self.S) if self.step_count % self.sort_every[s] == 0]
@@ -371,9 +416,10 @@ class Simulation:
             total += n - int(torch.isnan(sp_.buf[sp_.cur][0][:n]).sum().item())
         return total
 
-    def export_state(self, cap_ref=None, out=None):
+    def export_state(self, cap_ref=None, out=None, fields=True):
         """Reference pytrees: (TiledParticles, fields 8-tuple).  Slots are restored by id on a single GPU.
-        `out=(x, u, active)` reuses caller-owned tensors of the reference shape."""
+        `out=(x, u, active)` reuses caller-owned tensors of the reference shape; `fields=False` skips the field copies
+        (returns (particles, None))."""
         L = _lib.lib()
         st = ops._stream()
         cap = self.cap_ref if cap_ref is None else int(cap_ref)
@@ -398,6 +444,8 @@ class Simulation:
             live = self._counter[:self.S].cpu().tolist()
             if any(int(n) > cap for n in live):          # fixed-capacity contract of the reference layout (:169-230)
                 self.flags[0:1] |= 2
+        if not fields:
+            return TiledParticles(x=x, u=u, active=a), None
         if self._J_ghosts_stale:
             self.halo.refresh_(self.J, tuple(self.p.particle_bc))
             self._J_ghosts_stale = False
@@ -406,6 +454,42 @@ class Simulation:
         fields = (tuple(c.clone() for c in self.E), tuple(c.clone() for c in self.B), tuple(c.clone() for c in self.J), rho, phi, ext,
                   None, overflow)
         return TiledParticles(x=x, u=u, active=a), fields
+
+    # ------------------------------------------------------------------------------------------ conservation diagnostics
+    def charge_density(self):
+        """rho of the resident particles on this rank's ghosted tile: node deposit of every species (deposition/rho.py:66-150),
+        ghost deposits folded to their owners across ranks (particle BCs), ghosts left zero.  Diagnostics only: goes through
+        the reference-layout export."""
+        parts, _ = self.export_state(fields=False)
+        rho = ops.deposit(self.p, "rho", parts.x, parts.x, parts.active, self.E[0])
+        self.halo.fold_([rho], tuple(self.p.particle_bc))
+        return rho
+
+    def gauss_residual(self, rho=None):
+        """div E - rho/eps on the tile interior; E's guard cells are valid after every step."""
+        rho = self.charge_density() if rho is None else rho
+        return ops.div_residual(self.p, self.E, rho, -1.0 / float(self.p.eps))
+
+    def conservation_step(self):
+        """Advance ONE step and measure what Esirkepov's deposition promises (esirkepov_test.py:700-744 at any size, any number of
+        GPUs): max |(rho_new - rho_old)/dt + div J| against max |(rho_new - rho_old)/dt|, and the drift of the Gauss residual
+        div E - rho/eps over the step against max |rho|/eps.  Returns rank-local maxima (reduce with MAX over ranks)."""
+        rho0 = self.charge_density()
+        g0 = self.gauss_residual(rho0)
+        self.step(1)
+        rho1 = self.charge_density()
+        if self._J_ghosts_stale:                    # div J at the first interior plane reads the lower ghost plane
+            self.halo.refresh_(self.J, tuple(self.p.particle_bc))
+            self._J_ghosts_stale = False
+        inv_dt = 1.0 / float(self.p.dt)
+        cont = ops.div_residual(self.p, self.J, rho1, inv_dt, rho0, -inv_dt)
+        g1 = self.gauss_residual(rho1)
+        g = int(self.p.g)
+        I = (0, 0, 0, slice(g, -g), slice(g, -g), slice(g, -g))
+        return {"continuity_residual_max": float(cont[I].abs().max()),
+                "continuity_scale": float(((rho1[I] - rho0[I]) * inv_dt).abs().max()),
+                "gauss_drift_max": float((g1[I] - g0[I]).abs().max()),
+                "gauss_scale": float(rho1[I].abs().max()) / float(self.p.eps)}
 
 
 def time_loop_electrodynamic_resident(particles, species_config, fields, static_parameters, dynamic_parameters, n_steps=1, **kw):

@@ -13,5 +13,20 @@ def pytest_configure(config):
 
 
 def pytest_collection_modifyitems(config, items):
-    # -m gpu tests fail loudly (not skip) when there is no CUDA device: no silent fallback.
-    pass
+    # An explicit `-m gpu` run fails loudly (not skip) when there is no CUDA device: no silent fallback.  A plain `pytest` on a
+    # host without CUDA deselects the gpu-marked tests instead of turning the run red (`-m "not gpu"` is what CI runs there).
+    if config.getoption("-m"):
+        return
+    try:
+        import torch
+        has_cuda = torch.cuda.is_available()
+    except Exception:
+        has_cuda = False
+    if has_cuda:
+        return
+    keep, drop = [], []
+    for it in items:
+        (drop if it.get_closest_marker("gpu") else keep).append(it)
+    if drop:
+        config.hook.pytest_deselected(items=drop)
+        items[:] = keep

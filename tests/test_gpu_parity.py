@@ -179,6 +179,41 @@ def test_yee_update_E_and_B(N, tile, bcs, alpha, dtype):
             gu.assert_close(a, b, tol, "update_B")
 
 
+@pytest.mark.parametrize("N", [(8, 6, 4), (8, 1, 4), (36, 9, 5), (4, 20, 70)])
+@pytest.mark.parametrize("bcs", [(0, 0, 0), (1, 0, 1), (0, 1, 0)])
+@pytest.mark.parametrize("dtype", (F64, F32))
+def test_fused_yee_equals_the_three_sweeps(N, bcs, dtype):
+    """pic_yee_fused (B half -> E -> B half in one pass) against (a) the CUDA sweeps + guard-cell refreshes it replaces -- bit for
+    bit, guard cells included -- and (b) the oracle's update_B / update_E / update_B sequence (evolve.py:88-96).  Grids with a
+    reduced axis, widths that are not multiples of the 4 x 8 x 32 tile, periodic and conducting walls."""
+    import ctypes
+    from pypic3d_b200 import _lib, ops
+    from pypic3d_b200.solvers.first_order_yee import update_E, update_B
+    sp, dp, tp, sc, E, B = make_case(N, N, 1, boundary_conditions=bcs, alpha=1.0, C=1.3, eps=0.7)
+    rng = np.random.default_rng(5)
+    J = tuple(rng.normal(size=c.shape) for c in B)
+    # guard cells as the step finds them: refreshed E, B (field BCs); J folded + refreshed with the particle BCs (periodic here)
+    E = ohalo.update_tiled_vector_ghost_cells(E, sp, 2); B = ohalo.update_tiled_vector_ghost_cells(B, sp, 2)
+    J = ohalo.update_tiled_vector_ghost_cells(J, sp, 2, bc_type=1)
+    ps, pd = gu.to_pkg_params(sp, dp)
+    Eg, Bg, Jg = gu.vec_to_gpu(E, dtype), gu.vec_to_gpu(B, dtype), gu.vec_to_gpu(J, dtype)
+    p = ops.params_for(ps, pd, None, Eg[0])
+    E2 = [torch.zeros_like(c) for c in Eg]; B2 = [torch.zeros_like(c) for c in Bg]
+    _lib.check(_lib.lib().pic_yee_fused(ctypes.byref(p), ops._v(Eg), ops._v(Bg), ops._v(Jg), ops._v(E2), ops._v(B2), ops._stream()), "pic_yee_fused")
+    # (a) the sweeps of the drop-in path
+    Bh, _ = update_B(Eg, Bg, ps, pd, None, do_filter=False)
+    En, _ = update_E(Eg, Bh, Jg, ps, pd)
+    Bn, _ = update_B(En, Bh, ps, pd, None, do_filter=False)
+    for a, b in zip(E2 + B2, tuple(En) + tuple(Bn)):
+        assert torch.equal(a, b)
+    # (b) the oracle
+    oBh = oyee.update_B(E, B, sp, dp, do_filter=False)
+    oEn = oyee.update_E(E, oBh, J, sp, dp)
+    oBn = oyee.update_B(oEn, oBh, sp, dp, do_filter=False)
+    for a, b in zip(E2 + B2, tuple(oEn) + tuple(oBn)):
+        gu.assert_close(a, b, TOL[dtype], "fused Yee")
+
+
 def test_update_E_kat_from_reference():
     """esirkepov_test.py:510-529: J=4, dt=.25, eps=2 -> E=-0.5."""
     from pypic3d_b200.solvers.first_order_yee import update_E

@@ -58,7 +58,7 @@ def run(specs, bench_args):
     for spec in specs:
         name, _, env = split(spec)
         e = dict(os.environ, PIC_B200_LIB=lib_of(name), **env)
-        cmd = [sys.executable, os.path.join(ROOT, "bench.py"), "--no-e2e", "--no-cpu-baseline"] + bench_args
+        cmd = [sys.executable, os.path.join(ROOT, "bench.py"), "--no-e2e", "--no-cpu-baseline", "--no-second-leg", "--no-check"] + bench_args
         r = subprocess.run(cmd, env=e, capture_output=True, text=True, timeout=600)
         line = next((l for l in reversed(r.stdout.splitlines()) if l.startswith("{")), None)
         if line is None:
