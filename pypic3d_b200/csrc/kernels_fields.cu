@@ -62,12 +62,12 @@ __global__ void __launch_bounds__(256) k_update_B(Dims d, int nby, int nbz, T* _
     const size_t sx = (size_t)d.L[1] * d.L[2], sy = d.L[2];
     const size_t i = tile * d.tile_elems + ix * sx + iy * sy + iz;
     const T ex = Ex[i], ey = Ey[i], ez = Ez[i];
-    const T dEz_dy = (Ez[i + sy] - ez) / dy;   // forward differences
-    const T dEy_dz = (Ey[i + 1] - ey) / dz;
-    const T dEx_dz = (Ex[i + 1] - ex) / dz;
-    const T dEx_dy = (Ex[i + sy] - ex) / dy;
-    const T dEz_dx = (Ez[i + sx] - ez) / dx;
-    const T dEy_dx = (Ey[i + sx] - ey) / dx;
+    const T dEz_dy = (Ez[i + sy] - ez) * dy;   // forward differences (dx, dy, dz are the RECIPROCAL spacings here)
+    const T dEy_dz = (Ey[i + 1] - ey) * dz;
+    const T dEx_dz = (Ex[i + 1] - ex) * dz;
+    const T dEx_dy = (Ex[i + sy] - ex) * dy;
+    const T dEz_dx = (Ez[i + sx] - ez) * dx;
+    const T dEy_dx = (Ey[i + sx] - ey) * dx;
     Bx[i] = Bx[i] - hdt * (dEz_dy - dEy_dz);
     By[i] = By[i] - hdt * (dEx_dz - dEz_dx);
     Bz[i] = Bz[i] - hdt * (dEy_dx - dEx_dy);
@@ -83,15 +83,15 @@ __global__ void __launch_bounds__(256) k_update_E(Dims d, int nby, int nbz, T* _
     const size_t sx = (size_t)d.L[1] * d.L[2], sy = d.L[2];
     const size_t i = tile * d.tile_elems + ix * sx + iy * sy + iz;
     const T bx = Bx[i], by = By[i], bz = Bz[i];
-    const T dBz_dy = (bz - Bz[i - sy]) / dy;   // backward differences
-    const T dBy_dz = (by - By[i - 1]) / dz;
-    const T dBx_dz = (bx - Bx[i - 1]) / dz;
-    const T dBx_dy = (bx - Bx[i - sy]) / dy;
-    const T dBz_dx = (bz - Bz[i - sx]) / dx;
-    const T dBy_dx = (by - By[i - sx]) / dx;
-    Ex[i] = Ex[i] + (C2 * (dBz_dy - dBy_dz) - Jx[i] / eps) * dt;
-    Ey[i] = Ey[i] + (C2 * (dBx_dz - dBz_dx) - Jy[i] / eps) * dt;
-    Ez[i] = Ez[i] + (C2 * (dBy_dx - dBx_dy) - Jz[i] / eps) * dt;
+    const T dBz_dy = (bz - Bz[i - sy]) * dy;   // backward differences (dx, dy, dz, eps are RECIPROCALS here)
+    const T dBy_dz = (by - By[i - 1]) * dz;
+    const T dBx_dz = (bx - Bx[i - 1]) * dz;
+    const T dBx_dy = (bx - Bx[i - sy]) * dy;
+    const T dBz_dx = (bz - Bz[i - sx]) * dx;
+    const T dBy_dx = (by - By[i - sx]) * dx;
+    Ex[i] = Ex[i] + (C2 * (dBz_dy - dBy_dz) - Jx[i] * eps) * dt;
+    Ey[i] = Ey[i] + (C2 * (dBx_dz - dBz_dx) - Jy[i] * eps) * dt;
+    Ez[i] = Ez[i] + (C2 * (dBy_dx - dBx_dy) - Jz[i] * eps) * dt;
 }
 
 template <typename T>
@@ -99,7 +99,7 @@ static int launch_update_B(const PicParams* p, void* const B[3], const void* con
     const Dims d = dims_of(p);
     const CellGrid cg = cell_grid(d);
     k_update_B<T><<<cg.grid, cg.block, 0, st>>>(d, cg.nby, cg.nbz, (T*)B[0], (T*)B[1], (T*)B[2], (const T*)E[0], (const T*)E[1],
-                                                (const T*)E[2], (T)(p->dt / 2), (T)p->dx, (T)p->dy, (T)p->dz);
+                                                (const T*)E[2], (T)(p->dt / 2), (T)(1.0 / p->dx), (T)(1.0 / p->dy), (T)(1.0 / p->dz));
     PIC_LAUNCH_RET();
 }
 template <typename T>
@@ -107,8 +107,8 @@ static int launch_update_E(const PicParams* p, void* const E[3], const void* con
     const Dims d = dims_of(p);
     const CellGrid cg = cell_grid(d);
     k_update_E<T><<<cg.grid, cg.block, 0, st>>>(d, cg.nby, cg.nbz, (T*)E[0], (T*)E[1], (T*)E[2], (const T*)B[0], (const T*)B[1],
-                                                (const T*)B[2], (const T*)J[0], (const T*)J[1], (const T*)J[2], (T)p->dt, (T)p->dx,
-                                                (T)p->dy, (T)p->dz, (T)(p->C * p->C), (T)p->eps);
+                                                (const T*)B[2], (const T*)J[0], (const T*)J[1], (const T*)J[2], (T)p->dt, (T)(1.0 / p->dx),
+                                                (T)(1.0 / p->dy), (T)(1.0 / p->dz), (T)(p->C * p->C), (T)(1.0 / p->eps));
     PIC_LAUNCH_RET();
 }
 
@@ -445,140 +445,212 @@ static int launch_sumsq(const PicParams* p, const void* f, double* out, cudaStre
 //         intermediates there are zero; conducting walls zero the tangential E on the first / last interior plane.
 constexpr int YEE_WRAP = 0, YEE_HALO = 1, YEE_WALL = 2;
 struct YeeSides {
-    int lo[3], hi[3];        // YEE_* per axis side
+    int lo[3], hi[3];             // YEE_* per axis side
     int cond_lo[3], cond_hi[3];   // conducting wall on this rank's low / high side of the axis
 };
-constexpr int YTX = 4, YTY = 8, YTZ = 32;
+constexpr int YTY = 8, YTZ = 32;  // tile = TX x 8 x 32 cells, 256 threads = 8 (y) x 32 (z); a thread owns <= 2 x 2 (y, z) columns of a box
 
-template <typename T>
+// array index along axis a -> where to read it (WRAP: the interior cell it mirrors) / is it an exterior wall guard cell
+struct YeeAxis {
+    int src;      // source array index
+    int wall;     // exterior guard cell of a non-periodic wall: intermediates are zero there
+    int cond;     // first / last interior plane of a conducting wall
+};
+__device__ __forceinline__ YeeAxis yee_axis(const Dims& d, const YeeSides& sd, int a, int i) {
+    YeeAxis r;
+    const int g = d.g, L = d.L[a];
+    i = i < 0 ? 0 : (i > L - 1 ? L - 1 : i);                     // (partial tiles at the upper end read in-range garbage, never stored)
+    r.src = i;
+    r.wall = 0;
+    if (i < g) {
+        if (sd.lo[a] == YEE_WRAP) r.src = i + d.W[a];
+        r.wall = sd.lo[a] == YEE_WALL;
+    } else if (i >= L - g) {
+        if (sd.hi[a] == YEE_WRAP) r.src = i - d.W[a];
+        r.wall = sd.hi[a] == YEE_WALL;
+    }
+    r.cond = (sd.cond_lo[a] && i == g) || (sd.cond_hi[a] && i == L - g - 1);
+    return r;
+}
+
+template <typename T, int TX>
 __global__ void __launch_bounds__(256) k_yee_fused(Dims d, YeeSides sd, const T* __restrict__ Ex, const T* __restrict__ Ey,
                                                    const T* __restrict__ Ez, const T* __restrict__ Bx, const T* __restrict__ By,
                                                    const T* __restrict__ Bz, const T* __restrict__ Jx, const T* __restrict__ Jy,
                                                    const T* __restrict__ Jz, T* __restrict__ Ex2, T* __restrict__ Ey2, T* __restrict__ Ez2,
-                                                   T* __restrict__ Bx2, T* __restrict__ By2, T* __restrict__ Bz2, T dt, T hdt, T dx, T dy,
-                                                   T dz, T C2, T eps, int nbx, int nby, int nbz) {
-    constexpr int EX = YTX + 3, EY = YTY + 3, EZ = YTZ + 3;      // E box: cells [-1, T + 2)
-    constexpr int BX = YTX + 2, BY = YTY + 2, BZ = YTZ + 2;      // B box: cells [-1, T + 1)
+                                                   T* __restrict__ Bx2, T* __restrict__ By2, T* __restrict__ Bz2, T dt, T hdt, T idx, T idy,
+                                                   T idz, T C2, T ieps, int nby, int nbz) {
+    constexpr int EX = TX + 3, EY = YTY + 3, EZ = YTZ + 3;       // E box: cells [-1, T + 2)
+    constexpr int BX = TX + 2, BY = YTY + 2, BZ = YTZ + 2;       // B box: cells [-1, T + 1)
+    constexpr int ESX = EY * EZ, ESY = EZ, BSX = BY * BZ, BSY = BZ;
     extern __shared__ __align__(16) unsigned char yee_smem[];
-    T* sE = reinterpret_cast<T*>(yee_smem);                      // [3][EX][EY][EZ]
-    T* sB = sE + 3 * EX * EY * EZ;                               // [3][BX][BY][BZ]
+    T* sEx = reinterpret_cast<T*>(yee_smem);                     // [EX][EY][EZ] x 3
+    T* sEy = sEx + EX * EY * EZ;
+    T* sEz = sEy + EX * EY * EZ;
+    T* sBx = sEz + EX * EY * EZ;                                 // [BX][BY][BZ] x 3
+    T* sBy = sBx + BX * BY * BZ;
+    T* sBz = sBy + BX * BY * BZ;
     int b = blockIdx.x;
     const int bz = b % nbz; b /= nbz;
     const int by = b % nby; b /= nby;
-    const int bx = b;
-    const int o[3] = {d.g + bx * YTX, d.g + by * YTY, d.g + bz * YTZ};       // array index of the tile's first cell
-    const int g = d.g;
-    const size_t sx = (size_t)d.L[1] * d.L[2], sy = d.L[2];
-    const int tid = threadIdx.x;
-    // array index -> source index (WRAP) and "is an exterior guard cell of a wall" (WALL)
-    auto src = [&](int a, int i) {       // (modulo wrap: a reduced axis, W = 1, maps every guard index to its single interior plane)
-        if ((i < g && sd.lo[a] == YEE_WRAP) || (i >= d.L[a] - g && sd.hi[a] == YEE_WRAP)) {
-            int r = (i - g) % d.W[a];
-            if (r < 0) r += d.W[a];
-            return g + r;
-        }
-        return i;
-    };
-    auto wall = [&](int a, int i) { return (i < g && sd.lo[a] == YEE_WALL) || (i >= d.L[a] - g && sd.hi[a] == YEE_WALL); };
-    auto clampi = [&](int a, int i) { return i < 0 ? 0 : (i > d.L[a] - 1 ? d.L[a] - 1 : i); };
+    const int o0 = d.g + b * TX, o1 = d.g + by * YTY, o2 = d.g + bz * YTZ;    // array index of the tile's first cell
+    const int sx = d.L[1] * d.L[2], sy = d.L[2];
+    const int ty = threadIdx.x >> 5, tz = threadIdx.x & 31;
+    // the thread's columns of the boxes: box y = ty (+8), box z = tz (+32); box coordinate c <-> array index o - 1 + c
+    YeeAxis ay[2], az[2];
+    int cy[2], cz[2];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        cy[k] = ty + 8 * k; cz[k] = tz + 32 * k;
+        ay[k] = yee_axis(d, sd, 1, o1 - 1 + cy[k]);
+        az[k] = yee_axis(d, sd, 2, o2 - 1 + cz[k]);
+    }
     // ---- phase 0: stage E_old on [-1, +2] and B_old on [-1, +1]
-    for (int l = tid; l < EX * EY * EZ; l += 256) {
-        const int lz = l % EZ, ly = (l / EZ) % EY, lx = l / (EZ * EY);
-        const size_t gi = (size_t)src(0, clampi(0, o[0] - 1 + lx)) * sx + (size_t)src(1, clampi(1, o[1] - 1 + ly)) * sy + src(2, clampi(2, o[2] - 1 + lz));
-        sE[l] = Ex[gi]; sE[EX * EY * EZ + l] = Ey[gi]; sE[2 * EX * EY * EZ + l] = Ez[gi];
-    }
-    for (int l = tid; l < BX * BY * BZ; l += 256) {
-        const int lz = l % BZ, ly = (l / BZ) % BY, lx = l / (BZ * BY);
-        const size_t gi = (size_t)src(0, clampi(0, o[0] - 1 + lx)) * sx + (size_t)src(1, clampi(1, o[1] - 1 + ly)) * sy + src(2, clampi(2, o[2] - 1 + lz));
-        sB[l] = Bx[gi]; sB[BX * BY * BZ + l] = By[gi]; sB[2 * BX * BY * BZ + l] = Bz[gi];
-    }
-    __syncthreads();
-    constexpr int ESX = EY * EZ, ESY = EZ, BSX = BY * BZ, BSY = BZ;
-    T* sEx = sE; T* sEy = sE + EX * EY * EZ; T* sEz = sE + 2 * EX * EY * EZ;
-    T* sBx = sB; T* sBy = sB + BX * BY * BZ; T* sBz = sB + 2 * BX * BY * BZ;
-    // ---- phase 1: B' = B - (dt/2) curl_forward(E_old) on [-1, +1]  (k_update_B; exterior wall guards: zero)
-    for (int l = tid; l < BX * BY * BZ; l += 256) {
-        const int lz = l % BZ, ly = (l / BZ) % BY, lx = l / (BZ * BY);
-        const int ai[3] = {o[0] - 1 + lx, o[1] - 1 + ly, o[2] - 1 + lz};
-        const int e = lx * ESX + ly * ESY + lz;                  // same cell in the E box (both boxes start at -1)
-        const T ex = sEx[e], ey = sEy[e], ez = sEz[e];
-        const T dEz_dy = (sEz[e + ESY] - ez) / dy;
-        const T dEy_dz = (sEy[e + 1] - ey) / dz;
-        const T dEx_dz = (sEx[e + 1] - ex) / dz;
-        const T dEx_dy = (sEx[e + ESY] - ex) / dy;
-        const T dEz_dx = (sEz[e + ESX] - ez) / dx;
-        const T dEy_dx = (sEy[e + ESX] - ey) / dx;
-        const bool w = wall(0, ai[0]) || wall(1, ai[1]) || wall(2, ai[2]);
-        const bool inner = ai[0] >= g && ai[0] < d.L[0] - g && ai[1] >= g && ai[1] < d.L[1] - g && ai[2] >= g && ai[2] < d.L[2] - g;
-        // a guard cell of a HALO / WRAP side is recomputed like the interior cell it mirrors; wall guards hold zeros
-        (void)inner;
-        sBx[l] = w ? (T)0 : sBx[l] - hdt * (dEz_dy - dEy_dz);
-        sBy[l] = w ? (T)0 : sBy[l] - hdt * (dEx_dz - dEz_dx);
-        sBz[l] = w ? (T)0 : sBz[l] - hdt * (dEy_dx - dEx_dy);
-    }
-    __syncthreads();
-    // ---- phase 2: E_new = E + dt (C^2 curl_backward(B') - J / eps) on [0, +1]  (k_update_E; walls as above)
-    constexpr int PX = YTX + 1, PY = YTY + 1, PZ = YTZ + 1;
-    for (int l = tid; l < PX * PY * PZ; l += 256) {
-        const int lz = l % PZ, ly = (l / PZ) % PY, lx = l / (PZ * PY);
-        const int ai[3] = {o[0] + lx, o[1] + ly, o[2] + lz};
-        const int e = (lx + 1) * ESX + (ly + 1) * ESY + (lz + 1);
-        const int bb = (lx + 1) * BSX + (ly + 1) * BSY + (lz + 1);
-        const T bx_ = sBx[bb], by_ = sBy[bb], bz_ = sBz[bb];
-        const T dBz_dy = (bz_ - sBz[bb - BSY]) / dy;
-        const T dBy_dz = (by_ - sBy[bb - 1]) / dz;
-        const T dBx_dz = (bx_ - sBx[bb - 1]) / dz;
-        const T dBx_dy = (bx_ - sBx[bb - BSY]) / dy;
-        const T dBz_dx = (bz_ - sBz[bb - BSX]) / dx;
-        const T dBy_dx = (by_ - sBy[bb - BSX]) / dx;
-        const bool w = wall(0, ai[0]) || wall(1, ai[1]) || wall(2, ai[2]);
-        const size_t gi = (size_t)src(0, clampi(0, ai[0])) * sx + (size_t)src(1, clampi(1, ai[1])) * sy + src(2, clampi(2, ai[2]));
-        T ex = sEx[e] + (C2 * (dBz_dy - dBy_dz) - Jx[gi] / eps) * dt;
-        T ey = sEy[e] + (C2 * (dBx_dz - dBz_dx) - Jy[gi] / eps) * dt;
-        T ez = sEz[e] + (C2 * (dBy_dx - dBx_dy) - Jz[gi] / eps) * dt;
-        // conducting walls: tangential E vanishes on the first / last interior plane (first_order_yee.py:80-89)
-        const bool cx = (sd.cond_lo[0] && ai[0] == g) || (sd.cond_hi[0] && ai[0] == d.L[0] - g - 1);
-        const bool cy = (sd.cond_lo[1] && ai[1] == g) || (sd.cond_hi[1] && ai[1] == d.L[1] - g - 1);
-        const bool cz = (sd.cond_lo[2] && ai[2] == g) || (sd.cond_hi[2] && ai[2] == d.L[2] - g - 1);
-        if (cy || cz || w) ex = (T)0;
-        if (cx || cz || w) ey = (T)0;
-        if (cx || cy || w) ez = (T)0;
-        sEx[e] = ex; sEy[e] = ey; sEz[e] = ez;
-    }
-    __syncthreads();
-    // ---- phase 3: B_new = B' - (dt/2) curl_forward(E_new) on the tile's own cells; store E_new, B_new (+ wrapped guard copies)
-    for (int l = tid; l < YTX * YTY * YTZ; l += 256) {
-        const int lz = l % YTZ, ly = (l / YTZ) % YTY, lx = l / (YTZ * YTY);
-        const int ai[3] = {o[0] + lx, o[1] + ly, o[2] + lz};
-        if (ai[0] >= d.L[0] - g || ai[1] >= d.L[1] - g || ai[2] >= d.L[2] - g) continue;       // partial tile at the upper end
-        const int e = (lx + 1) * ESX + (ly + 1) * ESY + (lz + 1);
-        const int bb = (lx + 1) * BSX + (ly + 1) * BSY + (lz + 1);
-        const T ex = sEx[e], ey = sEy[e], ez = sEz[e];
-        const T dEz_dy = (sEz[e + ESY] - ez) / dy;
-        const T dEy_dz = (sEy[e + 1] - ey) / dz;
-        const T dEx_dz = (sEx[e + 1] - ex) / dz;
-        const T dEx_dy = (sEx[e + ESY] - ex) / dy;
-        const T dEz_dx = (sEz[e + ESX] - ez) / dx;
-        const T dEy_dx = (sEy[e + ESX] - ey) / dx;
-        const T bxn = sBx[bb] - hdt * (dEz_dy - dEy_dz);
-        const T byn = sBy[bb] - hdt * (dEx_dz - dEz_dx);
-        const T bzn = sBz[bb] - hdt * (dEy_dx - dEx_dy);
-        // guard copies along WRAP axes: a cell also lives at every index i + k W that falls into the guard layers
-        int off[3][6], noff[3];
-        for (int a = 0; a < 3; ++a) {
-            noff[a] = 1; off[a][0] = 0;
-            if (sd.lo[a] != YEE_WRAP) continue;                  // (WRAP closes both sides of an axis)
-            for (int kk = 1; kk * d.W[a] <= ai[a] && noff[a] < 6; ++kk) off[a][noff[a]++] = -kk * d.W[a];
-            for (int kk = 1; ai[a] + kk * d.W[a] < d.L[a] && noff[a] < 6; ++kk) off[a][noff[a]++] = kk * d.W[a];
-        }
-        for (int i0 = 0; i0 < noff[0]; ++i0)
-            for (int i1 = 0; i1 < noff[1]; ++i1)
-                for (int i2 = 0; i2 < noff[2]; ++i2) {
-                    const size_t gi = (size_t)(ai[0] + off[0][i0]) * sx + (size_t)(ai[1] + off[1][i1]) * sy + (ai[2] + off[2][i2]);
-                    Ex2[gi] = ex; Ey2[gi] = ey; Ez2[gi] = ez;
-                    Bx2[gi] = bxn; By2[gi] = byn; Bz2[gi] = bzn;
+#pragma unroll
+    for (int ky = 0; ky < 2; ++ky) {
+        if (cy[ky] >= EY) continue;
+#pragma unroll
+        for (int kz = 0; kz < 2; ++kz) {
+            if (cz[kz] >= EZ) continue;
+            const int gyz = ay[ky].src * sy + az[kz].src;
+            const bool inB = cy[ky] < BY && cz[kz] < BZ;
+#pragma unroll
+            for (int lx = 0; lx < EX; ++lx) {
+                const YeeAxis ax = yee_axis(d, sd, 0, o0 - 1 + lx);
+                const size_t gi = (size_t)ax.src * sx + gyz;
+                const int e = lx * ESX + cy[ky] * ESY + cz[kz];
+                sEx[e] = Ex[gi]; sEy[e] = Ey[gi]; sEz[e] = Ez[gi];
+                if (inB && lx < BX) {
+                    const int bb = lx * BSX + cy[ky] * BSY + cz[kz];
+                    sBx[bb] = Bx[gi]; sBy[bb] = By[gi]; sBz[bb] = Bz[gi];
                 }
+            }
+        }
     }
+    __syncthreads();
+    // ---- phase 1: B' = B - (dt/2) curl_forward(E_old) on [-1, +1]  (k_update_B; exterior wall guards: zero)
+#pragma unroll
+    for (int ky = 0; ky < 2; ++ky) {
+        if (cy[ky] >= BY) continue;
+#pragma unroll
+        for (int kz = 0; kz < 2; ++kz) {
+            if (cz[kz] >= BZ) continue;
+            const bool wyz = ay[ky].wall || az[kz].wall;
+#pragma unroll
+            for (int lx = 0; lx < BX; ++lx) {
+                const bool w = wyz || yee_axis(d, sd, 0, o0 - 1 + lx).wall;
+                const int e = lx * ESX + cy[ky] * ESY + cz[kz];
+                const int bb = lx * BSX + cy[ky] * BSY + cz[kz];
+                const T ex = sEx[e], ey = sEy[e], ez = sEz[e];
+                const T dEz_dy = (sEz[e + ESY] - ez) * idy;
+                const T dEy_dz = (sEy[e + 1] - ey) * idz;
+                const T dEx_dz = (sEx[e + 1] - ex) * idz;
+                const T dEx_dy = (sEx[e + ESY] - ex) * idy;
+                const T dEz_dx = (sEz[e + ESX] - ez) * idx;
+                const T dEy_dx = (sEy[e + ESX] - ey) * idx;
+                sBx[bb] = w ? (T)0 : sBx[bb] - hdt * (dEz_dy - dEy_dz);
+                sBy[bb] = w ? (T)0 : sBy[bb] - hdt * (dEx_dz - dEz_dx);
+                sBz[bb] = w ? (T)0 : sBz[bb] - hdt * (dEy_dx - dEx_dy);
+            }
+        }
+    }
+    __syncthreads();
+    // ---- phase 2: E_new = E + dt (C^2 curl_backward(B') - J / eps) on [0, +1]: box coordinates 1 .. T + 1
+#pragma unroll
+    for (int ky = 0; ky < 2; ++ky) {
+        if (cy[ky] < 1 || cy[ky] > YTY + 1) continue;
+#pragma unroll
+        for (int kz = 0; kz < 2; ++kz) {
+            if (cz[kz] < 1 || cz[kz] > YTZ + 1) continue;
+            const bool wyz = ay[ky].wall || az[kz].wall;
+            const int gyz = ay[ky].src * sy + az[kz].src;
+#pragma unroll
+            for (int lx = 1; lx <= TX + 1; ++lx) {
+                const YeeAxis ax = yee_axis(d, sd, 0, o0 - 1 + lx);
+                const bool w = wyz || ax.wall;
+                const int e = lx * ESX + cy[ky] * ESY + cz[kz];
+                const int bb = lx * BSX + cy[ky] * BSY + cz[kz];
+                const size_t gi = (size_t)ax.src * sx + gyz;
+                const T bx_ = sBx[bb], by_ = sBy[bb], bz_ = sBz[bb];
+                const T dBz_dy = (bz_ - sBz[bb - BSY]) * idy;
+                const T dBy_dz = (by_ - sBy[bb - 1]) * idz;
+                const T dBx_dz = (bx_ - sBx[bb - 1]) * idz;
+                const T dBx_dy = (bx_ - sBx[bb - BSY]) * idy;
+                const T dBz_dx = (bz_ - sBz[bb - BSX]) * idx;
+                const T dBy_dx = (by_ - sBy[bb - BSX]) * idx;
+                T ex = sEx[e] + (C2 * (dBz_dy - dBy_dz) - Jx[gi] * ieps) * dt;
+                T ey = sEy[e] + (C2 * (dBx_dz - dBz_dx) - Jy[gi] * ieps) * dt;
+                T ez = sEz[e] + (C2 * (dBy_dx - dBx_dy) - Jz[gi] * ieps) * dt;
+                // conducting walls: tangential E vanishes on the first / last interior plane (first_order_yee.py:80-89)
+                if (ay[ky].cond || az[kz].cond || w) ex = (T)0;
+                if (ax.cond || az[kz].cond || w) ey = (T)0;
+                if (ax.cond || ay[ky].cond || w) ez = (T)0;
+                sEx[e] = ex; sEy[e] = ey; sEz[e] = ez;
+            }
+        }
+    }
+    __syncthreads();
+    // ---- phase 3: B_new = B' - (dt/2) curl_forward(E_new) on the tile's own cells (box 1 .. T); store E_new, B_new and, along
+    // WRAP axes, their guard copies (a cell within g of an end also lives W further out on the other side)
+    const int iy = o1 + ty, iz = o2 + tz;
+    if (iy < d.L[1] - d.g && iz < d.L[2] - d.g) {
+        int ny = 1, nz = 1, offy[3] = {0, 0, 0}, offz[3] = {0, 0, 0};
+        if (sd.lo[1] == YEE_WRAP) {
+            if (iy - d.W[1] >= 0) offy[ny++] = -d.W[1] * sy;
+            if (iy + d.W[1] < d.L[1]) offy[ny++] = d.W[1] * sy;
+        }
+        if (sd.lo[2] == YEE_WRAP) {
+            if (iz - d.W[2] >= 0) offz[nz++] = -d.W[2];
+            if (iz + d.W[2] < d.L[2]) offz[nz++] = d.W[2];
+        }
+#pragma unroll
+        for (int lx = 1; lx <= TX; ++lx) {
+            const int ix = o0 - 1 + lx;
+            if (ix >= d.L[0] - d.g) break;
+            const int e = lx * ESX + (ty + 1) * ESY + (tz + 1);
+            const int bb = lx * BSX + (ty + 1) * BSY + (tz + 1);
+            const T ex = sEx[e], ey = sEy[e], ez = sEz[e];
+            const T dEz_dy = (sEz[e + ESY] - ez) * idy;
+            const T dEy_dz = (sEy[e + 1] - ey) * idz;
+            const T dEx_dz = (sEx[e + 1] - ex) * idz;
+            const T dEx_dy = (sEx[e + ESY] - ex) * idy;
+            const T dEz_dx = (sEz[e + ESX] - ez) * idx;
+            const T dEy_dx = (sEy[e + ESX] - ey) * idx;
+            const T bxn = sBx[bb] - hdt * (dEz_dy - dEy_dz);
+            const T byn = sBy[bb] - hdt * (dEx_dz - dEz_dx);
+            const T bzn = sBz[bb] - hdt * (dEy_dx - dEx_dy);
+            int nx = 1, offx[3] = {0, 0, 0};
+            if (sd.lo[0] == YEE_WRAP) {
+                if (ix - d.W[0] >= 0) offx[nx++] = -d.W[0];
+                if (ix + d.W[0] < d.L[0]) offx[nx++] = d.W[0];
+            }
+            for (int i0 = 0; i0 < nx; ++i0)
+                for (int i1 = 0; i1 < ny; ++i1)
+                    for (int i2 = 0; i2 < nz; ++i2) {
+                        const size_t gi = (size_t)(ix + offx[i0]) * sx + (size_t)(iy * sy + offy[i1]) + (iz + offz[i2]);
+                        Ex2[gi] = ex; Ey2[gi] = ey; Ez2[gi] = ez;
+                        Bx2[gi] = bxn; By2[gi] = byn; Bz2[gi] = bzn;
+                    }
+        }
+    }
+}
+
+template <typename T, int TX>
+static int launch_yee_fused_tx(const PicParams* p, const Dims& d, const YeeSides& sd, const void* const E[3], const void* const B[3],
+                               const void* const J[3], void* const E2[3], void* const B2[3], cudaStream_t st) {
+    const int nbx = (d.W[0] + TX - 1) / TX, nby = (d.W[1] + YTY - 1) / YTY, nbz = (d.W[2] + YTZ - 1) / YTZ;
+    const size_t smem = (size_t)(3 * (TX + 3) * (YTY + 3) * (YTZ + 3) + 3 * (TX + 2) * (YTY + 2) * (YTZ + 2)) * sizeof(T);
+    static size_t attr = 0;
+    if (attr < smem) {
+        cudaError_t e = cudaFuncSetAttribute(k_yee_fused<T, TX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        attr = smem;
+    }
+    k_yee_fused<T, TX><<<nbx * nby * nbz, 256, smem, st>>>(d, sd, (const T*)E[0], (const T*)E[1], (const T*)E[2], (const T*)B[0], (const T*)B[1],
+                                                           (const T*)B[2], (const T*)J[0], (const T*)J[1], (const T*)J[2], (T*)E2[0], (T*)E2[1],
+                                                           (T*)E2[2], (T*)B2[0], (T*)B2[1], (T*)B2[2], (T)p->dt, (T)(p->dt / 2), (T)(1.0 / p->dx),
+                                                           (T)(1.0 / p->dy), (T)(1.0 / p->dz), (T)(p->C * p->C), (T)(1.0 / p->eps), nby, nbz);
+    PIC_LAUNCH_RET();
 }
 
 template <typename T>
@@ -590,25 +662,16 @@ static int launch_yee_fused(const PicParams* p, const void* const E[3], const vo
         const bool split = p->gmesh[a] != p->mesh[a];
         const bool periodic = p->field_bc[a] == PIC_BC_PERIODIC;
         const bool at_lo = p->moff[a] == 0, at_hi = p->moff[a] + p->mesh[a] == p->gmesh[a];
-        sd.lo[a] = periodic ? (split ? YEE_HALO : YEE_WRAP) : (at_lo ? YEE_WALL : YEE_HALO);
-        sd.hi[a] = periodic ? (split ? YEE_HALO : YEE_WRAP) : (at_hi ? YEE_WALL : YEE_HALO);
+        // a periodic axis narrower than the guard depth (a reduced axis, W = 1) is served from its guard cells like a split axis;
+        // the caller refreshes them afterwards (pic_halo_refresh_axis) -- Simulation does
+        const bool wrap = periodic && !split && d.W[a] >= d.g;
+        sd.lo[a] = periodic ? (wrap ? YEE_WRAP : YEE_HALO) : (at_lo ? YEE_WALL : YEE_HALO);
+        sd.hi[a] = periodic ? (wrap ? YEE_WRAP : YEE_HALO) : (at_hi ? YEE_WALL : YEE_HALO);
         sd.cond_lo[a] = (p->field_bc[a] == PIC_BC_CONDUCTING && at_lo) ? 1 : 0;
         sd.cond_hi[a] = (p->field_bc[a] == PIC_BC_CONDUCTING && at_hi) ? 1 : 0;
-        if (d.W[a] > 1 && d.W[a] < d.g) return PIC_EUNSUPPORTED;     // (only reduced axes may be narrower than the guard depth)
     }
-    const int nbx = (d.W[0] + YTX - 1) / YTX, nby = (d.W[1] + YTY - 1) / YTY, nbz = (d.W[2] + YTZ - 1) / YTZ;
-    const size_t smem = (size_t)(3 * (YTX + 3) * (YTY + 3) * (YTZ + 3) + 3 * (YTX + 2) * (YTY + 2) * (YTZ + 2)) * sizeof(T);
-    static size_t attr = 0;
-    if (attr < smem) {
-        cudaError_t e = cudaFuncSetAttribute(k_yee_fused<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return (int)e;
-        attr = smem;
-    }
-    k_yee_fused<T><<<nbx * nby * nbz, 256, smem, st>>>(d, sd, (const T*)E[0], (const T*)E[1], (const T*)E[2], (const T*)B[0], (const T*)B[1],
-                                                       (const T*)B[2], (const T*)J[0], (const T*)J[1], (const T*)J[2], (T*)E2[0], (T*)E2[1],
-                                                       (T*)E2[2], (T*)B2[0], (T*)B2[1], (T*)B2[2], (T)p->dt, (T)(p->dt / 2), (T)p->dx,
-                                                       (T)p->dy, (T)p->dz, (T)(p->C * p->C), (T)p->eps, nbx, nby, nbz);
-    PIC_LAUNCH_RET();
+    if (sizeof(T) == 4 && d.W[0] >= 16) return launch_yee_fused_tx<T, 8>(p, d, sd, E, B, J, E2, B2, st);
+    return launch_yee_fused_tx<T, 4>(p, d, sd, E, B, J, E2, B2, st);
 }
 
 // ---------------------------------------------------------------- divergence residuals (conservation diagnostics)

@@ -39,7 +39,9 @@ namespace pic {
 #define PIC_K10_NSTAGE 3
 #endif
 #ifndef PIC_K10_DEAL
-#define PIC_K10_DEAL 0         /* chunks of a supercell reach the warps 0: round-robin continuing across supercells, 1: through a shared-memory counter */
+#define PIC_K10_DEAL 1         /* chunks of a supercell reach the warps 0: round-robin continuing across supercells (4.20 ms per launch),
+                                  1: through a shared-memory counter (3.91 ms: a warp held up by a queue flush no longer delays the
+                                  release of its ring slot) -- profiles/r02_ab3_run.log */
 #endif
 #ifndef PIC_K10_W
 #define PIC_K10_W 2            /* particles per thread in float (1 = scalar control) */

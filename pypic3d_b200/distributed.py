@@ -120,19 +120,17 @@ class DistributedHalo:
         return [int(v) for v in t.tolist()]
 
     # ------------------------------------------------------------------ guard cells
-    def refresh_split_(self, fields, bcs):
-        """Refresh only along the axes that are split across ranks (the caller has filled the other axes' guard cells itself,
-        e.g. pic_yee_fused); same x -> y -> z order and full transverse extent, so edges and corners still propagate."""
-        self.refresh_(fields, bcs, only_split=True)
-
-    def refresh_(self, fields, bcs, only_split=False):
-        """In-place refresh x -> y -> z (ghost_cells.py:181-215)."""
+    def refresh_(self, fields, bcs, skip_axes=()):
+        """In-place refresh x -> y -> z (ghost_cells.py:181-215).  `skip_axes`: axes whose guard cells the caller has already
+        filled (pic_yee_fused writes the guard copies of single-rank periodic axes itself); the order and the full transverse
+        extent of the remaining exchanges are unchanged, so edges and corners still propagate."""
         g, p = self.g, self.p
         for axis in range(3):
             bc = int(bcs[axis])
+            if axis in skip_axes:
+                continue
             if not self._is_split(axis):
-                if not only_split:
-                    self.k.refresh_axis(p, axis, bc, fields)
+                self.k.refresh_axis(p, axis, bc, fields)
                 continue
             n = self._plane_elems(axis, len(fields))
             L = self.L[axis]

@@ -33,14 +33,13 @@ class LocalHalo:
     def __init__(self, params):
         self.p = params
 
-    def refresh_(self, fields, bcs):
-        ops.halo_refresh_(self.p, fields, bcs)
-
     def fold_(self, fields, bcs):
         ops.halo_fold_(self.p, fields, bcs)
 
-    def refresh_split_(self, fields, bcs):
-        return None                 # no axis is split across ranks
+    def refresh_(self, fields, bcs, skip_axes=()):
+        for axis in range(3):
+            if axis not in skip_axes:
+                ops.halo_refresh_axis_(self.p, axis, int(bcs[axis]), fields)
 
     def migrate(self, sim):
         return None
@@ -377,9 +376,15 @@ class Simulation:
         if self._E2 is None:
             self._E2 = [torch.zeros_like(c) for c in self.E]
             self._B2 = [torch.zeros_like(c) for c in self.B]
-        if self.distributed:
-            self.halo.refresh_(self.J, pbc)
-            self._J_ghosts_stale = False
+        # axes whose guard cells the kernel serves itself: single-rank axes that are non-periodic (walls) or periodic and at least
+        # as wide as the guard depth (wrapped indices).  The others -- split across ranks, or reduced (one cell wide) -- are read
+        # from the guard cells, so J's must be refreshed there first and E's, B's afterwards.
+        done = tuple(a for a in range(3) if int(p.gmesh[a]) == int(p.mesh[a]) and (int(fbc[a]) != 0 or int(p.tile[a]) >= int(p.g)))
+        if len(done) < 3:
+            # (with the FIELD boundary conditions: what the kernel needs in J's guard plane is the J of the cell the field
+            # stencil continues into; the guard cells the reference leaves in J -- particle BCs -- are restored on export)
+            self.halo.refresh_(self.J, fbc, skip_axes=done)
+            self._J_ghosts_stale = True
         rc = _lib.lib().pic_yee_fused(ctypes.byref(p), ops._v(self.E), ops._v(self.B), ops._v(self.J), ops._v(self._E2), ops._v(self._B2),
                                       ops._stream())
         if rc == _lib.PIC_EUNSUPPORTED:
@@ -388,8 +393,8 @@ class Simulation:
         check(rc, "pic_yee_fused")
         self.E, self._E2 = self._E2, self.E
         self.B, self._B2 = self._B2, self.B
-        if self.distributed:
-            self.halo.refresh_split_(self.E + self.B, fbc)
+        if len(done) < 3:
+            self.halo.refresh_(self.E + self.B, fbc, skip_axes=done)
         return True
 
     def _after_fields(self):
