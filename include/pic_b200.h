@@ -242,7 +242,9 @@ int pic_fused_tile3d(const PicParams* p, int species, const PicSoA* soa, const i
  * two particles at once in packed f32x2 arithmetic (float; one at a time in double), a dedicated producer warp feeds the TMA
  * ring, and particles that change cell are finished by full warps.  Requires the supercell slices of `blk_off` to start on
  * 16-byte boundaries, i.e. the SoA to come from the blocked, padded sort below (flags[0] |= 8 otherwise).
- * options bit 1 as for pic_fused_tile3d.
+ * options bit 1 as for pic_fused_tile3d; bit 2 (float32): reduce the same-cell currents through per-warp shared-memory rows
+ * (one ballot finds the runs of equal cells, lane t sums one current component of run t / 3 and issues its four REDs) instead
+ * of the segmented warp scan.
  * Replaces, like pic_fused_push_deposit, PyPIC3D/evolve.py:33-79 (particle_push -> Esirkepov_current ->
  * update_tiled_particle_positions -> refresh_tiled_particle_tiles) for one local tile. */
 int pic_fused_pair3d(const PicParams* p, int species, const PicSoA* soa, const int32_t* blk_off, int nblk, int options,

@@ -670,8 +670,11 @@ static int launch_yee_fused(const PicParams* p, const void* const E[3], const vo
         sd.cond_lo[a] = (p->field_bc[a] == PIC_BC_CONDUCTING && at_lo) ? 1 : 0;
         sd.cond_hi[a] = (p->field_bc[a] == PIC_BC_CONDUCTING && at_hi) ? 1 : 0;
     }
-    if (sizeof(T) == 4 && d.W[0] >= 16) return launch_yee_fused_tx<T, 8>(p, d, sd, E, B, J, E2, B2, st);
-    return launch_yee_fused_tx<T, 4>(p, d, sd, E, B, J, E2, B2, st);
+#ifndef PIC_YEE_TX
+#define PIC_YEE_TX 2        /* x cells per tile (float): the kernel is latency-bound, more resident CTAs beat less redundancy */
+#endif
+    if (sizeof(T) == 4 && d.W[0] >= 2 * PIC_YEE_TX) return launch_yee_fused_tx<T, PIC_YEE_TX>(p, d, sd, E, B, J, E2, B2, st);
+    return launch_yee_fused_tx<T, 2>(p, d, sd, E, B, J, E2, B2, st);
 }
 
 // ---------------------------------------------------------------- divergence residuals (conservation diagnostics)

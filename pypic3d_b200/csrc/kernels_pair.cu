@@ -47,7 +47,7 @@ namespace pic {
 #define PIC_K10_W 2            /* particles per thread in float (1 = scalar control) */
 #endif
 // staged particle slots per supercell and array (mean 512 at 8 ppc per species); double with the wider tile: 576, to fit 227 KB
-template <typename T> struct K10Cap { static constexpr int PCAP = (sizeof(T) == 8 && PIC_TILE_YPAD > 1) ? 576 : 640; };
+template <typename T> struct K10Cap { static constexpr int PCAP = (sizeof(T) == 4 || PIC_TILE_YPAD > 1) ? 576 : 640; };
 // per-warp queue of cell-crossers: flushed in full warps, so at most 31 wait while up to 32 W join in one iteration
 template <int W> struct K10Queue { static constexpr int QW = 32 * (W + 1); };
 
@@ -75,6 +75,15 @@ __device__ __forceinline__ void st_vec(T* ptr, const Vec<T, W>& a) {
         for (int j = 0; j < W; ++j) ptr[j] = a.v[j];
     }
 }
+
+// Particle state of a chunk, read from the staged slice in shared memory every time it is asked (pic_pair.cuh ArrayLoader): the
+// slice stays valid until the warp releases the stage, so x need not live in registers across the gather nor v before the push.
+template <typename T, int W, int PCAP>
+struct ChunkLoader {
+    const T* st;            // staged slot of this thread's first particle: array c at st[c * PCAP]
+    __device__ __forceinline__ Vec<T, W> pos(int a) const { return ld_vec<T, W>(st + a * PCAP); }
+    __device__ __forceinline__ Vec<T, W> vel(int a) const { return ld_vec<T, W>(st + (3 + a) * PCAP); }
+};
 
 // the 12 same-cell currents of one cell -> global J (fire-and-forget REDs)
 template <typename T>
@@ -166,10 +175,57 @@ __device__ __forceinline__ void pair_group_red(T* v, int key, int lane, const Ti
 template <typename T> struct K10Stage { static constexpr int ELEMS = 6 * TILE_ELEMS + 6 * K10Cap<T>::PCAP; };
 constexpr int K10_HDR = 512;    // barriers + descriptors in front of the ring
 
+// Same-cell reduction through shared memory (float): every lane parks its 12 values in the warp's scratch rows; the contiguous
+// runs of equal keys (<= 32) are found with one ballot; then lane t sums quad q = t % 3 (the four values of current component q)
+// of run t / 3 over the run's rows -- one LDS.128 + 4 adds per row, independent accumulators -- and issues that component's four
+// REDs.  Against the segmented scan: ~70 instead of ~160 instructions per chunk, 4 instead of 12 RED instructions, no shuffle
+// chains on the critical path; 10 runs per pass (a freshly sorted chunk of 64 particles has 8 - 9).
+constexpr int K10_RED_ROW = 12;                       // floats per scratch row
+constexpr int K10_RED_BYTES = 32 * K10_RED_ROW * 4 + 32 * 8;    // scratch rows + (start, len, key) per run
+__device__ __forceinline__ void pair_smem_red(const float* lv, int key, int lane, const TileSink<float>& sink, int key0, int sx, int sy,
+                                              float* scratch, int2* runs) {
+    float4* row = reinterpret_cast<float4*>(scratch + lane * K10_RED_ROW);
+    row[0] = make_float4(lv[0], lv[1], lv[2], lv[3]);
+    row[1] = make_float4(lv[4], lv[5], lv[6], lv[7]);
+    row[2] = make_float4(lv[8], lv[9], lv[10], lv[11]);
+    const int key_prev = __shfl_up_sync(0xffffffffu, key, 1);
+    const bool head = (lane == 0) || (key != key_prev);
+    const unsigned heads = __ballot_sync(0xffffffffu, head);
+    if (head) {
+        const unsigned above = (lane == 31) ? 0u : (heads >> (lane + 1));
+        const int len = above ? __ffs(above) : 32 - lane;
+        runs[__popc(heads & ((1u << lane) - 1u))] = make_int2(lane | (len << 8), key);
+    }
+    __syncwarp();
+    const int nrun = __popc(heads);
+    const int t3 = lane / 3, q = lane - 3 * t3;
+    for (int base = 0; base < nrun; base += 10) {
+        const int r = base + t3;
+        if (lane < 30 && r < nrun) {
+            const int2 info = runs[r];
+            if (info.y >= 0) {
+                const int start = info.x & 0xff, len = info.x >> 8;
+                const float4* src = reinterpret_cast<const float4*>(scratch + start * K10_RED_ROW) + q;
+                float4 acc = src[0];
+                for (int i = 1; i < len; ++i) {
+                    const float4 v = src[i * (K10_RED_ROW / 4)];
+                    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+                }
+                const int k = info.y;
+                float* J = (q == 0 ? sink.J[0] : (q == 1 ? sink.J[1] : sink.J[2])) + (key0 + (k >> 6) * sx + ((k >> 3) & 7) * sy + (k & 7));
+                const int o1 = (q == 2) ? sy : 1, o2 = (q == 0) ? sy : sx;      // SameCell<1>::offset(c = q, 0, m1, m2)
+                atomicAdd(J, acc.x); atomicAdd(J + o1, acc.y); atomicAdd(J + o2, acc.z); atomicAdd(J + o1 + o2, acc.w);
+            }
+        }
+    }
+    __syncwarp();
+}
+
 template <typename T, int W, int NWC>
 struct PairSmem {
     static constexpr size_t bytes = (size_t)K10_HDR + (size_t)PIC_K10_NSTAGE * K10Stage<T>::ELEMS * sizeof(T)
-                                    + (size_t)NWC * K10Queue<W>::QW * (sizeof(int) + 6 * sizeof(T));
+                                    + (size_t)NWC * K10Queue<W>::QW * (sizeof(int) + 6 * sizeof(T))
+                                    + (sizeof(T) == 4 ? (size_t)NWC * K10_RED_BYTES : 0);
 };
 
 // MODE: 0 = segmented scan + RED, 2 = match-any groups + RED (same numbering as K1 v9)
@@ -207,49 +263,55 @@ k_pair3d(const __grid_constant__ PicParams p, int species, const __grid_constant
 
     // ------------------------------------------------------------------ producer warp: one thread feeds the ring
     if (warp == NWC) {
-        if (lane == 0 && b1 > b0) {
-            // slice bounds are read two supercells ahead of their use, so the producer never sits on a DRAM round trip between a
-            // stage being released and its refill being issued
-            int beg = blk_off[b0];
-            int end_next = blk_off[b0 + 1];
-            int end_next2 = (b0 + 2 <= nblk) ? blk_off[b0 + 2] : end_next;
-            for (int b = b0; b < b1; ++b) {
-                const int j = b - b0, sr = j % NSTAGE;
-                int end = end_next;
-                const int beg_following = end;
-                end_next = end_next2;
-                if (b + 3 <= nblk) end_next2 = blk_off[b + 3];
-                if (j >= NSTAGE) {                               // previous occupant: supercell b - NSTAGE (suspended wait, no spinning)
-                    while (!mbar_try_wait(empty + sr, ((j / NSTAGE) - 1) & 1, 20000)) {}
-                }
-                const int bz = b % nbz, by = (b / nbz) % nby, bx = b / (nbz * nby);
-                if (end > n_live) end = n_live;
-                int n = 0;
-                if (end > beg && !(beg & (AL - 1))) {
-                    n = (end - beg + AL - 1) & ~(AL - 1);
-                    if (n > PCAP) n = PCAP;
-                    if (beg + n > cap_al) n = cap_al - beg;
-                    if (n < 0) n = 0;
-                }
-                if (beg & (AL - 1)) atomicOr(flags, 8);          // contract: slices come from the padded sort (pic_sort_blocked_*)
-                int* d = desc + sr * 8;
-                const int ox = bx * TILE_B + gm.g - 2, oy = by * TILE_B + gm.g - 2, oz = bz * TILE_B + gm.g - 2;
-                d[0] = beg; d[1] = (beg & (AL - 1)) ? beg : end; d[2] = beg + n;
-                d[3] = (bx == 0 || bx == nbx - 1 || by == 0 || by == nby - 1 || bz == 0 || bz == nbz - 1) ? 1 : 0;
-                d[4] = ox * k.sx + oy * k.sy + oz;
-                d[5] = 0;                                        // (PIC_K10_DEAL == 1) next undealt chunk of this supercell
-                T* x0 = dx0 + sr * 4;
-                x0[0] = pic_fma((T)ox, k.sc[0], k.oc[0]); x0[1] = pic_fma((T)oy, k.sc[1], k.oc[1]); x0[2] = pic_fma((T)oz, k.sc[2], k.oc[2]);
-                T* st = stages + sr * STAGE_ELEMS;
-                mbar_arrive_expect_tx(full + sr, TILE_ALL * (int)sizeof(T) + 6 * n * (int)sizeof(T));
+        if (lane == 0) {
+            // The ring carries a stream of PARTS: a supercell with up to PCAP particles is one part, a denser one is cut into parts of
+            // PCAP slots (same tile, next slice), an empty one is skipped; a final part with the `done` mark ends the stream.
+            // Slice bounds are read two supercells ahead of their use, so the producer never sits on a DRAM round trip between a
+            // stage being released and its refill being issued.
+            int j = 0;                                           // parts issued so far
+            auto wait_slot = [&](int sr) {                       // previous occupant: part j - NSTAGE (suspended wait, no spinning)
+                if (j >= NSTAGE) while (!mbar_try_wait(empty + sr, ((j / NSTAGE) - 1) & 1, 20000)) {}
+            };
+            if (b1 > b0) {
+                int beg = blk_off[b0];
+                int end_next = blk_off[b0 + 1];
+                int end_next2 = (b0 + 2 <= nblk) ? blk_off[b0 + 2] : end_next;
+                for (int b = b0; b < b1; ++b) {
+                    int end = end_next;
+                    const int beg_following = end;
+                    end_next = end_next2;
+                    if (b + 3 <= nblk) end_next2 = blk_off[b + 3];
+                    if (end > n_live) end = n_live;
+                    if (beg & (AL - 1)) { atomicOr(flags, 8); end = beg; }   // contract: slices come from the padded sort (pic_sort_blocked_*)
+                    const int bz = b % nbz, by = (b / nbz) % nby, bx = b / (nbz * nby);
+                    const int ox = bx * TILE_B + gm.g - 2, oy = by * TILE_B + gm.g - 2, oz = bz * TILE_B + gm.g - 2;
+                    for (int pb = beg; pb < end; pb += PCAP, ++j) {
+                        const int sr = j % NSTAGE;
+                        const int pe = (pb + PCAP < end) ? pb + PCAP : end;
+                        int n = (pe - pb + AL - 1) & ~(AL - 1);
+                        if (pb + n > cap_al) n = cap_al - pb;
+                        wait_slot(sr);
+                        int* d = desc + sr * 8;
+                        d[0] = pb; d[1] = pe; d[2] = 0;
+                        d[3] = (bx == 0 || bx == nbx - 1 || by == 0 || by == nby - 1 || bz == 0 || bz == nbz - 1) ? 1 : 0;
+                        d[4] = ox * k.sx + oy * k.sy + oz;
+                        d[5] = 0;                                    // (PIC_K10_DEAL == 1) next undealt chunk of this part
+                        T* x0 = dx0 + sr * 4;
+                        x0[0] = pic_fma((T)ox, k.sc[0], k.oc[0]); x0[1] = pic_fma((T)oy, k.sc[1], k.oc[1]); x0[2] = pic_fma((T)oz, k.sc[2], k.oc[2]);
+                        T* st = stages + sr * STAGE_ELEMS;
+                        mbar_arrive_expect_tx(full + sr, TILE_ALL * (int)sizeof(T) + 6 * n * (int)sizeof(T));
 #pragma unroll
-                for (int c = 0; c < 6; ++c) tma_load_box(st + c * TILE_ELEMS, &tm.m[c], full + sr, oz, oy, ox);
-                if (n > 0) {
+                        for (int c = 0; c < 6; ++c) tma_load_box(st + c * TILE_ELEMS, &tm.m[c], full + sr, oz, oy, ox);
 #pragma unroll
-                    for (int c = 0; c < 6; ++c) tma_load_bytes(st + TILE_ALL + c * PCAP, s.c[c] + beg, n * (int)sizeof(T), full + sr);
+                        for (int c = 0; c < 6; ++c) tma_load_bytes(st + TILE_ALL + c * PCAP, s.c[c] + pb, n * (int)sizeof(T), full + sr);
+                    }
+                    beg = beg_following;
                 }
-                beg = beg_following;
             }
+            const int sr = j % NSTAGE;                           // end of the stream
+            wait_slot(sr);
+            desc[sr * 8 + 2] = 1;
+            mbar_arrive(full + sr);
         }
         return;
     }
@@ -264,6 +326,7 @@ k_pair3d(const __grid_constant__ PicParams p, int species, const __grid_constant
     int* qi = reinterpret_cast<int*>(qraw) + warp * QW;                                                 // [NWC][QW] particle index
     T* qo = reinterpret_cast<T*>(qraw + (size_t)NWC * QW * sizeof(int)) + (size_t)warp * 6 * QW;        // [NWC]([3][QW] old + [3][QW] new position)
     T* qx = qo + 3 * QW;
+    unsigned char* red_raw = qraw + (size_t)NWC * QW * (sizeof(int) + 6 * sizeof(T)) + (size_t)warp * K10_RED_BYTES;   // (float only)
     int qn = 0;                                              // warp-uniform queue fill
     auto flush = [&](int keep_below) {
         while (qn > keep_below) {
@@ -279,52 +342,40 @@ k_pair3d(const __grid_constant__ PicParams p, int species, const __grid_constant
         __syncwarp();
     };
     int slot = 0, par = 0, rot = 0;
-    for (int b = b0; b < b1; ++b) {
+    for (;;) {
         while (!mbar_try_wait(full + slot, par, 1000)) {}
         const int4 d0 = *reinterpret_cast<const int4*>(desc + slot * 8);
+        if (d0.z) break;                                         // end of this CTA's stream
         const int key0 = desc[slot * 8 + 4];
-        const int p_beg = d0.x, p_end = d0.y, staged_end = d0.z;
+        const int p_beg = d0.x, p_end = d0.y;
         const bool edge = d0.w != 0;
         const T x0[3] = {dx0[slot * 4], dx0[slot * 4 + 1], dx0[slot * 4 + 2]};
         const T* tile = stages + slot * STAGE_ELEMS;
         const T* pst = tile + TILE_ALL;
-        const int nchunk = p_end > p_beg ? (p_end - p_beg + CH - 1) / CH : 0;
+        const int nchunk = (p_end - p_beg + CH - 1) / CH;
 #if PIC_K10_DEAL == 1
+        // chunks are dealt through the part's counter; the NEXT chunk is claimed before the current one is processed, so the
+        // shared-memory atomic's round trip hides behind the body (a warp over-claims one chunk past the end: harmless)
+        int ch_claim = 0;
+        if (lane == 0) ch_claim = atomicAdd(desc + slot * 8 + 5, 1);
         for (;;) {
-            int ch = 0;
-            if (lane == 0) ch = atomicAdd(desc + slot * 8 + 5, 1);
-            ch = __shfl_sync(0xffffffffu, ch, 0);
+            const int ch = __shfl_sync(0xffffffffu, ch_claim, 0);
             if (ch >= nchunk) break;
+            if (lane == 0) ch_claim = atomicAdd(desc + slot * 8 + 5, 1);
 #else
         for (int ch = (warp + NWC - rot) % NWC; ch < nchunk; ch += NWC) {
 #endif
             const int i0 = p_beg + ch * CH + W * lane;
-            Vec<T, W> pos[3], vel[3];
+            const ChunkLoader<T, W, PCAP> ld{pst + (i0 - p_beg)};
             bool live[W];
-            // the chunk's live slots all sit in the staged slice (the lanes past p_end read stage memory that is never used)
-            const int ch_end = (p_beg + (ch + 1) * CH < p_end) ? p_beg + (ch + 1) * CH : p_end;
-            if (ch_end <= staged_end && (ch + 1) * CH <= PCAP) {
+            {
+                const Vec<T, W> px = ld.pos(0);                  // (lanes past p_end read stage memory that is never used)
 #pragma unroll
-                for (int c = 0; c < 3; ++c) {
-                    pos[c] = ld_vec<T, W>(pst + c * PCAP + (i0 - p_beg));
-                    vel[c] = ld_vec<T, W>(pst + (3 + c) * PCAP + (i0 - p_beg));
-                }
-            } else {
-#pragma unroll
-                for (int j = 0; j < W; ++j) {
-                    const bool in = i0 + j < p_end;
-#pragma unroll
-                    for (int c = 0; c < 3; ++c) {
-                        pos[c].v[j] = in ? s.c[c][i0 + j] : pic_nan<T>();
-                        vel[c].v[j] = in ? s.c[3 + c][i0 + j] : (T)0;
-                    }
-                }
+                for (int j = 0; j < W; ++j) live[j] = (i0 + j < p_end) && !pic_isnan(px.v[j]);
             }
-#pragma unroll
-            for (int j = 0; j < W; ++j) live[j] = (i0 + j < p_end) && !pic_isnan(pos[0].v[j]);
             Vec<T, W> pos_out[3], vel_out[3], xraw[3], vals[12];
             int kind[W], cid[W];
-            pair_advance<T, W, PUSHER, PER1>(k, pc, tile, x0, edge, pos, vel, live, pos_out, vel_out, xraw, kind, cid, vals);
+            pair_advance_ld<T, W, PUSHER, PER1, ChunkLoader<T, W, PCAP>>(k, pc, tile, x0, edge, ld, live, pos_out, vel_out, xraw, kind, cid, vals);
             // ---- not covered by the tile: the scalar global-memory body does the whole step for that particle
             {
                 unsigned slow = 0;
@@ -371,7 +422,7 @@ k_pair3d(const __grid_constant__ PicParams p, int species, const __grid_constant
                             const int e = base + __popc(m[j] & ((1u << lane) - 1u));
                             qi[e] = i0 + j;
 #pragma unroll
-                            for (int a = 0; a < 3; ++a) { qo[a * QW + e] = pos[a].v[j]; qx[a * QW + e] = xraw[a].v[j]; }
+                            for (int a = 0; a < 3; ++a) { qo[a * QW + e] = ld.pos(a).v[j]; qx[a * QW + e] = xraw[a].v[j]; }
                         }
                         base += __popc(m[j]);
                     }
@@ -401,7 +452,10 @@ k_pair3d(const __grid_constant__ PicParams p, int species, const __grid_constant
                     for (int n = 0; n < 12; ++n) lv[n] = vals[n].v[0];
                     key = (kind[0] == PAIR_SAME) ? cid[0] : -1 - lane;
                 }
-                if (MODE == 2) pair_group_red<T>(lv, key, lane, sink, key0, k.sx, k.sy);
+                if constexpr (MODE == 3 && sizeof(T) == 4)
+                    pair_smem_red(lv, key, lane, sink, key0, k.sx, k.sy, reinterpret_cast<float*>(red_raw),
+                                  reinterpret_cast<int2*>(red_raw + 32 * K10_RED_ROW * 4));
+                else if (MODE == 2) pair_group_red<T>(lv, key, lane, sink, key0, k.sx, k.sy);
                 else pair_scan_red<T, 3>(lv, key, lane, sink, key0, k.sx, k.sy);
             }
             if (qn >= 32) flush(31);
@@ -508,6 +562,7 @@ static int launch_pair3d(const PicParams* p, int species, const PicSoA* soa, con
     int distributed = 0;
     for (int c = 0; c < 3; ++c) distributed |= (p->gmesh[c] != p->mesh[c]);
     const bool grp = (options & 2) != 0;
+    const bool smr = !grp && (options & 4) != 0 && sizeof(T) == 4;      // shared-memory segmented reduction (float)
     TileMaps tm;
     if (!make_tile_maps<T>(gm.L, F.f, Jw.f, tm)) return PIC_EUNSUPPORTED;
     bool per1 = !distributed;
@@ -532,7 +587,7 @@ static int launch_pair3d(const PicParams* p, int species, const PicSoA* soa, con
         }                                                                                                                \
         k_pair3d<T, W, PUSH, NWC, CTAS, PER, MD><<<grid, (NWC + 1) * 32, smem, st>>>(*p, species, gm, k, pc, sv, F, Jw, lb, distributed, flags, tm, blk_off, nblk, nbx, nby, nbz); \
     } while (0)
-#define PIC_LAUNCH_K10_M(PUSH, PER) do { if (grp) PIC_LAUNCH_K10(PUSH, PER, 2); else PIC_LAUNCH_K10(PUSH, PER, 0); } while (0)
+#define PIC_LAUNCH_K10_M(PUSH, PER) do { if (grp) PIC_LAUNCH_K10(PUSH, PER, 2); else if (smr) PIC_LAUNCH_K10(PUSH, PER, 3); else PIC_LAUNCH_K10(PUSH, PER, 0); } while (0)
     if (p->pusher == PIC_PUSHER_BORIS) { if (per1) PIC_LAUNCH_K10_M(PIC_PUSHER_BORIS, true); else PIC_LAUNCH_K10_M(PIC_PUSHER_BORIS, false); }
     else { if (per1) PIC_LAUNCH_K10_M(PIC_PUSHER_BORIS_REL, true); else PIC_LAUNCH_K10_M(PIC_PUSHER_BORIS_REL, false); }
 #undef PIC_LAUNCH_K10_M

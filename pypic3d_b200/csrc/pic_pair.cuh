@@ -255,10 +255,33 @@ PIC_HD void make_pair_const(const FastConst<T>& k, PairConst<T>& pc) {
 
 // tile: [6][TILE_N][TILE_NY][TILE_N] (z fastest), component order Ex Ey Ez Bx By Bz; x0[a] = position of the tile's first
 // centre-line node.  pos/vel in: state at t; out: pos = (x_new + h) - h (not wrapped), vel = v_new.  xraw = x + v dt.
+// Where the body gets the particle state from.  The kernel's loader reads the staged shared-memory slice EVERY time it is asked,
+// so x is not kept in registers across the gather and v is not live before the push: fewer registers at the widest point.
+template <typename T, int W>
+struct ArrayLoader {
+    const Vec<T, W>* p;
+    const Vec<T, W>* v;
+    PIC_HD Vec<T, W> pos(int a) const { return p[a]; }
+    PIC_HD Vec<T, W> vel(int a) const { return v[a]; }
+};
+
+template <typename T, int W, int PUSHER, bool PER1, class Ld>
+PIC_HD void pair_advance_ld(const FastConst<T>& k, const PairConst<T>& pc, const T* tile, const T x0[3], bool edge, const Ld& ld,
+                            const bool live[W], Vec<T, W> pos_out[3], Vec<T, W> vel_out[3], Vec<T, W> xraw[3], int kind[W], int cid[W],
+                            Vec<T, W> vals[12]);
+
 template <typename T, int W, int PUSHER, bool PER1>
 PIC_HD void pair_advance(const FastConst<T>& k, const PairConst<T>& pc, const T* tile, const T x0[3], bool edge,
                          const Vec<T, W> pos[3], const Vec<T, W> vel[3], const bool live[W], Vec<T, W> pos_out[3],
                          Vec<T, W> vel_out[3], Vec<T, W> xraw[3], int kind[W], int cid[W], Vec<T, W> vals[12]) {
+    const ArrayLoader<T, W> ld{pos, vel};
+    pair_advance_ld<T, W, PUSHER, PER1, ArrayLoader<T, W>>(k, pc, tile, x0, edge, ld, live, pos_out, vel_out, xraw, kind, cid, vals);
+}
+
+template <typename T, int W, int PUSHER, bool PER1, class Ld>
+PIC_HD void pair_advance_ld(const FastConst<T>& k, const PairConst<T>& pc, const T* tile, const T x0[3], bool edge, const Ld& ld,
+                            const bool live[W], Vec<T, W> pos_out[3], Vec<T, W> vel_out[3], Vec<T, W> xraw[3], int kind[W], int cid[W],
+                            Vec<T, W> vals[12]) {
     typedef Vec<T, W> V;
     // ---- tile coordinates, coverage test (NaN fails it), safe substitution for everything that is not advanced here
     V q[3];
@@ -267,7 +290,7 @@ PIC_HD void pair_advance(const FastConst<T>& k, const PairConst<T>& pc, const T*
     for (int j = 0; j < W; ++j) ok[j] = live[j];
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
-        q[a] = vmuls(vsub(pos[a], vsplat<T, W>(x0[a])), k.inv_d[a]);
+        q[a] = vmuls(vsub(ld.pos(a), vsplat<T, W>(x0[a])), k.inv_d[a]);
         const V off = vadds(q[a], (T)-3.75);
 #pragma unroll
         for (int j = 0; j < W; ++j) ok[j] = ok[j] && (pic_abs(off.v[j]) < (T)3.2499);       // q in (0.5001, 6.9999): both Yee lines covered
@@ -323,6 +346,7 @@ PIC_HD void pair_advance(const FastConst<T>& k, const PairConst<T>& pc, const T*
     }
     // ---- push (boris.py:41-55 / 96-121): v is the velocity, u = gamma v only inside the relativistic rotation
     V vn[3];
+    const V vel[3] = {ld.vel(0), ld.vel(1), ld.vel(2)};
     {
         const V one = vsplat<T, W>((T)1);
         V hE[3], um[3];
@@ -380,7 +404,7 @@ PIC_HD void pair_advance(const FastConst<T>& k, const PairConst<T>& pc, const T*
         r1[a] = vsub(qn, vadds(tn, -Magic<T>::value));
 #pragma unroll
         for (int j = 0; j < W; ++j) same[j] = same[j] && (magic_int(tn.v[j]) == ic[a][j]);
-        xraw[a] = vfma(vn[a], vsplat<T, W>(pc.dt_move[a]), pos[a]);
+        xraw[a] = vfma(vn[a], vsplat<T, W>(pc.dt_move[a]), ld.pos(a));
         const V th = vadds(xraw[a], pc.half[a]);
         pos_out[a] = vadds(th, -pc.half[a]);                       // what mod(x + h, wind) - h leaves an interior particle with
         if (edge) {

@@ -114,6 +114,7 @@ class Simulation:
         # and the scan would pay one RED set per fragment; "1" always, "0" never.
         self._jtile_mode = os.environ.get("PIC_K9_JTILE", "0")
         self._groupred_mode = os.environ.get("PIC_K9_GROUPRED", "auto")
+        self._red_mode = os.environ.get("PIC_K10_RED", "smem")
         self._sorted_at = [0] * self.S
         self.leave_fraction = float(leave_fraction)
         if self.distributed:
@@ -139,6 +140,10 @@ class Simulation:
 
     def _k1_options(self, s):
         opt = 1 if self._jtile_mode == "1" else 0
+        # K1 v10, float: bit 2 = same-cell reduction through shared memory (pair_smem_red) instead of the segmented warp scan;
+        # PIC_K10_RED = "smem" (default) | "scan"
+        if self.k1_variant == "pair" and self._red_mode == "smem":
+            opt |= 4
         if self._groupred_mode == "1":
             opt |= 2
         elif self._groupred_mode == "auto":

@@ -418,7 +418,7 @@ TILE_CASES = [
 @pytest.mark.parametrize("c", TILE_CASES)
 @pytest.mark.parametrize("dtype", (F64, F32))
 @pytest.mark.parametrize("sort_interval", (1, 5, 0))
-@pytest.mark.parametrize("variant,jtile", [("pair", "0"), ("pair", "group"), ("tile", "0"), ("tile", "1"), ("tile", "group")])
+@pytest.mark.parametrize("variant,jtile", [("pair", "0"), ("pair", "scan"), ("pair", "group"), ("tile", "0"), ("tile", "1"), ("tile", "group")])
 def test_resident_tile_kernel_matches_oracle(c, dtype, sort_interval, variant, jtile, monkeypatch):
     """K1 v10 (pic_fused_pair3d) and K1 v9 (pic_fused_tile3d): E/B gathered from shared-memory supercell tiles.  Fast particles
     (up to 0.16 cells per step) and sort_interval 5 / never let particles drift into the tile margin and beyond it, so the tile
@@ -429,6 +429,7 @@ def test_resident_tile_kernel_matches_oracle(c, dtype, sort_interval, variant, j
     # "1": same-cell currents through shared-memory J tiles + TMA reduce (v9, f32 only); "group": match-any group reduction; "0": scan
     monkeypatch.setenv("PIC_K9_JTILE", "1" if jtile == "1" else "0")
     monkeypatch.setenv("PIC_K9_GROUPRED", "1" if jtile == "group" else "0")
+    monkeypatch.setenv("PIC_K10_RED", "scan" if jtile == "scan" else "smem")      # (pair, float32: shared-memory reduction unless "scan")
     N = c["N"]
     sp, dp, tp, sc, E, B = make_case(N, N, 1, current_deposition="esirkepov", relativistic=c["rel"],
                                      particle_boundary_conditions=c["pbc"], capacity=3.0, vmax=4.0, C=10.0, dt=0.015, n=200)

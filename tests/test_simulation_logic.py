@@ -10,7 +10,7 @@ def _bare(**kw):
     sim = Simulation.__new__(Simulation)
     base = dict(p=SimpleNamespace(dx=1.0, dy=2.0, dz=0.5, dt=0.1, shape_factor=1, g=2, pusher=1, tile=(8, 8, 4), gmesh=(1, 1, 1)),
                 deposition=0, ext_E=None, sort_interval=10, step_count=0, _vrms=[1.0, 0.01], _sorted_at=[0, 0],
-                _jtile_mode="0", _groupred_mode="auto")
+                _jtile_mode="0", _groupred_mode="auto", _red_mode="scan", k1_variant="tile")
     base.update(kw)
     for k, v in base.items():
         setattr(sim, k, v)
