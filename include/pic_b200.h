@@ -240,8 +240,13 @@ int pic_fused_tile3d(const PicParams* p, int species, const PicSoA* soa, const i
 
 /* K1 v10, the pair variant of pic_fused_tile3d (same configurations, same result, same arguments): the per-thread body advances
  * two particles at once in packed f32x2 arithmetic (float; one at a time in double), a dedicated producer warp feeds the TMA
- * ring, and particles that change cell are finished by full warps.  Requires the supercell slices of `blk_off` to start on
- * 16-byte boundaries, i.e. the SoA to come from the blocked, padded sort below (flags[0] |= 8 otherwise).
+ * ring.  Two launches: the tile kernel advances every particle that stays in its cell and is covered by its supercell's
+ * tile, and writes the slot indices of all others (cell changers: union-stencil deposit, wrap / reflect / absorb / ownership;
+ * particles that drifted out of their tile since the last sort) into `work`, with the pre-move position of every cell
+ * changer; the fix-up kernel then finishes the list (cell changers: deposit + boundary conditions + store; uncovered slots
+ * and slots appended since the sort: the whole step through the scalar global-memory body).  `work`: device scratch of
+ * work_len >= pic_pair_work_bytes(p, soa->cap) bytes, 16-byte aligned, contents meaningless between calls.  Requires the supercell slices of `blk_off` to
+ * start on 16-byte boundaries, i.e. the SoA to come from the blocked, padded sort below (flags[0] |= 8 otherwise).
  * options bit 1 as for pic_fused_tile3d; bit 2 (float32): reduce the same-cell currents through per-warp shared-memory rows
  * (one ballot finds the runs of equal cells, lane t sums one current component of run t / 3 and issues its four REDs) instead
  * of the segmented warp scan.
@@ -249,7 +254,8 @@ int pic_fused_tile3d(const PicParams* p, int species, const PicSoA* soa, const i
  * update_tiled_particle_positions -> refresh_tiled_particle_tiles) for one local tile. */
 int pic_fused_pair3d(const PicParams* p, int species, const PicSoA* soa, const int32_t* blk_off, int nblk, int options,
                      const void* const E[3], const void* const B[3], void* const J[3], const PicLeave* leave, int32_t* flags,
-                     void* stream);
+                     void* work, int64_t work_len, void* stream);
+int64_t pic_pair_work_bytes(const PicParams* p, int64_t cap);
 
 /* Blocked, padded counting sort (tile widths multiples of 4): cells in 4x4x4-supercell-major order, every supercell's slice
  * padded with dead slots (x = NaN) to a multiple of 4 slots.  Sequence: pic_sort_histogram -> pic_sort_blocked_offsets ->

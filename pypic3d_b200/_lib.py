@@ -224,7 +224,8 @@ SIGNATURES = {
     "pic_sort_scatter": [_PP, _SOA, _SOA, _VP, _VP, _VP],
     "pic_fused_push_deposit": [_PP, _INT, _INT, _SOA, _V3, _V3, _V3, _V3, _V3, _LEAVE, _VP, _VP],
     "pic_fused_tile3d": [_PP, _INT, _SOA, _VP, _INT, _INT, _V3, _V3, _V3, _LEAVE, _VP, _VP],
-    "pic_fused_pair3d": [_PP, _INT, _SOA, _VP, _INT, _INT, _V3, _V3, _V3, _LEAVE, _VP, _VP],
+    "pic_fused_pair3d": [_PP, _INT, _SOA, _VP, _INT, _INT, _V3, _V3, _V3, _LEAVE, _VP, _VP, _I64, _VP],
+    "pic_pair_work_bytes": [_PP, _I64],
     "pic_sort_blocked_offsets": [_PP, _VP, _VP, _VP, _VP, _VP, _I64, _VP, _VP],
     "pic_sort_blocked_finish": [_PP, _VP, _VP, _VP, _SOA, _VP],
     "pic_packets_reset": [_PP, _LEAVE, _VP],
@@ -250,7 +251,7 @@ def lib():
     for name, argtypes in SIGNATURES.items():
         fn = getattr(L, name)
         fn.argtypes = argtypes
-        fn.restype = ctypes.c_char_p if name == "pic_version" else ctypes.c_int
+        fn.restype = ctypes.c_char_p if name == "pic_version" else (ctypes.c_int64 if name == "pic_pair_work_bytes" else ctypes.c_int)
         setattr(ns, name, _Counted(fn, KERNELS_PER_CALL.get(name, 1)))
     if L.pic_params_size() != ctypes.sizeof(PicParams):
         raise RuntimeError("pypic3d_b200: PicParams layout mismatch between Python and libpic_b200.so")

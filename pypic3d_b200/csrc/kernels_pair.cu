@@ -10,11 +10,14 @@
 //                   * supercell slices start on 16-byte boundaries (padded sort below), so a thread's pair is one 8-byte
 //                     shared-memory load per array and one 8-byte global store per array, and no pair straddles two supercells;
 //                   * chunks of 32 W particles are dealt round-robin, continuing across supercells (no dealing atomics);
-//                   * particles that change cell are queued per warp (index, old and new position) and finished by full warps:
-//                     union-stencil deposit + wrap / reflect / absorb / ownership + store (crosser_finish);
-//                   * particles whose stencil the tile does not cover (they drifted more than a cell out of their supercell since
-//                     the last sort) and slots appended since the sort take the scalar global-memory body of K1 v8, so the result
-//                     never depends on how fresh the sort is.
+//                   * everything that is not "stays in its cell, covered by the tile" is DEFERRED, not handled in line: particles that
+//                     change cell (union-stencil deposit, wrap / reflect / absorb / ownership), particles whose stencil the tile
+//                     does not cover (they drifted more than a cell out of their supercell since the last sort) and slots appended
+//                     since the sort.  The tile kernel leaves such a slot untouched and writes its index into the CTA's segment of a
+//                     work list; k_pair_fixup then runs the scalar global-memory body of K1 v8 (fused_particle_fast3d) over the
+//                     list.  The result never depends on how fresh the sort is, and the hot kernel carries none of the rare
+//                     paths' code or registers (measured: their mere presence cost the proton launch 10 %, the in-line handling
+//                     of 4 % cell changers cost the electron launch 1.1 ms of 4.8 -- profiles/r02_k1_ablation.md).
 //   k_sortb_*     counting sort by cell in the 4^3-blocked order with every supercell's slice padded to a multiple of 4 slots
 //                 (NaN = dead slot, the convention of the resident layout), producing blk_off for K1 directly.
 #include <stdlib.h>
@@ -36,20 +39,32 @@ namespace pic {
 #define PIC_K10_NWC64 15       /* double: one CTA per SM (the ring is twice as large) */
 #endif
 #ifndef PIC_K10_NSTAGE
-#define PIC_K10_NSTAGE 3
+#define PIC_K10_NSTAGE 3       /* float: ring stages per CTA */
 #endif
+#ifndef PIC_K10_NSTAGE64
+#define PIC_K10_NSTAGE64 3     /* double */
+#endif
+#ifndef PIC_K10_CLAIM_ASM
+#define PIC_K10_CLAIM_ASM 1    /* chunk claim: 1 = predicated atom.shared by lane 0 (no divergence), 0 = if (lane == 0) atomicAdd */
+#endif
+template <typename T> struct K10Ring { static constexpr int NSTAGE = sizeof(T) == 4 ? PIC_K10_NSTAGE : PIC_K10_NSTAGE64; };
 #ifndef PIC_K10_DEAL
 #define PIC_K10_DEAL 1         /* chunks of a supercell reach the warps 0: round-robin continuing across supercells (4.20 ms per launch),
                                   1: through a shared-memory counter (3.91 ms: a warp held up by a queue flush no longer delays the
                                   release of its ring slot) -- profiles/r02_ab3_run.log */
+#endif
+#ifndef PIC_ABL10
+#define PIC_ABL10 0           /* profiling builds only (tools/ab.py): WRONG RESULTS, each removes one cost centre so that its share of the
+                                  launch can be read off a timing -- 1: tiles are loaded only for the first parts of a CTA (TMA tile fill);
+                                  2: the x vertex anchor follows the centre anchor (gather bank conflicts); 3: no REDs; 4: no reduction and no
+                                  REDs; 5: no particle stores; 6: cell changers are treated as stayers (queue, union deposit, wrap);
+                                  7: all lanes gather from one address (no conflicts at all) */
 #endif
 #ifndef PIC_K10_W
 #define PIC_K10_W 2            /* particles per thread in float (1 = scalar control) */
 #endif
 // staged particle slots per supercell and array (mean 512 at 8 ppc per species); double with the wider tile: 576, to fit 227 KB
 template <typename T> struct K10Cap { static constexpr int PCAP = (sizeof(T) == 4 || PIC_TILE_YPAD > 1) ? 576 : 640; };
-// per-warp queue of cell-crossers: flushed in full warps, so at most 31 wait while up to 32 W join in one iteration
-template <int W> struct K10Queue { static constexpr int QW = 32 * (W + 1); };
 
 template <typename T, int W>
 __device__ __forceinline__ Vec<T, W> ld_vec(const T* ptr) {
@@ -88,6 +103,9 @@ struct ChunkLoader {
 // the 12 same-cell currents of one cell -> global J (fire-and-forget REDs)
 template <typename T>
 __device__ __forceinline__ void red_cell(const TileSink<T>& sink, int base, int sx, int sy, const T* v) {
+#if PIC_ABL10 == 3 || PIC_ABL10 == 4
+    if (sx != 0x7fffffff) return;            // (always taken at run time; the values stay alive for the compiler)
+#endif
     int n = 0;
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
@@ -221,22 +239,46 @@ __device__ __forceinline__ void pair_smem_red(const float* lv, int key, int lane
     __syncwarp();
 }
 
-template <typename T, int W, int NWC>
+template <typename T, int W, int NWC, int MODE>
 struct PairSmem {
-    static constexpr size_t bytes = (size_t)K10_HDR + (size_t)PIC_K10_NSTAGE * K10Stage<T>::ELEMS * sizeof(T)
-                                    + (size_t)NWC * K10Queue<W>::QW * (sizeof(int) + 6 * sizeof(T))
-                                    + (sizeof(T) == 4 ? (size_t)NWC * K10_RED_BYTES : 0);
+    static constexpr size_t bytes = (size_t)K10_HDR + (size_t)K10Ring<T>::NSTAGE * K10Stage<T>::ELEMS * sizeof(T)
+                                    + ((sizeof(T) == 4 && MODE == 3) ? (size_t)NWC * K10_RED_BYTES : 0);
 };
 
-// MODE: 0 = segmented scan + RED, 2 = match-any groups + RED (same numbering as K1 v9)
+// Work list of the deferred slots (see the header): CTA c of the tile kernel appends to the segment that starts at the first slot of
+// its supercell range (a segment is as long as the range holds slots, so it cannot overflow) and leaves the entry count in
+// cnt[c].  An entry is the slot index plus, for a cell changer, its position BEFORE the move (the tile kernel has already stored
+// the new velocity and the new, not yet wrapped, position in the slot); bit 31 of the index marks a slot the tile did not cover:
+// untouched, the fix-up pass advances it from scratch (counted in flags[2]).
+template <typename T>
+struct DeferList {
+    int32_t* cnt;      // [K10_MAX_GRID]
+    int32_t* idx;      // [cap]
+    T* pos[3];         // [cap] each
+};
+constexpr int K10_DEFER_UNCOVERED = (int)0x80000000u;
+constexpr int K10_MAX_GRID = 1024;      // CTAs of the tile kernel = leading entries of the work array (include/pic_b200.h PIC_PAIR_WORK_HEAD)
+
+// next chunk of the part in stage `slot`: one shared-memory atomic by lane 0 (predicated, the warp does not diverge)
+__device__ __forceinline__ int claim_chunk(int* counter, int lane) {
+    int v = 0;
+#if !PIC_K10_CLAIM_ASM
+    if (lane == 0) v = atomicAdd(counter, 1);
+    return v;
+#endif
+    asm volatile("{\n .reg .pred p;\n setp.eq.s32 p, %2, 0;\n @p atom.shared.add.u32 %0, [%1], 1;\n}\n"
+                 : "+r"(v) : "r"(smem_u32(counter)), "r"(lane) : "memory");
+    return v;
+}
+
+// MODE: 0 = segmented scan + RED, 2 = match-any groups + RED (same numbering as K1 v9), 3 = shared-memory segmented reduction
 template <typename T, int W, int PUSHER, int NWC, int CTAS, bool PER1, int MODE>
 __global__ void __launch_bounds__((NWC + 1) * 32, CTAS)
-k_pair3d(const __grid_constant__ PicParams p, int species, const __grid_constant__ Geom<T> gm, const __grid_constant__ FastConst<T> k,
-         const __grid_constant__ PairConst<T> pc, const __grid_constant__ SoAView<T> s, const __grid_constant__ Field6<T> F, Field3W<T> J,
-         const __grid_constant__ LeaveBuf leave, int distributed, int32_t* flags, const __grid_constant__ TileMaps tm,
-         const int32_t* __restrict__ blk_off, int nblk, int nbx, int nby, int nbz) {
-    constexpr int NSTAGE = PIC_K10_NSTAGE;
-    constexpr int PCAP = K10Cap<T>::PCAP, QW = K10Queue<W>::QW;
+k_pair3d(const __grid_constant__ FastConst<T> k, const __grid_constant__ PairConst<T> pc, const __grid_constant__ SoAView<T> s, Field3W<T> J,
+         const __grid_constant__ DeferList<T> defer, int32_t* flags, const __grid_constant__ TileMaps tm,
+         const int32_t* __restrict__ blk_off, int nblk, int nbx, int nby, int nbz, int g) {
+    constexpr int NSTAGE = K10Ring<T>::NSTAGE;
+    constexpr int PCAP = K10Cap<T>::PCAP;
     constexpr int TILE_ALL = 6 * TILE_ELEMS;
     constexpr int STAGE_ELEMS = K10Stage<T>::ELEMS;
     constexpr int AL = 16 / (int)sizeof(T);
@@ -244,17 +286,18 @@ k_pair3d(const __grid_constant__ PicParams p, int species, const __grid_constant
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);  // [NSTAGE] tile + particles have landed (TMA complete_tx)
     uint64_t* empty = full + NSTAGE;                         // [NSTAGE] every consumer warp is done with the stage
-    int* desc = reinterpret_cast<int*>(smem_raw + 64);       // [NSTAGE][8]: slice begin, end, staged end, edge flag, J key of the tile origin
+    int* desc = reinterpret_cast<int*>(smem_raw + 64);       // [NSTAGE][8]: slice begin, end, end-of-stream, edge flag, J key of the tile origin, chunk counter
+    int* ctl = reinterpret_cast<int*>(smem_raw + 192);       // [0] entries in this CTA's work-list segment, [1] consumer warps that have finished
     T* dx0 = reinterpret_cast<T*>(smem_raw + 256);           // [NSTAGE][4]: position of the tile's first centre-line node
-    T* stages = reinterpret_cast<T*>(smem_raw + K10_HDR);    // [NSTAGE]([6][8][9][8] + [6][PCAP])
-    unsigned char* qraw = smem_raw + K10_HDR + (size_t)NSTAGE * STAGE_ELEMS * sizeof(T);
+    T* stages = reinterpret_cast<T*>(smem_raw + K10_HDR);    // [NSTAGE]([6][8][TILE_NY][8] + [6][PCAP])
+    unsigned char* red_raw0 = smem_raw + K10_HDR + (size_t)NSTAGE * STAGE_ELEMS * sizeof(T);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int per_cta = (nblk + (int)gridDim.x - 1) / (int)gridDim.x;
-    const int b0 = (int)blockIdx.x * per_cta;
-    int b1 = (b0 + per_cta < nblk) ? b0 + per_cta : nblk;
-    if (b1 < b0) b1 = b0;
+    const int b0 = (int)blockIdx.x * per_cta < nblk ? (int)blockIdx.x * per_cta : nblk;
+    const int b1 = (b0 + per_cta < nblk) ? b0 + per_cta : nblk;
     if (tid == 0) {
         for (int i = 0; i < NSTAGE; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, NWC); }
+        ctl[0] = 0; ctl[1] = 0;
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
     __syncthreads();
@@ -284,7 +327,7 @@ k_pair3d(const __grid_constant__ PicParams p, int species, const __grid_constant
                     if (end > n_live) end = n_live;
                     if (beg & (AL - 1)) { atomicOr(flags, 8); end = beg; }   // contract: slices come from the padded sort (pic_sort_blocked_*)
                     const int bz = b % nbz, by = (b / nbz) % nby, bx = b / (nbz * nby);
-                    const int ox = bx * TILE_B + gm.g - 2, oy = by * TILE_B + gm.g - 2, oz = bz * TILE_B + gm.g - 2;
+                    const int ox = bx * TILE_B + g - 2, oy = by * TILE_B + g - 2, oz = bz * TILE_B + g - 2;
                     for (int pb = beg; pb < end; pb += PCAP, ++j) {
                         const int sr = j % NSTAGE;
                         const int pe = (pb + PCAP < end) ? pb + PCAP : end;
@@ -295,13 +338,20 @@ k_pair3d(const __grid_constant__ PicParams p, int species, const __grid_constant
                         d[0] = pb; d[1] = pe; d[2] = 0;
                         d[3] = (bx == 0 || bx == nbx - 1 || by == 0 || by == nby - 1 || bz == 0 || bz == nbz - 1) ? 1 : 0;
                         d[4] = ox * k.sx + oy * k.sy + oz;
-                        d[5] = 0;                                    // (PIC_K10_DEAL == 1) next undealt chunk of this part
+                        d[5] = 0;                                    // next undealt chunk of this part
                         T* x0 = dx0 + sr * 4;
                         x0[0] = pic_fma((T)ox, k.sc[0], k.oc[0]); x0[1] = pic_fma((T)oy, k.sc[1], k.oc[1]); x0[2] = pic_fma((T)oz, k.sc[2], k.oc[2]);
                         T* st = stages + sr * STAGE_ELEMS;
-                        mbar_arrive_expect_tx(full + sr, TILE_ALL * (int)sizeof(T) + 6 * n * (int)sizeof(T));
+#if PIC_ABL10 == 1
+                        const bool fill_tile = j < NSTAGE;
+#else
+                        const bool fill_tile = true;
+#endif
+                        mbar_arrive_expect_tx(full + sr, (fill_tile ? TILE_ALL * (int)sizeof(T) : 0) + 6 * n * (int)sizeof(T));
+                        if (fill_tile) {
 #pragma unroll
-                        for (int c = 0; c < 6; ++c) tma_load_box(st + c * TILE_ELEMS, &tm.m[c], full + sr, oz, oy, ox);
+                            for (int c = 0; c < 6; ++c) tma_load_box(st + c * TILE_ELEMS, &tm.m[c], full + sr, oz, oy, ox);
+                        }
 #pragma unroll
                         for (int c = 0; c < 6; ++c) tma_load_bytes(st + TILE_ALL + c * PCAP, s.c[c] + pb, n * (int)sizeof(T), full + sr);
                     }
@@ -318,30 +368,12 @@ k_pair3d(const __grid_constant__ PicParams p, int species, const __grid_constant
 
     // ------------------------------------------------------------------ consumer warps
     TileSink<T> sink;
-    for (int c = 0; c < 3; ++c) { sink.J[c] = J.f[c]; sink.L[c] = gm.L[c]; }
+    for (int c = 0; c < 3; ++c) { sink.J[c] = J.f[c]; sink.L[c] = k.L[c]; }
     sink.off = 0;
     sink.flags = flags;
-    Field6<T> X;
-    for (int c = 0; c < 6; ++c) X.f[c] = nullptr;
-    int* qi = reinterpret_cast<int*>(qraw) + warp * QW;                                                 // [NWC][QW] particle index
-    T* qo = reinterpret_cast<T*>(qraw + (size_t)NWC * QW * sizeof(int)) + (size_t)warp * 6 * QW;        // [NWC]([3][QW] old + [3][QW] new position)
-    T* qx = qo + 3 * QW;
-    unsigned char* red_raw = qraw + (size_t)NWC * QW * (sizeof(int) + 6 * sizeof(T)) + (size_t)warp * K10_RED_BYTES;   // (float only)
-    int qn = 0;                                              // warp-uniform queue fill
-    auto flush = [&](int keep_below) {
-        while (qn > keep_below) {
-            const int n_now = qn < 32 ? qn : 32;
-            const int e = qn - n_now + lane;
-            if (lane < n_now) {
-                const T o3[3] = {qo[e], qo[QW + e], qo[2 * QW + e]};
-                const T n3[3] = {qx[e], qx[QW + e], qx[2 * QW + e]};
-                crosser_finish<T, PER1>(p, species, gm, k, qi[e], s, o3, n3, sink, leave, distributed != 0, flags);
-            }
-            qn -= n_now;
-        }
-        __syncwarp();
-    };
-    int slot = 0, par = 0, rot = 0;
+    unsigned char* red_raw = red_raw0 + (size_t)warp * K10_RED_BYTES;   // (MODE 3 only)
+    const int dq0 = b0 < nblk ? blk_off[b0] : 0;          // first entry of this CTA's work-list segment
+    int slot = 0, par = 0;
     for (;;) {
         while (!mbar_try_wait(full + slot, par, 1000)) {}
         const int4 d0 = *reinterpret_cast<const int4*>(desc + slot * 8);
@@ -353,18 +385,13 @@ k_pair3d(const __grid_constant__ PicParams p, int species, const __grid_constant
         const T* tile = stages + slot * STAGE_ELEMS;
         const T* pst = tile + TILE_ALL;
         const int nchunk = (p_end - p_beg + CH - 1) / CH;
-#if PIC_K10_DEAL == 1
         // chunks are dealt through the part's counter; the NEXT chunk is claimed before the current one is processed, so the
         // shared-memory atomic's round trip hides behind the body (a warp over-claims one chunk past the end: harmless)
-        int ch_claim = 0;
-        if (lane == 0) ch_claim = atomicAdd(desc + slot * 8 + 5, 1);
+        int ch_claim = claim_chunk(desc + slot * 8 + 5, lane);
         for (;;) {
             const int ch = __shfl_sync(0xffffffffu, ch_claim, 0);
             if (ch >= nchunk) break;
-            if (lane == 0) ch_claim = atomicAdd(desc + slot * 8 + 5, 1);
-#else
-        for (int ch = (warp + NWC - rot) % NWC; ch < nchunk; ch += NWC) {
-#endif
+            ch_claim = claim_chunk(desc + slot * 8 + 5, lane);
             const int i0 = p_beg + ch * CH + W * lane;
             const ChunkLoader<T, W, PCAP> ld{pst + (i0 - p_beg)};
             bool live[W];
@@ -376,26 +403,22 @@ k_pair3d(const __grid_constant__ PicParams p, int species, const __grid_constant
             Vec<T, W> pos_out[3], vel_out[3], xraw[3], vals[12];
             int kind[W], cid[W];
             pair_advance_ld<T, W, PUSHER, PER1, ChunkLoader<T, W, PCAP>>(k, pc, tile, x0, edge, ld, live, pos_out, vel_out, xraw, kind, cid, vals);
-            // ---- not covered by the tile: the scalar global-memory body does the whole step for that particle
-            {
-                unsigned slow = 0;
-#pragma unroll
-                for (int j = 0; j < W; ++j) slow |= (kind[j] == PAIR_SLOW) ? (1u << j) : 0u;
-                while (slow) {
-                    const int j = __ffs(slow) - 1;
-                    slow &= slow - 1;
-                    fused_particle_fast3d<T, 1, PUSHER, false>(p, species, gm, k, (int64_t)(i0 + j), s, F, X, sink, leave, distributed != 0, flags);
-                    atomic_add_i32(flags + 2, 1);
-                }
-            }
-            // ---- store (cell crossers get their final position from crosser_finish later)
+            // ---- store: stayers are finished; a cell changer leaves its new velocity and its raw new position (k_pair_fixup deposits
+            //      it over the union stencil and applies the boundary conditions); an uncovered particle keeps its old state
             {
                 bool stv[W];
 #pragma unroll
-                for (int j = 0; j < W; ++j) stv[j] = (kind[j] == PAIR_SAME) || (kind[j] == PAIR_CROSS);
+                for (int j = 0; j < W; ++j) {
+                    stv[j] = (kind[j] == PAIR_SAME) || (kind[j] == PAIR_CROSS);
+#pragma unroll
+                    for (int a = 0; a < 3; ++a) pos_out[a].v[j] = (kind[j] == PAIR_CROSS) ? xraw[a].v[j] : pos_out[a].v[j];
+                }
                 bool all = true;
 #pragma unroll
                 for (int j = 0; j < W; ++j) all = all && stv[j];
+#if PIC_ABL10 == 5
+                if (nblk != 0x7fffffff) all = false, stv[0] = stv[W - 1] = false;
+#endif
                 if (all) {
 #pragma unroll
                     for (int c = 0; c < 3; ++c) { st_vec<T, W>(s.c[c] + i0, pos_out[c]); st_vec<T, W>(s.c[3 + c] + i0, vel_out[c]); }
@@ -408,26 +431,29 @@ k_pair3d(const __grid_constant__ PicParams p, int species, const __grid_constant
                         }
                 }
             }
-            // ---- queue the cell crossers
+            // ---- defer the cell changers and the uncovered particles to the CTA's work-list segment
             {
                 unsigned m[W];
                 unsigned any = 0;
 #pragma unroll
-                for (int j = 0; j < W; ++j) { m[j] = __ballot_sync(0xffffffffu, kind[j] == PAIR_CROSS); any |= m[j]; }
+                for (int j = 0; j < W; ++j) { m[j] = __ballot_sync(0xffffffffu, kind[j] >= PAIR_CROSS); any |= m[j]; }
                 if (any) {
-                    int base = qn;
+                    int total = 0;
+#pragma unroll
+                    for (int j = 0; j < W; ++j) total += __popc(m[j]);
+                    int base = 0;
+                    if (lane == 0) base = atomicAdd(ctl, total);
+                    base = dq0 + __shfl_sync(0xffffffffu, base, 0);
 #pragma unroll
                     for (int j = 0; j < W; ++j) {
-                        if (kind[j] == PAIR_CROSS) {
+                        if (kind[j] >= PAIR_CROSS) {
                             const int e = base + __popc(m[j] & ((1u << lane) - 1u));
-                            qi[e] = i0 + j;
+                            defer.idx[e] = (i0 + j) | (kind[j] == PAIR_SLOW ? K10_DEFER_UNCOVERED : 0);
 #pragma unroll
-                            for (int a = 0; a < 3; ++a) { qo[a * QW + e] = ld.pos(a).v[j]; qx[a * QW + e] = xraw[a].v[j]; }
+                            for (int a = 0; a < 3; ++a) defer.pos[a][e] = ld.pos(a).v[j];
                         }
                         base += __popc(m[j]);
                     }
-                    qn = base;
-                    __syncwarp();
                 }
             }
             // ---- same-cell currents: join the thread's particles, reduce over the lanes of one cell, RED at the run tails
@@ -452,26 +478,74 @@ k_pair3d(const __grid_constant__ PicParams p, int species, const __grid_constant
                     for (int n = 0; n < 12; ++n) lv[n] = vals[n].v[0];
                     key = (kind[0] == PAIR_SAME) ? cid[0] : -1 - lane;
                 }
+#if PIC_ABL10 == 4
+                if (k.sx == 0x7fffffff)
+#endif
                 if constexpr (MODE == 3 && sizeof(T) == 4)
                     pair_smem_red(lv, key, lane, sink, key0, k.sx, k.sy, reinterpret_cast<float*>(red_raw),
                                   reinterpret_cast<int2*>(red_raw + 32 * K10_RED_ROW * 4));
                 else if (MODE == 2) pair_group_red<T>(lv, key, lane, sink, key0, k.sx, k.sy);
                 else pair_scan_red<T, 3>(lv, key, lane, sink, key0, k.sx, k.sy);
             }
-            if (qn >= 32) flush(31);
         }
-        rot = (rot + nchunk) % NWC;
         __syncwarp();
         if (lane == 0) mbar_arrive(empty + slot);            // this warp no longer reads the stage in `slot`
         if (++slot == NSTAGE) { slot = 0; par ^= 1; }
     }
-    // ---- tail pass: slots appended since the last sort (particles received from neighbour ranks): scalar global-memory body
-    {
-        const int tail0 = blk_off[nblk];
-        for (int i = tail0 + ((int)blockIdx.x * NWC + warp) * 32 + lane; i < n_live; i += (int)gridDim.x * NWC * 32)
-            fused_particle_fast3d<T, 1, PUSHER, false>(p, species, gm, k, (int64_t)i, s, F, X, sink, leave, distributed != 0, flags);
+    // ---- the last consumer warp to finish publishes the length of the CTA's work-list segment
+    __syncwarp();
+    if (lane == 0) {
+        // (an acq_rel atomic, not __threadfence_block(): with a fence in the kernel ptxas turns every fire-and-forget REDG of the
+        // deposit into a returning ATOMG -- measured 3.5 instead of 3.0 ms per launch)
+        unsigned done, n_def;
+        asm volatile("atom.acq_rel.cta.shared.add.u32 %0, [%1], 1;\n" : "=r"(done) : "r"(smem_u32(ctl + 1)) : "memory");
+        if (done == NWC - 1) {
+            asm volatile("ld.acquire.cta.shared.u32 %0, [%1];\n" : "=r"(n_def) : "r"(smem_u32(ctl)) : "memory");
+            defer.cnt[blockIdx.x] = (int)n_def;
+        }
     }
-    flush(0);
+}
+
+// Second pass of K1 v10: the deferred slots of every CTA's work-list segment -- cell changers: union-stencil Esirkepov deposit of
+// the move (old position from the list, new position from the slot), particle boundary conditions, ownership, store
+// (crosser_finish); uncovered slots: the whole step through the scalar global-memory body -- then the slots appended since the
+// last sort (particles received from neighbour ranks), also through the scalar body.
+template <typename T, int PUSHER, bool PER1>
+__global__ void __launch_bounds__(256)
+k_pair_fixup(const __grid_constant__ PicParams p, int species, const __grid_constant__ Geom<T> gm, const __grid_constant__ FastConst<T> k,
+             const __grid_constant__ SoAView<T> s, const __grid_constant__ Field6<T> F, Field3W<T> J, const __grid_constant__ LeaveBuf leave,
+             int distributed, int32_t* flags, const __grid_constant__ DeferList<T> defer, const int32_t* __restrict__ blk_off, int nblk,
+             int tile_grid, int sub) {
+    TileSink<T> sink;
+    for (int c = 0; c < 3; ++c) { sink.J[c] = J.f[c]; sink.L[c] = gm.L[c]; }
+    sink.off = 0;
+    sink.flags = flags;
+    Field6<T> X;
+    for (int c = 0; c < 6; ++c) X.f[c] = nullptr;
+    // `sub` CTAs of this kernel share the segment of one CTA of the tile kernel
+    const int seg = (int)blockIdx.x / sub, part = (int)blockIdx.x % sub;
+    const int per_cta = (nblk + tile_grid - 1) / tile_grid;
+    const int b0 = seg * per_cta < nblk ? seg * per_cta : nblk;
+    const int dq0 = blk_off[b0];
+    const int n = defer.cnt[seg];
+    int uncovered = 0;
+    for (int e = part * 256 + (int)threadIdx.x; e < n; e += sub * 256) {
+        const int v = defer.idx[dq0 + e];
+        const int i = v & 0x7fffffff;
+        if (v < 0) {
+            ++uncovered;
+            fused_particle_fast3d<T, 1, PUSHER, false>(p, species, gm, k, (int64_t)i, s, F, X, sink, leave, distributed != 0, flags);
+        } else {
+            const T po[3] = {defer.pos[0][dq0 + e], defer.pos[1][dq0 + e], defer.pos[2][dq0 + e]};
+            const T xn[3] = {s.c[0][i], s.c[1][i], s.c[2][i]};
+            crosser_finish<T, PER1>(p, species, gm, k, (int64_t)i, s, po, xn, sink, leave, distributed != 0, flags);
+        }
+    }
+    uncovered = __reduce_add_sync(0xffffffffu, uncovered);
+    if ((threadIdx.x & 31) == 0 && uncovered) atomic_add_i32(flags + 2, uncovered);
+    const int n_live = (int)s.count();
+    for (int i = blk_off[nblk] + (int)blockIdx.x * 256 + (int)threadIdx.x; i < n_live; i += (int)gridDim.x * 256)
+        fused_particle_fast3d<T, 1, PUSHER, false>(p, species, gm, k, (int64_t)i, s, F, X, sink, leave, distributed != 0, flags);
 }
 
 // ---------------------------------------------------------------- blocked, padded counting sort
@@ -532,9 +606,13 @@ __global__ void k_set_count_pair(int32_t* n_dev, const int32_t* src, int64_t cap
 }
 
 // ---------------------------------------------------------------- launchers
+}  // namespace pic
+extern "C" int64_t pic_pair_work_bytes(const PicParams* p, int64_t cap);
+namespace pic {
 template <typename T>
 static int launch_pair3d(const PicParams* p, int species, const PicSoA* soa, const int32_t* blk_off, int nblk, int options, const void* const E[3],
-                         const void* const B[3], void* const J[3], const PicLeave* leave, int32_t* flags, cudaStream_t st) {
+                         const void* const B[3], void* const J[3], const PicLeave* leave, int32_t* flags, void* work, int64_t work_len,
+                         cudaStream_t st) {
     static_assert(PIC_SORT_BLOCK == TILE_B, "the tile kernel walks the supercells of the blocked sort order");
     if (p->shape_factor != 1 || p->g != 2 || (p->pusher != PIC_PUSHER_BORIS && p->pusher != PIC_PUSHER_BORIS_REL)) return PIC_EUNSUPPORTED;
     for (int a = 0; a < 3; ++a) {
@@ -571,25 +649,41 @@ static int launch_pair3d(const PicParams* p, int species, const PicSoA* soa, con
     constexpr int W = F32 ? PIC_K10_W : 1;
     constexpr int NWC = F32 ? PIC_K10_NWC : PIC_K10_NWC64;
     constexpr int CTAS = F32 ? PIC_K10_CTAS : 1;
-    constexpr size_t smem = PairSmem<T, W, NWC>::bytes;
-    static_assert(smem <= 227 * 1024, "ring + queues exceed the shared memory of one CTA");
     int grid = num_sms() * CTAS;
     if (grid > nblk) grid = nblk;
+    if (grid > K10_MAX_GRID) grid = K10_MAX_GRID;
+    // work: [K10_MAX_GRID] segment lengths, [cap] slot indices, 3 x [cap] old positions (T)
+    const int64_t cap_w = (soa->cap + 3) & ~(int64_t)3;
+    if (work_len < (int64_t)pic_pair_work_bytes(p, soa->cap)) return PIC_EINVAL;
+    DeferList<T> defer;
+    defer.cnt = (int32_t*)work;
+    defer.idx = (int32_t*)work + K10_MAX_GRID;
+    for (int a = 0; a < 3; ++a) defer.pos[a] = (T*)((int32_t*)work + K10_MAX_GRID + cap_w) + a * cap_w;
     const SoAView<T> sv = view_of<T>(soa);
     const LeaveBuf lb = leave_of(leave);
 #define PIC_LAUNCH_K10(PUSH, PER, MD)                                                                                    \
     do {                                                                                                                 \
+        constexpr size_t smem = PairSmem<T, W, NWC, MD>::bytes;                                                          \
+        static_assert(smem <= 227 * 1024, "ring exceeds the shared memory of one CTA");                                 \
         static bool attr_set = false;                                                                                    \
         if (!attr_set) {                                                                                                 \
             cudaError_t e = cudaFuncSetAttribute(k_pair3d<T, W, PUSH, NWC, CTAS, PER, MD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
             if (e != cudaSuccess) return (int)e;                                                                         \
             attr_set = true;                                                                                             \
         }                                                                                                                \
-        k_pair3d<T, W, PUSH, NWC, CTAS, PER, MD><<<grid, (NWC + 1) * 32, smem, st>>>(*p, species, gm, k, pc, sv, F, Jw, lb, distributed, flags, tm, blk_off, nblk, nbx, nby, nbz); \
+        k_pair3d<T, W, PUSH, NWC, CTAS, PER, MD><<<grid, (NWC + 1) * 32, smem, st>>>(k, pc, sv, Jw, defer, flags, tm, blk_off, nblk, nbx, nby, nbz, p->g); \
     } while (0)
 #define PIC_LAUNCH_K10_M(PUSH, PER) do { if (grp) PIC_LAUNCH_K10(PUSH, PER, 2); else if (smr) PIC_LAUNCH_K10(PUSH, PER, 3); else PIC_LAUNCH_K10(PUSH, PER, 0); } while (0)
-    if (p->pusher == PIC_PUSHER_BORIS) { if (per1) PIC_LAUNCH_K10_M(PIC_PUSHER_BORIS, true); else PIC_LAUNCH_K10_M(PIC_PUSHER_BORIS, false); }
-    else { if (per1) PIC_LAUNCH_K10_M(PIC_PUSHER_BORIS_REL, true); else PIC_LAUNCH_K10_M(PIC_PUSHER_BORIS_REL, false); }
+    constexpr int SUB = 4;
+    if (p->pusher == PIC_PUSHER_BORIS) {
+        if (per1) PIC_LAUNCH_K10_M(PIC_PUSHER_BORIS, true); else PIC_LAUNCH_K10_M(PIC_PUSHER_BORIS, false);
+        if (per1) k_pair_fixup<T, PIC_PUSHER_BORIS, true><<<grid * SUB, 256, 0, st>>>(*p, species, gm, k, sv, F, Jw, lb, distributed, flags, defer, blk_off, nblk, grid, SUB);
+        else k_pair_fixup<T, PIC_PUSHER_BORIS, false><<<grid * SUB, 256, 0, st>>>(*p, species, gm, k, sv, F, Jw, lb, distributed, flags, defer, blk_off, nblk, grid, SUB);
+    } else {
+        if (per1) PIC_LAUNCH_K10_M(PIC_PUSHER_BORIS_REL, true); else PIC_LAUNCH_K10_M(PIC_PUSHER_BORIS_REL, false);
+        if (per1) k_pair_fixup<T, PIC_PUSHER_BORIS_REL, true><<<grid * SUB, 256, 0, st>>>(*p, species, gm, k, sv, F, Jw, lb, distributed, flags, defer, blk_off, nblk, grid, SUB);
+        else k_pair_fixup<T, PIC_PUSHER_BORIS_REL, false><<<grid * SUB, 256, 0, st>>>(*p, species, gm, k, sv, F, Jw, lb, distributed, flags, defer, blk_off, nblk, grid, SUB);
+    }
 #undef PIC_LAUNCH_K10_M
 #undef PIC_LAUNCH_K10
     PIC_LAUNCH_RET();
@@ -609,13 +703,22 @@ using namespace pic;
 extern "C" {
 
 int pic_fused_pair3d(const PicParams* p, int species, const PicSoA* soa, const int32_t* blk_off, int nblk, int options,
-                     const void* const E[3], const void* const B[3], void* const J[3], const PicLeave* leave, int32_t* flags, void* stream) {
-    PIC_CHECK_ARG(p && soa && blk_off && E && B && J && flags && species >= 0 && species < p->n_species && nblk > 0);
+                     const void* const E[3], const void* const B[3], void* const J[3], const PicLeave* leave, int32_t* flags,
+                     void* work, int64_t work_len, void* stream) {
+    PIC_CHECK_ARG(p && soa && blk_off && E && B && J && flags && work && species >= 0 && species < p->n_species && nblk > 0);
     PIC_CHECK_ARG(p->mesh[0] == 1 && p->mesh[1] == 1 && p->mesh[2] == 1);
     bool distributed = false;
     for (int c = 0; c < 3; ++c) distributed |= (p->gmesh[c] != p->mesh[c]);
     if (distributed) PIC_CHECK_ARG(leave && leave->buf);
-    PIC_DISPATCH_T(p, launch_pair3d, p, species, soa, blk_off, nblk, options, E, B, J, leave, flags, (cudaStream_t)stream);
+    PIC_DISPATCH_T(p, launch_pair3d, p, species, soa, blk_off, nblk, options, E, B, J, leave, flags, work, work_len, (cudaStream_t)stream);
+}
+
+// Size in bytes of the `work` array pic_fused_pair3d needs for an SoA of capacity `cap` in the dtype of `p`.
+int64_t pic_pair_work_bytes(const PicParams* p, int64_t cap) {
+    if (!p || cap < 0) return -1;
+    const int64_t cap_w = (cap + 3) & ~(int64_t)3;
+    const int64_t real = (p->dtype == PIC_F32) ? 4 : 8;
+    return 4 * ((int64_t)K10_MAX_GRID + cap_w) + 3 * cap_w * real;
 }
 
 // Offsets of the blocked, padded sort from the per-cell histogram (pic_sort_histogram): blk_off[nblk + 1] (first slot of every

@@ -311,6 +311,13 @@ PIC_HD void pair_advance_ld(const FastConst<T>& k, const PairConst<T>& pc, const
         rv[a] = vsub(qv, vadds(tv, -Magic<T>::value));
 #pragma unroll
         for (int j = 0; j < W; ++j) { ic[a][j] = magic_int(tc[a].v[j]); iv[a][j] = magic_int(tv.v[j]); }
+#if defined(PIC_ABL10) && PIC_ABL10 == 2
+        if (a == 0)
+            for (int j = 0; j < W; ++j) iv[a][j] = ic[a][j];
+#endif
+#if defined(PIC_ABL10) && PIC_ABL10 == 7
+        for (int j = 0; j < W; ++j) iv[a][j] = ic[a][j] = (ic[a][j] > 100) ? 1 : 3;
+#endif
     }
     // ---- gather: Ex(v,c,c) Ey(c,v,c) Ez(c,c,v) Bx(c,v,v) By(v,c,v) Bz(v,v,c), eight corners -> lerp z, y, x
     V EB[6];
@@ -420,6 +427,9 @@ PIC_HD void pair_advance_ld(const FastConst<T>& k, const PairConst<T>& pc, const
     }
 #pragma unroll
     for (int j = 0; j < W; ++j) {
+#if defined(PIC_ABL10) && PIC_ABL10 == 6
+        same[j] = true;
+#endif
         kind[j] = ok[j] ? (same[j] ? PAIR_SAME : PAIR_CROSS) : (live[j] ? PAIR_SLOW : PAIR_NONE);
         cid[j] = (ic[0][j] << 6) | (ic[1][j] << 3) | ic[2][j];
     }

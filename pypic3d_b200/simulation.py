@@ -114,7 +114,12 @@ class Simulation:
         # and the scan would pay one RED set per fragment; "1" always, "0" never.
         self._jtile_mode = os.environ.get("PIC_K9_JTILE", "0")
         self._groupred_mode = os.environ.get("PIC_K9_GROUPRED", "auto")
-        self._red_mode = os.environ.get("PIC_K10_RED", "smem")
+        self._red_mode = os.environ.get("PIC_K10_RED", "scan")   # (measured: scan 3.10 ms, smem 3.23 ms per proton launch)
+        # K1 v10 work list of deferred slots (include/pic_b200.h pic_fused_pair3d): shared by the species, launches are stream-ordered
+        self._pair_work = None
+        if self.k1_variant == "pair":
+            nbytes = int(_lib.lib().pic_pair_work_bytes(ctypes.byref(self.p), max(sp_.cap for sp_ in self.species)))
+            self._pair_work = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
         self._sorted_at = [0] * self.S
         self.leave_fraction = float(leave_fraction)
         if self.distributed:
@@ -141,7 +146,7 @@ class Simulation:
     def _k1_options(self, s):
         opt = 1 if self._jtile_mode == "1" else 0
         # K1 v10, float: bit 2 = same-cell reduction through shared memory (pair_smem_red) instead of the segmented warp scan;
-        # PIC_K10_RED = "smem" (default) | "scan"
+        # PIC_K10_RED = "scan" (default) | "smem"
         if self.k1_variant == "pair" and self._red_mode == "smem":
             opt |= 4
         if self._groupred_mode == "1":
@@ -321,10 +326,14 @@ class Simulation:
                 e0.record()
             leave = ctypes.byref(sp_.leave) if sp_.leave is not None else None
             rc = _lib.PIC_EUNSUPPORTED
+            if self.k1_variant == "pair":
+                rc = L.pic_fused_pair3d(ctypes.byref(p), s, ctypes.byref(soa), ops._p(sp_.blk_off), self.ncells // 64,
+                                        self._k1_options(s), ops._v(self.E), ops._v(self.B), ops._v(self.J), leave, ops._p(self.flags),
+                                        ops._p(self._pair_work), self._pair_work.numel(), st)
+            elif self.k1_variant == "tile":
+                rc = L.pic_fused_tile3d(ctypes.byref(p), s, ctypes.byref(soa), ops._p(sp_.blk_off), self.ncells // 64,
+                                        self._k1_options(s), ops._v(self.E), ops._v(self.B), ops._v(self.J), leave, ops._p(self.flags), st)
             if self.k1_variant in ("pair", "tile"):
-                fn = L.pic_fused_pair3d if self.k1_variant == "pair" else L.pic_fused_tile3d
-                rc = fn(ctypes.byref(p), s, ctypes.byref(soa), ops._p(sp_.blk_off), self.ncells // 64,
-                        self._k1_options(s), ops._v(self.E), ops._v(self.B), ops._v(self.J), leave, ops._p(self.flags), st)
                 if rc == _lib.PIC_EUNSUPPORTED:     # e.g. no TMA driver entry point: the global-gather K1 computes the same step
                     self.k1_variant = "global"      # (it reads the padded stream as it is: padding slots are dead slots)
                 else:
