@@ -653,6 +653,170 @@ static int launch_yee_fused_tx(const PicParams* p, const Dims& d, const YeeSides
     PIC_LAUNCH_RET();
 }
 
+// Streaming form of the fused Yee step: a CTA owns a TY x TZ column of cells and MARCHES along x.  Every thread owns one (y, z)
+// point of the widest box (E_old on [-1, +2]) and keeps its column's rolling x window in registers -- E_old(p), E_old(p + 1),
+// B'(p - 1), B'(p), E_new(p - 1), E_new(p) -- while the y / z neighbours of the current plane are exchanged through three small
+// shared-memory planes.  Every plane of E, B, J is therefore read once per (y, z) tile (+ a 1.5-cell rim), the loads of plane p + 2
+// are in flight while plane p is computed, and the kernel is bound by HBM instead of by the tile kernel's 3.8x redundant L2 reads.
+// Same expressions as k_update_B / k_update_E / k_yee_fused (bit-identical results); same YeeSides semantics.
+constexpr int YS_TY = 8, YS_TZ = 32, YS_NY = YS_TY + 3, YS_NZ = YS_TZ + 3, YS_PTS = YS_NY * YS_NZ, YS_THREADS = 416;
+#ifndef PIC_YEE_XC
+#define PIC_YEE_XC 32          /* planes per CTA along x */
+#endif
+template <typename T>
+__global__ void __launch_bounds__(YS_THREADS) k_yee_stream(Dims d, YeeSides sd, const T* __restrict__ Ex, const T* __restrict__ Ey,
+                                                           const T* __restrict__ Ez, const T* __restrict__ Bx, const T* __restrict__ By,
+                                                           const T* __restrict__ Bz, const T* __restrict__ Jx, const T* __restrict__ Jy,
+                                                           const T* __restrict__ Jz, T* __restrict__ Ex2, T* __restrict__ Ey2,
+                                                           T* __restrict__ Ez2, T* __restrict__ Bx2, T* __restrict__ By2, T* __restrict__ Bz2,
+                                                           T dt, T hdt, T idx, T idy, T idz, T C2, T ieps, int nby, int nbz, int xc) {
+    __shared__ T sEo[3][YS_PTS];          // E_old of the current plane
+    __shared__ T sBp[3][YS_PTS];          // B' of the current plane
+    __shared__ T sEn[2][3][YS_PTS];       // E_new of the current and the previous plane
+    int b = blockIdx.x;
+    const int bz = b % nbz; b /= nbz;
+    const int by = b % nby; b /= nby;
+    const int X0 = d.g + b * xc;                                  // first own plane (array index)
+    int X1 = X0 + xc;                                             // one past the last own plane
+    if (X1 > d.L[0] - d.g) X1 = d.L[0] - d.g;
+    const int o1 = d.g + by * YS_TY, o2 = d.g + bz * YS_TZ;
+    const int sx = d.L[1] * d.L[2], sy = d.L[2];
+    const int t = threadIdx.x;
+    const bool in_box = t < YS_PTS;
+    const int cy = in_box ? t / YS_NZ : 0, cz = in_box ? t % YS_NZ : 0;      // box coordinate c <-> array index o - 1 + c
+    const YeeAxis ay = yee_axis(d, sd, 1, o1 - 1 + cy), az = yee_axis(d, sd, 2, o2 - 1 + cz);
+    const int gyz = ay.src * sy + az.src;
+    const bool wyz = ay.wall || az.wall;
+    const bool boxB = in_box && cy <= YS_TY + 1 && cz <= YS_TZ + 1;          // B' lives on [-1, +1]
+    const bool boxE = in_box && cy >= 1 && cy <= YS_TY + 1 && cz >= 1 && cz <= YS_TZ + 1;   // E_new on [0, +1]
+    const int iy = o1 - 1 + cy, iz = o2 - 1 + cz;
+    const bool own = in_box && cy >= 1 && cy <= YS_TY && cz >= 1 && cz <= YS_TZ && iy < d.L[1] - d.g && iz < d.L[2] - d.g;
+    // guard copies of an own cell along WRAP axes
+    int ny = 1, nz = 1, offy[3] = {0, 0, 0}, offz[3] = {0, 0, 0};
+    if (own) {
+        if (sd.lo[1] == YEE_WRAP) {
+            if (iy - d.W[1] >= 0) offy[ny++] = -d.W[1] * sy;
+            if (iy + d.W[1] < d.L[1]) offy[ny++] = d.W[1] * sy;
+        }
+        if (sd.lo[2] == YEE_WRAP) {
+            if (iz - d.W[2] >= 0) offz[nz++] = -d.W[2];
+            if (iz + d.W[2] < d.L[2]) offz[nz++] = d.W[2];
+        }
+    }
+    auto store6 = [&](T* __restrict__ a0, T* __restrict__ a1, T* __restrict__ a2, int ix, T v0, T v1, T v2) {
+        int nx = 1, offx[3] = {0, 0, 0};
+        if (sd.lo[0] == YEE_WRAP) {
+            if (ix - d.W[0] >= 0) offx[nx++] = -d.W[0];
+            if (ix + d.W[0] < d.L[0]) offx[nx++] = d.W[0];
+        }
+        for (int i0 = 0; i0 < nx; ++i0)
+            for (int i1 = 0; i1 < ny; ++i1)
+                for (int i2 = 0; i2 < nz; ++i2) {
+                    const size_t gi = (size_t)(ix + offx[i0]) * sx + (size_t)(iy * sy + offy[i1]) + (iz + offz[i2]);
+                    a0[gi] = v0; a1[gi] = v1; a2[gi] = v2;
+                }
+    };
+    auto plane = [&](int p) { return yee_axis(d, sd, 0, p); };
+    // rolling window: eo = E_old(p), eo1 = E_old(p + 1), eo2 = E_old(p + 2) (in flight); bo = B_old(p), bo1 = B_old(p + 1) (in flight);
+    // jc = J(p), j1 = J(p + 1) (in flight)
+    T eo[3] = {0, 0, 0}, eo1[3] = {0, 0, 0}, eo2[3] = {0, 0, 0}, bo[3] = {0, 0, 0}, bo1[3] = {0, 0, 0}, jc[3] = {0, 0, 0}, j1[3] = {0, 0, 0};
+    T bp_prev[3] = {0, 0, 0}, en_prev[3] = {0, 0, 0};
+    int p = X0 - 1;
+    if (in_box) {
+        const size_t g0 = (size_t)plane(p).src * sx + gyz, g1 = (size_t)plane(p + 1).src * sx + gyz;
+        eo[0] = Ex[g0]; eo[1] = Ey[g0]; eo[2] = Ez[g0];
+        bo[0] = Bx[g0]; bo[1] = By[g0]; bo[2] = Bz[g0];
+        eo1[0] = Ex[g1]; eo1[1] = Ey[g1]; eo1[2] = Ez[g1];
+    }
+    for (; p <= X1; ++p) {
+        const YeeAxis ax = plane(p);
+        // ---- prefetch: E_old(p + 2), B_old(p + 1), J(p + 1)
+        if (in_box && p < X1) {
+            const size_t g1 = (size_t)plane(p + 1).src * sx + gyz, g2 = (size_t)plane(p + 2).src * sx + gyz;
+            eo2[0] = Ex[g2]; eo2[1] = Ey[g2]; eo2[2] = Ez[g2];
+            bo1[0] = Bx[g1]; bo1[1] = By[g1]; bo1[2] = Bz[g1];
+            j1[0] = Jx[g1]; j1[1] = Jy[g1]; j1[2] = Jz[g1];
+        }
+        if (in_box) { sEo[0][t] = eo[0]; sEo[1][t] = eo[1]; sEo[2][t] = eo[2]; }
+        __syncthreads();
+        // ---- B'(p) = B_old(p) - (dt/2) curl_forward(E_old)(p) on [-1, +1]; exterior wall guards: zero
+        T bp[3] = {0, 0, 0};
+        if (boxB) {
+            const bool w = wyz || ax.wall;
+            const T ex = eo[0], ey = eo[1], ez = eo[2];
+            const T dEz_dy = (sEo[2][t + YS_NZ] - ez) * idy;
+            const T dEy_dz = (sEo[1][t + 1] - ey) * idz;
+            const T dEx_dz = (sEo[0][t + 1] - ex) * idz;
+            const T dEx_dy = (sEo[0][t + YS_NZ] - ex) * idy;
+            const T dEz_dx = (eo1[2] - ez) * idx;
+            const T dEy_dx = (eo1[1] - ey) * idx;
+            bp[0] = w ? (T)0 : bo[0] - hdt * (dEz_dy - dEy_dz);
+            bp[1] = w ? (T)0 : bo[1] - hdt * (dEx_dz - dEz_dx);
+            bp[2] = w ? (T)0 : bo[2] - hdt * (dEy_dx - dEx_dy);
+            sBp[0][t] = bp[0]; sBp[1][t] = bp[1]; sBp[2][t] = bp[2];
+        }
+        __syncthreads();
+        // ---- E_new(p) = E_old(p) + dt (C^2 curl_backward(B')(p) - J(p) / eps) on [0, +1], planes X0 .. X1
+        T en[3] = {0, 0, 0};
+        const int q = p & 1;
+        if (boxE && p >= X0) {
+            const bool w = wyz || ax.wall;
+            const T bx_ = bp[0], by_ = bp[1], bz_ = bp[2];
+            const T dBz_dy = (bz_ - sBp[2][t - YS_NZ]) * idy;
+            const T dBy_dz = (by_ - sBp[1][t - 1]) * idz;
+            const T dBx_dz = (bx_ - sBp[0][t - 1]) * idz;
+            const T dBx_dy = (bx_ - sBp[0][t - YS_NZ]) * idy;
+            const T dBz_dx = (bz_ - bp_prev[2]) * idx;
+            const T dBy_dx = (by_ - bp_prev[1]) * idx;
+            T ex = eo[0] + (C2 * (dBz_dy - dBy_dz) - jc[0] * ieps) * dt;
+            T ey = eo[1] + (C2 * (dBx_dz - dBz_dx) - jc[1] * ieps) * dt;
+            T ez = eo[2] + (C2 * (dBy_dx - dBx_dy) - jc[2] * ieps) * dt;
+            if (ay.cond || az.cond || w) ex = (T)0;
+            if (ax.cond || az.cond || w) ey = (T)0;
+            if (ax.cond || ay.cond || w) ez = (T)0;
+            en[0] = ex; en[1] = ey; en[2] = ez;
+            sEn[q][0][t] = ex; sEn[q][1][t] = ey; sEn[q][2][t] = ez;
+            if (own && p < X1) store6(Ex2, Ey2, Ez2, p, ex, ey, ez);
+        }
+        __syncthreads();
+        // ---- B_new(p - 1) = B'(p - 1) - (dt/2) curl_forward(E_new)(p - 1) on the own cells, planes X0 .. X1 - 1
+        if (own && p >= X0 + 1) {
+            const int r = q ^ 1;
+            const T ex = en_prev[0], ey = en_prev[1], ez = en_prev[2];
+            const T dEz_dy = (sEn[r][2][t + YS_NZ] - ez) * idy;
+            const T dEy_dz = (sEn[r][1][t + 1] - ey) * idz;
+            const T dEx_dz = (sEn[r][0][t + 1] - ex) * idz;
+            const T dEx_dy = (sEn[r][0][t + YS_NZ] - ex) * idy;
+            const T dEz_dx = (en[2] - ez) * idx;
+            const T dEy_dx = (en[1] - ey) * idx;
+            const T bxn = bp_prev[0] - hdt * (dEz_dy - dEy_dz);
+            const T byn = bp_prev[1] - hdt * (dEx_dz - dEz_dx);
+            const T bzn = bp_prev[2] - hdt * (dEy_dx - dEx_dy);
+            store6(Bx2, By2, Bz2, p - 1, bxn, byn, bzn);
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            bp_prev[c] = bp[c]; en_prev[c] = en[c];
+            eo[c] = eo1[c]; eo1[c] = eo2[c]; bo[c] = bo1[c]; jc[c] = j1[c];
+        }
+    }
+}
+
+template <typename T>
+static int launch_yee_stream(const PicParams* p, const Dims& d, const YeeSides& sd, const void* const E[3], const void* const B[3],
+                             const void* const J[3], void* const E2[3], void* const B2[3], cudaStream_t st) {
+    // planes per CTA: enough CTAs to fill the chip several times over, few enough redundant rim planes
+    int xc = PIC_YEE_XC;
+    const int nby = (d.W[1] + YS_TY - 1) / YS_TY, nbz = (d.W[2] + YS_TZ - 1) / YS_TZ;
+    while (xc > 8 && (int64_t)((d.W[0] + xc - 1) / xc) * nby * nbz < 4 * 148) xc /= 2;
+    const int nbx = (d.W[0] + xc - 1) / xc;
+    k_yee_stream<T><<<nbx * nby * nbz, YS_THREADS, 0, st>>>(d, sd, (const T*)E[0], (const T*)E[1], (const T*)E[2], (const T*)B[0], (const T*)B[1],
+                                                            (const T*)B[2], (const T*)J[0], (const T*)J[1], (const T*)J[2], (T*)E2[0], (T*)E2[1],
+                                                            (T*)E2[2], (T*)B2[0], (T*)B2[1], (T*)B2[2], (T)p->dt, (T)(p->dt / 2), (T)(1.0 / p->dx),
+                                                            (T)(1.0 / p->dy), (T)(1.0 / p->dz), (T)(p->C * p->C), (T)(1.0 / p->eps), nby, nbz, xc);
+    PIC_LAUNCH_RET();
+}
+
 template <typename T>
 static int launch_yee_fused(const PicParams* p, const void* const E[3], const void* const B[3], const void* const J[3], void* const E2[3],
                             void* const B2[3], cudaStream_t st) {
@@ -673,6 +837,10 @@ static int launch_yee_fused(const PicParams* p, const void* const E[3], const vo
 #ifndef PIC_YEE_TX
 #define PIC_YEE_TX 2        /* x cells per tile (float): the kernel is latency-bound, more resident CTAs beat less redundancy */
 #endif
+#ifndef PIC_YEE_STREAM
+#define PIC_YEE_STREAM 1    /* 1: the x-marching kernel (HBM-bound); 0: the tile kernel k_yee_fused (A/B control) */
+#endif
+    if (PIC_YEE_STREAM) return launch_yee_stream<T>(p, d, sd, E, B, J, E2, B2, st);
     if (sizeof(T) == 4 && d.W[0] >= 2 * PIC_YEE_TX) return launch_yee_fused_tx<T, PIC_YEE_TX>(p, d, sd, E, B, J, E2, B2, st);
     return launch_yee_fused_tx<T, 2>(p, d, sd, E, B, J, E2, B2, st);
 }

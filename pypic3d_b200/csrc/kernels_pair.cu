@@ -44,6 +44,15 @@ namespace pic {
 #ifndef PIC_K10_NSTAGE64
 #define PIC_K10_NSTAGE64 3     /* double */
 #endif
+#ifndef PIC_K10_STRIDED
+#define PIC_K10_STRIDED 0      /* supercells -> CTAs: 0 = one contiguous range per CTA; G > 0 = groups of G consecutive supercells dealt
+                                  round-robin, so the CTAs that run at the same time work on neighbouring supercells (L2 reuse of the
+                                  overlapping E/B boxes and of J) */
+#endif
+#ifndef PIC_K10_EVICT
+#define PIC_K10_EVICT 0        /* 1: particle slices are loaded and stored with an L2 evict-first policy (they are touched once per launch;
+                                  the fields and J are what should stay in L2) */
+#endif
 #ifndef PIC_K10_CLAIM_ASM
 #define PIC_K10_CLAIM_ASM 1    /* chunk claim: 1 = predicated atom.shared by lane 0 (no divergence), 0 = if (lane == 0) atomicAdd */
 #endif
@@ -276,7 +285,7 @@ template <typename T, int W, int PUSHER, int NWC, int CTAS, bool PER1, int MODE>
 __global__ void __launch_bounds__((NWC + 1) * 32, CTAS)
 k_pair3d(const __grid_constant__ FastConst<T> k, const __grid_constant__ PairConst<T> pc, const __grid_constant__ SoAView<T> s, Field3W<T> J,
          const __grid_constant__ DeferList<T> defer, int32_t* flags, const __grid_constant__ TileMaps tm,
-         const int32_t* __restrict__ blk_off, int nblk, int nbx, int nby, int nbz, int g) {
+         const int32_t* __restrict__ blk_off, int nblk, int nbx, int nby, int nbz, int g, int seg_cap) {
     constexpr int NSTAGE = K10Ring<T>::NSTAGE;
     constexpr int PCAP = K10Cap<T>::PCAP;
     constexpr int TILE_ALL = 6 * TILE_ELEMS;
@@ -312,9 +321,25 @@ k_pair3d(const __grid_constant__ FastConst<T> k, const __grid_constant__ PairCon
             // Slice bounds are read two supercells ahead of their use, so the producer never sits on a DRAM round trip between a
             // stage being released and its refill being issued.
             int j = 0;                                           // parts issued so far
+#if PIC_K10_EVICT
+            const uint64_t pol_stream = l2_policy_evict_first();
+#endif
             auto wait_slot = [&](int sr) {                       // previous occupant: part j - NSTAGE (suspended wait, no spinning)
                 if (j >= NSTAGE) while (!mbar_try_wait(empty + sr, ((j / NSTAGE) - 1) & 1, 20000)) {}
             };
+#if PIC_K10_STRIDED > 0
+            {
+                constexpr int G = PIC_K10_STRIDED;
+                const int ngrp = (nblk + G - 1) / G;
+                auto blk_of = [&](int t) { const int grp = (t / G) * (int)gridDim.x + (int)blockIdx.x; return grp < ngrp ? grp * G + t % G : nblk; };
+                int bn = blk_of(0);
+                int beg_n = blk_off[bn < nblk ? bn : nblk], end_n = blk_off[bn < nblk ? bn + 1 : nblk];
+                for (int t = 0; bn < nblk; ++t) {
+                    const int b = bn;
+                    int beg = beg_n, end = end_n;
+                    bn = blk_of(t + 1);
+                    if (bn < nblk) { beg_n = blk_off[bn]; end_n = blk_off[bn + 1]; }     // (consumed in the next iteration)
+#else
             if (b1 > b0) {
                 int beg = blk_off[b0];
                 int end_next = blk_off[b0 + 1];
@@ -324,6 +349,7 @@ k_pair3d(const __grid_constant__ FastConst<T> k, const __grid_constant__ PairCon
                     const int beg_following = end;
                     end_next = end_next2;
                     if (b + 3 <= nblk) end_next2 = blk_off[b + 3];
+#endif
                     if (end > n_live) end = n_live;
                     if (beg & (AL - 1)) { atomicOr(flags, 8); end = beg; }   // contract: slices come from the padded sort (pic_sort_blocked_*)
                     const int bz = b % nbz, by = (b / nbz) % nby, bx = b / (nbz * nby);
@@ -353,9 +379,17 @@ k_pair3d(const __grid_constant__ FastConst<T> k, const __grid_constant__ PairCon
                             for (int c = 0; c < 6; ++c) tma_load_box(st + c * TILE_ELEMS, &tm.m[c], full + sr, oz, oy, ox);
                         }
 #pragma unroll
-                        for (int c = 0; c < 6; ++c) tma_load_bytes(st + TILE_ALL + c * PCAP, s.c[c] + pb, n * (int)sizeof(T), full + sr);
+                        for (int c = 0; c < 6; ++c) {
+#if PIC_K10_EVICT
+                            tma_load_bytes_hint(st + TILE_ALL + c * PCAP, s.c[c] + pb, n * (int)sizeof(T), full + sr, pol_stream);
+#else
+                            tma_load_bytes(st + TILE_ALL + c * PCAP, s.c[c] + pb, n * (int)sizeof(T), full + sr);
+#endif
+                        }
                     }
+#if PIC_K10_STRIDED == 0
                     beg = beg_following;
+#endif
                 }
             }
             const int sr = j % NSTAGE;                           // end of the stream
@@ -372,7 +406,14 @@ k_pair3d(const __grid_constant__ FastConst<T> k, const __grid_constant__ PairCon
     sink.off = 0;
     sink.flags = flags;
     unsigned char* red_raw = red_raw0 + (size_t)warp * K10_RED_BYTES;   // (MODE 3 only)
+#if PIC_K10_STRIDED > 0
+    const int dq0 = (int)blockIdx.x * seg_cap;             // equal shares of the list (overflow: flags |= 16)
+#else
     const int dq0 = b0 < nblk ? blk_off[b0] : 0;          // first entry of this CTA's work-list segment
+#endif
+#if PIC_K10_EVICT
+    const uint64_t pol_store = l2_policy_evict_first();
+#endif
     int slot = 0, par = 0;
     for (;;) {
         while (!mbar_try_wait(full + slot, par, 1000)) {}
@@ -420,6 +461,15 @@ k_pair3d(const __grid_constant__ FastConst<T> k, const __grid_constant__ PairCon
                 if (nblk != 0x7fffffff) all = false, stv[0] = stv[W - 1] = false;
 #endif
                 if (all) {
+#if PIC_K10_EVICT
+                    if constexpr (W == 2 && sizeof(T) == 4) {
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) {
+                            st_f2_hint(s.c[c] + i0, pos_out[c].v[0], pos_out[c].v[1], pol_store);
+                            st_f2_hint(s.c[3 + c] + i0, vel_out[c].v[0], vel_out[c].v[1], pol_store);
+                        }
+                    } else
+#endif
 #pragma unroll
                     for (int c = 0; c < 3; ++c) { st_vec<T, W>(s.c[c] + i0, pos_out[c]); st_vec<T, W>(s.c[3 + c] + i0, vel_out[c]); }
                 } else {
@@ -443,7 +493,11 @@ k_pair3d(const __grid_constant__ FastConst<T> k, const __grid_constant__ PairCon
                     for (int j = 0; j < W; ++j) total += __popc(m[j]);
                     int base = 0;
                     if (lane == 0) base = atomicAdd(ctl, total);
-                    base = dq0 + __shfl_sync(0xffffffffu, base, 0);
+                    base = __shfl_sync(0xffffffffu, base, 0);
+#if PIC_K10_STRIDED > 0
+                    if (base + total > seg_cap) { if (lane == 0) atomicOr(flags, 16); total = 0; for (int j = 0; j < W; ++j) m[j] = 0, kind[j] = PAIR_NONE; }
+#endif
+                    base += dq0;
 #pragma unroll
                     for (int j = 0; j < W; ++j) {
                         if (kind[j] >= PAIR_CROSS) {
@@ -515,7 +569,7 @@ __global__ void __launch_bounds__(256)
 k_pair_fixup(const __grid_constant__ PicParams p, int species, const __grid_constant__ Geom<T> gm, const __grid_constant__ FastConst<T> k,
              const __grid_constant__ SoAView<T> s, const __grid_constant__ Field6<T> F, Field3W<T> J, const __grid_constant__ LeaveBuf leave,
              int distributed, int32_t* flags, const __grid_constant__ DeferList<T> defer, const int32_t* __restrict__ blk_off, int nblk,
-             int tile_grid, int sub) {
+             int tile_grid, int sub, int seg_cap) {
     TileSink<T> sink;
     for (int c = 0; c < 3; ++c) { sink.J[c] = J.f[c]; sink.L[c] = gm.L[c]; }
     sink.off = 0;
@@ -526,7 +580,12 @@ k_pair_fixup(const __grid_constant__ PicParams p, int species, const __grid_cons
     const int seg = (int)blockIdx.x / sub, part = (int)blockIdx.x % sub;
     const int per_cta = (nblk + tile_grid - 1) / tile_grid;
     const int b0 = seg * per_cta < nblk ? seg * per_cta : nblk;
+#if PIC_K10_STRIDED > 0
+    const int dq0 = seg * seg_cap;
+    (void)b0;
+#else
     const int dq0 = blk_off[b0];
+#endif
     const int n = defer.cnt[seg];
     int uncovered = 0;
     for (int e = part * 256 + (int)threadIdx.x; e < n; e += sub * 256) {
@@ -661,6 +720,7 @@ static int launch_pair3d(const PicParams* p, int species, const PicSoA* soa, con
     for (int a = 0; a < 3; ++a) defer.pos[a] = (T*)((int32_t*)work + K10_MAX_GRID + cap_w) + a * cap_w;
     const SoAView<T> sv = view_of<T>(soa);
     const LeaveBuf lb = leave_of(leave);
+    const int seg_cap = (int)((cap_w / grid) & ~(int64_t)3);
 #define PIC_LAUNCH_K10(PUSH, PER, MD)                                                                                    \
     do {                                                                                                                 \
         constexpr size_t smem = PairSmem<T, W, NWC, MD>::bytes;                                                          \
@@ -671,18 +731,18 @@ static int launch_pair3d(const PicParams* p, int species, const PicSoA* soa, con
             if (e != cudaSuccess) return (int)e;                                                                         \
             attr_set = true;                                                                                             \
         }                                                                                                                \
-        k_pair3d<T, W, PUSH, NWC, CTAS, PER, MD><<<grid, (NWC + 1) * 32, smem, st>>>(k, pc, sv, Jw, defer, flags, tm, blk_off, nblk, nbx, nby, nbz, p->g); \
+        k_pair3d<T, W, PUSH, NWC, CTAS, PER, MD><<<grid, (NWC + 1) * 32, smem, st>>>(k, pc, sv, Jw, defer, flags, tm, blk_off, nblk, nbx, nby, nbz, p->g, seg_cap); \
     } while (0)
 #define PIC_LAUNCH_K10_M(PUSH, PER) do { if (grp) PIC_LAUNCH_K10(PUSH, PER, 2); else if (smr) PIC_LAUNCH_K10(PUSH, PER, 3); else PIC_LAUNCH_K10(PUSH, PER, 0); } while (0)
     constexpr int SUB = 4;
     if (p->pusher == PIC_PUSHER_BORIS) {
         if (per1) PIC_LAUNCH_K10_M(PIC_PUSHER_BORIS, true); else PIC_LAUNCH_K10_M(PIC_PUSHER_BORIS, false);
-        if (per1) k_pair_fixup<T, PIC_PUSHER_BORIS, true><<<grid * SUB, 256, 0, st>>>(*p, species, gm, k, sv, F, Jw, lb, distributed, flags, defer, blk_off, nblk, grid, SUB);
-        else k_pair_fixup<T, PIC_PUSHER_BORIS, false><<<grid * SUB, 256, 0, st>>>(*p, species, gm, k, sv, F, Jw, lb, distributed, flags, defer, blk_off, nblk, grid, SUB);
+        if (per1) k_pair_fixup<T, PIC_PUSHER_BORIS, true><<<grid * SUB, 256, 0, st>>>(*p, species, gm, k, sv, F, Jw, lb, distributed, flags, defer, blk_off, nblk, grid, SUB, seg_cap);
+        else k_pair_fixup<T, PIC_PUSHER_BORIS, false><<<grid * SUB, 256, 0, st>>>(*p, species, gm, k, sv, F, Jw, lb, distributed, flags, defer, blk_off, nblk, grid, SUB, seg_cap);
     } else {
         if (per1) PIC_LAUNCH_K10_M(PIC_PUSHER_BORIS_REL, true); else PIC_LAUNCH_K10_M(PIC_PUSHER_BORIS_REL, false);
-        if (per1) k_pair_fixup<T, PIC_PUSHER_BORIS_REL, true><<<grid * SUB, 256, 0, st>>>(*p, species, gm, k, sv, F, Jw, lb, distributed, flags, defer, blk_off, nblk, grid, SUB);
-        else k_pair_fixup<T, PIC_PUSHER_BORIS_REL, false><<<grid * SUB, 256, 0, st>>>(*p, species, gm, k, sv, F, Jw, lb, distributed, flags, defer, blk_off, nblk, grid, SUB);
+        if (per1) k_pair_fixup<T, PIC_PUSHER_BORIS_REL, true><<<grid * SUB, 256, 0, st>>>(*p, species, gm, k, sv, F, Jw, lb, distributed, flags, defer, blk_off, nblk, grid, SUB, seg_cap);
+        else k_pair_fixup<T, PIC_PUSHER_BORIS_REL, false><<<grid * SUB, 256, 0, st>>>(*p, species, gm, k, sv, F, Jw, lb, distributed, flags, defer, blk_off, nblk, grid, SUB, seg_cap);
     }
 #undef PIC_LAUNCH_K10_M
 #undef PIC_LAUNCH_K10

@@ -59,6 +59,20 @@ __device__ __forceinline__ void tma_load_bytes(void* smem_dst, const void* gmem_
                  ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
+// L2 eviction-priority policy for data that is touched once (particle slices)
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;\n" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void tma_load_bytes_hint(void* smem_dst, const void* gmem_src, int bytes, uint64_t* bar, uint64_t pol) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;\n"
+                 ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol)
+                 : "memory");
+}
+__device__ __forceinline__ void st_f2_hint(float* ptr, float a, float b, uint64_t pol) {
+    asm volatile("st.global.L2::cache_hint.v2.f32 [%0], {%1, %2}, %3;\n" ::"l"(ptr), "f"(a), "f"(b), "l"(pol) : "memory");
+}
 // TMA reduce: global J box (8 x 8 x 8 nodes at z, y, x) += the shared-memory tile (element-wise add performed in L2)
 __device__ __forceinline__ void tma_reduce_add_box(const CUtensorMap* map, const void* smem_src, int z, int y, int x) {
     asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.bulk_group [%0, {%2, %3, %4}], [%1];\n"
