@@ -431,7 +431,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=("ours", "reference"))
-    ap.add_argument("--n", type=int, default=256, help="cells per axis per GPU")
+    ap.add_argument("--n", "--cells-per-axis", dest="n", type=int, default=256, help="cells per axis per GPU (use --cells-per-axis under torchrun: its parser claims --n)")
     ap.add_argument("--ppc", type=int, default=16)
     ap.add_argument("--shape-factor", type=int, default=1)
     ap.add_argument("--dtype", default="f32", choices=("f32", "f64"), help="dtype of the headline leg (the other one is reported under legs)")

@@ -483,8 +483,7 @@ PIC_HD void crosser_finish(const PicParams& p, int species, const Geom<T>& gm, c
     for (int a = 0; a < 3; ++a) {
         int off;
         if (k.pbc[a] == PIC_BC_PERIODIC) {
-            off = (pos[a] >= k.box_hi[a]) ? 1 : ((pos[a] < k.box_lo[a]) ? -1 : 0);
-            pos[a] = wrap_periodic_fast<T>(pos[a], k.wind[a]);
+            off = owner_offset_periodic<T>(pos[a], k.box_lo[a], k.box_hi[a], k.wind[a]);
         } else {
             alive = apply_axis_bc<T>(pos[a], v[a], k.wind[a], k.pbc[a]) && alive;
             off = (pos[a] >= k.box_hi[a]) ? 1 : ((pos[a] < k.box_lo[a]) ? -1 : 0);

@@ -483,6 +483,29 @@ PIC_HD T wrap_periodic_fast(T x, T wind) {
 #endif
 }
 
+// Owner of a particle on a periodic axis that is split across ranks: the physical crossing direction of the local box [lo, hi),
+// taken before the wrap (first -> last tile is -1, last -> first is +1, particle_tile_communication.py:145-165), made CONSISTENT
+// with what the wrap returns at the seam of the global domain.  Two round-off cases would otherwise strand a particle on a rank
+// whose tile does not contain it (one electron per step at 128^3 cells per rank in float32, visible as a charge-conservation
+// violation in a single node): (i) x + h rounds up to `wind` although x < h: the wrap lands on -h, so the particle has crossed to
+// the +1 neighbour; (ii) x == +h exactly: the wrap keeps the reference's +h alias (grid_and_stencil.py:31-35), which only the top
+// rank can hold -- a particle handed across the seam travels as -h.
+template <typename T>
+PIC_HD int owner_offset_periodic(T& pos, T box_lo, T box_hi, T wind) {
+    const T raw = pos, half = (T)0.5 * wind;
+    int off = (raw >= box_hi) ? 1 : ((raw < box_lo) ? -1 : 0);
+    T w = wrap_periodic_fast<T>(raw, wind);
+    if (box_hi < (T)INFINITY) {          // (an axis that is not split has box = (-inf, inf): the wrap stays on this rank)
+        if (off == 0) {
+            if (w < raw - half) off = 1;
+            else if (w > raw + half) off = -1;
+        }
+        if (off > 0 && w >= half) w = -half;
+    }
+    pos = w;
+    return off;
+}
+
 // Esirkepov deposit on the union stencil of NS = SF+2 nodes per axis based at min(a_old, a_new) (- 1 for TSC): handles any
 // anchor shift in {-1, 0, +1}; anything else (or a stencil leaving the ghosted tile) goes to the bounds-checked general body.
 template <typename T, int SF>
@@ -945,8 +968,7 @@ PIC_HD int fast3d_advance(const PicParams& p, int species, const FastConst<T>& k
         pos[a] = xn[a];
         int off;
         if (k.pbc[a] == PIC_BC_PERIODIC) {
-            off = (pos[a] >= k.box_hi[a]) ? 1 : ((pos[a] < k.box_lo[a]) ? -1 : 0);
-            pos[a] = wrap_periodic_fast<T>(pos[a], k.wind[a]);
+            off = owner_offset_periodic<T>(pos[a], k.box_lo[a], k.box_hi[a], k.wind[a]);
         } else {
             alive = apply_axis_bc<T>(pos[a], v[a], k.wind[a], k.pbc[a]) && alive;
             off = (pos[a] >= k.box_hi[a]) ? 1 : ((pos[a] < k.box_lo[a]) ? -1 : 0);

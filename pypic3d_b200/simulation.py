@@ -238,15 +238,16 @@ class Simulation:
     def _sort_intervals(self, particles):
         """Per-species sort cadence: `sort_interval` for the fastest species, proportionally longer (up to 20x) for species
         whose rms displacement per step is smaller -- a heavy, cold species stays cell-sorted far longer than electrons.
-        Sorting never changes results (only memory order), so this is purely a cost knob.  Multi-GPU runs keep the base
-        interval for every species because the sort is also what compacts migrated slots."""
+        Sorting never changes results (only memory order), so this is purely a cost knob.  Multi-GPU runs use the same cadence:
+        the sort is also what compacts migrated slots, but a slow species receives proportionally few arrivals per step (they
+        wait in the SoA tail, which the fix-up pass of K1 advances through the scalar body), so its tail stays short."""
         base = max(1, self.sort_interval)
         self._vrms = [0.0] * self.S
         if particles.x.shape[4] > 0:
             a = particles.active.reshape(self.S, -1)
             v2 = (particles.u.to(torch.float64) ** 2).sum(-1).reshape(self.S, -1)
             self._vrms = torch.sqrt((v2 * a).sum(1) / a.sum(1).clamp(min=1)).tolist()
-        if self.sort_interval <= 0 or self.distributed or particles.x.shape[4] == 0:
+        if self.sort_interval <= 0 or particles.x.shape[4] == 0:
             return [base] * self.S
         vrms = self._vrms
         vmax = max(vrms) if max(vrms) > 0 else 1.0

@@ -289,4 +289,6 @@ void hc_fused(const PicParams* p, int species, int dep, void* const comp[6], int
               const void* const B[3], void* const J[3], void* leave, int64_t leave_cap, int32_t* leave_count, int32_t* flags) {
     HC_DISPATCH(p, t_fused, p, species, dep, comp, n, E, B, J, leave, leave_cap, leave_count, flags);
 }
+// seam-consistent owner of a particle on a split periodic axis (pic_slots.cuh owner_offset_periodic), float32
+int hc_owner_offset_f32(float* pos, float box_lo, float box_hi, float wind) { return owner_offset_periodic<float>(*pos, box_lo, box_hi, wind); }
 }

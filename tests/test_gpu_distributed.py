@@ -18,7 +18,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, mesh, sf, pbc, steps, q, tile=(8, 6, 4), expect_variant=None):
+def _worker(rank, world, port, mesh, sf, pbc, steps, q, tile=(8, 6, 4), expect_variant=None, dtype=None):
     import torch.distributed as dist
     from oracle import evolve as oevolve
     from tests import gpu_util as gu
@@ -40,7 +40,7 @@ def _worker(rank, world, port, mesh, sf, pbc, steps, q, tile=(8, 6, 4), expect_v
           c = coords_of(rank, mesh)
           sl = (slice(c[0], c[0] + 1), slice(c[1], c[1] + 1), slice(c[2], c[2] + 1))
           ps, pd = gu.to_pkg_params(sp, dp)
-          t = lambda a: gu.tt(np.ascontiguousarray(a[sl]), dev=dev)
+          t = lambda a: gu.tt(np.ascontiguousarray(a[sl]), dtype, dev=dev) if (dtype is not None and a.dtype.kind == "f") else gu.tt(np.ascontiguousarray(a[sl]), dev=dev)
           v = lambda F: tuple(t(x) for x in F)
           parts = pp.TiledParticles(t(tp.x), t(tp.u), t(tp.active))
           f8 = (v(fields[0]), v(fields[1]), v(fields[2]), t(fields[3]), t(fields[4]), (v(fields[5][0]), v(fields[5][1])), None,
@@ -125,4 +125,34 @@ def test_distributed_tile_kernel_matches_oracle(mesh, pbc, variant, monkeypatch)
         assert n_got == n_want, (rank, n_got, n_want)
         assert err < 1e-11, (rank, err)
         assert perr < 1e-11, (rank, perr)
+        assert ovf == oovf
+
+
+@pytest.mark.parametrize("dtype", ("f64", "f32"))
+def test_distributed_2x2x2_matches_oracle(dtype, monkeypatch):
+    """The mesh the 8-GPU scaling run uses: every rank has a neighbour on every axis (faces, edges and corners all cross ranks), K1
+    v10 with leaver packets in all 26 directions, in the reference's dtype and in the throughput dtype."""
+    mesh, world = (2, 2, 2), 8
+    if not torch.cuda.is_available():
+        pytest.fail("-m gpu tests need a CUDA device")
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs, found {torch.cuda.device_count()}")
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    td = torch.float64 if dtype == "f64" else torch.float32
+    procs = [ctx.Process(target=_worker, args=(r, world, port, mesh, 1, (0, 0, 0), 5, q, (8, 8, 4), "pair", td)) for r in range(world)]
+    for pr in procs:
+        pr.start()
+    res = [q.get(timeout=180) for _ in range(world)]
+    for r in res:
+        assert len(r) == 7, r[1]
+    for pr in procs:
+        pr.join(timeout=120)
+        assert pr.exitcode == 0
+    tol = 1e-11 if dtype == "f64" else 2e-4
+    for rank, err, perr, n_got, n_want, ovf, oovf in res:
+        assert n_got == n_want, (rank, n_got, n_want)
+        assert err < tol, (rank, err)
+        assert perr < tol, (rank, perr)
         assert ovf == oovf

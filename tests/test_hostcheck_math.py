@@ -326,3 +326,38 @@ def test_kernel_push_body_passes_schmitz_oscillating_E(hc, pn):
     v = _kernel_push(hc, pn, (u / gamma_perp, 0.0, 0.0), None, (0.0, 0.0, 1.0), dt, 500,
                      E_of_step=lambda s: (0.0, 0.0, E0 * np.cos(omega0 * (s + 0.5) * dt)))
     assert abs(v[2]) <= 1.0e-9 and abs(_g(v) - gamma_perp) <= 1.0e-9
+
+
+def test_owner_offset_is_consistent_with_the_wrap_at_the_seam(hc):
+    """Distributed ownership on a split periodic axis (top rank of two, box [0, h)) in float32: a particle whose x + h rounds up to
+    `wind` is wrapped to -h and must be handed to the +1 neighbour (not kept with a position outside the local tile); a particle
+    exactly on +h keeps the reference's alias only on the top rank -- handed across the seam it travels as -h; inside the box
+    nothing changes.  (The charge-conservation check of bench.py at 128^3 cells per rank found one stranded electron per step.)"""
+    f = np.float32
+    wind = f(256 * 2.66e-4); h = f(0.5) * wind
+    fn = hc.hc_owner_offset_f32
+    fn.restype = ctypes.c_int
+    fn.argtypes = [ctypes.POINTER(ctypes.c_float), ctypes.c_float, ctypes.c_float, ctypes.c_float]
+    def call(x, lo, hi):
+        v = ctypes.c_float(float(x))
+        off = fn(ctypes.byref(v), ctypes.c_float(float(lo)), ctypes.c_float(float(hi)), ctypes.c_float(float(wind)))
+        return off, f(v.value)
+    # (ii) exactly on the upper wall of the top rank: leaves upward, arrives as -h
+    off, w = call(h, f(0), h)
+    assert off == 1 and w == -h
+    # (i) the largest float below +h: x + h rounds to wind
+    x = np.nextafter(h, f(0))
+    assert f(x + h) == wind
+    off, w = call(x, f(0), h)
+    assert off == 1 and w == -h
+    # interior particle of the top rank: untouched
+    x = f(0.25) * h
+    off, w = call(x, f(0), h)
+    assert off == 0 and w == f(f(x + h) - h)
+    # bottom rank [-h, 0): leaving downward wraps to just below +h (or the +h alias, which the top rank can hold)
+    x = f(-h - f(1e-6))
+    off, w = call(x, -h, f(0))
+    assert off == -1 and f(0) < w <= h
+    # an axis that is not split: the wrap stays on this rank
+    off, w = call(f(h + f(1e-5)), f(-np.inf), f(np.inf))
+    assert off == 0 and w < f(0)
