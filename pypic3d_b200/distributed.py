@@ -198,6 +198,33 @@ class DistributedHalo:
             self.k.unpack(p, axis, 0, g, fields, z, HALO_SET)
             self.k.unpack(p, axis, L - g, g, fields, z, HALO_SET)
 
+    def fold_refresh_(self, fields, bcs):
+        """fold_ followed by refresh_ along the split axes in ONE exchange per axis (periodic axes only; the caller checks):
+        both sides send their 2g boundary planes (g ghost + g interior) and add what they receive plane by plane, so the interior
+        planes receive the neighbour's ghost deposits (the fold) and the ghost planes end up with the neighbour's totals (the
+        refresh) -- every node, owned or ghost, holds the sum of all ranks' deposits, the same values as fold_ + refresh_ up to
+        the order of two additions.  Axes that are not split are folded locally (their ghosts are left zero: the fused Yee kernel
+        wraps those indices itself).  x -> y -> z with the full transverse extent, so edges and corners propagate as in
+        ghost_cells.py:199-215 / :263-316."""
+        g, p = self.g, self.p
+        for axis in range(3):
+            bc = int(bcs[axis])
+            if not self._is_split(axis):
+                self.k.fold_axis(p, axis, bc, fields)
+                continue
+            assert bc == 0, "fold_refresh_ handles periodic split axes"
+            n = 2 * self._plane_elems(axis, len(fields))
+            L = self.L[axis]
+            up = neighbor(self.coords, self.mesh, axis, +1, True)
+            dn = neighbor(self.coords, self.mesh, axis, -1, True)
+            s_hi, s_lo = self._buf(("fr_s_hi", axis), n, fields[0]), self._buf(("fr_s_lo", axis), n, fields[0])
+            r_dn, r_up = self._buf(("fr_r_dn", axis), n, fields[0]), self._buf(("fr_r_up", axis), n, fields[0])
+            self.k.pack(p, axis, L - 2 * g, 2 * g, fields, s_hi)   # my upper interior + upper ghost -> +1 neighbour's lower ghost + lower interior
+            self.k.pack(p, axis, 0, 2 * g, fields, s_lo)           # my lower ghost + lower interior -> -1 neighbour's upper interior + upper ghost
+            self._exchange([(up, s_hi), (dn, s_lo)], [(dn, r_dn), (up, r_up)])
+            self.k.unpack(p, axis, 0, 2 * g, fields, r_dn, HALO_ADD)
+            self.k.unpack(p, axis, L - 2 * g, 2 * g, fields, r_up, HALO_ADD)
+
     # ------------------------------------------------------------------ particles
     def active_dirs(self, particle_bcs):
         """Direction codes that can carry leavers: offsets only along split axes, existing neighbour on every offset axis."""

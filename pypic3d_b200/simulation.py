@@ -347,7 +347,14 @@ class Simulation:
                 self.k1_events.append((e0, e1))
         self.halo.migrate(self)
         # J: fold ghost deposits to their owners, then refresh (Esirkepov.py:357-359 / J_from_rhov.py:226-228)
-        self.halo.fold_(self.J, pbc)
+        self._J_merged = (self.distributed and self._yee_fused and self.current_filter == "none" and hasattr(self.halo, "fold_refresh_")
+                          and all((int(pbc[a]) == 0 and int(fbc[a]) == 0) if int(p.gmesh[a]) != int(p.mesh[a])
+                                  else (int(fbc[a]) != 0 or int(p.tile[a]) >= int(p.g)) for a in range(3))
+                          and os.environ.get("PIC_J_MERGED", "1") == "1")
+        if self._J_merged:      # multi-GPU, periodic split axes: fold and refresh of J in one exchange per axis
+            self.halo.fold_refresh_(self.J, pbc)
+        else:
+            self.halo.fold_(self.J, pbc)
         if self.current_filter in ("bilinear", "digital"):                       # J_from_rhov.py:234-255
             self.halo.refresh_(self.J, pbc)
             self.J = [ops.filter27(p, self.current_filter, self.alpha, c) for c in self.J]
@@ -395,7 +402,7 @@ class Simulation:
         # as wide as the guard depth (wrapped indices).  The others -- split across ranks, or reduced (one cell wide) -- are read
         # from the guard cells, so J's must be refreshed there first and E's, B's afterwards.
         done = tuple(a for a in range(3) if int(p.gmesh[a]) == int(p.mesh[a]) and (int(fbc[a]) != 0 or int(p.tile[a]) >= int(p.g)))
-        if len(done) < 3:
+        if len(done) < 3 and not getattr(self, "_J_merged", False):
             # (with the FIELD boundary conditions: what the kernel needs in J's guard plane is the J of the cell the field
             # stencil continues into; the guard cells the reference leaves in J -- particle BCs -- are restored on export)
             self.halo.refresh_(self.J, fbc, skip_axes=done)

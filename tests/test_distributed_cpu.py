@@ -122,6 +122,11 @@ def _worker(rank, world, port, mesh, tile, g, bcs, q):
         f = mine(full); halo.fold_(f, bcs)
         ref = [ohalo.fold(a, tile, bcs, g) for a in full]
         out["fold"] = max(float(np.abs(f[c].numpy()[0, 0, 0] - ref[c][coords]).max()) for c in range(3))
+        if all(b == 0 for b in bcs):     # merged fold + refresh (one exchange per split axis, periodic axes): == refresh(fold(.))
+            f = mine(full); halo.fold_refresh_(f, bcs)
+            ref = [ohalo.refresh(ohalo.fold(a, tile, bcs, g), tile, bcs, g) for a in full]
+            interior = tuple(slice(g, -g) if mesh[a] == 1 else slice(None) for a in range(3))    # (local axes: ghosts left zero)
+            out["fold_refresh"] = max(float(np.abs(f[c].numpy()[0, 0, 0][interior] - ref[c][coords][interior]).max()) for c in range(3))
         # particle packets: fixed-size packets (header row + cap rows) tagged with (species, rank, direction)
         dirs = halo.active_dirs((0, 0, 0))
         S = 2
@@ -170,6 +175,7 @@ def test_two_rank_halo_and_packets(mesh, tile, g, bcs):
     for rank, out in res:
         assert out["refresh"] < 1e-13, (rank, out)
         assert out["fold"] < 1e-13, (rank, out)
+        assert out.get("fold_refresh", 0.0) < 1e-13, (rank, out)
         assert out["packets_ok"], (rank, out)
         assert out["gather"] == 0.0, (rank, out)
 
