@@ -387,7 +387,8 @@ def run_leg(args, dtype_name, device, world, rank, local_rank, dist, *, e2e, che
     roof = None
     if k1_avg_ms:
         achieved = k1_bytes_pp * per_launch_particles / (k1_avg_ms * 1e-3) / 1e9
-        kname = {"pair": "k_pair3d (K1 v10: supercell E/B tiles in shared memory, two particles per thread in packed f32x2",
+        kname = {"pair": "k_pair3d + k_pair_fixup (K1 v10: supercell E/B tiles in shared memory, two particles per thread in packed f32x2; "
+                         "cell changers finished by the fix-up pass -- both launches are inside the timed launch pair",
                  "tile": "k_tile3d (K1 v9: supercell E/B tiles in shared memory"}.get(sim.k1_variant, "k_fused3d (K1 v8: global gather")
         roof = {"bound": "hbm", "kernel": kname + "; gather+push+deposit+move+BC, one species per launch)", "achieved": achieved,
                 "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,

@@ -4,6 +4,8 @@ import ctypes
 import os
 import re
 
+import pytest
+
 from pypic3d_b200 import _lib
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))

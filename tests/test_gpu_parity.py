@@ -89,6 +89,31 @@ def test_compute_rho(N, tile, sf, filt):
     gu.assert_close(rho / np.abs(ref).max(), ref / np.abs(ref).max(), 1e-12, "rho")
 
 
+@pytest.mark.parametrize("N,tile", CASES[:3])
+@pytest.mark.parametrize("sf", (1, 2))
+def test_direct_deposits_float32(N, tile, sf):
+    """J_from_rhov (+ bilinear filter), compute_rho and the position update in the throughput dtype: same operators, float32 leaves,
+    against the float64 oracle at the float32 tolerance of the module header."""
+    from pypic3d_b200.deposition.J_from_rhov import J_from_rhov
+    from pypic3d_b200.deposition.rho import compute_rho
+    from pypic3d_b200.particles.particle_tile_communication import update_tiled_particle_positions
+    sp, dp, tp, sc, E, B = make_case(N, tile, sf, current_filter="bilinear", alpha=0.6)
+    ps, pd = gu.to_pkg_params(sp, dp)
+    gp, gs = gu.particles_to_gpu(tp, F32), gu.species_to_pkg(sc)
+    z = fx.empty_tiled_vector(sp, dp)
+    ref = odep.J_from_rhov(tp, sc, z, sp, dp)
+    J = J_from_rhov(gp, gs, gu.vec_to_gpu(z, F32), ps, pd)
+    assert J[0].dtype == F32
+    scale = max(np.abs(r).max() for r in ref)
+    for c in range(3):
+        gu.assert_close(J[c] / scale, ref[c] / scale, TOL[F32], f"J{c} f32")
+    rref = odep.compute_rho(tp, sc, fx.empty_tiled_scalar(sp, dp), sp, dp)
+    rho = compute_rho(gp, gs, gu.tt(fx.empty_tiled_scalar(sp, dp), F32), ps, pd)
+    gu.assert_close(rho / np.abs(rref).max(), rref / np.abs(rref).max(), TOL[F32], "rho f32")
+    moved = update_tiled_particle_positions(gp, gs, 1.0)
+    gu.assert_close(moved.x, opart.update_tiled_particle_positions(tp, sc, 1.0).x, 1e-6, "move f32")
+
+
 @pytest.mark.parametrize("sf,x", list(itertools.product((1, 2), [(-1.32, 0.0, 0.0), (-0.03, 0.0, 0.0), (1.97, 0.0, 0.0)])))
 def test_single_particle_manual_stencils(sf, x):
     """tests/code_tests/single_particle_pipeline_test.py:408-485 on the GPU path (independent scalar restatement)."""
