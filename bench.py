@@ -341,6 +341,7 @@ def run_leg(args, dtype_name, device, world, rank, local_rank, dist, *, e2e, che
     if sampler:
         sampler.start()
     sim.k1_events = []
+    sim.phase_events = {} if os.environ.get("PIC_BENCH_PHASES", "1") == "1" else None
     _lib.LAUNCHES = 0
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -352,6 +353,8 @@ def run_leg(args, dtype_name, device, world, rank, local_rank, dist, *, e2e, che
     launches = _lib.LAUNCHES
     k1_ms = [a.elapsed_time(b) for a, b in sim.k1_events]
     sim.k1_events = None
+    phases = sim.phase_summary(args.steps) if sim.phase_events is not None else None
+    sim.phase_events = None
     if sampler:
         sampler.stop_flag = True
         sampler.join(timeout=2)
@@ -401,7 +404,8 @@ def run_leg(args, dtype_name, device, world, rank, local_rank, dist, *, e2e, che
     leg = {"dtype": dtype_name, "value": value, "unit": "particle-steps/s", "ms_per_step": ms_total / args.steps, "particles": total_particles,
            "overflow": overflow, "roofline": roof, "roofline_step": roof_step, "gpu_launches": launches, "k1_variant": sim.k1_variant,
            "k1_options_now": [sim._k1_options(i) for i in range(sim.S)], "k1_global_fallback_particles": int(sim.flags[2].item()),
-           "clocks": sampler.summary() if sampler else None}
+           "clocks": sampler.summary() if sampler else None,
+           "phases_ms": phases}      # rank 0's device time per step and phase (CUDA events between the phases of Simulation._step_once)
 
     # ---- end-to-end through the public API with HOST buffers (rank-local): H2D -> load_state -> step -> export -> D2H
     if e2e:

@@ -476,7 +476,11 @@ PIC_HD void crosser_finish(const PicParams& p, int species, const Geom<T>& gm, c
         return;
     }
     T pos[3] = {xn[0], xn[1], xn[2]};
-    T v[3] = {s.c[3][i], s.c[4][i], s.c[5][i]};
+    // the velocity is only needed where a wall can change it (reflect) or when the particle leaves this rank (it travels in the
+    // packet); on periodic axes it stays what the tile kernel stored -- most cell changers cost three stores, not six + three loads
+    const bool walls = (k.pbc[0] != PIC_BC_PERIODIC) || (k.pbc[1] != PIC_BC_PERIODIC) || (k.pbc[2] != PIC_BC_PERIODIC);
+    T v[3] = {(T)0, (T)0, (T)0};
+    if (walls) { v[0] = s.c[3][i]; v[1] = s.c[4][i]; v[2] = s.c[5][i]; }
     bool alive = true;
     int dir = 13;
 #pragma unroll
@@ -491,12 +495,17 @@ PIC_HD void crosser_finish(const PicParams& p, int species, const Geom<T>& gm, c
         dir -= off * (a == 0 ? 9 : (a == 1 ? 3 : 1));
     }
     if (alive && distributed && dir != 13) {
+        if (!walls) { v[0] = s.c[3][i]; v[1] = s.c[4][i]; v[2] = s.c[5][i]; }
         leave.push<T>(dir, pos, v, species, flags);
         alive = false;
     }
     if (!alive) pos[0] = pic_nan<T>();
 #pragma unroll
-    for (int c = 0; c < 3; ++c) { s.c[c][i] = pos[c]; s.c[3 + c][i] = v[c]; }
+    for (int c = 0; c < 3; ++c) s.c[c][i] = pos[c];
+    if (walls) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) s.c[3 + c][i] = v[c];
+    }
 }
 
 }  // namespace pic

@@ -72,6 +72,31 @@ def gather_tiles(tile, gmesh, group=None):
 DIRS = [(1 - sx, 1 - sy, 1 - sz) for sx in range(3) for sy in range(3) for sz in range(3)]   # dir code -> offset (ox,oy,oz)
 
 
+def grouped_packet_layout(dirs, caps, key):
+    """Row layout of the shared packet buffer that makes everything exchanged with one peer ONE contiguous message.
+    dirs: [(direction code, destination rank or None, source rank or None)] (DistributedHalo.active_dirs); caps[s][dcode]: packet
+    capacity in rows per species (0: unused direction); key: 1 = group by destination rank (the leave buffer K1 writes), 2 = by
+    source rank (the receive buffer the append reads).  Within a peer: species, then direction code ascending -- the sender's
+    group for (me -> peer) and the receiver's group for (peer <- me) hold the same directions in the same order, so a message can
+    be copied verbatim.  Returns (row_off[s][27], rows, [(peer, first element, one-past-last element)]); a packet is
+    cap + 1 rows (header row with the count) of 7 reals."""
+    S = len(caps)
+    row_off = [[0] * 27 for _ in range(S)]
+    peers = sorted({t[key] for t in dirs if t[key] is not None})
+    rows, slices = 0, []
+    for peer in peers + [None]:
+        lo = rows
+        for s_ in range(S):
+            for dc, dst, src in dirs:
+                if (dst, src)[key - 1] != peer or caps[s_][dc] == 0:
+                    continue
+                row_off[s_][dc] = rows
+                rows += caps[s_][dc] + 1
+        if peer is not None and rows > lo:
+            slices.append((peer, lo * 7, rows * 7))
+    return row_off, rows, slices
+
+
 class DistributedHalo:
     def __init__(self, params, group=None, device=None, kernels=None):
         self.p = params
@@ -264,13 +289,17 @@ class DistributedHalo:
                     recvs.append((src, recv_bufs[s][lo:hi]))
         self._exchange(sends, recvs)
 
+    def exchange_grouped(self, send_buf, recv_buf, send_slices, recv_slices):
+        """One batched round with ONE message per peer: send_slices / recv_slices are [(peer rank, lo, hi)] element ranges of the
+        shared packet buffers whose layout groups the packets by peer (Simulation._alloc_packets)."""
+        self._exchange([(peer, send_buf[lo:hi]) for peer, lo, hi in send_slices], [(peer, recv_buf[lo:hi]) for peer, lo, hi in recv_slices])
+
     def migrate(self, sim):
         """Exchange the leaver packets written by K1 and append the arrivals to the resident SoA (K3/K4 of SURVEY.md
         section 7).  No host synchronisation: packet sizes are fixed and the row counts travel in the packet headers."""
         L = _lib.lib()
         st = ops._stream()
-        self.exchange_packets([sp_.leave_buf for sp_ in sim.species], [sp_.recv_buf for sp_ in sim.species],
-                              [sp_.leave for sp_ in sim.species], tuple(self.p.particle_bc))
+        self.exchange_grouped(sim._leave_all, sim._recv_all, sim._send_slices, sim._recv_slices)
         for sp_ in sim.species:
             soa = sim._soa(sp_)
             _lib.check(L.pic_soa_append_packets(ctypes.byref(self.p), ctypes.byref(soa), ctypes.byref(sp_.recv), ops._p(sim.flags), st),

@@ -82,6 +82,7 @@ class Simulation:
         self._yee_fused = (os.environ.get("PIC_YEE", "fused") == "fused") and float(self.p.alpha) == 1.0 and int(self.p.g) >= 2
         self._E2 = self._B2 = None
         self.k1_events = None   # set to [] to record (start, end) CUDA events around every K1 launch (bench.py roofline)
+        self.phase_events = None   # set to {} to record CUDA events around the phases of every step (bench.py `phases_ms`)
         self.distributed = any(self.p.gmesh[a] != self.p.mesh[a] for a in range(3))
         E, B, J, rho, phi, ext, pml_state, overflow = fields
         if pml_state is not None:
@@ -172,32 +173,48 @@ class Simulation:
     def _alloc_packets(self):
         """Fixed-size per-direction migration packets (PicLeave).  Capacity of a face packet = the particles that could
         cross that face in one step at light speed from a uniform plasma x `leave_fraction` (thermal plasmas use ~1 % of it);
-        edges and corners scale with the product of the per-axis fractions.  Identical on every rank by construction."""
+        edges and corners scale with the product of the per-axis fractions.  Identical on every rank by construction.
+        Layout: ONE buffer for all species, packets grouped by the rank they travel to (leave) / come from (recv) -- then by
+        species, then by direction code -- so that everything exchanged with one peer is one contiguous message (on a (2,2,2) mesh:
+        7 messages per step instead of 52)."""
         p = self.p
         d = (p.dx, p.dy, p.dz)
         frac = [min(1.0, p.C * p.dt / (p.tile[a] * d[a])) for a in range(3)]
         split = [p.gmesh[a] != p.mesh[a] for a in range(3)]
-        real = 4 if self.dtype == torch.float32 else 8
         # packet sizes must agree on every rank: base them on the largest per-species capacity of the whole job
         n0s = self.halo.allreduce_max([max(1, int(sp_.cap)) for sp_ in self.species])
-        for sp_, n0 in zip(self.species, n0s):
-            L, R = PicLeave(), PicLeave()
-            rows = 0
+        caps = []
+        for n0 in n0s:
+            c = [0] * 27
             for dcode in range(27):
                 off = (1 - dcode // 9, 1 - (dcode // 3) % 3, 1 - dcode % 3)
-                cap = 0
                 if off != (0, 0, 0) and all(off[a] == 0 or split[a] for a in range(3)):
                     f = 1.0
                     for a in range(3):
                         if off[a] != 0:
                             f *= frac[a]
-                    cap = int(n0 * f * self.leave_fraction) + 1024
-                L.row_off[dcode] = R.row_off[dcode] = rows
-                L.cap[dcode] = R.cap[dcode] = cap
-                rows += (cap + 1) if cap else 0
-            sp_.leave_buf = torch.zeros(max(rows, 1) * 7, dtype=self.dtype, device=self.device)
-            sp_.recv_buf = torch.zeros(max(rows, 1) * 7, dtype=self.dtype, device=self.device)
-            L.buf, R.buf = sp_.leave_buf.data_ptr(), sp_.recv_buf.data_ptr()
+                    c[dcode] = int(n0 * f * self.leave_fraction) + 1024
+            caps.append(c)
+        dirs = self.halo.active_dirs(tuple(p.particle_bc)) if hasattr(self.halo, "active_dirs") else [(dc, None, None) for dc in range(27)]
+
+        from .distributed import grouped_packet_layout
+
+        def layout(key):        # key: 1 = destination rank (leave), 2 = source rank (recv)
+            row_off, rows, slices = grouped_packet_layout(dirs, caps, key)
+            tables = [PicLeave() for _ in self.species]
+            used = {dc for dc, _, _ in dirs}
+            for s_, t in enumerate(tables):
+                for dc in range(27):
+                    t.row_off[dc] = row_off[s_][dc]
+                    t.cap[dc] = caps[s_][dc] if dc in used else 0
+            return tables, rows, slices
+        Ls, rows_l, self._send_slices = layout(1)
+        Rs, rows_r, self._recv_slices = layout(2)
+        self._leave_all = torch.zeros(max(rows_l, 1) * 7, dtype=self.dtype, device=self.device)
+        self._recv_all = torch.zeros(max(rows_r, 1) * 7, dtype=self.dtype, device=self.device)
+        for sp_, L, R in zip(self.species, Ls, Rs):
+            sp_.leave_buf, sp_.recv_buf = self._leave_all, self._recv_all
+            L.buf, R.buf = self._leave_all.data_ptr(), self._recv_all.data_ptr()
             sp_.leave, sp_.recv = L, R
 
     def _import(self, particles, capacity_factor):
@@ -308,11 +325,29 @@ class Simulation:
         for _ in range(int(n_steps)):
             self._step_once()
 
+    def _mark(self, name):
+        """Phase boundary for the per-phase timeline (only when `phase_events` is a dict): the time since the previous mark is
+        booked under `name`."""
+        if self.phase_events is None:
+            return
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        prev = self.phase_events.get("_last")
+        if prev is not None and name is not None:
+            self.phase_events.setdefault(name, []).append((prev, e))
+        self.phase_events["_last"] = e
+
+    def phase_summary(self, n_steps):
+        """{phase: ms per step} from the recorded events (host sync)."""
+        torch.cuda.synchronize()
+        return {k: sum(a.elapsed_time(b) for a, b in v) / max(1, n_steps) for k, v in (self.phase_events or {}).items() if k != "_last"}
+
     def _step_once(self):
         L = _lib.lib()
         p, st = self.p, ops._stream()
         fbc = tuple(p.field_bc)
         pbc = tuple(p.particle_bc)
+        self._mark(None)
         for c in self.J:
             c.zero_()
         if self.distributed:
@@ -345,7 +380,9 @@ class Simulation:
             if self.k1_events is not None:
                 e1.record()
                 self.k1_events.append((e0, e1))
+        self._mark("zero_J+K1")
         self.halo.migrate(self)
+        self._mark("migrate")
         # J: fold ghost deposits to their owners, then refresh (Esirkepov.py:357-359 / J_from_rhov.py:226-228)
         self._J_merged = (self.distributed and self._yee_fused and self.current_filter == "none" and hasattr(self.halo, "fold_refresh_")
                           and all((int(pbc[a]) == 0 and int(fbc[a]) == 0) if int(p.gmesh[a]) != int(p.mesh[a])
@@ -362,8 +399,11 @@ class Simulation:
         # (Esirkepov.py:359 / J_from_rhov.py:228,246) is deferred until somebody looks at J (export_state): one guard-cell
         # exchange less per step; the exported J is identical.
         self._J_ghosts_stale = True
+        self._mark("J_fold_refresh")
         if self._yee_fused and self._step_fields_fused(fbc, pbc):
+            self._mark("yee+EB_refresh")
             self._after_fields()
+            self._mark("sort")
             return
         # B half step from E_old (evolve.py:88); E halos are valid from the previous step
         ops.update_B_(p, self.B, self.E)

@@ -151,6 +151,28 @@ def _worker(rank, world, port, mesh, tile, g, bcs, q):
                 want = float(1000 * s_ + 100 * src + d) if src is not None else 0.0
                 ok = ok and bool((blk == want).all())
         out["packets_ok"] = ok
+        # grouped layout: one message per peer, all species (what Simulation._alloc_packets / migrate use)
+        from pypic3d_b200.distributed import grouped_packet_layout
+        caps = [[0] * 27 for _ in range(S)]
+        for s_ in range(S):
+            for d, dst, src in dirs:
+                caps[s_][d] = 2 + (d + s_) % 3
+        lo_off, lo_rows, send_sl = grouped_packet_layout(dirs, caps, 1)
+        ro_off, ro_rows, recv_sl = grouped_packet_layout(dirs, caps, 2)
+        sb = torch.zeros(max(lo_rows, 1) * 7, dtype=torch.float64); rb = torch.zeros(max(ro_rows, 1) * 7, dtype=torch.float64)
+        v = sb.view(-1, 7)
+        for s_ in range(S):
+            for d, dst, src in dirs:
+                if dst is not None:
+                    v[lo_off[s_][d]:lo_off[s_][d] + caps[s_][d] + 1] = float(1000 * s_ + 100 * rank + d)
+        halo.exchange_grouped(sb, rb, send_sl, recv_sl)
+        v = rb.view(-1, 7)
+        okg = len(send_sl) <= len({t[1] for t in dirs if t[1] is not None})
+        for s_ in range(S):
+            for d, dst, src in dirs:
+                if src is not None:
+                    okg = okg and bool((v[ro_off[s_][d]:ro_off[s_][d] + caps[s_][d] + 1] == float(1000 * s_ + 100 * src + d)).all())
+        out["grouped_ok"] = okg
         # diagnostics boundary: every rank gets the tile-major array of the whole job
         whole = gather_tiles(mine(full)[0], mesh)
         out["gather"] = float(np.abs(whole.numpy() - full[0]).max()) if tuple(whole.shape) == full[0].shape else 1e9
@@ -177,6 +199,7 @@ def test_two_rank_halo_and_packets(mesh, tile, g, bcs):
         assert out["fold"] < 1e-13, (rank, out)
         assert out.get("fold_refresh", 0.0) < 1e-13, (rank, out)
         assert out["packets_ok"], (rank, out)
+        assert out["grouped_ok"], (rank, out)
         assert out["gather"] == 0.0, (rank, out)
 
 

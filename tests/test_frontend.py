@@ -485,20 +485,23 @@ def test_two_stream_growth_rate_and_energy_history(tmp_path):
 @pytest.mark.parametrize("dep", ["j_from_rhov", "esirkepov"])
 def test_weibel_growth_rate_and_magnetic_energy_history(tmp_path, dep):
     """The north star's second observable: demos/weibel/weibel.toml as packaged (1-D, 201 cells, TSC, 40 + 40 particles per cell,
-    Tz / Tx = 100), 600 steps, with the packaged current deposition (j_from_rhov + bilinear filter) and with Esirkepov.  The
-    magnetic-field energy history written by `run_PyPIC3D` (reference file format) equals the oracle's from the identical initial
-    state, the anisotropy-driven B energy grows by orders of magnitude, and the growth rates fitted to both histories agree."""
+    Tz / Tx = 100), 1200 steps, with the packaged current deposition (j_from_rhov + bilinear filter) and with Esirkepov.  The noise
+    of the initial load rings as a standing electromagnetic mode (its magnetic energy swings between ~2e-5 and ~1e-7 with a period
+    of 200 steps) on top of which the anisotropy-driven field grows; sampled every 200 steps -- at the minima of the ringing -- the
+    magnetic energy rises ~20x between steps 200 and 1200 (a 6000-step oracle run of the packaged demo carries on to 4e-4).  The
+    history written by `run_PyPIC3D` (reference file format) equals the oracle's from the identical initial state, and the growth
+    rates fitted to both agree."""
     from tests import gpu_util as gu
     gu.require_cuda()
     from pypic3d_b200.initialization import initialize_simulation
     from pypic3d_b200.__main__ import run_PyPIC3D
     from oracle import evolve as oevolve, diagnostics as odiag
     from oracle.params import StaticParameters as OS, DynamicParameters as OD, GridParameters as OG, TiledParticles as OT, SpeciesConfig as OC
-    NT = 601
+    NT, every = 1201, 200
     cfg = {k: dict(v) for k, v in WEIBEL.items()}
     cfg["simulation_parameters"].update(output_dir=str(tmp_path), Nt=NT, current_calculation=dep,
                                         filter_j="bilinear" if dep == "j_from_rhov" else "none")
-    every = int(cfg["plotting"]["plotting_interval"])
+    cfg["plotting"]["plotting_interval"] = every
     np.random.seed(0)
     loop, particles, fields, sp, dp, plotting, plasma, species = initialize_simulation(cfg, verbose=False)
     osp = OS(**sp._asdict()); odp = OD(**{**dp._asdict(), "grids": OG(**dp.grids._asdict())})
@@ -517,16 +520,16 @@ def test_weibel_growth_rate_and_magnetic_energy_history(tmp_path, dep):
     rows = [r.split(",") for r in open(os.path.join(str(tmp_path), "data", "magnetic_field_energy.txt")).read().strip().splitlines()]
     t_gpu = np.array([float(r[0]) for r in rows]); b_gpu = np.array([float(r[1]) for r in rows])
     t_ref, b_ref = np.array(t_ref), np.array(b_ref)
-    assert t_gpu.shape == t_ref.shape and np.allclose(t_gpu, t_ref, rtol=1e-12, atol=0)
-    assert b_gpu[0] == 0.0 and np.allclose(b_gpu[1:], b_ref[1:], rtol=1e-5)
-    print("weibel", dep, "B energy history (oracle):", b_ref.tolist())
-    assert b_ref[-1] > 2 * b_ref[1]                                    # the anisotropy did drive the magnetic field up
-    sel = slice(1, len(t_ref))
+    print("weibel", dep, "B energy every 200 steps (oracle):", b_ref.tolist())
+    assert t_gpu.shape == t_ref.shape == (7,) and np.allclose(t_gpu, t_ref, rtol=1e-12, atol=0)
+    assert b_gpu[0] == 0.0 and np.allclose(b_gpu[1:], b_ref[1:], rtol=1e-4)
+    assert b_ref[-1] > 5 * b_ref[1]                                    # the anisotropy did drive the magnetic field up
+    sel = slice(1, 7)                                                  # steps 200 .. 1200
     rate = lambda t, e: np.polyfit(t[sel], np.log(e[sel]), 1)[0] / 2
     g_gpu, g_ref = rate(t_gpu, b_gpu), rate(t_ref, b_ref)
     print("weibel", dep, "growth rate", g_ref, g_gpu)
-    assert g_ref > 0 and abs(g_gpu - g_ref) <= 1e-4 * abs(g_ref)
-    # sanity band against the cold, strongly anisotropic limit (growth <~ w_pe * v_hot / c): the 1-D demo sits well below it
+    assert g_ref > 0 and abs(g_gpu - g_ref) <= 1e-3 * abs(g_ref)
+    # below the cold, strongly anisotropic bound w_pe * v_hot / c
     wpe = np.sqrt(1.0e15 * 1.602e-19 ** 2 / (float(dp.eps) * 9.1093837e-31))
     vz = np.sqrt(1.380649e-23 * 29649482.87173552 / 9.1093837e-31)
     assert g_ref < wpe * vz / 299792458.0
