@@ -127,8 +127,8 @@ def update_B_(p, B, E):
     check(_lib.lib().pic_update_B(ctypes.byref(p), _v(B), _v(E), _stream()), "pic_update_B")
 
 
-def filter27(p, kind, alpha, f):
-    out = torch.empty_like(f)
+def filter27(p, kind, alpha, f, out=None):
+    out = torch.empty_like(f) if out is None else out
     check(_lib.lib().pic_filter(ctypes.byref(p), 0 if kind == "digital" else 1, float(alpha), _p(f), _p(out), _stream()), "pic_filter")
     return out
 

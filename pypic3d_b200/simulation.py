@@ -80,7 +80,10 @@ class Simulation:
         # the field half of the step in one kernel (pic_yee_fused) unless the digital filter is on; PIC_YEE=sweeps keeps the three
         # sweeps + refreshes (A/B control, same result bit for bit)
         self._yee_fused = (os.environ.get("PIC_YEE", "fused") == "fused") and float(self.p.alpha) == 1.0 and int(self.p.g) >= 2
-        self._E2 = self._B2 = None
+        self._E2 = self._B2 = self._J2 = None
+        self._swapped = []        # buffer swaps performed by the current step ("J", "EB"): replayed after a CUDA-graph replay
+        self._graphs = {}         # (sort buffers, K1 options) -> (CUDAGraph, swaps)
+        self._graph_warm = 0
         self.k1_events = None   # set to [] to record (start, end) CUDA events around every K1 launch (bench.py roofline)
         self.phase_events = None   # set to {} to record CUDA events around the phases of every step (bench.py `phases_ms`)
         self.distributed = any(self.p.gmesh[a] != self.p.mesh[a] for a in range(3))
@@ -323,7 +326,10 @@ class Simulation:
     # ------------------------------------------------------------------------------------------ the step
     def step(self, n_steps=1):
         for _ in range(int(n_steps)):
-            self._step_once()
+            if self._use_graph():
+                self._step_graphed()
+            else:
+                self._step_once()
 
     def _mark(self, name):
         """Phase boundary for the per-phase timeline (only when `phase_events` is a dict): the time since the previous mark is
@@ -342,7 +348,54 @@ class Simulation:
         torch.cuda.synchronize()
         return {k: sum(a.elapsed_time(b) for a, b in v) / max(1, n_steps) for k, v in (self.phase_events or {}).items() if k != "_last"}
 
+    def _use_graph(self):
+        """Replay the step as ONE CUDA graph launch where launch latency is what a step costs (the packaged demos: 6 k - 260 k
+        particles, ~25 launches of a few microseconds each).  Single GPU, fused Yee, no per-launch timing requested;
+        PIC_GRAPH=0 disables, PIC_GRAPH=1 forces (any size)."""
+        mode = os.environ.get("PIC_GRAPH", "auto")
+        if mode == "0" or self.distributed or self.k1_events is not None or self.phase_events is not None or not self._yee_fused:
+            return False
+        return mode == "1" or sum(sp_.cap for sp_ in self.species) <= (1 << 22)
+
+    def _step_graphed(self):
+        """One step through the graph cache.  A graph is valid for one set of buffer identities: the key is which sort buffer every
+        species currently lives in, the parity of the E/B (and filtered-J) ping-pong and the K1 options; the sort itself runs
+        outside the graph (it flips the buffers, and a new key is captured -- at most a handful of graphs exist)."""
+        if self._graph_warm < 3:                       # lazily allocated scratch, function attributes, ... : first steps eagerly
+            self._graph_warm += 1
+            return self._step_once()
+        key = (tuple(sp_.cur for sp_ in self.species), self.E[0].data_ptr(), self.B[0].data_ptr(), self.J[0].data_ptr(),
+               tuple(self._k1_options(s) for s in range(self.S)), self.k1_variant)
+        ent = self._graphs.get(key)
+        if ent is None:
+            g = torch.cuda.CUDAGraph()
+            state = (self.E, self._E2, self.B, self._B2, self.J, self._J2, self._J_ghosts_stale)
+            self._swapped = []
+            with torch.cuda.graph(g):
+                self._step_core()
+            swaps = tuple(self._swapped)
+            # the capture performed the buffer swaps on the host but executed nothing: restore, replay applies them again
+            self.E, self._E2, self.B, self._B2, self.J, self._J2, self._J_ghosts_stale = state
+            ent = self._graphs[key] = (g, swaps)
+        g, swaps = ent
+        g.replay()
+        for what in swaps:
+            if what == "EB":
+                self.E, self._E2 = self._E2, self.E
+                self.B, self._B2 = self._B2, self.B
+            elif what == "J":
+                self.J, self._J2 = self._J2, self.J
+        self._J_ghosts_stale = True
+        self._after_fields()
+
     def _step_once(self):
+        self._swapped = []
+        self._step_core()
+        self._mark("yee+EB_refresh")
+        self._after_fields()
+        self._mark("sort")
+
+    def _step_core(self):
         L = _lib.lib()
         p, st = self.p, ops._stream()
         fbc = tuple(p.field_bc)
@@ -394,16 +447,18 @@ class Simulation:
             self.halo.fold_(self.J, pbc)
         if self.current_filter in ("bilinear", "digital"):                       # J_from_rhov.py:234-255
             self.halo.refresh_(self.J, pbc)
-            self.J = [ops.filter27(p, self.current_filter, self.alpha, c) for c in self.J]
+            if self._J2 is None:
+                self._J2 = [torch.empty_like(c) for c in self.J]
+            for c, o in zip(self.J, self._J2):
+                ops.filter27(p, self.current_filter, self.alpha, c, out=o)
+            self.J, self._J2 = self._J2, self.J
+            self._swapped.append("J")
         # update_E reads J on the tile interior only, so the ghost refresh the reference performs here
         # (Esirkepov.py:359 / J_from_rhov.py:228,246) is deferred until somebody looks at J (export_state): one guard-cell
         # exchange less per step; the exported J is identical.
         self._J_ghosts_stale = True
         self._mark("J_fold_refresh")
         if self._yee_fused and self._step_fields_fused(fbc, pbc):
-            self._mark("yee+EB_refresh")
-            self._after_fields()
-            self._mark("sort")
             return
         # B half step from E_old (evolve.py:88); E halos are valid from the previous step
         ops.update_B_(p, self.B, self.E)
@@ -428,7 +483,6 @@ class Simulation:
             self.halo.refresh_(self.B, fbc)
             self.B = [ops.filter27(p, "digital", self.alpha, c) for c in self.B]
         self.halo.refresh_(self.B, fbc)
-        self._after_fields()
 
     def _step_fields_fused(self, fbc, pbc):
         """B(half) -> E -> B(half) in one pass over the fields (pic_yee_fused) into the spare E/B arrays, then swap.  Guard cells of
@@ -455,6 +509,7 @@ class Simulation:
         check(rc, "pic_yee_fused")
         self.E, self._E2 = self._E2, self.E
         self.B, self._B2 = self._B2, self.B
+        self._swapped.append("EB")
         if len(done) < 3:
             self.halo.refresh_(self.E + self.B, fbc, skip_axes=done)
         return True
