@@ -48,13 +48,13 @@ def physical_setup(n_local, mesh, ppc, shape_factor, dtype_name):
                 wind=[N[a] * dx for a in range(3)])
 
 
-def make_params(cfg, n_local, mesh, shape_factor, deposition="esirkepov"):
+def make_params(cfg, n_local, mesh, shape_factor, deposition="esirkepov", current_filter="none"):
     from pypic3d_b200.parameters import StaticParameters, DynamicParameters, GridParameters
     from pypic3d_b200.utilities.grids import build_yee_grid
     N, dx = cfg["N"], cfg["dx"]
     sp = StaticParameters(name="bench", output_dir=".", Nt=0, verbose=False, GPUs=True, benchmark=True, solver="electrodynamic_yee",
                           electrostatic=False, relativistic=True, particle_pusher="boris", current_deposition=deposition,
-                          current_filter="none", shape_factor=shape_factor, guard_cells=2, tile_shape=(n_local,) * 3,
+                          current_filter=current_filter, shape_factor=shape_factor, guard_cells=2, tile_shape=(n_local,) * 3,
                           particle_tile_capacity_factor=1.25, pml_active=False, boundary_conditions=(0, 0, 0),
                           particle_boundary_conditions=(0, 0, 0), field_mesh=tuple(mesh))
     dp = DynamicParameters(dt=cfg["dt"], dx=dx, dy=dx, dz=dx, Nx=N[0], Ny=N[1], Nz=N[2], x_wind=cfg["wind"][0], y_wind=cfg["wind"][1],
@@ -204,7 +204,8 @@ def run_reference_arm(args):
 def workload_config(args, n_gpus):
     mesh = mesh_for(n_gpus)
     return {"workload": f"synthetic 3D periodic thermal plasma, {args.n}^3 cells per GPU x {args.ppc} ppc (2 species), "
-                        f"Esirkepov + first-order Yee, shape_factor={args.shape_factor}, relativistic Boris, g=2",
+                        f"{'Esirkepov' if getattr(args, 'deposition', 'esirkepov') == 'esirkepov' else 'j_from_rhov (' + args.current_filter + ' filter)'}"
+                        f" + first-order Yee, shape_factor={args.shape_factor}, relativistic Boris, g=2",
             "cells_per_gpu": args.n ** 3, "ppc": args.ppc, "mesh": list(mesh), "sort_interval": args.sort_interval,
             "cache": "inputs >> L2 (particles 6.4 GB f32 at 256^3 x 16 ppc); no L2 flush needed"}
 
@@ -309,7 +310,8 @@ def run_leg(args, dtype_name, device, world, rank, local_rank, dist, *, e2e, che
     mesh = mesh_for(n_gpus)
     dtype = torch.float32 if dtype_name == "f32" else torch.float64
     cfg = physical_setup(args.n, mesh, args.ppc, args.shape_factor, dtype_name)
-    sp, dp = make_params(cfg, args.n, mesh, args.shape_factor)
+    sp, dp = make_params(cfg, args.n, mesh, args.shape_factor, deposition="direct" if args.deposition == "j_from_rhov" else "esirkepov",
+                         current_filter=args.current_filter)
     moff = (rank // (mesh[1] * mesh[2]), (rank // mesh[2]) % mesh[1], rank % mesh[2])
     particles, species = device_plasma(cfg, sp, dp, args.n, moff, args.ppc, dtype, device, seed=1234 + rank,
                                        cap_factor=1.02 if world > 1 else 1.0)
@@ -440,6 +442,9 @@ def main():
     ap.add_argument("--ppc", type=int, default=16)
     ap.add_argument("--shape-factor", type=int, default=1)
     ap.add_argument("--dtype", default="f32", choices=("f32", "f64"), help="dtype of the headline leg (the other one is reported under legs)")
+    ap.add_argument("--deposition", default="esirkepov", choices=("esirkepov", "j_from_rhov"),
+                    help="secondary configurations only (the headline metric is Esirkepov): the reference's default is j_from_rhov + bilinear")
+    ap.add_argument("--current-filter", default="none", choices=("none", "bilinear"))
     ap.add_argument("--sort-interval", type=int, default=10)
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--cpu-n", type=int, default=16)
