@@ -142,6 +142,15 @@ int pic_pack_planes(const PicParams* p, int axis, int start, int nplanes, int nc
 int pic_unpack_planes(const PicParams* p, int axis, int start, int nplanes, int ncomp, void* const* fields,
                       const void* buf, int mode, void* stream);
 
+/* The same for up to 26 axis-aligned boxes of one ghosted tile in ONE launch: box b = [lo[3b..], lo + size[3b..]) in array
+ * indices, packed as [comp][x][y][z] one box after the other.  These are the faces, edges and corners a rank exchanges with its
+ * neighbours when all split axes are served in one round (the x -> y -> z sequence of ghost_cells.py:199-215 carries edges and
+ * corners through three dependent rounds; sending them explicitly needs one). */
+int pic_pack_boxes(const PicParams* p, int nbox, const int32_t* lo, const int32_t* size, int ncomp, const void* const* fields,
+                   void* buf, void* stream);
+int pic_unpack_boxes(const PicParams* p, int nbox, const int32_t* lo, const int32_t* size, int ncomp, void* const* fields,
+                     const void* buf, int mode, void* stream);
+
 /* ---- electrostatic field solve, one ghosted tile (mesh == 1,1,1) ----
  * solvers/electrostatic_yee.py:71-156 solve_poisson_with_conjugate_gradient: matrix-free CG for -lapl(phi) = rho/eps with the
  * reference's update order and stopping rule (k < max_iter && sum r^2 > tol^2); phi is the initial guess on entry and the

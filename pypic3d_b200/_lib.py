@@ -224,6 +224,8 @@ SIGNATURES = {
     "pic_sort_scatter": [_PP, _SOA, _SOA, _VP, _VP, _VP],
     "pic_fused_push_deposit": [_PP, _INT, _INT, _SOA, _V3, _V3, _V3, _V3, _V3, _LEAVE, _VP, _VP],
     "pic_fused_tile3d": [_PP, _INT, _SOA, _VP, _INT, _INT, _V3, _V3, _V3, _LEAVE, _VP, _VP],
+    "pic_pack_boxes": [_PP, _INT, _VP, _VP, _INT, _V3, _VP, _VP],
+    "pic_unpack_boxes": [_PP, _INT, _VP, _VP, _INT, _V3, _VP, _INT, _VP],
     "pic_fused_pair3d": [_PP, _INT, _SOA, _VP, _INT, _INT, _V3, _V3, _V3, _LEAVE, _VP, _VP, _I64, _VP],
     "pic_pair_work_bytes": [_PP, _I64],
     "pic_sort_blocked_offsets": [_PP, _VP, _VP, _VP, _VP, _VP, _I64, _VP, _VP],

@@ -405,6 +405,59 @@ static int launch_planes(const PicParams* p, int dir, int axis, int start, int n
     PIC_LAUNCH_RET();
 }
 
+// ---------------------------------------------------------------- box pack / unpack (one-shot 26-neighbour exchange)
+// Up to 26 axis-aligned boxes of one ghosted tile <-> one packed buffer, in ONE launch for all components: box b occupies
+// buf[off[b] .. off[b] + ncomp * nx * ny * nz) as [comp][x][y][z].  The boxes are the faces, edges and corners a rank exchanges
+// with its neighbours when all split axes are handled in one round instead of x -> y -> z (distributed.py exchange_boxes_).
+struct BoxTable {
+    int n;
+    int lo[26][3];
+    int sz[26][3];
+    long long off[27];       // element offset of every box in the buffer; off[n] = total
+};
+template <typename T, int DIR /*0 pack, 1 unpack*/>
+__global__ void __launch_bounds__(256) k_boxes(Dims d, int ncomp, Ptrs8 F, const __grid_constant__ BoxTable bt, T* buf, int mode) {
+    const long long total = bt.off[bt.n];
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        int b = 0;
+        while (b + 1 < bt.n && i >= bt.off[b + 1]) ++b;                      // (<= 26 boxes, sorted offsets)
+        long long r = i - bt.off[b];
+        const int nz = bt.sz[b][2], ny = bt.sz[b][1], nx = bt.sz[b][0];
+        const int z = (int)(r % nz); r /= nz;
+        const int y = (int)(r % ny); r /= ny;
+        const int x = (int)(r % nx);
+        const int comp = (int)(r / nx);
+        T* f = (T*)F.f[comp] + ((size_t)(bt.lo[b][0] + x) * d.L[1] + (bt.lo[b][1] + y)) * d.L[2] + (bt.lo[b][2] + z);
+        if (DIR == 0) buf[i] = *f;
+        else if (mode == PIC_HALO_SET) *f = buf[i];
+        else if (mode == PIC_HALO_ADD) *f += buf[i];
+        else *f -= buf[i];
+    }
+}
+template <typename T>
+static int launch_boxes(const PicParams* p, int dir, int nbox, const int32_t* lo, const int32_t* sz, int ncomp, void* const* fields, void* buf,
+                        int mode, cudaStream_t st) {
+    const Dims d = dims_of(p);
+    Ptrs8 F;
+    for (int c = 0; c < ncomp; ++c) F.f[c] = fields[c];
+    BoxTable bt;
+    bt.n = nbox;
+    long long off = 0;
+    for (int b = 0; b < nbox; ++b) {
+        for (int a = 0; a < 3; ++a) {
+            bt.lo[b][a] = lo[3 * b + a]; bt.sz[b][a] = sz[3 * b + a];
+            if (lo[3 * b + a] < 0 || sz[3 * b + a] < 0 || lo[3 * b + a] + sz[3 * b + a] > d.L[a]) return PIC_EINVAL;
+        }
+        bt.off[b] = off;
+        off += (long long)ncomp * sz[3 * b] * sz[3 * b + 1] * sz[3 * b + 2];
+    }
+    bt.off[nbox] = off;
+    if (off == 0) return 0;
+    if (dir == 0) k_boxes<T, 0><<<grid_for(off, 256), 256, 0, st>>>(d, ncomp, F, bt, (T*)buf, mode);
+    else k_boxes<T, 1><<<grid_for(off, 256), 256, 0, st>>>(d, ncomp, F, bt, (T*)buf, mode);
+    PIC_LAUNCH_RET();
+}
+
 // ---------------------------------------------------------------- sum of squares over tile interiors (utils.py:160-166)
 template <typename T>
 __global__ void __launch_bounds__(256) k_sumsq(Dims d, const T* __restrict__ f, double* out) {
@@ -936,6 +989,20 @@ int pic_unpack_planes(const PicParams* p, int axis, int start, int nplanes, int 
     PIC_CHECK_ARG(halo_args_ok(p, axis, ncomp, fields) && buf && start >= 0 && nplanes >= 0 &&
                   start + nplanes <= p->tile[axis] + 2 * p->g && mode >= 0 && mode <= 2);
     PIC_DISPATCH_T(p, launch_planes, p, 1, axis, start, nplanes, ncomp, fields, (void*)buf, mode, (cudaStream_t)stream);
+}
+
+int pic_pack_boxes(const PicParams* p, int nbox, const int32_t* lo, const int32_t* size, int ncomp, const void* const* fields, void* buf,
+                   void* stream) {
+    PIC_CHECK_ARG(p && lo && size && fields && buf && nbox >= 0 && nbox <= 26 && ncomp >= 1 && ncomp <= 8);
+    PIC_CHECK_ARG(p->mesh[0] == 1 && p->mesh[1] == 1 && p->mesh[2] == 1);
+    PIC_DISPATCH_T(p, launch_boxes, p, 0, nbox, lo, size, ncomp, (void* const*)fields, buf, 0, (cudaStream_t)stream);
+}
+
+int pic_unpack_boxes(const PicParams* p, int nbox, const int32_t* lo, const int32_t* size, int ncomp, void* const* fields, const void* buf,
+                     int mode, void* stream) {
+    PIC_CHECK_ARG(p && lo && size && fields && buf && nbox >= 0 && nbox <= 26 && ncomp >= 1 && ncomp <= 8 && mode >= 0 && mode <= 2);
+    PIC_CHECK_ARG(p->mesh[0] == 1 && p->mesh[1] == 1 && p->mesh[2] == 1);
+    PIC_DISPATCH_T(p, launch_boxes, p, 1, nbox, lo, size, ncomp, fields, (void*)buf, mode, (cudaStream_t)stream);
 }
 
 int pic_yee_fused(const PicParams* p, const void* const E[3], const void* const B[3], const void* const J[3], void* const E_out[3],

@@ -35,6 +35,12 @@ class CudaHaloKernels:
     def fold_axis(self, p, axis, bc, fields):
         ops.halo_fold_axis_(p, axis, bc, fields)
 
+    def pack_boxes(self, p, boxes, fields, buf):
+        ops.pack_boxes(p, boxes, fields, buf)
+
+    def unpack_boxes(self, p, boxes, fields, buf, mode):
+        ops.unpack_boxes_(p, boxes, fields, buf, mode)
+
 
 def rank_of(coords, mesh):
     return (coords[0] * mesh[1] + coords[1]) * mesh[2] + coords[2]
@@ -228,7 +234,8 @@ class DistributedHalo:
         both sides send their 2g boundary planes (g ghost + g interior) and add what they receive plane by plane, so the interior
         planes receive the neighbour's ghost deposits (the fold) and the ghost planes end up with the neighbour's totals (the
         refresh) -- every node, owned or ghost, holds the sum of all ranks' deposits, the same values as fold_ + refresh_ up to
-        the order of two additions.  Axes that are not split are folded locally (their ghosts are left zero: the fused Yee kernel
+        the order of two additions.  Valid for split axes at least 2g cells wide (the two 2g slabs of a tile must not overlap:
+        a ghost plane then has exactly one owner-side partner); Simulation checks and falls back to fold_ + refresh_.  Axes that are not split are folded locally (their ghosts are left zero: the fused Yee kernel
         wraps those indices itself).  x -> y -> z with the full transverse extent, so edges and corners propagate as in
         ghost_cells.py:199-215 / :263-316."""
         g, p = self.g, self.p
@@ -249,6 +256,93 @@ class DistributedHalo:
             self._exchange([(up, s_hi), (dn, s_lo)], [(dn, r_dn), (up, r_up)])
             self.k.unpack(p, axis, 0, 2 * g, fields, r_dn, HALO_ADD)
             self.k.unpack(p, axis, L - 2 * g, 2 * g, fields, r_up, HALO_ADD)
+
+    # ------------------------------------------------------------------ one-shot exchange (all split axes in ONE round)
+    def _box_plan(self, ncomp, kind):
+        """Boxes this rank sends / receives when every split (periodic) axis is served in one round, grouped by peer.
+        kind "refresh": direction o -> my interior slab next to the (+o) face goes to the (+o) neighbour's ghost slab on its (-o)
+        side; a split axis with o = 0 spans its INTERIOR (its guard cells are other boxes), an axis that is not split its FULL
+        extent (its guard cells are valid already, or refreshed locally afterwards).  kind "sum": my 2g-thick slab (interior + ghost) next to the (+o) face goes to the (+o) neighbour's
+        2g-thick slab on its (-o) side and is ADDED there; axes with o = 0 span the FULL extent -- after the round every node, owned
+        or ghost, holds the sum of all ranks' deposits (fold + refresh of J at once).  Returns (send boxes, recv boxes,
+        send slices, recv slices): boxes in message order, slices = [(peer, lo, hi)] element ranges of the packed buffers."""
+        key = (ncomp, kind)
+        plan = getattr(self, "_plans", {}).get(key)
+        if plan is not None:
+            return plan
+        g, L = self.g, self.L
+        split = [self._is_split(a) for a in range(3)]
+        dirs = [o for o in DIRS if o != (0, 0, 0) and all(o[a] == 0 or split[a] for a in range(3))]
+
+        def box(o, side):
+            # side "send": the slab next to my (+o) face; side "recv": the slab next to my (-o) face (what the (-o) neighbour sent)
+            lo, sz = [], []
+            for a in range(3):
+                s_ = o[a] if side == "send" else -o[a]
+                if o[a] == 0:
+                    # an axis that is not split travels with its guard cells (valid already when the Yee kernel wrote them, refreshed
+                    # locally afterwards otherwise); a split axis contributes its interior: its guard cells are other boxes
+                    r = (0, L[a]) if (kind == "sum" or not split[a]) else (g, L[a] - g)
+                elif kind == "refresh":
+                    r = ((L[a] - 2 * g, L[a] - g) if s_ > 0 else (g, 2 * g)) if side == "send" else ((L[a] - g, L[a]) if s_ > 0 else (0, g))
+                else:
+                    r = (L[a] - 2 * g, L[a]) if s_ > 0 else (0, 2 * g)
+                lo.append(r[0]); sz.append(r[1] - r[0])
+            return (tuple(lo), tuple(sz))
+
+        def peer_of(o, sign):
+            c = [(self.coords[a] + sign * o[a]) % self.mesh[a] for a in range(3)]
+            return rank_of(c, self.mesh)
+
+        def grouped(side):
+            # sender: group by destination N(+o); receiver: group by source N(-o); inside a group the direction order is the same
+            items = sorted(((peer_of(o, +1 if side == "send" else -1), DIRS.index(o), o) for o in dirs))
+            boxes, slices, off = [], [], 0
+            cur, lo_ = None, 0
+            for peer, _, o in items:
+                if peer != cur:
+                    if cur is not None:
+                        slices.append((cur, lo_, off))
+                    cur, lo_ = peer, off
+                b = box(o, side)
+                boxes.append(b)
+                off += ncomp * b[1][0] * b[1][1] * b[1][2]
+            if cur is not None:
+                slices.append((cur, lo_, off))
+            return boxes, slices, off
+        sb, ss, sn = grouped("send")
+        rb, rs, rn = grouped("recv")
+        plan = (sb, rb, ss, rs, sn, rn)
+        if not hasattr(self, "_plans"):
+            self._plans = {}
+        self._plans[key] = plan
+        return plan
+
+    def exchange_boxes_(self, fields, kind):
+        """One round for all split axes: `kind` "refresh" (E, B guard cells) or "sum" (J: fold and refresh at once).  Periodic
+        split axes only (the caller checks); axes that are not split are left to the caller's local pass."""
+        sb, rb, ss, rs, sn, rn = self._box_plan(len(fields), kind)
+        sbuf = self._buf(("box_s", kind), sn, fields[0])
+        rbuf = self._buf(("box_r", kind), rn, fields[0])
+        self.k.pack_boxes(self.p, sb, fields, sbuf)
+        self._exchange([(peer, sbuf[lo:hi]) for peer, lo, hi in ss], [(peer, rbuf[lo:hi]) for peer, lo, hi in rs])
+        self.k.unpack_boxes(self.p, rb, fields, rbuf, HALO_SET if kind == "refresh" else HALO_ADD)
+
+    def refresh_oneshot_(self, fields, bcs, skip_axes=()):
+        """refresh_ with ONE exchange round: faces, edges and corners of all split axes travel explicitly, then the axes that are
+        not split (and not in `skip_axes`) are refreshed locally over the full extent."""
+        self.exchange_boxes_(fields, "refresh")
+        for axis in range(3):
+            if not self._is_split(axis) and axis not in skip_axes:
+                self.k.refresh_axis(self.p, axis, int(bcs[axis]), fields)
+
+    def fold_refresh_oneshot_(self, fields, bcs):
+        """fold_refresh_ with ONE exchange round: every rank adds its neighbours' overlapping 2g-thick slabs, then the axes that are
+        not split are folded locally."""
+        self.exchange_boxes_(fields, "sum")
+        for axis in range(3):
+            if not self._is_split(axis):
+                self.k.fold_axis(self.p, axis, int(bcs[axis]), fields)
 
     # ------------------------------------------------------------------ particles
     def active_dirs(self, particle_bcs):

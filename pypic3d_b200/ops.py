@@ -177,6 +177,24 @@ def pack_planes(p, axis, start, nplanes, fields, buf):
     check(_lib.lib().pic_pack_planes(ctypes.byref(p), axis, start, nplanes, len(fields), _v(fields), _p(buf), _stream()), "pic_pack_planes")
 
 
+def _box_arrays(boxes):
+    n = len(boxes)
+    lo = (ctypes.c_int32 * (3 * n))(*[int(v) for b in boxes for v in b[0]])
+    sz = (ctypes.c_int32 * (3 * n))(*[int(v) for b in boxes for v in b[1]])
+    return n, lo, sz
+
+
+def pack_boxes(p, boxes, fields, buf):
+    """boxes: [((lo_x, lo_y, lo_z), (n_x, n_y, n_z))] in array indices of the ghosted tile; buf receives them back to back."""
+    n, lo, sz = _box_arrays(boxes)
+    check(_lib.lib().pic_pack_boxes(ctypes.byref(p), n, lo, sz, len(fields), _v(fields), _p(buf), _stream()), "pic_pack_boxes")
+
+
+def unpack_boxes_(p, boxes, fields, buf, mode):
+    n, lo, sz = _box_arrays(boxes)
+    check(_lib.lib().pic_unpack_boxes(ctypes.byref(p), n, lo, sz, len(fields), _v(fields), _p(buf), int(mode), _stream()), "pic_unpack_boxes")
+
+
 def unpack_planes_(p, axis, start, nplanes, fields, buf, mode):
     check(_lib.lib().pic_unpack_planes(ctypes.byref(p), axis, start, nplanes, len(fields), _v(fields), _p(buf), int(mode), _stream()),
           "pic_unpack_planes")

@@ -438,10 +438,13 @@ class Simulation:
         self._mark("migrate")
         # J: fold ghost deposits to their owners, then refresh (Esirkepov.py:357-359 / J_from_rhov.py:226-228)
         self._J_merged = (self.distributed and self._yee_fused and self.current_filter == "none" and hasattr(self.halo, "fold_refresh_")
-                          and all((int(pbc[a]) == 0 and int(fbc[a]) == 0) if int(p.gmesh[a]) != int(p.mesh[a])
+                          and all((int(pbc[a]) == 0 and int(fbc[a]) == 0 and int(p.tile[a]) >= 2 * int(p.g)) if int(p.gmesh[a]) != int(p.mesh[a])
                                   else (int(fbc[a]) != 0 or int(p.tile[a]) >= int(p.g)) for a in range(3))
                           and os.environ.get("PIC_J_MERGED", "1") == "1")
-        if self._J_merged:      # multi-GPU, periodic split axes: fold and refresh of J in one exchange per axis
+        self._oneshot = self._J_merged and hasattr(self.halo, "fold_refresh_oneshot_") and os.environ.get("PIC_HALO_ONESHOT", "1") == "1"
+        if self._oneshot:       # ... and all split axes in ONE round (faces, edges and corners sent explicitly)
+            self.halo.fold_refresh_oneshot_(self.J, pbc)
+        elif self._J_merged:    # multi-GPU, periodic split axes: fold and refresh of J in one exchange per axis
             self.halo.fold_refresh_(self.J, pbc)
         else:
             self.halo.fold_(self.J, pbc)
@@ -511,7 +514,10 @@ class Simulation:
         self.B, self._B2 = self._B2, self.B
         self._swapped.append("EB")
         if len(done) < 3:
-            self.halo.refresh_(self.E + self.B, fbc, skip_axes=done)
+            if getattr(self, "_oneshot", False):
+                self.halo.refresh_oneshot_(self.E + self.B, fbc, skip_axes=done)
+            else:
+                self.halo.refresh_(self.E + self.B, fbc, skip_axes=done)
         return True
 
     def _after_fields(self):

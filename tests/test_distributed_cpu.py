@@ -43,6 +43,26 @@ class NumpyHaloKernels:
             else:
                 v.sub_(b[c])
 
+    def pack_boxes(self, p, boxes, fields, buf):
+        out = [f.numpy()[0, 0, 0][lo[0]:lo[0] + sz[0], lo[1]:lo[1] + sz[1], lo[2]:lo[2] + sz[2]].reshape(-1) for lo, sz in boxes for f in fields]
+        # layout: box after box, inside a box [comp][x][y][z]
+        buf.numpy()[:] = np.concatenate(out) if out else np.zeros(0)
+
+    def unpack_boxes(self, p, boxes, fields, buf, mode):
+        b = buf.numpy(); off = 0
+        for lo, sz in boxes:
+            n = sz[0] * sz[1] * sz[2]
+            for f in fields:
+                v = f.numpy()[0, 0, 0][lo[0]:lo[0] + sz[0], lo[1]:lo[1] + sz[1], lo[2]:lo[2] + sz[2]]
+                blk = b[off:off + n].reshape(sz)
+                if mode == 0:
+                    v[...] = blk
+                elif mode == 1:
+                    v[...] += blk
+                else:
+                    v[...] -= blk
+                off += n
+
     def refresh_axis(self, p, axis, bc, fields):
         tile = tuple(int(p.tile[a]) for a in range(3))
         bcs = [0, 0, 0]; bcs[axis] = bc
@@ -122,11 +142,19 @@ def _worker(rank, world, port, mesh, tile, g, bcs, q):
         f = mine(full); halo.fold_(f, bcs)
         ref = [ohalo.fold(a, tile, bcs, g) for a in full]
         out["fold"] = max(float(np.abs(f[c].numpy()[0, 0, 0] - ref[c][coords]).max()) for c in range(3))
-        if all(b == 0 for b in bcs):     # merged fold + refresh (one exchange per split axis, periodic axes): == refresh(fold(.))
+        wide = all(mesh[a] == 1 or tile[a] >= 2 * g for a in range(3))       # (the 2g slabs of a split axis must not overlap)
+        if all(b == 0 for b in bcs) and wide:     # merged fold + refresh (one exchange per split axis, periodic axes): == refresh(fold(.))
             f = mine(full); halo.fold_refresh_(f, bcs)
             ref = [ohalo.refresh(ohalo.fold(a, tile, bcs, g), tile, bcs, g) for a in full]
             interior = tuple(slice(g, -g) if mesh[a] == 1 else slice(None) for a in range(3))    # (local axes: ghosts left zero)
             out["fold_refresh"] = max(float(np.abs(f[c].numpy()[0, 0, 0][interior] - ref[c][coords][interior]).max()) for c in range(3))
+            # the same two operations with ONE exchange round (faces, edges, corners sent explicitly)
+            f = mine(full); halo.refresh_oneshot_(f, bcs)
+            ref = [ohalo.refresh(a, tile, bcs, g) for a in full]
+            out["refresh_oneshot"] = max(float(np.abs(f[c].numpy()[0, 0, 0] - ref[c][coords]).max()) for c in range(3))
+            f = mine(full); halo.fold_refresh_oneshot_(f, bcs)
+            ref = [ohalo.refresh(ohalo.fold(a, tile, bcs, g), tile, bcs, g) for a in full]
+            out["fold_refresh_oneshot"] = max(float(np.abs(f[c].numpy()[0, 0, 0][interior] - ref[c][coords][interior]).max()) for c in range(3))
         # particle packets: fixed-size packets (header row + cap rows) tagged with (species, rank, direction)
         dirs = halo.active_dirs((0, 0, 0))
         S = 2
@@ -198,6 +226,8 @@ def test_two_rank_halo_and_packets(mesh, tile, g, bcs):
         assert out["refresh"] < 1e-13, (rank, out)
         assert out["fold"] < 1e-13, (rank, out)
         assert out.get("fold_refresh", 0.0) < 1e-13, (rank, out)
+        assert out.get("refresh_oneshot", 0.0) < 1e-13, (rank, out)
+        assert out.get("fold_refresh_oneshot", 0.0) < 1e-13, (rank, out)
         assert out["packets_ok"], (rank, out)
         assert out["grouped_ok"], (rank, out)
         assert out["gather"] == 0.0, (rank, out)
@@ -215,3 +245,22 @@ def test_topology_helpers():
     assert [(d, dst, src) for d, dst, src in dirs] == [(4, 1, 3), (22, 3, 1)]     # +x and -x only on a slab mesh
     dirs = halo.active_dirs((2, 0, 0))                                           # absorbing walls: no wrap-around peers
     assert [(d, dst, src) for d, dst, src in dirs] == [(4, 1, None), (22, None, 1)]
+
+
+@pytest.mark.parametrize("mesh,tile,g", [((2, 2, 1), (4, 5, 2), 2), ((2, 1, 2), (3, 2, 4), 1)])
+def test_four_rank_oneshot_exchange(mesh, tile, g):
+    """Two split axes (edges cross ranks diagonally): the one-round box exchange equals the x -> y -> z sequence."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 4, port, mesh, tile, g, (0, 0, 0), q)) for r in range(4)]
+    for pr in procs:
+        pr.start()
+    res = [q.get(timeout=180) for _ in range(4)]
+    for pr in procs:
+        pr.join(timeout=60)
+        assert pr.exitcode == 0
+    for rank, out in res:
+        for k in ("refresh", "fold", "fold_refresh", "refresh_oneshot", "fold_refresh_oneshot"):
+            assert out[k] < 1e-13, (rank, k, out)
+        assert out["packets_ok"] and out["grouped_ok"], (rank, out)
