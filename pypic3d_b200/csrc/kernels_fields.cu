@@ -428,10 +428,12 @@ __global__ void __launch_bounds__(256) k_boxes(Dims d, int ncomp, Ptrs8 F, const
         const int x = (int)(r % nx);
         const int comp = (int)(r / nx);
         T* f = (T*)F.f[comp] + ((size_t)(bt.lo[b][0] + x) * d.L[1] + (bt.lo[b][1] + y)) * d.L[2] + (bt.lo[b][2] + z);
+        // (the boxes of a sum-exchange OVERLAP in the array -- a face slab spans the edge and corner regions too -- so the
+        // accumulating modes must be atomic; SET boxes are disjoint)
         if (DIR == 0) buf[i] = *f;
         else if (mode == PIC_HALO_SET) *f = buf[i];
-        else if (mode == PIC_HALO_ADD) *f += buf[i];
-        else *f -= buf[i];
+        else if (mode == PIC_HALO_ADD) atomicAdd(f, buf[i]);
+        else atomicAdd(f, -buf[i]);
     }
 }
 template <typename T>
