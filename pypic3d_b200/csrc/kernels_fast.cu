@@ -43,18 +43,79 @@ __global__ void __launch_bounds__(256) k_export(int species, SoAView<T> s, T* __
 }
 
 // ---------------------------------------------------------------- counting sort by local cell
-// (Warp-aggregating these atomics with __match_any_sync was measured: the sort got 0.9 ms slower, the plain version stays.)
+// The stream is nearly sorted when it is re-sorted (a few per cent of the particles have changed cell), so the 32 consecutive
+// particles of a warp form a handful of RUNS of equal cell: the head lane of a run issues ONE atomic for the whole run (the
+// histogram's add; the scatter's returning cursor add, whose result the run shares by shuffle) and the members of a run write
+// consecutive destination slots.  Runs are found with one shuffle and one ballot (neighbour compare) -- the __match_any_sync
+// grouping tried in round 1 cost more than the atomics it saved.  PIC_SORT_RUNS=0 keeps the one-atomic-per-particle form.
+#ifndef PIC_SORT_RUNS
+#define PIC_SORT_RUNS 1
+#endif
+struct WarpRun {
+    int head_lane;     // lane of the first particle of my run
+    int len;           // (head lanes) particles in the run
+    bool head;
+};
+__device__ __forceinline__ WarpRun warp_run(int cell, bool valid, int lane) {
+    const int prev = __shfl_up_sync(0xffffffffu, cell, 1);
+    const unsigned vmask = __ballot_sync(0xffffffffu, valid);          // (valid lanes are a prefix of the warp)
+    WarpRun r;
+    r.head = valid && (lane == 0 || cell != prev);
+    const unsigned heads = __ballot_sync(0xffffffffu, r.head);
+    const unsigned below = heads & (0xffffffffu >> (31 - lane));       // heads at or below my lane
+    r.head_lane = below ? 31 - __clz(below) : 0;
+    const unsigned above = (lane == 31) ? 0u : (heads >> (lane + 1));
+    r.len = above ? __ffs(above) : __popc(vmask) - lane;
+    return r;
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256) k_sort_hist(const __grid_constant__ PicParams p, SoAView<T> s, int32_t* __restrict__ count) {
     const int64_t n = s.count();
+#if PIC_SORT_RUNS
+    const int lane = threadIdx.x & 31;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t b = blockIdx.x * (int64_t)blockDim.x + threadIdx.x - lane; b < n; b += stride) {
+        const int64_t j = b + lane;
+        const bool valid = j < n;
+        const int cell = valid ? local_cell<T>(p, s.c[0][j], s.c[1][j], s.c[2][j]) : -1;
+        const WarpRun r = warp_run(cell, valid, lane);
+        if (r.head) atomicAdd(&count[cell], r.len);
+    }
+#else
     for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x)
         atomicAdd(&count[local_cell<T>(p, s.c[0][j], s.c[1][j], s.c[2][j])], 1);
+#endif
 }
 
 template <typename T>
 __global__ void __launch_bounds__(256) k_sort_scatter(const __grid_constant__ PicParams p, SoAView<T> s, SoAView<T> d,
                                                       const int32_t* __restrict__ offset, int32_t* __restrict__ cursor) {
     const int64_t n = s.count();
+#if PIC_SORT_RUNS
+    const int lane = threadIdx.x & 31;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t b = blockIdx.x * (int64_t)blockDim.x + threadIdx.x - lane; b < n; b += stride) {
+        const int64_t j = b + lane;
+        const bool valid = j < n;
+        T px = (T)0, py = (T)0, pz = (T)0;
+        int cell = -1;
+        if (valid) {
+            px = s.c[0][j]; py = s.c[1][j]; pz = s.c[2][j];
+            cell = local_cell<T>(p, px, py, pz);
+        }
+        const WarpRun r = warp_run(cell, valid, lane);
+        int base = 0;
+        if (r.head) base = atomicAdd(&cursor[cell], r.len);
+        base = __shfl_sync(0xffffffffu, base, r.head_lane);
+        if (!valid) continue;
+        const int64_t dst = (int64_t)offset[cell] + base + (lane - r.head_lane);
+        if (dst >= d.cap) continue;
+        d.c[0][dst] = px; d.c[1][dst] = py; d.c[2][dst] = pz;
+        d.c[3][dst] = s.c[3][j]; d.c[4][dst] = s.c[4][j]; d.c[5][dst] = s.c[5][j];
+        if (s.id && d.id) d.id[dst] = s.id[j];
+    }
+#else
     for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x) {
         const T px = s.c[0][j], py = s.c[1][j], pz = s.c[2][j];
         const int cell = local_cell<T>(p, px, py, pz);
@@ -64,6 +125,7 @@ __global__ void __launch_bounds__(256) k_sort_scatter(const __grid_constant__ Pi
         d.c[3][dst] = s.c[3][j]; d.c[4][dst] = s.c[4][j]; d.c[5][dst] = s.c[5][j];
         if (s.id && d.id) d.id[dst] = s.id[j];
     }
+#endif
 }
 
 // exclusive scan of int32: 2048 elements per CTA (256 threads x 8), block sums scanned by one CTA, then added back.
