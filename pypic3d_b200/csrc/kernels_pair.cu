@@ -57,7 +57,7 @@ namespace pic {
 #define PIC_K10_CLAIM_ASM 1    /* chunk claim: 1 = predicated atom.shared by lane 0 (no divergence), 0 = if (lane == 0) atomicAdd */
 #endif
 template <typename T> struct K10Ring { static constexpr int NSTAGE = sizeof(T) == 4 ? PIC_K10_NSTAGE : PIC_K10_NSTAGE64; };
-#ifndef PIC_K10_DEAL
+#ifndef PIC_K10_DEAL   /* (historical: the kernel now always deals through the counter) */
 #define PIC_K10_DEAL 1         /* chunks of a supercell reach the warps 0: round-robin continuing across supercells (4.20 ms per launch),
                                   1: through a shared-memory counter (3.91 ms: a warp held up by a queue flush no longer delays the
                                   release of its ring slot) -- profiles/r02_ab3_run.log */

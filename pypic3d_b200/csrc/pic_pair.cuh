@@ -18,7 +18,7 @@
 //     1/3 (S1a S1b + S0a S0b) + 1/6 (S1a S0b + S0a S1b)  ==  Sm_a Sm_b + (1/12) dS_a dS_b,  Sm = (S0 + S1) / 2, dS = S1 - S0
 //     (Esirkepov.py:381-406 expanded): 10 instead of 19 operations per current component.
 //   * the periodic wrap, reflect / absorb and the ownership test only matter for particles that change cell; those are handed
-//     back to the kernel (kind 2), which finishes them with full warps (crosser_finish); everybody else just rounds
+//     back to the kernel (kind 2), which defers them to the fix-up pass (k_pair_fixup -> crosser_finish); everybody else just rounds
 //     (x + h) - h like the reference's mod().
 // Everything here is __host__ __device__: tests/hostcheck compiles it with g++ and checks it against the oracle without a GPU.
 #pragma once
