@@ -36,7 +36,8 @@ rho1 = sim.charge_density()
 if sim._J_ghosts_stale:
     sim.halo.refresh_(sim.J, tuple(p.particle_bc)); sim._J_ghosts_stale = False
 inv_dt = 1.0 / float(p.dt)
-cont = ops.div_residual(p, sim.J, rho1, inv_dt, rho0, -inv_dt)
+pd, _, cast = sim._diag()
+cont = ops.div_residual(pd, [cast(c) for c in sim.J], rho1, inv_dt, rho0, -inv_dt)
 g1 = sim.gauss_residual(rho1)
 g = int(p.g)
 I = (0, 0, 0, slice(g, -g), slice(g, -g), slice(g, -g))
@@ -49,7 +50,7 @@ print("bad cells", bad.shape[0], "of", c.numel())
 if bad.shape[0]:
     print("bad min idx", bad.min(0).values.tolist(), "max idx", bad.max(0).values.tolist())
     print("first bad", bad[:8].tolist())
-    dj = ops.div_residual(p, sim.J, rho1, 0.0, rho0, 0.0)
+    dj = ops.div_residual(pd, [cast(c) for c in sim.J], rho1, 0.0, rho0, 0.0)
     for b_ in bad[:4].tolist():
         ix, iy, iz = b_[0] + g, b_[1] + g, b_[2] + g
         print(" cell", b_, "cont", cont[0, 0, 0, ix, iy, iz].item(), "drho/dt", ((rho1 - rho0) * inv_dt)[0, 0, 0, ix, iy, iz].item(), "divJ", dj[0, 0, 0, ix, iy, iz].item(),
