@@ -356,7 +356,8 @@ class Simulation:
         particles, ~25 launches of a few microseconds each).  Single GPU, fused Yee, no per-launch timing requested;
         PIC_GRAPH=0 disables, PIC_GRAPH=1 forces (any size)."""
         mode = os.environ.get("PIC_GRAPH", "auto")
-        if mode == "0" or self.distributed or self.k1_events is not None or self.phase_events is not None or not self._yee_fused:
+        if (mode == "0" or getattr(self, "_graph_off", False) or self.distributed or self.k1_events is not None
+                or self.phase_events is not None or not self._yee_fused):
             return False
         return mode == "1" or sum(sp_.cap for sp_ in self.species) <= (1 << 22)
 
@@ -374,8 +375,15 @@ class Simulation:
             g = torch.cuda.CUDAGraph()
             state = (self.E, self._E2, self.B, self._B2, self.J, self._J2, self._J_ghosts_stale)
             self._swapped = []
-            with torch.cuda.graph(g):
-                self._step_core()
+            try:
+                with torch.cuda.graph(g):
+                    self._step_core()
+            except Exception:
+                # something on this configuration's path cannot be captured: run eagerly from now on (nothing was executed)
+                self.E, self._E2, self.B, self._B2, self.J, self._J2, self._J_ghosts_stale = state
+                self._graph_off = True
+                torch.cuda.synchronize()
+                return self._step_once()
             swaps = tuple(self._swapped)
             # the capture performed the buffer swaps on the host but executed nothing: restore, replay applies them again
             self.E, self._E2, self.B, self._B2, self.J, self._J2, self._J_ghosts_stale = state
