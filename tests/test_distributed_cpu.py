@@ -247,16 +247,18 @@ def test_topology_helpers():
     assert [(d, dst, src) for d, dst, src in dirs] == [(4, 1, None), (22, None, 1)]
 
 
-@pytest.mark.parametrize("mesh,tile,g", [((2, 2, 1), (4, 5, 2), 2), ((2, 1, 2), (3, 2, 4), 1)])
+@pytest.mark.parametrize("mesh,tile,g", [((2, 2, 1), (4, 5, 2), 2), ((2, 1, 2), (3, 2, 4), 1), ((3, 1, 2), (4, 2, 6), 2)])
 def test_four_rank_oneshot_exchange(mesh, tile, g):
-    """Two split axes (edges cross ranks diagonally): the one-round box exchange equals the x -> y -> z sequence."""
+    """Two split axes (edges cross ranks diagonally; a mesh of three along x: the +1 and -1 neighbours differ): the one-round box
+    exchange equals the x -> y -> z sequence."""
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 4, port, mesh, tile, g, (0, 0, 0), q)) for r in range(4)]
+    world = mesh[0] * mesh[1] * mesh[2]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, mesh, tile, g, (0, 0, 0), q)) for r in range(world)]
     for pr in procs:
         pr.start()
-    res = [q.get(timeout=180) for _ in range(4)]
+    res = [q.get(timeout=180) for _ in range(world)]
     for pr in procs:
         pr.join(timeout=60)
         assert pr.exitcode == 0
@@ -264,3 +266,34 @@ def test_four_rank_oneshot_exchange(mesh, tile, g):
         for k in ("refresh", "fold", "fold_refresh", "refresh_oneshot", "fold_refresh_oneshot"):
             assert out[k] < 1e-13, (rank, k, out)
         assert out["packets_ok"] and out["grouped_ok"], (rank, out)
+
+
+@pytest.mark.parametrize("mesh,tile,g", [((2, 2, 2), (4, 4, 4), 2), ((3, 1, 2), (4, 2, 6), 2), ((4, 3, 1), (2, 2, 2), 1)])
+@pytest.mark.parametrize("kind", ("refresh", "sum"))
+def test_box_plans_of_all_ranks_agree(mesh, tile, g, kind):
+    """The one-round exchange is only correct if, for every pair of ranks, what A packs for B is byte for byte what B expects from
+    A: same number of boxes in the same order with the same shapes.  Pure host logic, every rank's plan built in this process
+    (covers mesh sizes > 2, where the +1 and -1 neighbours differ)."""
+    world = mesh[0] * mesh[1] * mesh[2]
+    plans = {}
+    for r in range(world):
+        halo = DistributedHalo(_params(mesh, tile, g, coords_of(r, mesh)), None, torch.device("cpu"), kernels=NumpyHaloKernels())
+        plans[r] = halo._box_plan(3, kind)
+    for a in range(world):
+        sb, rb, ss, rs, sn, rn = plans[a]
+        assert sn == sum(3 * b[1][0] * b[1][1] * b[1][2] for b in sb) and rn == sum(3 * b[1][0] * b[1][1] * b[1][2] for b in rb)
+        assert [p for p, _, _ in ss] == sorted({p for p, _, _ in ss})            # one message per peer
+        for peer, lo, hi in ss:
+            back = [(l2, h2) for p2, l2, h2 in plans[peer][3] if p2 == a]         # what the peer expects from me
+            assert len(back) == 1 and back[0][1] - back[0][0] == hi - lo, (a, peer)
+            # box shapes inside the message, in order
+            def shapes(boxes, slices, who):
+                out, off = [], 0
+                span = next((l, h) for p_, l, h in slices if p_ == who)
+                for b in boxes:
+                    n = 3 * b[1][0] * b[1][1] * b[1][2]
+                    if span[0] <= off < span[1]:
+                        out.append(b[1])
+                    off += n
+                return out
+            assert shapes(sb, ss, peer) == shapes(plans[peer][1], plans[peer][3], a), (a, peer)
